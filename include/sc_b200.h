@@ -1,0 +1,200 @@
+/*
+ * sc_b200.h — C ABI of libsc_b200.so: sm_100a CUDA kernels for the spatial-statistics hot path
+ * of mcap91/SpatialCore (spatialcore.spatial).
+ *
+ * The reference has no FFI: its boundary is the Python function API
+ * (src/spatialcore/spatial/__init__.py:11-52).  Each export below replaces the third-party
+ * compiled routine the reference calls at the cited line; the Python layer
+ * (spatialcore_b200/spatial/*.py) keeps the reference's signatures and calls these through ctypes.
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer on the current CUDA device unless marked host;
+ *   - the caller owns every buffer; the library allocates nothing and keeps no global state:
+ *     scratch comes from a caller-provided workspace sized by the matching *_workspace_bytes();
+ *   - all work is enqueued on `stream` (a cudaStream_t) and is stream-ordered and re-entrant;
+ *   - return 0 on success, a negative sc_status otherwise; sc_last_error() gives a thread-local
+ *     message.  No exception crosses the ABI.
+ *   - matrices are row-major "cell-major": element (cell i, gene g) at base[i*ld + g].
+ */
+#ifndef SC_B200_H
+#define SC_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#if defined(__GNUC__)
+#define SC_API __attribute__((visibility("default")))
+#else
+#define SC_API
+#endif
+
+typedef void* sc_stream_t; /* cudaStream_t */
+
+enum sc_status {
+  SC_OK = 0,
+  SC_ERR_INVALID = -1,     /* bad argument */
+  SC_ERR_WORKSPACE = -2,   /* workspace too small */
+  SC_ERR_CUDA = -3,        /* CUDA runtime error (message in sc_last_error) */
+  SC_ERR_UNSUPPORTED = -4  /* valid request outside the compiled limits */
+};
+
+enum sc_dtype { SC_F32 = 0, SC_F64 = 1 };
+enum sc_perm_source { SC_PERM_REPLAY = 0, SC_PERM_PHILOX = 1 };
+
+#define SC_KNN_MAX_K 128
+
+SC_API int sc_version(void);
+SC_API const char* sc_last_error(void);
+
+/* ---------------------------------------------------------------------------------------------
+ * Neighbour graphs.  Replace sklearn BallTree kneighbors (autocorrelation.py:393-395), squidpy's
+ * kd_tree kneighbors()/radius_neighbors() (autocorrelation.py:565-570) and scipy cKDTree
+ * query / query_ball_point (neighborhoods.py:213-241).
+ *
+ * Exact: neighbours ranked by FP64 d² = dx*dx + dy*dy (no FMA contraction), ties by index, self
+ * excluded by index; each output row sorted by column index (canonical CSR order).
+ * ------------------------------------------------------------------------------------------- */
+
+SC_API size_t sc_grid_knn_workspace_bytes(int64_t n, int k);
+
+/* coords f64[n,2]; idx i32[n, k+include_self]; dist f64[n, k+include_self] or NULL (aligned with
+ * idx); order_out i32[n] or NULL (grid-sorted position -> original cell id, a spatial ordering).
+ * labels/profile: optional fused neighbourhood composition (neighborhoods.py:226-237):
+ * labels i32[n] in [0,n_types), profile f32[n,n_types] raw counts; pass NULL/0 to skip; idx may be
+ * NULL when only the profile is wanted.  Requires 1 <= k <= SC_KNN_MAX_K and k < n. */
+SC_API int sc_grid_knn(const double* coords, int64_t n, int k, int include_self, int32_t* idx,
+                double* dist, int32_t* order_out, const int32_t* labels, int n_types,
+                float* profile, void* ws, size_t ws_bytes, sc_stream_t stream);
+
+SC_API size_t sc_grid_radius_workspace_bytes(int64_t n);
+
+/* Pass 1: degrees + exclusive scan.  indptr i32[n+1]; nnz_out i64[1] (device).  Inclusive
+ * d² <= r*r, self excluded.  The workspace keeps the binning for pass 2 and must not be touched
+ * in between.  Optional fused composition as above (raw counts; empty rows stay zero). */
+SC_API int sc_grid_radius_count(const double* coords, int64_t n, double r, int32_t* indptr,
+                         int64_t* nnz_out, const int32_t* labels, int n_types, float* profile,
+                         void* ws, size_t ws_bytes, sc_stream_t stream);
+
+/* Pass 2: indices i32[nnz] column-sorted per row; dist f64[nnz] or NULL;
+ * scratch: nnz*4 bytes (+ nnz*8 when dist != NULL). */
+SC_API int sc_grid_radius_fill(const double* coords, int64_t n, double r, const int32_t* indptr,
+                        int32_t* indices, double* dist, void* scratch, size_t scratch_bytes,
+                        void* ws, size_t ws_bytes, sc_stream_t stream);
+
+/* Neighbourhood composition from an existing CSR graph (k_fixed>0 and indptr==NULL: every row has
+ * k_fixed entries).  profile f32[n,n_types] raw counts. */
+SC_API int sc_nbhd_counts(const int32_t* indptr, const int32_t* indices, int64_t n, int k_fixed,
+                   const int32_t* labels, int n_types, float* profile, sc_stream_t stream);
+
+/* Row-normalise counts to proportions in place; n_empty_out i64[1] = rows with zero sum
+ * (neighborhoods.py:253-264). */
+SC_API int sc_profile_normalize(float* profile, int64_t n, int n_types, int normalize,
+                         int64_t* n_empty_out, sc_stream_t stream);
+
+/* Analytic graph moments s0,s1,s2 of the row-standardised (weights==NULL: w_ij = 1/deg_i) or
+ * explicitly weighted graph; rows must be column-sorted.  out f64[3].  Feeds var_norm / z_score
+ * (autocorrelation.py:599-608; squidpy analytic moments). */
+SC_API size_t sc_graph_moments_workspace_bytes(int64_t n);
+SC_API int sc_graph_moments(const int32_t* indptr, const int32_t* indices, const float* weights,
+                     int64_t n, int k_fixed, double* out, void* ws, size_t ws_bytes,
+                     sc_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Standardisation.  Replaces _compute_{mean,variance,std}_sparse and the z-scoring at
+ * autocorrelation.py:66-124, 853-858, 1126-1143 (ddof = 0, FP64 accumulation).
+ * ------------------------------------------------------------------------------------------- */
+
+SC_API size_t sc_zscore_workspace_bytes(int64_t n, int g);
+
+/* X: dense [n, ldx] of `dtype`.  cols i32[g] or NULL selects/reorders columns of X.
+ * rows i32[n] or NULL: output row a is built from input row rows[a].
+ * Z f32[n, ldz] (ldz % 4 == 0, ldz >= g; padding columns are zeroed).
+ * mean, std f64[g]; zero_var u8[g].  Zero-variance genes get Z = 0. */
+SC_API int sc_zscore(const void* X, int dtype, int64_t n, int64_t ldx, int g, const int32_t* cols,
+              const int32_t* rows, float* Z, int64_t ldz, double* mean, double* std,
+              uint8_t* zero_var, void* ws, size_t ws_bytes, sc_stream_t stream);
+
+/* Scatter CSR expression (indptr i64[n+1], indices i32, data of `dtype`) into dense f32 [n, ldo]
+ * (zero-filled first).  colmap i32[n_cols_x] or NULL: source column -> output column, -1 = drop. */
+SC_API int sc_csr_densify(const int64_t* indptr, const int32_t* indices, const void* data, int dtype,
+                   int64_t n, const int32_t* colmap, int g_out, float* out, int64_t ldo,
+                   sc_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Spatial lag + Moran numerator/denominator in one pass.  Replaces scanpy's numba Moran kernel
+ * (via squidpy, autocorrelation.py:576-583) and `W @ Z` (autocorrelation.py:307, 864).
+ * lag f32[n, ldl] or NULL; local f32[n, ldl] or NULL (= Z∘lag, autocorrelation.py:870);
+ * num[g] = Σ_i z·lag, den[g] = Σ_i z² (FP64).
+ * ------------------------------------------------------------------------------------------- */
+
+SC_API size_t sc_csr_lag_moran_workspace_bytes(int64_t n, int g);
+SC_API int sc_csr_lag_moran(const int32_t* indptr, const int32_t* indices, const float* weights,
+                     int64_t n, int k_fixed, const float* Z, int64_t ldz, int g, float* lag,
+                     float* local, int64_t ldl, double* num, double* den, void* ws,
+                     size_t ws_bytes, sc_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Permutation nulls.
+ *
+ * graph_rows (squidpy semantics, the null behind morans_i; autocorrelation.py:576-583):
+ *     sims[p, c] = Σ_i A[i, c] · B[π_p(i), c]          (A = Z, B = cached lag)
+ * values (the reference's own null; autocorrelation.py:322-328, 877-884):
+ *     sims[p, c] = Σ_i S_p[i, c] · Σ_j w_ij · Zy[π_p(j), c]
+ *     with S_p[i] = Zy[π_p(i)] when Zx == NULL (Moran) or Zx[i] (Lee: only y is permuted).
+ *
+ * Permutation p (0-based, global index perm_offset + p):
+ *     SC_PERM_REPLAY : π_p(i) = perm_idx[p*n + i]  (host-generated, e.g. numpy's stream)
+ *     SC_PERM_PHILOX : on-the-fly bijection keyed by Philox4x32-10(seed, perm_offset + p)
+ * sims f64[n_perms, g] receives raw sums (no N/S0/den scaling).
+ * ------------------------------------------------------------------------------------------- */
+
+SC_API size_t sc_perm_null_workspace_bytes(int64_t n, int g);
+
+SC_API int sc_perm_null_graph_rows(const float* A, int64_t lda, const float* B, int64_t ldb, int64_t n,
+                            int g, int source, const int32_t* perm_idx, uint64_t seed,
+                            int64_t perm_offset, int n_perms, double* sims, void* ws,
+                            size_t ws_bytes, sc_stream_t stream);
+
+/* cell_obs f32[n, ldc] / cell_cnt i32[n, ldc] or NULL: when given, cell_cnt[i,c] is incremented
+ * for every permutation with |local_p[i,c]| >= |cell_obs[i,c]| (autocorrelation.py:888-896,
+ * 1411-1413). */
+SC_API int sc_perm_null_values(const int32_t* indptr, const int32_t* indices, const float* weights,
+                        int64_t n, int k_fixed, const float* Zx, const float* Zy, int64_t ldz,
+                        int g, int source, const int32_t* perm_idx, uint64_t seed,
+                        int64_t perm_offset, int n_perms, double* sims, const float* cell_obs,
+                        int32_t* cell_cnt, int64_t ldc, void* ws, size_t ws_bytes,
+                        sc_stream_t stream);
+
+/* Materialise Philox permutation `perm_index` of [0,n) into out i32[n] (tests, replay export). */
+SC_API int sc_philox_permutation(uint64_t seed, int64_t perm_index, int64_t n, int32_t* out,
+                          sc_stream_t stream);
+
+/* Same permutation evaluated on the HOST into host memory (no GPU needed): lets a Philox-mode run be
+ * replayed through any CPU implementation. */
+SC_API int sc_philox_permutation_host(uint64_t seed, int64_t perm_index, int64_t n, int32_t* out_host);
+
+/* Fold a batch of simulated statistics into running null summaries:
+ * s = sims[p,c]*scale[c]; cnt_ge += (s >= obs[c]); cnt_abs_ge += (|s| >= |obs[c]|);
+ * sum += s; sumsq += s*s.  (squidpy pval_sim / var_sim; autocorrelation.py:331-332.) */
+SC_API int sc_null_accumulate(const double* sims, int n_perms, int g, const double* scale,
+                       const double* obs, int64_t* cnt_ge, int64_t* cnt_abs_ge, double* sum,
+                       double* sumsq, sc_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Lee's L for all ordered gene pairs: L[x, y] = Σ_i A[i, x] · B[i, y]  (A = Z, B = W Z), i.e. the
+ * matrix of autocorrelation.py:307-315 over every pair.  Tensor cores (tcgen05, 3xTF32, FP32
+ * accumulation in TMEM) when available for the shape, otherwise an FP32 CUDA-core kernel.
+ * L f32[g, ldl].  impl: 0 = auto, 1 = CUDA-core FP32, 2 = tcgen05 3xTF32.
+ * ------------------------------------------------------------------------------------------- */
+SC_API size_t sc_lee_gemm_workspace_bytes(int64_t n, int g);
+SC_API int sc_lee_gemm(const float* A, int64_t lda, const float* B, int64_t ldb, int64_t n, int g,
+                float* L, int64_t ldl, int impl, void* ws, size_t ws_bytes, sc_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SC_B200_H */

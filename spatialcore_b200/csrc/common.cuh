@@ -1,0 +1,176 @@
+// Shared helpers for libsc_b200 (sm_100a).  Internal header, not part of the C ABI.
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include "../../include/sc_b200.h"
+
+namespace sc {
+
+void set_error(const char* fmt, ...);
+
+#define SC_CHECK_ARG(cond, ...)      \
+  do {                               \
+    if (!(cond)) {                   \
+      sc::set_error(__VA_ARGS__);    \
+      return SC_ERR_INVALID;         \
+    }                                \
+  } while (0)
+
+#define SC_CUDA_OK(expr)                                                              \
+  do {                                                                                \
+    cudaError_t _e = (expr);                                                          \
+    if (_e != cudaSuccess) {                                                          \
+      sc::set_error("%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), __FILE__, \
+                    __LINE__);                                                        \
+      return SC_ERR_CUDA;                                                             \
+    }                                                                                 \
+  } while (0)
+
+#define SC_LAUNCH_OK() SC_CUDA_OK(cudaGetLastError())
+
+constexpr int kWarp = 32;
+constexpr unsigned kFull = 0xffffffffu;
+
+inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+
+// Bump allocator over the caller's workspace (256-byte aligned slices).
+struct Arena {
+  char* base;
+  size_t cap;
+  size_t off;
+  Arena(void* p, size_t bytes) : base(static_cast<char*>(p)), cap(bytes), off(0) {}
+  template <typename T>
+  T* take(size_t count) {
+    size_t bytes = align_up(count * sizeof(T), 256);
+    if (off + bytes > cap) return nullptr;
+    T* r = reinterpret_cast<T*>(base + off);
+    off += bytes;
+    return r;
+  }
+};
+
+// Number of SMs of the current device (cached per thread).
+int sm_count();
+
+__device__ __forceinline__ float4 ldg4(const float* p) {
+  return __ldg(reinterpret_cast<const float4*>(p));
+}
+// Streaming 128-bit load: read once, do not keep in L1.
+__device__ __forceinline__ float4 ld_stream4(const float* p) {
+  float4 r;
+  asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];"
+               : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w)
+               : "l"(p));
+  return r;
+}
+
+__device__ __forceinline__ double shfl_f64(double v, int src) {
+  int lo = __double2loint(v), hi = __double2hiint(v);
+  lo = __shfl_sync(kFull, lo, src);
+  hi = __shfl_sync(kFull, hi, src);
+  return __hiloint2double(hi, lo);
+}
+__device__ __forceinline__ double shfl_up_f64(double v, int d) {
+  int lo = __double2loint(v), hi = __double2hiint(v);
+  lo = __shfl_up_sync(kFull, lo, d);
+  hi = __shfl_up_sync(kFull, hi, d);
+  return __hiloint2double(hi, lo);
+}
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    int lo = __double2loint(v), hi = __double2hiint(v);
+    lo = __shfl_xor_sync(kFull, lo, o);
+    hi = __shfl_xor_sync(kFull, hi, o);
+    v += __hiloint2double(hi, lo);
+  }
+  return v;
+}
+
+// ---- Philox4x32-10 and the keyed Feistel bijection used for on-the-fly permutations ----------
+// Mirrored bit-for-bit by spatialcore_b200/philox.py (host) so tests can replay device
+// permutations on the CPU oracle.
+
+constexpr int kFeistelRounds = 8;
+
+__host__ __device__ __forceinline__ void philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2,
+                                                       uint32_t c3, uint32_t k0, uint32_t k1,
+                                                       uint32_t out[4]) {
+#pragma unroll
+  for (int r = 0; r < 10; ++r) {
+    uint64_t p0 = (uint64_t)0xD2511F53u * c0;
+    uint64_t p1 = (uint64_t)0xCD9E8D57u * c2;
+    uint32_t n0 = (uint32_t)(p1 >> 32) ^ c1 ^ k0;
+    uint32_t n1 = (uint32_t)p1;
+    uint32_t n2 = (uint32_t)(p0 >> 32) ^ c3 ^ k1;
+    uint32_t n3 = (uint32_t)p0;
+    c0 = n0; c1 = n1; c2 = n2; c3 = n3;
+    k0 += 0x9E3779B9u;
+    k1 += 0xBB67AE85u;
+  }
+  out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
+}
+
+// Round keys of permutation `perm_index` under `seed`.
+__host__ __device__ __forceinline__ void perm_round_keys(uint64_t seed, uint64_t perm_index,
+                                                         uint32_t keys[kFeistelRounds]) {
+#pragma unroll
+  for (int b = 0; b < kFeistelRounds / 4; ++b) {
+    uint32_t o[4];
+    philox4x32_10((uint32_t)perm_index, (uint32_t)(perm_index >> 32), (uint32_t)b, 0x5C0B200u,
+                  (uint32_t)seed, (uint32_t)(seed >> 32), o);
+    keys[4 * b + 0] = o[0]; keys[4 * b + 1] = o[1];
+    keys[4 * b + 2] = o[2]; keys[4 * b + 3] = o[3];
+  }
+}
+
+__host__ __device__ __forceinline__ uint32_t mix32(uint32_t x) {
+  x ^= x >> 16; x *= 0x85EBCA6Bu;
+  x ^= x >> 13; x *= 0xC2B2AE35u;
+  x ^= x >> 16;
+  return x;
+}
+
+// Alternating unbalanced Feistel network on m = bl + br bits (bl = m/2, br = m - bl), kFeistelRounds
+// (even) rounds, cycle-walked into [0, n).  A bijection of [0, n) for every key set.
+struct PermDomain {
+  uint32_t n;
+  uint32_t bl, br;  // bit widths of the left / right halves
+};
+
+__host__ __device__ __forceinline__ PermDomain make_perm_domain(uint32_t n) {
+  uint32_t m = 2;
+  while (m < 32 && (1ull << m) < (uint64_t)n) ++m;
+  PermDomain d;
+  d.n = n;
+  d.bl = m / 2;
+  d.br = m - d.bl;
+  return d;
+}
+
+__host__ __device__ __forceinline__ uint32_t feistel_once(uint32_t v, const PermDomain& d,
+                                                          const uint32_t* keys) {
+  uint32_t wl = d.bl, wr = d.br;
+  uint32_t L = v >> wr, R = v & ((1u << wr) - 1u);
+#pragma unroll
+  for (int r = 0; r < kFeistelRounds; ++r) {
+    uint32_t f = mix32(R * 0x9E3779B1u + keys[r]) & ((1u << wl) - 1u);
+    uint32_t nR = L ^ f;  // wl bits
+    L = R;                // wr bits
+    R = nR;
+    uint32_t t = wl; wl = wr; wr = t;
+  }
+  return (L << wr) | R;
+}
+
+__host__ __device__ __forceinline__ uint32_t perm_apply(uint32_t i, const PermDomain& d,
+                                                        const uint32_t* keys) {
+  uint32_t v = feistel_once(i, d, keys);
+  while (v >= d.n) v = feistel_once(v, d, keys);
+  return v;
+}
+
+}  // namespace sc

@@ -1,0 +1,834 @@
+// Grid-hashed exact neighbour graphs on sm_100a: kNN, radius, neighbourhood composition, graph
+// moments.  See include/sc_b200.h for the contract and the reference lines each export replaces.
+//
+// Data layout: points are counting-sorted into a uniform grid (row-major cells); xs/ys/order hold the
+// coordinates and original ids in cell order, cell_start[c] the first sorted position of cell c.  A
+// cell-row segment [cx0,cx1] is therefore one contiguous range of the sorted arrays, which is what
+// the query warps stream through.
+#include <cub/cub.cuh>
+#include <float.h>
+#include <limits.h>
+
+#include "common.cuh"
+
+namespace sc {
+
+struct GridParams {
+  double x0, y0, inv_h, h, margin;
+  int nx, ny, ncells, pad;
+};
+
+constexpr int kBboxBlocks = 256;
+
+// ------------------------------------------------------------------------------------------------
+// binning
+// ------------------------------------------------------------------------------------------------
+
+__global__ void bbox_partial_kernel(const double* __restrict__ coords, int64_t n,
+                                    double* __restrict__ partial) {
+  double xmin = DBL_MAX, xmax = -DBL_MAX, ymin = DBL_MAX, ymax = -DBL_MAX;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n;
+       i += (int64_t)gridDim.x * blockDim.x) {
+    double2 p = reinterpret_cast<const double2*>(coords)[i];
+    xmin = fmin(xmin, p.x); xmax = fmax(xmax, p.x);
+    ymin = fmin(ymin, p.y); ymax = fmax(ymax, p.y);
+  }
+  __shared__ double s[4][32];
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    xmin = fmin(xmin, shfl_f64(xmin, (threadIdx.x & 31) ^ o));
+    xmax = fmax(xmax, shfl_f64(xmax, (threadIdx.x & 31) ^ o));
+    ymin = fmin(ymin, shfl_f64(ymin, (threadIdx.x & 31) ^ o));
+    ymax = fmax(ymax, shfl_f64(ymax, (threadIdx.x & 31) ^ o));
+  }
+  int w = threadIdx.x >> 5, l = threadIdx.x & 31;
+  if (l == 0) { s[0][w] = xmin; s[1][w] = xmax; s[2][w] = ymin; s[3][w] = ymax; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    int nw = blockDim.x >> 5;
+    for (int j = 1; j < nw; ++j) {
+      xmin = fmin(xmin, s[0][j]); xmax = fmax(xmax, s[1][j]);
+      ymin = fmin(ymin, s[2][j]); ymax = fmax(ymax, s[3][j]);
+    }
+    partial[4 * blockIdx.x + 0] = xmin; partial[4 * blockIdx.x + 1] = xmax;
+    partial[4 * blockIdx.x + 2] = ymin; partial[4 * blockIdx.x + 3] = ymax;
+  }
+}
+
+// One thread: final bbox + grid geometry.  pts_per_cell > 0: occupancy-driven cell edge (kNN);
+// h_fixed > 0: cell edge >= h_fixed (radius).  The cell count is clamped to max_cells.
+__global__ void grid_setup_kernel(const double* __restrict__ partial, int nblocks, int64_t n,
+                                  double pts_per_cell, double h_fixed, int max_cells,
+                                  GridParams* __restrict__ gp) {
+  double xmin = DBL_MAX, xmax = -DBL_MAX, ymin = DBL_MAX, ymax = -DBL_MAX;
+  for (int j = 0; j < nblocks; ++j) {
+    xmin = fmin(xmin, partial[4 * j + 0]); xmax = fmax(xmax, partial[4 * j + 1]);
+    ymin = fmin(ymin, partial[4 * j + 2]); ymax = fmax(ymax, partial[4 * j + 3]);
+  }
+  double w = xmax - xmin, hg = ymax - ymin;
+  double h;
+  if (h_fixed > 0) {
+    h = h_fixed;
+  } else {
+    h = sqrt(pts_per_cell * w * hg / (double)n);
+    if (!(h > 0)) h = pts_per_cell * fmax(w, hg) / (double)n;
+    if (!(h > 0)) h = 1.0;
+  }
+  double fx, fy;
+  for (int it = 0; it < 64; ++it) {
+    fx = floor(w / h) + 1.0;
+    fy = floor(hg / h) + 1.0;
+    if (fx * fy <= (double)max_cells) break;
+    h *= 1.05 * sqrt(fx * fy / (double)max_cells);
+  }
+  gp->x0 = xmin; gp->y0 = ymin; gp->h = h; gp->inv_h = 1.0 / h;
+  gp->nx = (int)fx; gp->ny = (int)fy; gp->ncells = gp->nx * gp->ny;
+  double ext = fmax(fmax(fabs(xmin), fabs(xmax)), fmax(fabs(ymin), fabs(ymax)));
+  gp->margin = 1e-9 * (ext + h);
+  gp->pad = 0;
+}
+
+__device__ __forceinline__ int cell_coord(double v, double v0, double inv_h, int nmax) {
+  int c = (int)floor((v - v0) * inv_h);
+  return min(max(c, 0), nmax - 1);
+}
+
+__global__ void assign_cells_kernel(const double* __restrict__ coords, int64_t n,
+                                    const GridParams* __restrict__ gp, int32_t* __restrict__ keys,
+                                    int32_t* __restrict__ vals) {
+  GridParams g = *gp;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n;
+       i += (int64_t)gridDim.x * blockDim.x) {
+    double2 p = reinterpret_cast<const double2*>(coords)[i];
+    int cx = cell_coord(p.x, g.x0, g.inv_h, g.nx);
+    int cy = cell_coord(p.y, g.y0, g.inv_h, g.ny);
+    keys[i] = cy * g.nx + cx;
+    vals[i] = (int32_t)i;
+  }
+}
+
+// cell_start[c] = first sorted position whose key >= c, for c in [0, ncells].
+__global__ void cell_bounds_kernel(const int32_t* __restrict__ keys_sorted, int64_t n,
+                                   const GridParams* __restrict__ gp,
+                                   int32_t* __restrict__ cell_start) {
+  int ncells = gp->ncells;
+  for (int64_t s = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; s <= n;
+       s += (int64_t)gridDim.x * blockDim.x) {
+    int prev = (s == 0) ? -1 : keys_sorted[s - 1];
+    int cur = (s == n) ? ncells : keys_sorted[s];
+    for (int c = prev + 1; c <= cur; ++c) cell_start[c] = (int32_t)s;
+  }
+}
+
+__global__ void gather_coords_kernel(const double* __restrict__ coords,
+                                     const int32_t* __restrict__ order, int64_t n,
+                                     double* __restrict__ xs, double* __restrict__ ys) {
+  for (int64_t s = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; s < n;
+       s += (int64_t)gridDim.x * blockDim.x) {
+    double2 p = reinterpret_cast<const double2*>(coords)[order[s]];
+    xs[s] = p.x; ys[s] = p.y;
+  }
+}
+
+struct Binning {
+  GridParams* gp;
+  double* partial;
+  int32_t *keys, *vals, *keys_sorted, *order, *cell_start;
+  double *xs, *ys;
+  void* cub_tmp;
+  size_t cub_bytes;
+  int max_cells;
+};
+
+static int key_bits(int max_cells) {
+  int b = 1;
+  while ((1ll << b) < (long long)max_cells + 1) ++b;
+  return b;
+}
+
+static size_t binning_cub_bytes(int64_t n, int max_cells) {
+  size_t bytes = 0;
+  cub::DeviceRadixSort::SortPairs(nullptr, bytes, (const int32_t*)nullptr, (int32_t*)nullptr,
+                                  (const int32_t*)nullptr, (int32_t*)nullptr, (int)n, 0,
+                                  key_bits(max_cells));
+  size_t scan = 0;
+  cub::DeviceScan::ExclusiveSum(nullptr, scan, (const int32_t*)nullptr, (int32_t*)nullptr,
+                                (int)(n + 1));
+  return bytes > scan ? bytes : scan;
+}
+
+static int max_cells_for(int64_t n) { return (int)(n + 1024); }
+
+static size_t binning_bytes(int64_t n) {
+  int mc = max_cells_for(n);
+  size_t b = 0;
+  b += align_up(sizeof(GridParams), 256);
+  b += align_up(sizeof(double) * 4 * kBboxBlocks, 256);
+  b += 4 * align_up(sizeof(int32_t) * n, 256);
+  b += align_up(sizeof(int32_t) * ((size_t)mc + 1), 256);
+  b += 2 * align_up(sizeof(double) * n, 256);
+  b += align_up(binning_cub_bytes(n, mc), 256);
+  return b;
+}
+
+static bool carve_binning(Arena& a, int64_t n, Binning* b) {
+  b->max_cells = max_cells_for(n);
+  b->gp = a.take<GridParams>(1);
+  b->partial = a.take<double>(4 * kBboxBlocks);
+  b->keys = a.take<int32_t>(n);
+  b->vals = a.take<int32_t>(n);
+  b->keys_sorted = a.take<int32_t>(n);
+  b->order = a.take<int32_t>(n);
+  b->cell_start = a.take<int32_t>((size_t)b->max_cells + 1);
+  b->xs = a.take<double>(n);
+  b->ys = a.take<double>(n);
+  b->cub_bytes = binning_cub_bytes(n, b->max_cells);
+  b->cub_tmp = a.take<char>(b->cub_bytes);
+  return b->cub_tmp != nullptr;
+}
+
+static int run_binning(const double* coords, int64_t n, double pts_per_cell, double h_fixed,
+                       const Binning& b, cudaStream_t st) {
+  int blocks = (int)((n + 255) / 256);
+  if (blocks > 148 * 8) blocks = 148 * 8;
+  bbox_partial_kernel<<<kBboxBlocks, 256, 0, st>>>(coords, n, b.partial);
+  SC_LAUNCH_OK();
+  grid_setup_kernel<<<1, 1, 0, st>>>(b.partial, kBboxBlocks, n, pts_per_cell, h_fixed, b.max_cells,
+                                     b.gp);
+  SC_LAUNCH_OK();
+  assign_cells_kernel<<<blocks, 256, 0, st>>>(coords, n, b.gp, b.keys, b.vals);
+  SC_LAUNCH_OK();
+  size_t bytes = b.cub_bytes;
+  SC_CUDA_OK(cub::DeviceRadixSort::SortPairs(b.cub_tmp, bytes, b.keys, b.keys_sorted, b.vals,
+                                             b.order, (int)n, 0, key_bits(b.max_cells), st));
+  cell_bounds_kernel<<<blocks, 256, 0, st>>>(b.keys_sorted, n, b.gp, b.cell_start);
+  SC_LAUNCH_OK();
+  gather_coords_kernel<<<blocks, 256, 0, st>>>(coords, b.order, n, b.xs, b.ys);
+  SC_LAUNCH_OK();
+  return SC_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// kNN: one warp per query point, sorted top-k list distributed over the warp's lanes
+// ------------------------------------------------------------------------------------------------
+
+__device__ __forceinline__ bool cand_less(double da, int ia, double db, int ib) {
+  return da < db || (da == db && ia < ib);
+}
+
+// d² exactly as the CPU tree libraries evaluate it: separate multiply and add, no FMA contraction.
+__device__ __forceinline__ double sq_dist(double qx, double qy, double px, double py) {
+  double dx = __dsub_rn(qx, px), dy = __dsub_rn(qy, py);
+  return __dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy));
+}
+
+template <int E>
+struct WarpTopK {
+  double d[E];
+  int id[E];
+  double thr_d;
+  int thr_id;
+  int k;
+
+  __device__ __forceinline__ void init(int k_) {
+    k = k_;
+#pragma unroll
+    for (int e = 0; e < E; ++e) { d[e] = INFINITY; id[e] = INT_MAX; }
+    thr_d = INFINITY; thr_id = INT_MAX;
+  }
+
+  // Warp-uniform call: insert (cd, cid), known to be below the current threshold.
+  __device__ __forceinline__ void insert(double cd, int cid, int lane) {
+    int pos = 0;
+#pragma unroll
+    for (int e = 0; e < E; ++e) {
+      bool less = (e * 32 + lane < k) && cand_less(d[e], id[e], cd, cid);
+      pos += __popc(__ballot_sync(kFull, less));
+    }
+#pragma unroll
+    for (int e = E - 1; e >= 0; --e) {
+      double pd = shfl_up_f64(d[e], 1);
+      int pi = __shfl_up_sync(kFull, id[e], 1);
+      if (e > 0) {
+        double cdn = shfl_f64(d[e - 1], 31);
+        int cin = __shfl_sync(kFull, id[e - 1], 31);
+        if (lane == 0) { pd = cdn; pi = cin; }
+      }
+      int gpos = e * 32 + lane;
+      if (gpos > pos) { d[e] = pd; id[e] = pi; }
+      else if (gpos == pos) { d[e] = cd; id[e] = cid; }
+    }
+    int te = (k - 1) >> 5, tl = (k - 1) & 31;
+#pragma unroll
+    for (int e = 0; e < E; ++e)
+      if (e == te) { thr_d = shfl_f64(d[e], tl); thr_id = __shfl_sync(kFull, id[e], tl); }
+  }
+};
+
+// Stream the sorted range [b, e): lane-strided candidates, ballot the ones beating the threshold,
+// insert them one by one (warp-uniform).
+template <int E>
+__device__ __forceinline__ void scan_range_knn(WarpTopK<E>& tk, int b, int e, double qx, double qy,
+                                               int self_id, const double* __restrict__ xs,
+                                               const double* __restrict__ ys,
+                                               const int32_t* __restrict__ order, int lane) {
+  for (int base = b; base < e; base += 32) {
+    int s = base + lane;
+    bool valid = s < e;
+    double cd = INFINITY;
+    int cid = INT_MAX;
+    if (valid) {
+      cid = order[s];
+      cd = sq_dist(qx, qy, xs[s], ys[s]);
+      valid = cid != self_id;
+    }
+    unsigned m = __ballot_sync(kFull, valid && cand_less(cd, cid, tk.thr_d, tk.thr_id));
+    while (m) {
+      int src = __ffs(m) - 1;
+      m &= m - 1;
+      double bd = shfl_f64(cd, src);
+      int bi = __shfl_sync(kFull, cid, src);
+      if (cand_less(bd, bi, tk.thr_d, tk.thr_id)) tk.insert(bd, bi, lane);
+    }
+  }
+}
+
+template <int E>
+__global__ void __launch_bounds__(256)
+knn_query_kernel(const GridParams* __restrict__ gp, const int32_t* __restrict__ cell_start,
+                 const double* __restrict__ xs, const double* __restrict__ ys,
+                 const int32_t* __restrict__ order, int64_t n, int k, int include_self,
+                 int32_t* __restrict__ idx_out, double* __restrict__ dist_out,
+                 const int32_t* __restrict__ labels, int n_types, float* __restrict__ profile) {
+  extern __shared__ int s_hist[];  // [warps][n_types] when the fused composition is requested
+  const GridParams g = *gp;
+  const int lane = threadIdx.x & 31;
+  const int warp_in_block = threadIdx.x >> 5;
+  const int warps_per_block = blockDim.x >> 5;
+  int* hist = s_hist + warp_in_block * n_types;
+  if (profile)
+    for (int t = lane; t < n_types; t += 32) hist[t] = 0;
+
+  // contiguous chunk of sorted positions per block: neighbouring queries share candidate cells in L1
+  const int64_t per_block = (n + gridDim.x - 1) / gridDim.x;
+  const int64_t s_begin = blockIdx.x * per_block;
+  const int64_t s_end = min(n, s_begin + per_block);
+
+  for (int64_t s = s_begin + warp_in_block; s < s_end; s += warps_per_block) {
+    const double qx = xs[s], qy = ys[s];
+    const int self_id = order[s];
+    const double ux = (qx - g.x0) * g.inv_h, uy = (qy - g.y0) * g.inv_h;
+    const int cx = min(max((int)floor(ux), 0), g.nx - 1);
+    const int cy = min(max((int)floor(uy), 0), g.ny - 1);
+
+    WarpTopK<E> tk;
+    tk.init(k);
+    {
+      int c = cy * g.nx + cx;
+      scan_range_knn<E>(tk, cell_start[c], cell_start[c + 1], qx, qy, self_id, xs, ys, order, lane);
+    }
+    for (int r = 1;; ++r) {
+      const int xlo = max(cx - r, 0), xhi = min(cx + r, g.nx - 1);
+      for (int yy = max(cy - r, 0); yy <= min(cy + r, g.ny - 1); ++yy) {
+        const int rowbase = yy * g.nx;
+        if (yy == cy - r || yy == cy + r) {
+          scan_range_knn<E>(tk, cell_start[rowbase + xlo], cell_start[rowbase + xhi + 1], qx, qy,
+                            self_id, xs, ys, order, lane);
+        } else {
+          if (cx - r >= 0)
+            scan_range_knn<E>(tk, cell_start[rowbase + cx - r], cell_start[rowbase + cx - r + 1],
+                              qx, qy, self_id, xs, ys, order, lane);
+          if (cx + r <= g.nx - 1)
+            scan_range_knn<E>(tk, cell_start[rowbase + cx + r], cell_start[rowbase + cx + r + 1],
+                              qx, qy, self_id, xs, ys, order, lane);
+        }
+      }
+      // exactness: every unseen point lies outside the (2r+1)² block; stop when the k-th best is
+      // closer than the nearest block side that still has cells beyond it.
+      double gap = INFINITY;
+      if (cx - r > 0) gap = fmin(gap, ux - (double)(cx - r));
+      if (cx + r < g.nx - 1) gap = fmin(gap, (double)(cx + r + 1) - ux);
+      if (cy - r > 0) gap = fmin(gap, uy - (double)(cy - r));
+      if (cy + r < g.ny - 1) gap = fmin(gap, (double)(cy + r + 1) - uy);
+      if (isinf(gap)) break;
+      double safe = gap * g.h * (1.0 - 1e-6) - g.margin;
+      if (safe > 0 && tk.thr_d <= safe * safe) break;
+    }
+
+    // ---- epilogue: rank by column index and write row `self_id` ------------------------------
+    const int kk = k + (include_self ? 1 : 0);
+    const int64_t row = (int64_t)self_id * kk;
+    int rank[E];
+    int self_rank = 0;
+#pragma unroll
+    for (int e = 0; e < E; ++e) rank[e] = 0;
+    for (int j = 0; j < k; ++j) {
+      int idj = 0;
+#pragma unroll
+      for (int e = 0; e < E; ++e)
+        if (e == (j >> 5)) idj = __shfl_sync(kFull, tk.id[e], j & 31);
+#pragma unroll
+      for (int e = 0; e < E; ++e) rank[e] += idj < tk.id[e];
+      self_rank += idj < self_id;
+    }
+#pragma unroll
+    for (int e = 0; e < E; ++e) {
+      if (e * 32 + lane < k) {
+        int rk = rank[e] + ((include_self && tk.id[e] > self_id) ? 1 : 0);
+        if (idx_out) idx_out[row + rk] = tk.id[e];
+        if (dist_out) dist_out[row + rk] = sqrt(tk.d[e]);
+        if (profile) atomicAdd(&hist[labels[tk.id[e]]], 1);
+      }
+    }
+    if (include_self && lane == 0) {
+      if (idx_out) idx_out[row + self_rank] = self_id;
+      if (dist_out) dist_out[row + self_rank] = 0.0;
+      if (profile) atomicAdd(&hist[labels[self_id]], 1);
+    }
+    if (profile) {
+      __syncwarp();
+      float* prow = profile + (int64_t)self_id * n_types;
+      for (int t = lane; t < n_types; t += 32) { prow[t] = (float)hist[t]; hist[t] = 0; }
+      __syncwarp();
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// radius graph: count pass, scan, fill pass with in-row rank sort
+// ------------------------------------------------------------------------------------------------
+
+template <bool FILL>
+__global__ void __launch_bounds__(256)
+radius_query_kernel(const GridParams* __restrict__ gp, const int32_t* __restrict__ cell_start,
+                    const double* __restrict__ xs, const double* __restrict__ ys,
+                    const int32_t* __restrict__ order, int64_t n, double r2,
+                    int32_t* __restrict__ deg_out,          // COUNT: degree per original row
+                    const int32_t* __restrict__ indptr,     // FILL
+                    int32_t* tmp_idx, double* tmp_dist,     // FILL scratch (read back: no restrict)
+                    int32_t* __restrict__ indices, double* __restrict__ dist,
+                    const int32_t* __restrict__ labels, int n_types, float* __restrict__ profile) {
+  extern __shared__ int s_hist[];
+  const GridParams g = *gp;
+  const int lane = threadIdx.x & 31;
+  const int warp_in_block = threadIdx.x >> 5;
+  const int warps_per_block = blockDim.x >> 5;
+  int* hist = s_hist + warp_in_block * n_types;
+  if (!FILL && profile)
+    for (int t = lane; t < n_types; t += 32) hist[t] = 0;
+
+  const int64_t per_block = (n + gridDim.x - 1) / gridDim.x;
+  const int64_t s_begin = blockIdx.x * per_block;
+  const int64_t s_end = min(n, s_begin + per_block);
+
+  for (int64_t s = s_begin + warp_in_block; s < s_end; s += warps_per_block) {
+    const double qx = xs[s], qy = ys[s];
+    const int self_id = order[s];
+    const int cx = cell_coord(qx, g.x0, g.inv_h, g.nx);
+    const int cy = cell_coord(qy, g.y0, g.inv_h, g.ny);
+    const int xlo = max(cx - 1, 0), xhi = min(cx + 1, g.nx - 1);
+    int count = 0;
+    const int64_t start = FILL ? (int64_t)indptr[self_id] : 0;
+    for (int yy = max(cy - 1, 0); yy <= min(cy + 1, g.ny - 1); ++yy) {
+      const int b = cell_start[yy * g.nx + xlo], e = cell_start[yy * g.nx + xhi + 1];
+      for (int base = b; base < e; base += 32) {
+        int t = base + lane;
+        bool hit = false;
+        int cid = 0;
+        double d2 = 0;
+        if (t < e) {
+          cid = order[t];
+          d2 = sq_dist(qx, qy, xs[t], ys[t]);
+          hit = (cid != self_id) && (d2 <= r2);
+        }
+        unsigned m = __ballot_sync(kFull, hit);
+        if (FILL) {
+          if (hit) {
+            int off = count + __popc(m & ((1u << lane) - 1u));
+            tmp_idx[start + off] = cid;
+            if (tmp_dist) tmp_dist[start + off] = sqrt(d2);
+          }
+        } else if (profile && hit) {
+          atomicAdd(&hist[labels[cid]], 1);
+        }
+        count += __popc(m);
+      }
+    }
+    if (!FILL) {
+      if (lane == 0 && deg_out) deg_out[self_id] = count;
+      if (profile) {
+        __syncwarp();
+        float* prow = profile + (int64_t)self_id * n_types;
+        for (int t = lane; t < n_types; t += 32) { prow[t] = (float)hist[t]; hist[t] = 0; }
+        __syncwarp();
+      }
+    } else {
+      __syncwarp();  // orders the warp's tmp writes before the reads below
+      for (int e = lane; e < count; e += 32) {
+        int my = tmp_idx[start + e];
+        int rk = 0;
+        for (int j = 0; j < count; ++j) rk += tmp_idx[start + j] < my;
+        indices[start + rk] = my;
+        if (dist) dist[start + rk] = tmp_dist[start + e];
+      }
+    }
+  }
+}
+
+__global__ void sum_degrees_kernel(const int32_t* __restrict__ deg, int64_t n,
+                                   unsigned long long* __restrict__ total) {
+  unsigned long long acc = 0;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n;
+       i += (int64_t)gridDim.x * blockDim.x)
+    acc += (unsigned long long)deg[i];
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(kFull, acc, o);
+  if ((threadIdx.x & 31) == 0 && acc) atomicAdd(total, acc);
+}
+
+// ------------------------------------------------------------------------------------------------
+// neighbourhood composition from an existing graph; profile normalisation
+// ------------------------------------------------------------------------------------------------
+
+__global__ void __launch_bounds__(256)
+nbhd_counts_kernel(const int32_t* __restrict__ indptr, const int32_t* __restrict__ indices,
+                   int64_t n, int k_fixed, const int32_t* __restrict__ labels, int n_types,
+                   float* __restrict__ profile) {
+  extern __shared__ int s_hist[];
+  const int lane = threadIdx.x & 31;
+  const int w = threadIdx.x >> 5;
+  int* hist = s_hist + w * n_types;
+  for (int t = lane; t < n_types; t += 32) hist[t] = 0;
+  __syncwarp();
+  const int64_t warps = (int64_t)gridDim.x * (blockDim.x >> 5);
+  for (int64_t i = (int64_t)blockIdx.x * (blockDim.x >> 5) + w; i < n; i += warps) {
+    int64_t b = indptr ? indptr[i] : i * k_fixed;
+    int64_t e = indptr ? indptr[i + 1] : b + k_fixed;
+    for (int64_t j = b + lane; j < e; j += 32) atomicAdd(&hist[labels[indices[j]]], 1);
+    __syncwarp();
+    float* prow = profile + i * n_types;
+    for (int t = lane; t < n_types; t += 32) { prow[t] = (float)hist[t]; hist[t] = 0; }
+    __syncwarp();
+  }
+}
+
+__global__ void __launch_bounds__(256)
+profile_normalize_kernel(float* __restrict__ profile, int64_t n, int n_types, int normalize,
+                         unsigned long long* __restrict__ n_empty) {
+  const int lane = threadIdx.x & 31;
+  const int64_t warps = (int64_t)gridDim.x * (blockDim.x >> 5);
+  unsigned long long empty = 0;
+  for (int64_t i = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); i < n;
+       i += warps) {
+    float* prow = profile + i * n_types;
+    float sum = 0.f;  // counts are small integers: exact in FP32 in any order
+    for (int t = lane; t < n_types; t += 32) sum += prow[t];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(kFull, sum, o);
+    if (sum == 0.f) { empty += (lane == 0); continue; }
+    if (normalize)
+      for (int t = lane; t < n_types; t += 32) prow[t] = __fdiv_rn(prow[t], sum);
+  }
+  if (lane == 0 && empty) atomicAdd(n_empty, empty);
+}
+
+// ------------------------------------------------------------------------------------------------
+// graph moments
+// ------------------------------------------------------------------------------------------------
+
+__device__ __forceinline__ double edge_weight(const float* __restrict__ weights, int64_t e,
+                                              int deg) {
+  return weights ? (double)weights[e] : 1.0 / (double)deg;
+}
+
+// warp per row: s0/s1 partials (deterministic two-stage), rowsum[i], colsum scatter (FP64 atomics).
+__global__ void __launch_bounds__(256)
+moments_edges_kernel(const int32_t* __restrict__ indptr, const int32_t* __restrict__ indices,
+                     const float* __restrict__ weights, int64_t n, int k_fixed,
+                     double* __restrict__ rowsum, double* __restrict__ colsum,
+                     double* __restrict__ partial) {
+  const int lane = threadIdx.x & 31;
+  const int w = threadIdx.x >> 5;
+  const int64_t warps = (int64_t)gridDim.x * (blockDim.x >> 5);
+  double s0 = 0, s1 = 0;
+  for (int64_t i = (int64_t)blockIdx.x * (blockDim.x >> 5) + w; i < n; i += warps) {
+    int64_t b = indptr ? indptr[i] : i * k_fixed;
+    int64_t e = indptr ? indptr[i + 1] : b + k_fixed;
+    int deg = (int)(e - b);
+    double rs = 0;
+    for (int64_t t = b + lane; t < e; t += 32) {
+      int j = indices[t];
+      double wij = edge_weight(weights, t, deg);
+      // reverse edge (j -> i): binary search in row j (column-sorted)
+      int64_t jb = indptr ? indptr[j] : (int64_t)j * k_fixed;
+      int64_t je = indptr ? indptr[j + 1] : jb + k_fixed;
+      int degj = (int)(je - jb);
+      int64_t lo = jb, hi = je;
+      while (lo < hi) {
+        int64_t mid = (lo + hi) >> 1;
+        if (indices[mid] < (int)i) lo = mid + 1; else hi = mid;
+      }
+      bool rev = lo < je && indices[lo] == (int)i;
+      if (rev) {
+        double t2 = wij + edge_weight(weights, lo, degj);
+        s1 += 0.5 * t2 * t2;
+      } else {
+        s1 += wij * wij;
+      }
+      rs += wij;
+      atomicAdd(&colsum[j], wij);
+    }
+    rs = warp_sum(rs);
+    if (lane == 0) rowsum[i] = rs;
+    s0 += (lane == 0) ? rs : 0.0;
+  }
+  s0 = warp_sum(s0);
+  s1 = warp_sum(s1);
+  __shared__ double sh[2][8];
+  if (lane == 0) { sh[0][w] = s0; sh[1][w] = s1; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double a = 0, b2 = 0;
+    for (int j = 0; j < (blockDim.x >> 5); ++j) { a += sh[0][j]; b2 += sh[1][j]; }
+    partial[2 * blockIdx.x] = a;
+    partial[2 * blockIdx.x + 1] = b2;
+  }
+}
+
+__global__ void __launch_bounds__(256)
+moments_s2_kernel(const double* __restrict__ rowsum, const double* __restrict__ colsum, int64_t n,
+                  double* __restrict__ partial) {
+  double s2 = 0;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n;
+       i += (int64_t)gridDim.x * blockDim.x) {
+    double t = rowsum[i] + colsum[i];
+    s2 += t * t;
+  }
+  s2 = warp_sum(s2);
+  __shared__ double sh[8];
+  if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = s2;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double a = 0;
+    for (int j = 0; j < (blockDim.x >> 5); ++j) a += sh[j];
+    partial[blockIdx.x] = a;
+  }
+}
+
+__global__ void moments_final_kernel(const double* __restrict__ p01, const double* __restrict__ p2,
+                                     int nblocks, double* __restrict__ out) {
+  double s0 = 0, s1 = 0, s2 = 0;
+  for (int j = 0; j < nblocks; ++j) { s0 += p01[2 * j]; s1 += p01[2 * j + 1]; s2 += p2[j]; }
+  out[0] = s0; out[1] = s1; out[2] = s2;
+}
+
+constexpr int kMomentBlocks = 592;
+
+}  // namespace sc
+
+using namespace sc;
+
+// ================================================================================================
+// C ABI
+// ================================================================================================
+
+extern "C" size_t sc_grid_knn_workspace_bytes(int64_t n, int k) {
+  (void)k;
+  if (n <= 0) return 256;
+  return binning_bytes(n) + 1024;
+}
+
+extern "C" int sc_grid_knn(const double* coords, int64_t n, int k, int include_self, int32_t* idx,
+                           double* dist, int32_t* order_out, const int32_t* labels, int n_types,
+                           float* profile, void* ws, size_t ws_bytes, sc_stream_t stream) {
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  SC_CHECK_ARG(coords && ws, "sc_grid_knn: null coords/workspace");
+  SC_CHECK_ARG(n >= 2 && n < (1ll << 31) - 2048, "sc_grid_knn: n=%lld out of range", (long long)n);
+  SC_CHECK_ARG(k >= 1 && k <= SC_KNN_MAX_K, "sc_grid_knn: k=%d outside [1,%d]", k, SC_KNN_MAX_K);
+  SC_CHECK_ARG(k < n, "k must be < number of cells (%lld), got %d", (long long)n, k);
+  SC_CHECK_ARG(idx || profile, "sc_grid_knn: nothing to compute (idx and profile are NULL)");
+  SC_CHECK_ARG(!profile || (labels && n_types >= 1 && n_types <= 2048),
+               "sc_grid_knn: fused composition needs labels and 1 <= n_types <= 2048");
+  if (ws_bytes < sc_grid_knn_workspace_bytes(n, k)) {
+    set_error("sc_grid_knn: workspace %zu < %zu", ws_bytes, sc_grid_knn_workspace_bytes(n, k));
+    return SC_ERR_WORKSPACE;
+  }
+  Arena arena(ws, ws_bytes);
+  Binning b;
+  if (!carve_binning(arena, n, &b)) { set_error("sc_grid_knn: workspace carve failed"); return SC_ERR_WORKSPACE; }
+  // occupancy: a circle of radius h (guaranteed covered by the 3x3 block) holds ~pi*c points
+  double c = k / 2.0;
+  if (c < 1.0) c = 1.0;
+  int rc = run_binning(coords, n, c, 0.0, b, st);
+  if (rc) return rc;
+  if (order_out)
+    SC_CUDA_OK(cudaMemcpyAsync(order_out, b.order, sizeof(int32_t) * n, cudaMemcpyDeviceToDevice, st));
+
+  const int threads = 256;
+  int64_t want = (n + 255) / 256;  // ~256 queries per block
+  int blocks = (int)(want < 1 ? 1 : want);
+  size_t smem = profile ? sizeof(int) * (threads / 32) * (size_t)n_types : 0;
+#define SC_KNN_LAUNCH(E)                                                                          \
+  do {                                                                                            \
+    if (smem > 48 * 1024)                                                                         \
+      SC_CUDA_OK(cudaFuncSetAttribute(knn_query_kernel<E>,                                        \
+                                      cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));   \
+    knn_query_kernel<E><<<blocks, threads, smem, st>>>(b.gp, b.cell_start, b.xs, b.ys, b.order, n, \
+                                                      k, include_self, idx, dist, labels,         \
+                                                      n_types, profile);                          \
+  } while (0)
+  if (k <= 32) SC_KNN_LAUNCH(1);
+  else if (k <= 64) SC_KNN_LAUNCH(2);
+  else SC_KNN_LAUNCH(4);
+#undef SC_KNN_LAUNCH
+  SC_LAUNCH_OK();
+  return SC_OK;
+}
+
+extern "C" size_t sc_grid_radius_workspace_bytes(int64_t n) {
+  if (n <= 0) return 256;
+  return binning_bytes(n) + align_up(sizeof(unsigned long long), 256) + 1024;
+}
+
+static int radius_prepare(Arena& arena, int64_t n, Binning* b, unsigned long long** total) {
+  if (!carve_binning(arena, n, b)) return SC_ERR_WORKSPACE;
+  *total = arena.take<unsigned long long>(1);
+  return *total ? SC_OK : SC_ERR_WORKSPACE;
+}
+
+extern "C" int sc_grid_radius_count(const double* coords, int64_t n, double r, int32_t* indptr,
+                                    int64_t* nnz_out, const int32_t* labels, int n_types,
+                                    float* profile, void* ws, size_t ws_bytes,
+                                    sc_stream_t stream) {
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  SC_CHECK_ARG(coords && ws, "sc_grid_radius_count: null coords/workspace");
+  SC_CHECK_ARG(n >= 1 && n < (1ll << 31) - 2048, "sc_grid_radius_count: n out of range");
+  SC_CHECK_ARG(r > 0, "radius must be > 0, got %g", r);
+  SC_CHECK_ARG(indptr || profile, "sc_grid_radius_count: nothing to compute");
+  SC_CHECK_ARG(!profile || (labels && n_types >= 1 && n_types <= 2048),
+               "sc_grid_radius_count: fused composition needs labels and 1 <= n_types <= 2048");
+  if (ws_bytes < sc_grid_radius_workspace_bytes(n)) {
+    set_error("sc_grid_radius_count: workspace too small");
+    return SC_ERR_WORKSPACE;
+  }
+  Arena arena(ws, ws_bytes);
+  Binning b;
+  unsigned long long* total;
+  if (radius_prepare(arena, n, &b, &total)) { set_error("sc_grid_radius_count: carve failed"); return SC_ERR_WORKSPACE; }
+  // cell edge slightly above r so that |dx| <= r implies a cell-index difference <= 1 under rounding
+  int rc = run_binning(coords, n, 0.0, r * (1.0 + 1e-9), b, st);
+  if (rc) return rc;
+  const int threads = 256;
+  int blocks = (int)((n + 255) / 256);
+  size_t smem = profile ? sizeof(int) * (threads / 32) * (size_t)n_types : 0;
+  if (smem > 48 * 1024)
+    SC_CUDA_OK(cudaFuncSetAttribute(radius_query_kernel<false>,
+                                    cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  radius_query_kernel<false><<<blocks, threads, smem, st>>>(
+      b.gp, b.cell_start, b.xs, b.ys, b.order, n, r * r, indptr, nullptr, nullptr, nullptr, nullptr,
+      nullptr, labels, n_types, profile);
+  SC_LAUNCH_OK();
+  if (indptr) {
+    SC_CUDA_OK(cudaMemsetAsync(total, 0, sizeof(unsigned long long), st));
+    sum_degrees_kernel<<<296, 256, 0, st>>>(indptr, n, total);
+    SC_LAUNCH_OK();
+    if (nnz_out)
+      SC_CUDA_OK(cudaMemcpyAsync(nnz_out, total, sizeof(int64_t), cudaMemcpyDeviceToDevice, st));
+    SC_CUDA_OK(cudaMemsetAsync(indptr + n, 0, sizeof(int32_t), st));
+    size_t bytes = b.cub_bytes;
+    SC_CUDA_OK(cub::DeviceScan::ExclusiveSum(b.cub_tmp, bytes, indptr, indptr, (int)(n + 1), st));
+  }
+  return SC_OK;
+}
+
+extern "C" int sc_grid_radius_fill(const double* coords, int64_t n, double r,
+                                   const int32_t* indptr, int32_t* indices, double* dist,
+                                   void* scratch, size_t scratch_bytes, void* ws, size_t ws_bytes,
+                                   sc_stream_t stream) {
+  (void)coords;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  SC_CHECK_ARG(indptr && indices && ws && scratch, "sc_grid_radius_fill: null argument");
+  SC_CHECK_ARG(ws_bytes >= sc_grid_radius_workspace_bytes(n), "sc_grid_radius_fill: workspace too small");
+  Arena arena(ws, ws_bytes);
+  Binning b;
+  unsigned long long* total;
+  if (radius_prepare(arena, n, &b, &total)) { set_error("sc_grid_radius_fill: carve failed"); return SC_ERR_WORKSPACE; }
+  // scratch = [tmp_idx i32[nnz]] [tmp_dist f64[nnz]]; the caller sized it from nnz
+  size_t per = dist ? 12 : 4;
+  size_t nnz_cap = scratch_bytes / per;
+  int32_t* tmp_idx;
+  double* tmp_dist = nullptr;
+  if (dist) {
+    tmp_dist = static_cast<double*>(scratch);
+    tmp_idx = reinterpret_cast<int32_t*>(tmp_dist + nnz_cap);
+  } else {
+    tmp_idx = static_cast<int32_t*>(scratch);
+  }
+  const int threads = 256;
+  int blocks = (int)((n + 255) / 256);
+  radius_query_kernel<true><<<blocks, threads, 0, st>>>(b.gp, b.cell_start, b.xs, b.ys, b.order, n,
+                                                       r * r, nullptr, indptr, tmp_idx, tmp_dist,
+                                                       indices, dist, nullptr, 0, nullptr);
+  SC_LAUNCH_OK();
+  return SC_OK;
+}
+
+extern "C" int sc_nbhd_counts(const int32_t* indptr, const int32_t* indices, int64_t n,
+                              int k_fixed, const int32_t* labels, int n_types, float* profile,
+                              sc_stream_t stream) {
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  SC_CHECK_ARG(indices && labels && profile, "sc_nbhd_counts: null argument");
+  SC_CHECK_ARG(indptr || k_fixed > 0, "sc_nbhd_counts: need indptr or k_fixed");
+  SC_CHECK_ARG(n_types >= 1 && n_types <= 2048, "sc_nbhd_counts: n_types outside [1,2048]");
+  const int threads = 256;
+  size_t smem = sizeof(int) * (threads / 32) * (size_t)n_types;
+  if (smem > 48 * 1024)
+    SC_CUDA_OK(cudaFuncSetAttribute(nbhd_counts_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                    (int)smem));
+  int64_t want = (n + 7) / 8;
+  int blocks = (int)(want > 148 * 16 ? 148 * 16 : (want < 1 ? 1 : want));
+  nbhd_counts_kernel<<<blocks, threads, smem, st>>>(indptr, indices, n, k_fixed, labels, n_types,
+                                                    profile);
+  SC_LAUNCH_OK();
+  return SC_OK;
+}
+
+extern "C" int sc_profile_normalize(float* profile, int64_t n, int n_types, int normalize,
+                                    int64_t* n_empty_out, sc_stream_t stream) {
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  SC_CHECK_ARG(profile && n_empty_out, "sc_profile_normalize: null argument");
+  SC_CUDA_OK(cudaMemsetAsync(n_empty_out, 0, sizeof(int64_t), st));
+  int64_t want = (n + 7) / 8;
+  int blocks = (int)(want > 148 * 16 ? 148 * 16 : (want < 1 ? 1 : want));
+  profile_normalize_kernel<<<blocks, 256, 0, st>>>(
+      profile, n, n_types, normalize, reinterpret_cast<unsigned long long*>(n_empty_out));
+  SC_LAUNCH_OK();
+  return SC_OK;
+}
+
+extern "C" size_t sc_graph_moments_workspace_bytes(int64_t n) {
+  return 2 * align_up(sizeof(double) * (size_t)(n > 0 ? n : 1), 256) +
+         align_up(sizeof(double) * 3 * kMomentBlocks, 256) + 512;
+}
+
+extern "C" int sc_graph_moments(const int32_t* indptr, const int32_t* indices,
+                                const float* weights, int64_t n, int k_fixed, double* out,
+                                void* ws, size_t ws_bytes, sc_stream_t stream) {
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  SC_CHECK_ARG(indices && out && ws, "sc_graph_moments: null argument");
+  SC_CHECK_ARG(indptr || k_fixed > 0, "sc_graph_moments: need indptr or k_fixed");
+  if (ws_bytes < sc_graph_moments_workspace_bytes(n)) { set_error("sc_graph_moments: workspace too small"); return SC_ERR_WORKSPACE; }
+  Arena arena(ws, ws_bytes);
+  double* rowsum = arena.take<double>(n);
+  double* colsum = arena.take<double>(n);
+  double* partial = arena.take<double>(3 * kMomentBlocks);
+  SC_CUDA_OK(cudaMemsetAsync(colsum, 0, sizeof(double) * n, st));
+  moments_edges_kernel<<<kMomentBlocks, 256, 0, st>>>(indptr, indices, weights, n, k_fixed, rowsum,
+                                                     colsum, partial);
+  SC_LAUNCH_OK();
+  moments_s2_kernel<<<kMomentBlocks, 256, 0, st>>>(rowsum, colsum, n, partial + 2 * kMomentBlocks);
+  SC_LAUNCH_OK();
+  moments_final_kernel<<<1, 1, 0, st>>>(partial, partial + 2 * kMomentBlocks, kMomentBlocks, out);
+  SC_LAUNCH_OK();
+  return SC_OK;
+}

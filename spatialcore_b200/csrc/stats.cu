@@ -1,0 +1,744 @@
+// Standardisation, spatial lag + Moran statistic, and the two permutation nulls on sm_100a.
+// See include/sc_b200.h for the contract and the reference lines each export replaces.
+//
+// Layout: all N x G matrices are cell-major (a cell's genes contiguous, ld % 4 == 0).  A warp owns
+// one row and 32 consecutive gene quads (128 genes, 512 contiguous bytes per request); a CTA of
+// 8 warps covers `wpr` warps per row x 8/wpr rows per pass and strides over the rows persistently.
+// Every N-long reduction is accumulated in FP64 per thread, reduced per CTA, written to a partial
+// buffer and finished by a second kernel in fixed order (bitwise reproducible, no float atomics).
+#include <math.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include "common.cuh"
+
+namespace sc {
+
+constexpr int kStatThreads = 256;
+constexpr int kStatWarps = kStatThreads / 32;
+
+// ------------------------------------------------------------------------------------------------
+// column statistics and z-scoring
+// ------------------------------------------------------------------------------------------------
+
+// blockDim = (128, 2): 128 consecutive columns x 2 row phases; gridDim = (col tiles, row groups).
+// Shifted one-pass moments in FP64 (shift = first row's value) -> exact zero variance for constant
+// columns, no catastrophic cancellation.
+template <typename T>
+__global__ void __launch_bounds__(256)
+colstats_kernel(const T* __restrict__ X, int64_t n, int64_t ldx, int g,
+                const int32_t* __restrict__ cols, double* __restrict__ partial) {
+  const int col = blockIdx.x * 128 + threadIdx.x;
+  const bool active = col < g;
+  const int64_t src = active ? (cols ? cols[col] : col) : 0;
+  const double shift = active ? (double)X[src] : 0.0;
+  double s = 0, ss = 0;
+  if (active) {
+    const int64_t step = (int64_t)gridDim.y * 2;
+    int64_t r = (int64_t)blockIdx.y * 2 + threadIdx.y;
+    for (; r + 3 * step < n; r += 4 * step) {
+      double v0 = (double)X[r * ldx + src] - shift;
+      double v1 = (double)X[(r + step) * ldx + src] - shift;
+      double v2 = (double)X[(r + 2 * step) * ldx + src] - shift;
+      double v3 = (double)X[(r + 3 * step) * ldx + src] - shift;
+      s += v0; ss += v0 * v0;
+      s += v1; ss += v1 * v1;
+      s += v2; ss += v2 * v2;
+      s += v3; ss += v3 * v3;
+    }
+    for (; r < n; r += step) {
+      double v = (double)X[r * ldx + src] - shift;
+      s += v; ss += v * v;
+    }
+  }
+  __shared__ double sh[2][128];
+  if (threadIdx.y == 1) { sh[0][threadIdx.x] = s; sh[1][threadIdx.x] = ss; }
+  __syncthreads();
+  if (threadIdx.y == 0 && active) {
+    s += sh[0][threadIdx.x];
+    ss += sh[1][threadIdx.x];
+    double* p = partial + ((int64_t)blockIdx.y * g + col) * 2;
+    p[0] = s; p[1] = ss;
+  }
+}
+
+template <typename T>
+__global__ void colstats_final_kernel(const T* __restrict__ X, int64_t n, int g,
+                                      const int32_t* __restrict__ cols,
+                                      const double* __restrict__ partial, int ngroups,
+                                      double* __restrict__ mean, double* __restrict__ std,
+                                      uint8_t* __restrict__ zero_var) {
+  int col = blockIdx.x * blockDim.x + threadIdx.x;
+  if (col >= g) return;
+  double s = 0, ss = 0;
+  for (int j = 0; j < ngroups; ++j) {
+    s += partial[((int64_t)j * g + col) * 2];
+    ss += partial[((int64_t)j * g + col) * 2 + 1];
+  }
+  double shift = (double)X[cols ? cols[col] : col];
+  double m = s / (double)n;
+  double var = ss / (double)n - m * m;
+  if (!(var > 0)) var = 0;
+  mean[col] = shift + m;
+  std[col] = sqrt(var);
+  zero_var[col] = var == 0;
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256)
+zscore_write_kernel(const T* __restrict__ X, int64_t n, int64_t ldx, int g,
+                    const int32_t* __restrict__ cols, const int32_t* __restrict__ rows,
+                    const double* __restrict__ mean, const double* __restrict__ std,
+                    const uint8_t* __restrict__ zero_var, float* __restrict__ Z, int64_t ldz) {
+  const int64_t Q = ldz / 4;
+  const int64_t total = n * Q;
+  for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < total;
+       t += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t a = t / Q;
+    const int q = (int)(t - a * Q);
+    const int64_t src_row = rows ? rows[a] : a;
+    float o[4];
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+      int col = 4 * q + c;
+      float z = 0.f;
+      if (col < g && !zero_var[col]) {
+        double v = (double)X[src_row * ldx + (cols ? cols[col] : col)];
+        z = (float)((v - mean[col]) / std[col]);
+      }
+      o[c] = z;
+    }
+    *reinterpret_cast<float4*>(Z + a * ldz + 4 * q) = make_float4(o[0], o[1], o[2], o[3]);
+  }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256)
+csr_densify_kernel(const int64_t* __restrict__ indptr, const int32_t* __restrict__ indices,
+                   const T* __restrict__ data, int64_t n, const int32_t* __restrict__ colmap,
+                   int g_out, float* __restrict__ out, int64_t ldo) {
+  const int lane = threadIdx.x & 31;
+  const int64_t warps = (int64_t)gridDim.x * (blockDim.x >> 5);
+  for (int64_t i = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); i < n;
+       i += warps) {
+    const int64_t b = indptr[i], e = indptr[i + 1];
+    for (int64_t t = b + lane; t < e; t += 32) {
+      int c = indices[t];
+      int oc = colmap ? colmap[c] : c;
+      if (oc >= 0 && oc < g_out) out[i * ldo + oc] = (float)data[t];
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// shared thread geometry of the row-streaming kernels
+// ------------------------------------------------------------------------------------------------
+
+struct RowGeom {
+  int wpr;  // warps per row (1,2,4,8)
+  int rpp;  // rows per CTA pass = 8 / wpr
+};
+
+static RowGeom row_geom(int64_t ld) {
+  int64_t quads = ld / 4;
+  RowGeom rg;
+  rg.wpr = quads > 128 ? 8 : quads > 64 ? 4 : quads > 32 ? 2 : 1;
+  rg.rpp = kStatWarps / rg.wpr;
+  return rg;
+}
+
+// Sum per-thread FP64 values over the CTA's row phases: threads with the same (warp % wpr, lane)
+// own the same columns.  Result valid in row phase 0.
+__device__ __forceinline__ void reduce_row_phases(double (&v)[4], int wpr, double* sh /*[8*32*4]*/) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int rphase = warp / wpr;
+  __syncthreads();
+  if (rphase > 0) {
+#pragma unroll
+    for (int c = 0; c < 4; ++c) sh[(warp * 32 + lane) * 4 + c] = v[c];
+  }
+  __syncthreads();
+  if (rphase == 0) {
+    for (int w2 = warp + wpr; w2 < kStatWarps; w2 += wpr) {
+#pragma unroll
+      for (int c = 0; c < 4; ++c) v[c] += sh[(w2 * 32 + lane) * 4 + c];
+    }
+  }
+}
+
+// out[r*ld_out + col] = Σ_b partial[(b*rows + r)*ldp + col], fixed order.
+__global__ void reduce_partials_kernel(const double* __restrict__ partial, int nblocks, int rows,
+                                       int64_t ldp, int g, double* __restrict__ out,
+                                       int64_t ld_out) {
+  int col = blockIdx.x * blockDim.x + threadIdx.x;
+  int r = blockIdx.y;
+  if (col >= g) return;
+  double s = 0;
+  for (int b = 0; b < nblocks; ++b) s += partial[((int64_t)b * rows + r) * ldp + col];
+  out[(int64_t)r * ld_out + col] = s;
+}
+
+// ------------------------------------------------------------------------------------------------
+// spatial lag + Moran numerator / denominator
+// ------------------------------------------------------------------------------------------------
+
+template <bool HAS_W>
+__global__ void __launch_bounds__(kStatThreads)
+lag_moran_kernel(const int32_t* __restrict__ indptr, const int32_t* __restrict__ indices,
+                 const float* __restrict__ weights, int64_t n, int k_fixed,
+                 const float* __restrict__ Z, int64_t ldz, float* __restrict__ lag,
+                 float* __restrict__ local, int64_t ldl, double* __restrict__ partial, int wpr) {
+  __shared__ double sh[kStatWarps * 32 * 4];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int rphase = warp / wpr, rpp = kStatWarps / wpr;
+  const int64_t col = ((int64_t)blockIdx.y * 256 + (warp % wpr) * 32 + lane) * 4;
+  const bool active = col < ldz;
+  double num[4] = {0, 0, 0, 0}, den[4] = {0, 0, 0, 0};
+
+  for (int64_t row = (int64_t)blockIdx.x * rpp + rphase; row < n; row += (int64_t)gridDim.x * rpp) {
+    const int64_t b = indptr ? indptr[row] : row * k_fixed;
+    const int64_t e = indptr ? indptr[row + 1] : b + k_fixed;
+    if (!active) continue;
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    int64_t t = b;
+    for (; t + 4 <= e; t += 4) {
+      int j0 = indices[t], j1 = indices[t + 1], j2 = indices[t + 2], j3 = indices[t + 3];
+      float4 v0 = ldg4(Z + (int64_t)j0 * ldz + col);
+      float4 v1 = ldg4(Z + (int64_t)j1 * ldz + col);
+      float4 v2 = ldg4(Z + (int64_t)j2 * ldz + col);
+      float4 v3 = ldg4(Z + (int64_t)j3 * ldz + col);
+      float w0 = 1.f, w1 = 1.f, w2 = 1.f, w3 = 1.f;
+      if (HAS_W) { w0 = weights[t]; w1 = weights[t + 1]; w2 = weights[t + 2]; w3 = weights[t + 3]; }
+      acc.x += w0 * v0.x + w1 * v1.x + w2 * v2.x + w3 * v3.x;
+      acc.y += w0 * v0.y + w1 * v1.y + w2 * v2.y + w3 * v3.y;
+      acc.z += w0 * v0.z + w1 * v1.z + w2 * v2.z + w3 * v3.z;
+      acc.w += w0 * v0.w + w1 * v1.w + w2 * v2.w + w3 * v3.w;
+    }
+    for (; t < e; ++t) {
+      float4 v = ldg4(Z + (int64_t)indices[t] * ldz + col);
+      float w = HAS_W ? weights[t] : 1.f;
+      acc.x += w * v.x; acc.y += w * v.y; acc.z += w * v.z; acc.w += w * v.w;
+    }
+    if (!HAS_W) {
+      float inv = (e > b) ? 1.f / (float)(e - b) : 0.f;
+      acc.x *= inv; acc.y *= inv; acc.z *= inv; acc.w *= inv;
+    }
+    const float4 z = ldg4(Z + row * ldz + col);
+    if (lag) *reinterpret_cast<float4*>(lag + row * ldl + col) = acc;
+    if (local)
+      *reinterpret_cast<float4*>(local + row * ldl + col) =
+          make_float4(z.x * acc.x, z.y * acc.y, z.z * acc.z, z.w * acc.w);
+    num[0] += (double)z.x * (double)acc.x; den[0] += (double)z.x * (double)z.x;
+    num[1] += (double)z.y * (double)acc.y; den[1] += (double)z.y * (double)z.y;
+    num[2] += (double)z.z * (double)acc.z; den[2] += (double)z.z * (double)z.z;
+    num[3] += (double)z.w * (double)acc.w; den[3] += (double)z.w * (double)z.w;
+  }
+  reduce_row_phases(num, wpr, sh);
+  reduce_row_phases(den, wpr, sh);
+  if (rphase == 0 && active) {
+    double* p = partial + ((int64_t)blockIdx.x * 2) * ldz + col;
+#pragma unroll
+    for (int c = 0; c < 4; ++c) { p[c] = num[c]; p[ldz + c] = den[c]; }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// permutation sources
+// ------------------------------------------------------------------------------------------------
+
+constexpr int kMaxPermBatch = 16;
+
+struct PermBatch {
+  int source;               // sc_perm_source
+  int count;                // permutations in this launch (<= template PB)
+  const int32_t* replay;    // [count, n] when source == REPLAY (already offset to this batch)
+  PermDomain dom;
+  uint32_t keys[kMaxPermBatch][kFeistelRounds];
+};
+
+__device__ __forceinline__ int perm_lookup(const PermBatch& pb, const uint32_t (*s_keys)[kFeistelRounds],
+                                           int p, int64_t i, int64_t n) {
+  if (pb.source == SC_PERM_REPLAY) return pb.replay[(int64_t)p * n + i];
+  return (int)perm_apply((uint32_t)i, pb.dom, s_keys[p]);
+}
+
+// ------------------------------------------------------------------------------------------------
+// graph-row null: sims[p,c] = Σ_i A[i,c] · B[π_p(i),c]
+// ------------------------------------------------------------------------------------------------
+
+template <int PB, typename AccT>
+__global__ void __launch_bounds__(kStatThreads)
+perm_rows_kernel(const float* __restrict__ A, int64_t lda, const float* __restrict__ B,
+                 int64_t ldb, int64_t n, const __grid_constant__ PermBatch pb,
+                 double* __restrict__ partial, int64_t ldp, int wpr) {
+  __shared__ double sh[kStatWarps * 32 * 4];
+  __shared__ uint32_t s_keys[kMaxPermBatch][kFeistelRounds];
+  for (int t = threadIdx.x; t < kMaxPermBatch * kFeistelRounds; t += blockDim.x)
+    s_keys[t / kFeistelRounds][t % kFeistelRounds] = pb.keys[t / kFeistelRounds][t % kFeistelRounds];
+  __syncthreads();
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int rphase = warp / wpr, rpp = kStatWarps / wpr;
+  const int64_t col = ((int64_t)blockIdx.y * 256 + (warp % wpr) * 32 + lane) * 4;
+  const bool active = col < lda;
+  const int count = pb.count;
+
+  AccT acc[PB][4];
+#pragma unroll
+  for (int p = 0; p < PB; ++p)
+#pragma unroll
+    for (int c = 0; c < 4; ++c) acc[p][c] = 0;
+
+  for (int64_t row = (int64_t)blockIdx.x * rpp + rphase; row < n; row += (int64_t)gridDim.x * rpp) {
+    // lane p resolves π_p(row); broadcast by shuffle (one evaluation per warp, not per thread)
+    int src_l = 0;
+    if (lane < count) src_l = perm_lookup(pb, s_keys, lane, row, n);
+    float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (active) a = ld_stream4(A + row * lda + col);
+    float4 v[PB];
+#pragma unroll
+    for (int p = 0; p < PB; ++p) {
+      int src = __shfl_sync(kFull, src_l, p);
+      v[p] = (active && p < count) ? ldg4(B + (int64_t)src * ldb + col)
+                                   : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+#pragma unroll
+    for (int p = 0; p < PB; ++p) {
+      acc[p][0] += (AccT)a.x * (AccT)v[p].x;
+      acc[p][1] += (AccT)a.y * (AccT)v[p].y;
+      acc[p][2] += (AccT)a.z * (AccT)v[p].z;
+      acc[p][3] += (AccT)a.w * (AccT)v[p].w;
+    }
+  }
+#pragma unroll
+  for (int p = 0; p < PB; ++p) {
+    double v4[4] = {(double)acc[p][0], (double)acc[p][1], (double)acc[p][2], (double)acc[p][3]};
+    reduce_row_phases(v4, wpr, sh);
+    if (rphase == 0 && active && p < count) {
+      double* dst = partial + ((int64_t)blockIdx.x * PB + p) * ldp + col;
+#pragma unroll
+      for (int c = 0; c < 4; ++c) dst[c] = v4[c];
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// value-permuting null (gather-SpMM):
+//   sims[p,c] = Σ_i S_p[i,c] · Σ_j w_ij Zy[π_p(j),c],  S_p[i] = Zx ? Zx[i] : Zy[π_p(i)]
+// ------------------------------------------------------------------------------------------------
+
+template <int PB, bool HAS_W>
+__global__ void __launch_bounds__(kStatThreads)
+perm_values_kernel(const int32_t* __restrict__ indptr, const int32_t* __restrict__ indices,
+                   const float* __restrict__ weights, int64_t n, int k_fixed,
+                   const float* __restrict__ Zx, const float* __restrict__ Zy, int64_t ldz,
+                   const __grid_constant__ PermBatch pb, double* __restrict__ partial, int64_t ldp,
+                   const float* __restrict__ cell_obs, int32_t* __restrict__ cell_cnt, int64_t ldc,
+                   int wpr) {
+  __shared__ double sh[kStatWarps * 32 * 4];
+  __shared__ uint32_t s_keys[kMaxPermBatch][kFeistelRounds];
+  for (int t = threadIdx.x; t < kMaxPermBatch * kFeistelRounds; t += blockDim.x)
+    s_keys[t / kFeistelRounds][t % kFeistelRounds] = pb.keys[t / kFeistelRounds][t % kFeistelRounds];
+  __syncthreads();
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int rphase = warp / wpr, rpp = kStatWarps / wpr;
+  const int64_t col = ((int64_t)blockIdx.y * 256 + (warp % wpr) * 32 + lane) * 4;
+  const bool active = col < ldz;
+  const int count = pb.count;
+
+  double acc[PB][4];
+#pragma unroll
+  for (int p = 0; p < PB; ++p)
+#pragma unroll
+    for (int c = 0; c < 4; ++c) acc[p][c] = 0;
+
+  for (int64_t row = (int64_t)blockIdx.x * rpp + rphase; row < n; row += (int64_t)gridDim.x * rpp) {
+    const int64_t b = indptr ? indptr[row] : row * k_fixed;
+    const int64_t e = indptr ? indptr[row + 1] : b + k_fixed;
+    int self_l = 0;
+    if (!Zx && lane < count) self_l = perm_lookup(pb, s_keys, lane, row, n);
+    float4 lagp[PB];
+#pragma unroll
+    for (int p = 0; p < PB; ++p) lagp[p] = make_float4(0.f, 0.f, 0.f, 0.f);
+
+    for (int64_t t0 = b; t0 < e; t0 += 32) {
+      const int cnt = (int)min((int64_t)32, e - t0);
+      // lane j resolves neighbour t0+j under every permutation of the batch
+      int nb_l[PB];
+      float w_l = 1.f;
+#pragma unroll
+      for (int p = 0; p < PB; ++p) nb_l[p] = 0;
+      if (lane < cnt) {
+        int j = indices[t0 + lane];
+        if (HAS_W) w_l = weights[t0 + lane];
+#pragma unroll
+        for (int p = 0; p < PB; ++p)
+          if (p < count) nb_l[p] = perm_lookup(pb, s_keys, p, j, n);
+      }
+      for (int jj = 0; jj < cnt; ++jj) {
+        float w = HAS_W ? __shfl_sync(kFull, w_l, jj) : 1.f;
+#pragma unroll
+        for (int p = 0; p < PB; ++p) {
+          int src = __shfl_sync(kFull, nb_l[p], jj);
+          if (active && p < count) {
+            float4 v = ldg4(Zy + (int64_t)src * ldz + col);
+            lagp[p].x += w * v.x; lagp[p].y += w * v.y; lagp[p].z += w * v.z; lagp[p].w += w * v.w;
+          }
+        }
+      }
+    }
+    const float inv = HAS_W ? 1.f : ((e > b) ? 1.f / (float)(e - b) : 0.f);
+    int4 hits = make_int4(0, 0, 0, 0);
+    float4 obs = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (cell_cnt && active) obs = ldg4(cell_obs + row * ldc + col);
+#pragma unroll
+    for (int p = 0; p < PB; ++p) {
+      int self = __shfl_sync(kFull, self_l, p);
+      if (active && p < count) {
+        float4 s = Zx ? ldg4(Zx + row * ldz + col) : ldg4(Zy + (int64_t)self * ldz + col);
+        float4 l = make_float4(lagp[p].x * inv, lagp[p].y * inv, lagp[p].z * inv, lagp[p].w * inv);
+        acc[p][0] += (double)s.x * (double)l.x;
+        acc[p][1] += (double)s.y * (double)l.y;
+        acc[p][2] += (double)s.z * (double)l.z;
+        acc[p][3] += (double)s.w * (double)l.w;
+        if (cell_cnt) {
+          hits.x += fabsf(s.x * l.x) >= fabsf(obs.x);
+          hits.y += fabsf(s.y * l.y) >= fabsf(obs.y);
+          hits.z += fabsf(s.z * l.z) >= fabsf(obs.z);
+          hits.w += fabsf(s.w * l.w) >= fabsf(obs.w);
+        }
+      }
+    }
+    if (cell_cnt && active) {
+      int4* cp = reinterpret_cast<int4*>(cell_cnt + row * ldc + col);
+      int4 c = *cp;
+      c.x += hits.x; c.y += hits.y; c.z += hits.z; c.w += hits.w;
+      *cp = c;
+    }
+  }
+#pragma unroll
+  for (int p = 0; p < PB; ++p) {
+    double v4[4] = {acc[p][0], acc[p][1], acc[p][2], acc[p][3]};
+    reduce_row_phases(v4, wpr, sh);
+    if (rphase == 0 && active && p < count) {
+      double* dst = partial + ((int64_t)blockIdx.x * PB + p) * ldp + col;
+#pragma unroll
+      for (int c = 0; c < 4; ++c) dst[c] = v4[c];
+    }
+  }
+}
+
+__global__ void philox_permutation_kernel(PermDomain dom, const __grid_constant__ PermBatch pb,
+                                          int32_t* __restrict__ out) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < dom.n;
+       i += (int64_t)gridDim.x * blockDim.x)
+    out[i] = (int32_t)perm_apply((uint32_t)i, dom, pb.keys[0]);
+}
+
+__global__ void null_accumulate_kernel(const double* __restrict__ sims, int n_perms, int g,
+                                       const double* __restrict__ scale,
+                                       const double* __restrict__ obs, int64_t* __restrict__ cnt_ge,
+                                       int64_t* __restrict__ cnt_abs_ge, double* __restrict__ sum,
+                                       double* __restrict__ sumsq) {
+  int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= g) return;
+  const double sc_ = scale ? scale[c] : 1.0, o = obs[c];
+  int64_t ge = 0, age = 0;
+  double s = 0, ss = 0;
+  for (int p = 0; p < n_perms; ++p) {
+    double v = sims[(int64_t)p * g + c] * sc_;
+    ge += v >= o;
+    age += fabs(v) >= fabs(o);
+    s += v; ss += v * v;
+  }
+  if (cnt_ge) cnt_ge[c] += ge;
+  if (cnt_abs_ge) cnt_abs_ge[c] += age;
+  if (sum) sum[c] += s;
+  if (sumsq) sumsq[c] += ss;
+}
+
+static int persistent_blocks(const void* kernel, int threads, size_t smem) {
+  int per_sm = 1;
+  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, threads, smem);
+  if (per_sm < 1) per_sm = 1;
+  return sm_count() * per_sm;
+}
+
+static void fill_batch(PermBatch* pb, int source, const int32_t* perm_idx, uint64_t seed,
+                       int64_t first_perm, int64_t local_first, int count, int64_t n) {
+  pb->source = source;
+  pb->count = count;
+  pb->replay = (source == SC_PERM_REPLAY) ? perm_idx + local_first * n : nullptr;
+  pb->dom = make_perm_domain((uint32_t)n);
+  for (int p = 0; p < kMaxPermBatch; ++p) {
+    if (p < count && source == SC_PERM_PHILOX) {
+      perm_round_keys(seed, (uint64_t)(first_perm + p), pb->keys[p]);
+    } else {
+      for (int r = 0; r < kFeistelRounds; ++r) pb->keys[p][r] = 0;
+    }
+  }
+}
+
+constexpr int kMaxStatBlocks = 148 * 8;
+
+}  // namespace sc
+
+using namespace sc;
+
+// ================================================================================================
+// C ABI
+// ================================================================================================
+
+extern "C" size_t sc_zscore_workspace_bytes(int64_t n, int g) {
+  (void)n;
+  return align_up(sizeof(double) * 2 * (size_t)kMaxStatBlocks * (size_t)(g > 0 ? g : 1), 256) + 512;
+}
+
+template <typename T>
+static int zscore_impl(const T* X, int64_t n, int64_t ldx, int g, const int32_t* cols,
+                       const int32_t* rows, float* Z, int64_t ldz, double* mean, double* std,
+                       uint8_t* zero_var, double* partial, cudaStream_t st) {
+  int tiles = (g + 127) / 128;
+  int groups = (sm_count() * 8 + tiles - 1) / tiles;
+  int64_t max_groups = (n + 1) / 2;
+  if (groups > max_groups) groups = (int)max_groups;
+  if (groups < 1) groups = 1;
+  if ((int64_t)groups * tiles > kMaxStatBlocks) groups = kMaxStatBlocks / tiles;
+  if (groups < 1) groups = 1;
+  colstats_kernel<T><<<dim3(tiles, groups), dim3(128, 2), 0, st>>>(X, n, ldx, g, cols, partial);
+  SC_LAUNCH_OK();
+  colstats_final_kernel<T><<<(g + 127) / 128, 128, 0, st>>>(X, n, g, cols, partial, groups, mean, std,
+                                                            zero_var);
+  SC_LAUNCH_OK();
+  if (Z) {
+    int64_t total = n * (ldz / 4);
+    int64_t want = (total + 255) / 256;
+    int blocks = (int)(want > sm_count() * 16 ? sm_count() * 16 : (want < 1 ? 1 : want));
+    zscore_write_kernel<T><<<blocks, 256, 0, st>>>(X, n, ldx, g, cols, rows, mean, std, zero_var, Z,
+                                                   ldz);
+    SC_LAUNCH_OK();
+  }
+  return SC_OK;
+}
+
+extern "C" int sc_zscore(const void* X, int dtype, int64_t n, int64_t ldx, int g,
+                         const int32_t* cols, const int32_t* rows, float* Z, int64_t ldz,
+                         double* mean, double* std, uint8_t* zero_var, void* ws, size_t ws_bytes,
+                         sc_stream_t stream) {
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  SC_CHECK_ARG(X && mean && std && zero_var && ws, "sc_zscore: null argument");
+  SC_CHECK_ARG(n >= 1 && g >= 1, "sc_zscore: empty matrix (%lld x %d)", (long long)n, g);
+  SC_CHECK_ARG(!Z || (ldz % 4 == 0 && ldz >= g), "sc_zscore: ldz=%lld must be a multiple of 4 and >= g", (long long)ldz);
+  SC_CHECK_ARG(dtype == SC_F32 || dtype == SC_F64, "sc_zscore: bad dtype %d", dtype);
+  if (ws_bytes < sc_zscore_workspace_bytes(n, g)) { set_error("sc_zscore: workspace too small"); return SC_ERR_WORKSPACE; }
+  double* partial = static_cast<double*>(ws);
+  if (dtype == SC_F32)
+    return zscore_impl<float>(static_cast<const float*>(X), n, ldx, g, cols, rows, Z, ldz, mean, std, zero_var, partial, st);
+  return zscore_impl<double>(static_cast<const double*>(X), n, ldx, g, cols, rows, Z, ldz, mean, std, zero_var, partial, st);
+}
+
+extern "C" int sc_csr_densify(const int64_t* indptr, const int32_t* indices, const void* data,
+                              int dtype, int64_t n, const int32_t* colmap, int g_out, float* out,
+                              int64_t ldo, sc_stream_t stream) {
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  SC_CHECK_ARG(indptr && out && (indices || n == 0), "sc_csr_densify: null argument");
+  SC_CHECK_ARG(ldo >= g_out, "sc_csr_densify: ldo < g_out");
+  SC_CUDA_OK(cudaMemsetAsync(out, 0, sizeof(float) * (size_t)n * (size_t)ldo, st));
+  int64_t want = (n + 7) / 8;
+  int blocks = (int)(want > sm_count() * 16 ? sm_count() * 16 : (want < 1 ? 1 : want));
+  if (dtype == SC_F32)
+    csr_densify_kernel<float><<<blocks, 256, 0, st>>>(indptr, indices, static_cast<const float*>(data), n, colmap, g_out, out, ldo);
+  else if (dtype == SC_F64)
+    csr_densify_kernel<double><<<blocks, 256, 0, st>>>(indptr, indices, static_cast<const double*>(data), n, colmap, g_out, out, ldo);
+  else { set_error("sc_csr_densify: bad dtype %d", dtype); return SC_ERR_INVALID; }
+  SC_LAUNCH_OK();
+  return SC_OK;
+}
+
+// Largest leading dimension the partial buffers are sized for.
+static size_t max_ld(int g) { return align_up((size_t)(g > 0 ? g : 1), 32); }
+
+extern "C" size_t sc_csr_lag_moran_workspace_bytes(int64_t n, int g) {
+  (void)n;
+  size_t ld = max_ld(g);
+  return align_up(sizeof(double) * 2 * (size_t)kMaxStatBlocks * ld, 256) + 512;
+}
+
+extern "C" int sc_csr_lag_moran(const int32_t* indptr, const int32_t* indices,
+                                const float* weights, int64_t n, int k_fixed, const float* Z,
+                                int64_t ldz, int g, float* lag, float* local, int64_t ldl,
+                                double* num, double* den, void* ws, size_t ws_bytes,
+                                sc_stream_t stream) {
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  SC_CHECK_ARG(indices && Z && num && den && ws, "sc_csr_lag_moran: null argument");
+  SC_CHECK_ARG(indptr || k_fixed > 0, "sc_csr_lag_moran: need indptr or k_fixed");
+  SC_CHECK_ARG(ldz % 4 == 0 && ldz >= g && g >= 1 && (size_t)ldz <= max_ld(g),
+               "sc_csr_lag_moran: ldz must be a multiple of 4 in [g, round_up(g,32)]");
+  SC_CHECK_ARG((!lag && !local) || (ldl % 4 == 0 && ldl >= ldz), "sc_csr_lag_moran: ldl must be a multiple of 4 and >= ldz");
+  if (ws_bytes < sc_csr_lag_moran_workspace_bytes(n, g)) { set_error("sc_csr_lag_moran: workspace too small"); return SC_ERR_WORKSPACE; }
+  RowGeom rg = row_geom(ldz);
+  const void* kern = weights ? (const void*)lag_moran_kernel<true> : (const void*)lag_moran_kernel<false>;
+  int bx = persistent_blocks(kern, kStatThreads, 0);
+  int64_t max_bx = (n + rg.rpp - 1) / rg.rpp;
+  if (bx > max_bx) bx = (int)max_bx;
+  if (bx > kMaxStatBlocks) bx = kMaxStatBlocks;
+  int by = (int)((ldz / 4 + 255) / 256);
+  double* partial = static_cast<double*>(ws);
+  dim3 grid(bx, by);
+  if (weights)
+    lag_moran_kernel<true><<<grid, kStatThreads, 0, st>>>(indptr, indices, weights, n, k_fixed, Z, ldz, lag, local, ldl, partial, rg.wpr);
+  else
+    lag_moran_kernel<false><<<grid, kStatThreads, 0, st>>>(indptr, indices, weights, n, k_fixed, Z, ldz, lag, local, ldl, partial, rg.wpr);
+  SC_LAUNCH_OK();
+  // partial rows: [block][0]=num, [block][1]=den  -> view as (nblocks, rows=2, ldp=ldz)
+  reduce_partials_kernel<<<dim3((g + 127) / 128, 1), 128, 0, st>>>(partial, bx, 2, ldz, g, num, g);
+  SC_LAUNCH_OK();
+  reduce_partials_kernel<<<dim3((g + 127) / 128, 1), 128, 0, st>>>(partial + ldz, bx, 2, ldz, g, den, g);
+  SC_LAUNCH_OK();
+  return SC_OK;
+}
+
+extern "C" size_t sc_perm_null_workspace_bytes(int64_t n, int g) {
+  (void)n;
+  size_t ld = max_ld(g);
+  return align_up(sizeof(double) * (size_t)kMaxStatBlocks * kMaxPermBatch * ld, 256) + 512;
+}
+
+static int check_perm_args(const char* who, int source, const int32_t* perm_idx, int64_t n,
+                           int n_perms, const double* sims) {
+  SC_CHECK_ARG(source == SC_PERM_REPLAY || source == SC_PERM_PHILOX, "%s: bad permutation source %d", who, source);
+  SC_CHECK_ARG(source != SC_PERM_REPLAY || perm_idx, "%s: replay source needs perm_idx", who);
+  SC_CHECK_ARG(n >= 1 && n < (1ll << 31), "%s: n out of range", who);
+  SC_CHECK_ARG(n_perms >= 0 && sims, "%s: bad n_perms/sims", who);
+  return SC_OK;
+}
+
+template <int PB, typename AccT>
+static int launch_perm_rows(const float* A, int64_t lda, const float* B, int64_t ldb, int64_t n,
+                            int g, int source, const int32_t* perm_idx, uint64_t seed,
+                            int64_t perm_offset, int n_perms, double* sims, double* partial,
+                            cudaStream_t st) {
+  RowGeom rg = row_geom(lda);
+  int bx = persistent_blocks((const void*)perm_rows_kernel<PB, AccT>, kStatThreads, 0);
+  int64_t max_bx = (n + rg.rpp - 1) / rg.rpp;
+  if (bx > max_bx) bx = (int)max_bx;
+  if (bx > kMaxStatBlocks) bx = kMaxStatBlocks;
+  int by = (int)((lda / 4 + 255) / 256);
+  for (int p0 = 0; p0 < n_perms; p0 += PB) {
+    int count = n_perms - p0 < PB ? n_perms - p0 : PB;
+    PermBatch pb;
+    fill_batch(&pb, source, perm_idx, seed, perm_offset + p0, p0, count, n);
+    perm_rows_kernel<PB, AccT><<<dim3(bx, by), kStatThreads, 0, st>>>(A, lda, B, ldb, n, pb, partial, lda, rg.wpr);
+    SC_LAUNCH_OK();
+    reduce_partials_kernel<<<dim3((g + 127) / 128, count), 128, 0, st>>>(partial, bx, PB, lda, g, sims + (int64_t)p0 * g, g);
+    SC_LAUNCH_OK();
+  }
+  return SC_OK;
+}
+
+// Tunable from the host for experiments: SC_PERM_ROWS_VARIANT = "8d" | "16d" | "16f" | "8f"
+static int perm_rows_variant() {
+  const char* v = getenv("SC_PERM_ROWS_VARIANT");
+  if (!v) return 0;
+  if (!strcmp(v, "16d")) return 1;
+  if (!strcmp(v, "16f")) return 2;
+  if (!strcmp(v, "8f")) return 3;
+  if (!strcmp(v, "4d")) return 4;
+  return 0;
+}
+
+extern "C" int sc_perm_null_graph_rows(const float* A, int64_t lda, const float* B, int64_t ldb,
+                                       int64_t n, int g, int source, const int32_t* perm_idx,
+                                       uint64_t seed, int64_t perm_offset, int n_perms,
+                                       double* sims, void* ws, size_t ws_bytes,
+                                       sc_stream_t stream) {
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  int rc = check_perm_args("sc_perm_null_graph_rows", source, perm_idx, n, n_perms, sims);
+  if (rc) return rc;
+  SC_CHECK_ARG(A && B && ws, "sc_perm_null_graph_rows: null argument");
+  SC_CHECK_ARG(lda % 4 == 0 && lda >= g && ldb >= lda && ldb % 4 == 0 && g >= 1 &&
+                   (size_t)lda <= max_ld(g),
+               "sc_perm_null_graph_rows: lda/ldb must be multiples of 4, g <= lda <= round_up(g,32), ldb >= lda");
+  if (ws_bytes < sc_perm_null_workspace_bytes(n, g)) { set_error("sc_perm_null_graph_rows: workspace too small"); return SC_ERR_WORKSPACE; }
+  double* partial = static_cast<double*>(ws);
+  switch (perm_rows_variant()) {
+    case 1: return launch_perm_rows<16, double>(A, lda, B, ldb, n, g, source, perm_idx, seed, perm_offset, n_perms, sims, partial, st);
+    case 2: return launch_perm_rows<16, float>(A, lda, B, ldb, n, g, source, perm_idx, seed, perm_offset, n_perms, sims, partial, st);
+    case 3: return launch_perm_rows<8, float>(A, lda, B, ldb, n, g, source, perm_idx, seed, perm_offset, n_perms, sims, partial, st);
+    case 4: return launch_perm_rows<4, double>(A, lda, B, ldb, n, g, source, perm_idx, seed, perm_offset, n_perms, sims, partial, st);
+    default: return launch_perm_rows<8, double>(A, lda, B, ldb, n, g, source, perm_idx, seed, perm_offset, n_perms, sims, partial, st);
+  }
+}
+
+template <int PB, bool HAS_W>
+static int launch_perm_values(const int32_t* indptr, const int32_t* indices, const float* weights,
+                              int64_t n, int k_fixed, const float* Zx, const float* Zy,
+                              int64_t ldz, int g, int source, const int32_t* perm_idx,
+                              uint64_t seed, int64_t perm_offset, int n_perms, double* sims,
+                              const float* cell_obs, int32_t* cell_cnt, int64_t ldc,
+                              double* partial, cudaStream_t st) {
+  RowGeom rg = row_geom(ldz);
+  int bx = persistent_blocks((const void*)perm_values_kernel<PB, HAS_W>, kStatThreads, 0);
+  int64_t max_bx = (n + rg.rpp - 1) / rg.rpp;
+  if (bx > max_bx) bx = (int)max_bx;
+  if (bx > kMaxStatBlocks) bx = kMaxStatBlocks;
+  int by = (int)((ldz / 4 + 255) / 256);
+  for (int p0 = 0; p0 < n_perms; p0 += PB) {
+    int count = n_perms - p0 < PB ? n_perms - p0 : PB;
+    PermBatch pb;
+    fill_batch(&pb, source, perm_idx, seed, perm_offset + p0, p0, count, n);
+    perm_values_kernel<PB, HAS_W><<<dim3(bx, by), kStatThreads, 0, st>>>(
+        indptr, indices, weights, n, k_fixed, Zx, Zy, ldz, pb, partial, ldz, cell_obs, cell_cnt, ldc, rg.wpr);
+    SC_LAUNCH_OK();
+    reduce_partials_kernel<<<dim3((g + 127) / 128, count), 128, 0, st>>>(partial, bx, PB, ldz, g, sims + (int64_t)p0 * g, g);
+    SC_LAUNCH_OK();
+  }
+  return SC_OK;
+}
+
+extern "C" int sc_perm_null_values(const int32_t* indptr, const int32_t* indices,
+                                   const float* weights, int64_t n, int k_fixed, const float* Zx,
+                                   const float* Zy, int64_t ldz, int g, int source,
+                                   const int32_t* perm_idx, uint64_t seed, int64_t perm_offset,
+                                   int n_perms, double* sims, const float* cell_obs,
+                                   int32_t* cell_cnt, int64_t ldc, void* ws, size_t ws_bytes,
+                                   sc_stream_t stream) {
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  int rc = check_perm_args("sc_perm_null_values", source, perm_idx, n, n_perms, sims);
+  if (rc) return rc;
+  SC_CHECK_ARG(indices && Zy && ws, "sc_perm_null_values: null argument");
+  SC_CHECK_ARG(indptr || k_fixed > 0, "sc_perm_null_values: need indptr or k_fixed");
+  SC_CHECK_ARG(ldz % 4 == 0 && ldz >= g && g >= 1 && (size_t)ldz <= max_ld(g),
+               "sc_perm_null_values: ldz must be a multiple of 4 in [g, round_up(g,32)]");
+  SC_CHECK_ARG((cell_cnt == nullptr) == (cell_obs == nullptr), "sc_perm_null_values: cell_obs and cell_cnt go together");
+  SC_CHECK_ARG(!cell_cnt || (ldc % 4 == 0 && ldc >= ldz), "sc_perm_null_values: ldc must be a multiple of 4 and >= ldz");
+  if (ws_bytes < sc_perm_null_workspace_bytes(n, g)) { set_error("sc_perm_null_values: workspace too small"); return SC_ERR_WORKSPACE; }
+  double* partial = static_cast<double*>(ws);
+  if (weights)
+    return launch_perm_values<4, true>(indptr, indices, weights, n, k_fixed, Zx, Zy, ldz, g, source, perm_idx, seed, perm_offset, n_perms, sims, cell_obs, cell_cnt, ldc, partial, st);
+  return launch_perm_values<4, false>(indptr, indices, weights, n, k_fixed, Zx, Zy, ldz, g, source, perm_idx, seed, perm_offset, n_perms, sims, cell_obs, cell_cnt, ldc, partial, st);
+}
+
+extern "C" int sc_philox_permutation(uint64_t seed, int64_t perm_index, int64_t n, int32_t* out,
+                                     sc_stream_t stream) {
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  SC_CHECK_ARG(out && n >= 1 && n < (1ll << 31), "sc_philox_permutation: bad argument");
+  PermBatch pb;
+  fill_batch(&pb, SC_PERM_PHILOX, nullptr, seed, perm_index, 0, 1, n);
+  int64_t want = (n + 255) / 256;
+  int blocks = (int)(want > sm_count() * 8 ? sm_count() * 8 : want);
+  philox_permutation_kernel<<<blocks, 256, 0, st>>>(pb.dom, pb, out);
+  SC_LAUNCH_OK();
+  return SC_OK;
+}
+
+extern "C" int sc_null_accumulate(const double* sims, int n_perms, int g, const double* scale,
+                                  const double* obs, int64_t* cnt_ge, int64_t* cnt_abs_ge,
+                                  double* sum, double* sumsq, sc_stream_t stream) {
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  SC_CHECK_ARG(sims && obs && g >= 1 && n_perms >= 0, "sc_null_accumulate: bad argument");
+  null_accumulate_kernel<<<(g + 127) / 128, 128, 0, st>>>(sims, n_perms, g, scale, obs, cnt_ge, cnt_abs_ge, sum, sumsq);
+  SC_LAUNCH_OK();
+  return SC_OK;
+}

@@ -1,0 +1,462 @@
+"""Device-side building blocks: thin wrappers that pass torch CUDA tensors to ``libsc_b200.so``.
+
+PyTorch is plumbing here (device memory, streams, ``torch.distributed``); every numeric step is a
+hand-written sm_100a kernel behind the C ABI (``include/sc_b200.h``).  No function in this module
+has a CPU path: inputs must live on a CUDA device.
+"""
+
+from __future__ import annotations
+
+from dataclasses import dataclass
+from typing import Optional, Tuple
+
+import numpy as np
+import torch
+
+from spatialcore_b200 import _lib
+from spatialcore_b200._lib import SC_F32, SC_F64, SC_PERM_PHILOX, SC_PERM_REPLAY, check
+
+_launches = 0  # kernels-API calls issued (bench.py reports it as gpu_launches)
+
+
+def launches() -> int:
+    return _launches
+
+
+def _count(n: int = 1) -> None:
+    global _launches
+    _launches += n
+
+
+def _ptr(t: Optional[torch.Tensor]) -> Optional[int]:
+    return None if t is None else t.data_ptr()
+
+
+def _stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _require_cuda(t: torch.Tensor, name: str) -> None:
+    if not t.is_cuda:
+        raise RuntimeError(f"spatialcore_b200: {name} must be a CUDA tensor (there is no CPU path)")
+
+
+def _workspace(nbytes: int, device) -> torch.Tensor:
+    return torch.empty(max(int(nbytes), 256), dtype=torch.uint8, device=device)
+
+
+def padded_ld(g: int) -> int:
+    """Leading dimension used for every N x G matrix: multiple of 8 floats (32-byte sectors)."""
+    return (g + 7) // 8 * 8
+
+
+@dataclass
+class DeviceGraph:
+    """CSR neighbour graph on the device.  ``indptr is None`` means every row has ``k_fixed``
+    entries (kNN).  ``weights is None`` means row-standardised binary weights ``1/deg_i``."""
+
+    n: int
+    indices: torch.Tensor
+    indptr: Optional[torch.Tensor] = None
+    k_fixed: int = 0
+    weights: Optional[torch.Tensor] = None
+    dist: Optional[torch.Tensor] = None
+
+    @property
+    def nnz(self) -> int:
+        return int(self.indices.numel())
+
+    def indptr_tensor(self) -> torch.Tensor:
+        if self.indptr is not None:
+            return self.indptr
+        return torch.arange(0, (self.n + 1) * self.k_fixed, self.k_fixed, dtype=torch.int32, device=self.indices.device)
+
+    def to_scipy(self, data: str = "weights", dtype=np.float32):
+        """Host scipy CSR: ``data`` in {"weights" (row-standardised), "ones", "dist"}."""
+        from scipy import sparse
+
+        indptr = self.indptr_tensor().cpu().numpy()
+        indices = self.indices.reshape(-1).cpu().numpy()
+        if data == "dist":
+            vals = self.dist.reshape(-1).cpu().numpy().astype(dtype)
+        elif data == "ones":
+            vals = np.ones(indices.size, dtype=dtype)
+        elif self.weights is not None:
+            vals = self.weights.reshape(-1).cpu().numpy().astype(dtype)
+        else:
+            deg = np.diff(indptr)
+            with np.errstate(divide="ignore"):
+                vals = np.repeat((np.ones(1, dtype) / np.maximum(deg, 1).astype(dtype)).astype(dtype), deg)
+        return sparse.csr_matrix((vals, indices, indptr), shape=(self.n, self.n))
+
+
+# --------------------------------------------------------------------------------------------------
+# graphs
+# --------------------------------------------------------------------------------------------------
+
+
+def _coords_tensor(coords, device) -> torch.Tensor:
+    if isinstance(coords, torch.Tensor):
+        c = coords.to(device=device, dtype=torch.float64)
+    else:
+        a = np.asarray(coords)
+        if a.ndim != 2 or a.shape[1] < 2:
+            raise ValueError(f"spatial coordinates must have shape (n_cells, >=2), got {a.shape}")
+        if not np.isfinite(a[:, :2]).all():
+            raise ValueError("spatial coordinates contain NaN or infinite values")
+        c = torch.from_numpy(np.ascontiguousarray(a[:, :2], dtype=np.float64)).to(device)
+    return c[:, :2].contiguous()
+
+
+def knn_graph(
+    coords,
+    k: int,
+    include_self: bool = False,
+    want_dist: bool = False,
+    want_order: bool = False,
+    labels: Optional[torch.Tensor] = None,
+    n_types: int = 0,
+    want_idx: bool = True,
+    device="cuda",
+):
+    """Exact kNN graph (``sc_grid_knn``).  Returns ``(DeviceGraph|None, order|None, profile|None)``."""
+    c = _coords_tensor(coords, device)
+    n = c.shape[0]
+    if k < 1:
+        raise ValueError(f"n_neighbors must be >= 1, got {k}")
+    if k >= n:
+        raise ValueError(f"k must be < number of cells ({n}), got {k}")
+    if k > _lib.SC_KNN_MAX_K:
+        raise ValueError(f"k={k} exceeds the compiled limit SC_KNN_MAX_K={_lib.SC_KNN_MAX_K}")
+    L = _lib.lib()
+    kk = k + (1 if include_self else 0)
+    idx = torch.empty((n, kk), dtype=torch.int32, device=c.device) if want_idx else None
+    dist = torch.empty((n, kk), dtype=torch.float64, device=c.device) if (want_dist and want_idx) else None
+    order = torch.empty(n, dtype=torch.int32, device=c.device) if want_order else None
+    profile = None
+    if labels is not None:
+        _require_cuda(labels, "labels")
+        profile = torch.empty((n, n_types), dtype=torch.float32, device=c.device)
+    ws = _workspace(L.sc_grid_knn_workspace_bytes(n, k), c.device)
+    check(
+        L.sc_grid_knn(_ptr(c), n, k, int(include_self), _ptr(idx), _ptr(dist), _ptr(order), _ptr(labels),
+                      int(n_types), _ptr(profile), _ptr(ws), ws.numel(), _stream()),
+        "sc_grid_knn",
+    )
+    _count(7)
+    graph = DeviceGraph(n=n, indices=idx, k_fixed=kk, dist=dist) if want_idx else None
+    return graph, order, profile
+
+
+def radius_graph(
+    coords,
+    radius: float,
+    want_dist: bool = False,
+    labels: Optional[torch.Tensor] = None,
+    n_types: int = 0,
+    want_graph: bool = True,
+    device="cuda",
+):
+    """Radius graph, inclusive ``d <= r``, self excluded (``sc_grid_radius_count`` / ``_fill``).
+    Returns ``(DeviceGraph|None, profile|None)``."""
+    if radius is None or not radius > 0:
+        raise ValueError(f"radius must be > 0, got {radius}")
+    c = _coords_tensor(coords, device)
+    n = c.shape[0]
+    L = _lib.lib()
+    ws = _workspace(L.sc_grid_radius_workspace_bytes(n), c.device)
+    indptr = torch.empty(n + 1, dtype=torch.int32, device=c.device) if want_graph else None
+    nnz_t = torch.zeros(1, dtype=torch.int64, device=c.device)
+    profile = None
+    if labels is not None:
+        _require_cuda(labels, "labels")
+        profile = torch.empty((n, n_types), dtype=torch.float32, device=c.device)
+    check(
+        L.sc_grid_radius_count(_ptr(c), n, float(radius), _ptr(indptr), _ptr(nnz_t), _ptr(labels), int(n_types),
+                               _ptr(profile), _ptr(ws), ws.numel(), _stream()),
+        "sc_grid_radius_count",
+    )
+    _count(9)
+    if not want_graph:
+        return None, profile
+    nnz = int(nnz_t.item())  # host sync: the caller-owned index buffer must be sized
+    if nnz >= 2**31 - 1:
+        raise ValueError(f"radius graph has {nnz} edges, beyond int32 CSR capacity; reduce the radius")
+    indices = torch.empty(nnz, dtype=torch.int32, device=c.device)
+    dist = torch.empty(nnz, dtype=torch.float64, device=c.device) if want_dist else None
+    scratch = _workspace(nnz * (12 if want_dist else 4), c.device)
+    if nnz > 0:
+        check(
+            L.sc_grid_radius_fill(_ptr(c), n, float(radius), _ptr(indptr), _ptr(indices), _ptr(dist), _ptr(scratch),
+                                  nnz * (12 if want_dist else 4), _ptr(ws), ws.numel(), _stream()),
+            "sc_grid_radius_fill",
+        )
+        _count(1)
+    return DeviceGraph(n=n, indices=indices, indptr=indptr, dist=dist), profile
+
+
+def graph_from_scipy(adj, device="cuda", use_weights: bool = False) -> DeviceGraph:
+    """Upload an existing scipy CSR connectivity matrix (``use_existing_graph`` path)."""
+    from scipy import sparse
+
+    a = sparse.csr_matrix(adj)
+    a.sort_indices()
+    a.sum_duplicates()
+    n = a.shape[0]
+    indptr = torch.from_numpy(a.indptr.astype(np.int32)).to(device)
+    indices = torch.from_numpy(a.indices.astype(np.int32)).to(device)
+    weights = torch.from_numpy(a.data.astype(np.float32)).to(device) if use_weights else None
+    return DeviceGraph(n=n, indices=indices, indptr=indptr, weights=weights)
+
+
+def nbhd_counts(graph: DeviceGraph, labels: torch.Tensor, n_types: int) -> torch.Tensor:
+    L = _lib.lib()
+    prof = torch.empty((graph.n, n_types), dtype=torch.float32, device=labels.device)
+    check(
+        L.sc_nbhd_counts(_ptr(graph.indptr), _ptr(graph.indices), graph.n, int(graph.k_fixed), _ptr(labels),
+                         int(n_types), _ptr(prof), _stream()),
+        "sc_nbhd_counts",
+    )
+    _count()
+    return prof
+
+
+def profile_normalize(profile: torch.Tensor, normalize: bool) -> int:
+    """Normalises in place; returns the number of empty rows (host sync)."""
+    L = _lib.lib()
+    n_empty = torch.zeros(1, dtype=torch.int64, device=profile.device)
+    check(
+        L.sc_profile_normalize(_ptr(profile), profile.shape[0], profile.shape[1], int(normalize), _ptr(n_empty), _stream()),
+        "sc_profile_normalize",
+    )
+    _count()
+    return int(n_empty.item())
+
+
+def graph_moments(graph: DeviceGraph) -> Tuple[float, float, float]:
+    L = _lib.lib()
+    dev = graph.indices.device
+    out = torch.empty(3, dtype=torch.float64, device=dev)
+    ws = _workspace(L.sc_graph_moments_workspace_bytes(graph.n), dev)
+    check(
+        L.sc_graph_moments(_ptr(graph.indptr), _ptr(graph.indices), _ptr(graph.weights), graph.n, int(graph.k_fixed),
+                           _ptr(out), _ptr(ws), ws.numel(), _stream()),
+        "sc_graph_moments",
+    )
+    _count(3)
+    s = out.cpu().numpy()
+    return float(s[0]), float(s[1]), float(s[2])
+
+
+# --------------------------------------------------------------------------------------------------
+# standardisation
+# --------------------------------------------------------------------------------------------------
+
+
+@dataclass
+class Standardized:
+    Z: torch.Tensor  # [n, ld] float32, padding columns zero
+    g: int
+    mean: torch.Tensor  # [g] float64
+    std: torch.Tensor  # [g] float64
+    zero_var: torch.Tensor  # [g] uint8
+
+
+def zscore_dense(X: torch.Tensor, cols: Optional[torch.Tensor] = None, rows: Optional[torch.Tensor] = None,
+                 want_z: bool = True) -> Standardized:
+    """``sc_zscore`` on a dense device matrix (float32 or float64, row-major, any row stride)."""
+    _require_cuda(X, "X")
+    if X.dim() != 2:
+        raise ValueError("X must be 2-D")
+    if X.dtype not in (torch.float32, torch.float64):
+        X = X.to(torch.float32)
+    if X.stride(1) != 1:
+        X = X.contiguous()
+    n = X.shape[0]
+    g = int(cols.numel()) if cols is not None else X.shape[1]
+    ld = padded_ld(g)
+    L = _lib.lib()
+    dev = X.device
+    Z = torch.empty((n, ld), dtype=torch.float32, device=dev) if want_z else None
+    mean = torch.empty(g, dtype=torch.float64, device=dev)
+    std = torch.empty(g, dtype=torch.float64, device=dev)
+    zero = torch.empty(g, dtype=torch.uint8, device=dev)
+    ws = _workspace(L.sc_zscore_workspace_bytes(n, g), dev)
+    check(
+        L.sc_zscore(_ptr(X), SC_F32 if X.dtype == torch.float32 else SC_F64, n, X.stride(0), g, _ptr(cols), _ptr(rows),
+                    _ptr(Z), ld, _ptr(mean), _ptr(std), _ptr(zero), _ptr(ws), ws.numel(), _stream()),
+        "sc_zscore",
+    )
+    _count(3)
+    return Standardized(Z=Z, g=g, mean=mean, std=std, zero_var=zero)
+
+
+def densify_csr(indptr: torch.Tensor, indices: torch.Tensor, data: torch.Tensor, n: int, n_cols: int,
+                colmap: Optional[torch.Tensor], g_out: int) -> torch.Tensor:
+    """``sc_csr_densify``: CSR expression -> dense float32 [n, padded_ld(g_out)] on the device."""
+    L = _lib.lib()
+    ld = padded_ld(g_out)
+    out = torch.empty((n, ld), dtype=torch.float32, device=data.device)
+    if data.dtype not in (torch.float32, torch.float64):
+        data = data.to(torch.float32)
+    check(
+        L.sc_csr_densify(_ptr(indptr), _ptr(indices), _ptr(data), SC_F32 if data.dtype == torch.float32 else SC_F64, n,
+                         _ptr(colmap), g_out, _ptr(out), ld, _stream()),
+        "sc_csr_densify",
+    )
+    _count(2)
+    return out
+
+
+def expression_to_device(X, gene_idx: Optional[np.ndarray], device="cuda") -> Tuple[torch.Tensor, Optional[torch.Tensor]]:
+    """Bring an AnnData expression matrix to the device as a dense matrix plus an optional column
+    selector.  Accepts numpy, scipy sparse (CSR/CSC/…), or torch tensors (host or device)."""
+    from scipy import sparse
+
+    cols = None
+    if sparse.issparse(X):
+        csr = X.tocsr()
+        if not csr.has_canonical_format:
+            csr = csr.copy()
+            csr.sum_duplicates()
+        n, n_cols = csr.shape
+        if gene_idx is None:
+            g_out, colmap = n_cols, None
+        else:
+            g_out = len(gene_idx)
+            if len(np.unique(gene_idx)) != g_out:
+                # duplicated genes: densify all requested source columns once, select afterwards
+                uniq, inv = np.unique(gene_idx, return_inverse=True)
+                cm = np.full(n_cols, -1, dtype=np.int32)
+                cm[uniq] = np.arange(len(uniq), dtype=np.int32)
+                dense = densify_csr(
+                    torch.from_numpy(csr.indptr.astype(np.int64)).to(device),
+                    torch.from_numpy(csr.indices.astype(np.int32)).to(device),
+                    torch.from_numpy(csr.data).to(device), n, n_cols, torch.from_numpy(cm).to(device), len(uniq))
+                return dense, torch.from_numpy(inv.astype(np.int32)).to(device)
+            cm = np.full(n_cols, -1, dtype=np.int32)
+            cm[gene_idx] = np.arange(g_out, dtype=np.int32)
+            colmap = torch.from_numpy(cm).to(device)
+        dense = densify_csr(
+            torch.from_numpy(csr.indptr.astype(np.int64)).to(device),
+            torch.from_numpy(csr.indices.astype(np.int32)).to(device),
+            torch.from_numpy(csr.data).to(device), n, n_cols, colmap, g_out)
+        return dense[:, :g_out], None
+    if isinstance(X, torch.Tensor):
+        Xd = X.to(device, non_blocking=True)
+    else:
+        a = np.asarray(X)
+        if a.dtype not in (np.float32, np.float64):
+            a = a.astype(np.float32)
+        Xd = torch.from_numpy(a).to(device, non_blocking=True)
+    if gene_idx is not None:
+        cols = torch.from_numpy(np.asarray(gene_idx, dtype=np.int32)).to(device)
+    return Xd, cols
+
+
+# --------------------------------------------------------------------------------------------------
+# lag, nulls, contraction
+# --------------------------------------------------------------------------------------------------
+
+
+def lag_moran(graph: DeviceGraph, Z: torch.Tensor, g: int, want_lag: bool = True, want_local: bool = False):
+    """``sc_csr_lag_moran``: returns ``(num[g], den[g], lag|None, local|None)``."""
+    _require_cuda(Z, "Z")
+    L = _lib.lib()
+    n, ld = Z.shape
+    dev = Z.device
+    lag = torch.empty((n, ld), dtype=torch.float32, device=dev) if want_lag else None
+    local = torch.empty((n, ld), dtype=torch.float32, device=dev) if want_local else None
+    num = torch.empty(g, dtype=torch.float64, device=dev)
+    den = torch.empty(g, dtype=torch.float64, device=dev)
+    ws = _workspace(L.sc_csr_lag_moran_workspace_bytes(n, g), dev)
+    check(
+        L.sc_csr_lag_moran(_ptr(graph.indptr), _ptr(graph.indices), _ptr(graph.weights), n, int(graph.k_fixed), _ptr(Z),
+                           ld, g, _ptr(lag), _ptr(local), ld, _ptr(num), _ptr(den), _ptr(ws), ws.numel(), _stream()),
+        "sc_csr_lag_moran",
+    )
+    _count(3)
+    return num, den, lag, local
+
+
+def _perm_source(perm_idx: Optional[torch.Tensor], n: int, n_perms: int):
+    if perm_idx is None:
+        return SC_PERM_PHILOX, None
+    _require_cuda(perm_idx, "perm_idx")
+    if perm_idx.dtype != torch.int32 or perm_idx.shape != (n_perms, n) or not perm_idx.is_contiguous():
+        raise ValueError("perm_idx must be a contiguous int32 tensor of shape (n_perms, n)")
+    return SC_PERM_REPLAY, perm_idx
+
+
+def perm_null_graph_rows(A: torch.Tensor, B: torch.Tensor, g: int, n_perms: int,
+                         perm_idx: Optional[torch.Tensor] = None, seed: int = 0, perm_offset: int = 0,
+                         out: Optional[torch.Tensor] = None, ws: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """``sc_perm_null_graph_rows``: ``sims[p,c] = Σ_i A[i,c]·B[π_p(i),c]`` (raw sums, float64)."""
+    L = _lib.lib()
+    n, ld = A.shape
+    source, pidx = _perm_source(perm_idx, n, n_perms)
+    sims = out if out is not None else torch.empty((n_perms, g), dtype=torch.float64, device=A.device)
+    if ws is None:
+        ws = _workspace(L.sc_perm_null_workspace_bytes(n, g), A.device)
+    check(
+        L.sc_perm_null_graph_rows(_ptr(A), ld, _ptr(B), B.shape[1], n, g, source, _ptr(pidx), int(seed) & (2**64 - 1),
+                                  int(perm_offset), int(n_perms), _ptr(sims), _ptr(ws), ws.numel(), _stream()),
+        "sc_perm_null_graph_rows",
+    )
+    _count(2 * ((n_perms + 7) // 8))
+    return sims
+
+
+def perm_null_values(graph: DeviceGraph, Zy: torch.Tensor, g: int, n_perms: int, Zx: Optional[torch.Tensor] = None,
+                     perm_idx: Optional[torch.Tensor] = None, seed: int = 0, perm_offset: int = 0,
+                     cell_obs: Optional[torch.Tensor] = None, cell_cnt: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """``sc_perm_null_values``: the reference's own value-permuting null (gather-SpMM)."""
+    L = _lib.lib()
+    n, ld = Zy.shape
+    source, pidx = _perm_source(perm_idx, n, n_perms)
+    sims = torch.empty((n_perms, g), dtype=torch.float64, device=Zy.device)
+    ws = _workspace(L.sc_perm_null_workspace_bytes(n, g), Zy.device)
+    ldc = cell_cnt.shape[1] if cell_cnt is not None else 0
+    check(
+        L.sc_perm_null_values(_ptr(graph.indptr), _ptr(graph.indices), _ptr(graph.weights), n, int(graph.k_fixed),
+                              _ptr(Zx), _ptr(Zy), ld, g, source, _ptr(pidx), int(seed) & (2**64 - 1), int(perm_offset),
+                              int(n_perms), _ptr(sims), _ptr(cell_obs), _ptr(cell_cnt), ldc, _ptr(ws), ws.numel(),
+                              _stream()),
+        "sc_perm_null_values",
+    )
+    _count(2 * ((n_perms + 3) // 4))
+    return sims
+
+
+def philox_permutation(seed: int, perm_index: int, n: int, device="cuda") -> torch.Tensor:
+    L = _lib.lib()
+    out = torch.empty(n, dtype=torch.int32, device=device)
+    check(L.sc_philox_permutation(int(seed) & (2**64 - 1), int(perm_index), n, _ptr(out), _stream()), "sc_philox_permutation")
+    _count()
+    return out
+
+
+def null_accumulate(sims: torch.Tensor, scale: Optional[torch.Tensor], obs: torch.Tensor, cnt_ge: torch.Tensor,
+                    cnt_abs_ge: torch.Tensor, ssum: torch.Tensor, ssq: torch.Tensor) -> None:
+    L = _lib.lib()
+    n_perms, g = sims.shape
+    check(
+        L.sc_null_accumulate(_ptr(sims), n_perms, g, _ptr(scale), _ptr(obs), _ptr(cnt_ge), _ptr(cnt_abs_ge), _ptr(ssum),
+                             _ptr(ssq), _stream()),
+        "sc_null_accumulate",
+    )
+    _count()
+
+
+def lee_gemm(A: torch.Tensor, B: torch.Tensor, g: int, impl: int = 0) -> torch.Tensor:
+    """``sc_lee_gemm``: ``L[x,y] = Σ_i A[i,x]·B[i,y]`` (float32 [g,g])."""
+    L = _lib.lib()
+    n = A.shape[0]
+    out = torch.empty((g, g), dtype=torch.float32, device=A.device)
+    ws = _workspace(L.sc_lee_gemm_workspace_bytes(n, g), A.device)
+    check(
+        L.sc_lee_gemm(_ptr(A), A.shape[1], _ptr(B), B.shape[1], n, g, _ptr(out), g, int(impl), _ptr(ws), ws.numel(), _stream()),
+        "sc_lee_gemm",
+    )
+    _count(2)
+    return out

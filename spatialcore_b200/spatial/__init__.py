@@ -1,0 +1,28 @@
+"""B200 drop-in for the hot path of ``spatialcore.spatial`` [R src/spatialcore/spatial/__init__.py:11-52].
+
+In scope: neighbour graphs, global/local Moran's I, global/local Lee's L,
+neighbourhood composition.  ``identify_niches``, ``make_spatial_domains``, ``get_domain_summary``,
+``calculate_domain_distances`` and ``get_distance_matrix`` are out of scope for this build.
+"""
+
+from spatialcore_b200.spatial.autocorrelation import (
+    build_spatial_weights,
+    lees_l,
+    lees_l_local,
+    lees_l_matrix,
+    local_morans_i,
+    morans_i,
+    spatial_neighbors,
+)
+from spatialcore_b200.spatial.neighborhoods import compute_neighborhood_profile
+
+__all__ = [
+    "morans_i",
+    "local_morans_i",
+    "lees_l",
+    "lees_l_local",
+    "lees_l_matrix",
+    "build_spatial_weights",
+    "spatial_neighbors",
+    "compute_neighborhood_profile",
+]

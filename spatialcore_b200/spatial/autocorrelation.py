@@ -1,0 +1,752 @@
+"""Drop-in ``spatialcore.spatial`` autocorrelation API on B200.
+
+Same names, arguments, AnnData slots and error behaviour as the reference
+[R src/spatialcore/spatial/autocorrelation.py]; the arithmetic runs in ``libsc_b200.so``
+(hand-written sm_100a kernels) through :mod:`spatialcore_b200.engine`.  There is no CPU path.
+
+Extensions are keyword-only and default to the reference behaviour:
+
+``perm_source``  ``"replay"`` draws the reference's own numpy permutation stream on the host and
+                 uploads it (identical p-values); ``"philox"`` generates permutations on the device;
+                 ``"auto"`` replays while the index arrays stay small, else uses Philox.
+``radius``       (``morans_i``) build a radius graph instead of kNN.
+``device``       CUDA device.
+"""
+
+from __future__ import annotations
+
+import time
+from itertools import combinations
+from typing import List, Literal, Optional, Tuple, Union
+
+import numpy as np
+import pandas as pd
+import torch
+from scipy import sparse
+from scipy.special import ndtr
+
+from spatialcore_b200 import distributed as dist_util
+from spatialcore_b200 import engine
+from spatialcore_b200.core.logging import get_logger
+from spatialcore_b200.core.metadata import update_metadata
+
+logger = get_logger(__name__)
+
+QUADRANT_LABELS = {0: "NS", 1: "HH", 2: "LL", 3: "HL", 4: "LH"}
+
+# replaying numpy permutations costs 4*N bytes of upload per permutation; beyond this many index
+# elements "auto" switches to the on-device Philox bijection
+_AUTO_REPLAY_LIMIT = 200_000_000
+_REPLAY_CHUNK_ELEMS = 64_000_000
+
+
+# --------------------------------------------------------------------------------------------------
+# shared helpers
+# --------------------------------------------------------------------------------------------------
+
+
+def _check_spatial(adata, spatial_key: str, what: str = "Spatial coordinates are required.") -> None:
+    if spatial_key not in adata.obsm:
+        raise ValueError(f"adata.obsm['{spatial_key}'] not found. {what}")
+
+
+def _check_counts(n_neighbors: int, n_permutations: int) -> None:
+    if n_neighbors < 1:
+        raise ValueError(f"n_neighbors must be >= 1, got {n_neighbors}")
+    if n_permutations < 0:
+        raise ValueError(f"n_permutations must be >= 0, got {n_permutations}")
+
+
+def _resolve_genes(adata, genes, slow_note: str) -> List[str]:
+    if genes is None:
+        names = list(adata.var_names)
+        logger.warning(f"No genes specified, analyzing all {len(names)} genes. {slow_note}")
+    elif isinstance(genes, str):
+        names = [genes]
+    else:
+        names = list(genes)
+    missing = set(names) - set(adata.var_names)
+    if missing:
+        raise ValueError(f"Genes not found in adata.var_names: {list(missing)[:10]}")
+    return names
+
+
+def _expression(adata, layer: Optional[str]):
+    return adata.layers[layer] if layer is not None else adata.X
+
+
+def _gene_positions(adata, names: List[str]) -> Optional[np.ndarray]:
+    pos = np.asarray([adata.var_names.get_loc(g) for g in names], dtype=np.int64)
+    if len(pos) == adata.n_vars and np.array_equal(pos, np.arange(adata.n_vars)):
+        return None
+    return pos
+
+
+def _standardize(adata, layer, names: List[str], device) -> engine.Standardized:
+    Xd, cols = engine.expression_to_device(_expression(adata, layer), _gene_positions(adata, names), device)
+    return engine.zscore_dense(Xd, cols=cols)
+
+
+def _pick_perm_source(perm_source: str, n: int, n_perms: int) -> str:
+    if perm_source not in ("auto", "replay", "philox"):
+        raise ValueError(f"perm_source must be 'auto', 'replay' or 'philox', got '{perm_source}'")
+    if perm_source == "auto":
+        return "replay" if n * max(n_perms, 1) <= _AUTO_REPLAY_LIMIT else "philox"
+    return perm_source
+
+
+def _replay_chunks(rng: np.random.Generator, n: int, n_perms: int, device):
+    """Yield ``(first_perm, int32 tensor [count, n])`` drawn from ``rng.permutation(n)`` in order."""
+    per = max(1, min(n_perms, _REPLAY_CHUNK_ELEMS // max(n, 1)))
+    done = 0
+    while done < n_perms:
+        cnt = min(per, n_perms - done)
+        host = np.empty((cnt, n), dtype=np.int32)
+        for j in range(cnt):
+            host[j] = rng.permutation(n)
+        yield done, torch.from_numpy(host).to(device)
+        done += cnt
+
+
+def _build_knn(adata, spatial_key: str, k: int, device, include_self: bool = False, want_dist: bool = False):
+    graph, _, _ = engine.knn_graph(adata.obsm[spatial_key], k, include_self=include_self, want_dist=want_dist, device=device)
+    return graph
+
+
+def _fdr_bh(p: np.ndarray) -> np.ndarray:
+    """Benjamini-Hochberg step-up [R autocorrelation.py:132-164]."""
+    n = len(p)
+    if n == 0:
+        return p.copy()
+    order = np.argsort(p)
+    adj = p[order] * n / np.arange(1, n + 1)
+    adj = np.minimum.accumulate(adj[::-1])[::-1]
+    out = np.empty(n)
+    out[order] = adj
+    return np.clip(out, 0, 1)
+
+
+def _fdr(p: np.ndarray, method: str) -> np.ndarray:
+    if method == "none":
+        return p.copy()
+    if method == "bonferroni":
+        return np.clip(p * len(p), 0, 1) if len(p) else p.copy()
+    if method == "fdr_bh":
+        return _fdr_bh(p)
+    raise ValueError(f"Unknown FDR method: {method}")
+
+
+def _classify_quadrants(z, lag, p_values=None, alpha: float = 0.05) -> np.ndarray:
+    """LISA quadrants 0 NS / 1 HH / 2 LL / 3 HL / 4 LH [R autocorrelation.py:219-265]."""
+    q = np.zeros(z.shape, dtype=np.int8)
+    q[(z > 0) & (lag > 0)] = 1
+    q[(z < 0) & (lag < 0)] = 2
+    q[(z > 0) & (lag < 0)] = 3
+    q[(z < 0) & (lag > 0)] = 4
+    if p_values is not None:
+        q[p_values >= alpha] = 0
+    return q
+
+
+# --------------------------------------------------------------------------------------------------
+# spatial weights
+# --------------------------------------------------------------------------------------------------
+
+
+def build_spatial_weights(
+    adata,
+    n_neighbors: int = 6,
+    spatial_key: str = "spatial",
+    include_self: bool = False,
+    *,
+    device="cuda",
+) -> sparse.csr_matrix:
+    """Row-normalised kNN weights as scipy CSR (FP32 data, int32 indices, columns sorted), as
+    [R autocorrelation.py:342-413].  The graph is built by ``sc_grid_knn`` on the device; self is
+    excluded by index (the reference drops column 0 positionally, identical for unique coordinates)."""
+    _check_spatial(adata, spatial_key)
+    graph = _build_knn(adata, spatial_key, n_neighbors, device, include_self=include_self)
+    return graph.to_scipy("weights", np.float32)
+
+
+def spatial_neighbors(adata, n_neighs: int = 6, radius: Optional[float] = None, spatial_key: str = "spatial",
+                      *, device="cuda", write: bool = True) -> engine.DeviceGraph:
+    """squidpy-style ``spatial_neighbors(coord_type='generic')`` side effects, as triggered by
+    ``morans_i`` [R autocorrelation.py:565-570]: binary FP64 ``obsp['spatial_connectivities']``,
+    FP64 ``obsp['spatial_distances']`` and ``uns['spatial_neighbors']``."""
+    _check_spatial(adata, spatial_key)
+    if radius is None:
+        graph, _, _ = engine.knn_graph(adata.obsm[spatial_key], n_neighs, want_dist=write, device=device)
+    else:
+        graph, _ = engine.radius_graph(adata.obsm[spatial_key], radius, want_dist=write, device=device)
+    if write:
+        adata.obsp["spatial_connectivities"] = graph.to_scipy("ones", np.float64)
+        adata.obsp["spatial_distances"] = graph.to_scipy("dist", np.float64)
+        adata.uns["spatial_neighbors"] = {
+            "connectivities_key": "spatial_connectivities",
+            "distances_key": "spatial_distances",
+            "params": {"n_neighbors": n_neighs, "coord_type": "generic", "radius": radius, "transform": None},
+        }
+    return graph
+
+
+def _existing_graph(adata, device) -> engine.DeviceGraph:
+    """``use_existing_graph=True``: squidpy L1-row-normalises whatever is stored
+    (``transformation=True``), so binary graphs map to implicit 1/deg weights."""
+    adj = sparse.csr_matrix(adata.obsp["spatial_connectivities"])
+    if adj.nnz and np.all(adj.data == 1):
+        return engine.graph_from_scipy(adj, device, use_weights=False)
+    adj = adj.astype(np.float64)
+    rs = np.asarray(np.abs(adj).sum(axis=1)).ravel()
+    rs[rs == 0] = 1.0
+    adj.data = adj.data / np.repeat(rs, np.diff(adj.indptr))
+    return engine.graph_from_scipy(adj, device, use_weights=True)
+
+
+# --------------------------------------------------------------------------------------------------
+# global Moran's I
+# --------------------------------------------------------------------------------------------------
+
+
+class MoranNull:
+    """Running summaries of the permutation null for G genes on one device."""
+
+    def __init__(self, g: int, device) -> None:
+        self.cnt_ge = torch.zeros(g, dtype=torch.int64, device=device)
+        self.cnt_abs_ge = torch.zeros(g, dtype=torch.int64, device=device)
+        self.sum = torch.zeros(g, dtype=torch.float64, device=device)
+        self.sumsq = torch.zeros(g, dtype=torch.float64, device=device)
+
+    def packed(self) -> torch.Tensor:
+        return torch.stack([self.cnt_ge.double(), self.cnt_abs_ge.double(), self.sum, self.sumsq])
+
+    def unpack(self, t: torch.Tensor) -> None:
+        self.cnt_ge = t[0].round().long()
+        self.cnt_abs_ge = t[1].round().long()
+        self.sum, self.sumsq = t[2], t[3]
+
+
+def moran_graph_rows_null(Z: torch.Tensor, lag: torch.Tensor, g: int, scale: torch.Tensor, obs: torch.Tensor,
+                          n_perms: int, seed: int, source: str, null: MoranNull, perm_range: Tuple[int, int],
+                          keep_sims: bool = False):
+    """Run permutations ``perm_range`` of the graph-row null and fold them into ``null``.
+    Philox permutations are addressed by global index, so any partition of ``[0, P)`` over ranks
+    or batches yields the same counts."""
+    n = Z.shape[0]
+    first, last = perm_range
+    sims_all = []
+    if last <= first:
+        return sims_all
+    if source == "philox":
+        step = 256
+        ws = None
+        for p0 in range(first, last, step):
+            cnt = min(step, last - p0)
+            sims = engine.perm_null_graph_rows(Z, lag, g, cnt, seed=seed, perm_offset=p0, ws=ws)
+            engine.null_accumulate(sims, scale, obs, null.cnt_ge, null.cnt_abs_ge, null.sum, null.sumsq)
+            if keep_sims:
+                sims_all.append(sims * scale)
+    else:
+        # numpy stream: permutation p is the p-th draw of default_rng(seed); ranks skip by drawing
+        rng = np.random.default_rng(seed)
+        for _ in range(first):
+            rng.permutation(n)
+        for _, idx in _replay_chunks(rng, n, last - first, Z.device):
+            sims = engine.perm_null_graph_rows(Z, lag, g, idx.shape[0], perm_idx=idx)
+            engine.null_accumulate(sims, scale, obs, null.cnt_ge, null.cnt_abs_ge, null.sum, null.sumsq)
+            if keep_sims:
+                sims_all.append(sims * scale)
+    return sims_all
+
+
+def morans_i(
+    adata,
+    genes: Optional[Union[str, List[str]]] = None,
+    layer: Optional[str] = None,
+    spatial_key: str = "spatial",
+    n_neighbors: int = 6,
+    n_permutations: int = 10,
+    seed: int = 0,
+    key_added: str = "morans_i",
+    copy: bool = False,
+    use_existing_graph: bool = False,
+    *,
+    perm_source: str = "auto",
+    radius: Optional[float] = None,
+    write_graph: bool = True,
+    device="cuda",
+):
+    """Global Moran's I with the squidpy permutation null, API of [R autocorrelation.py:421-648].
+
+    Writes ``adata.uns[key_added]`` (DataFrame ``gene, I, expected_I, z_score, p_value`` in input gene
+    order), the squidpy graph slots, and a metadata entry.  With ``torch.distributed`` initialised
+    the permutations are sharded over ranks and the per-gene null summaries all-reduced."""
+    t0 = time.time()
+    _check_spatial(adata, spatial_key)
+    _check_counts(n_neighbors, n_permutations)
+    adata = adata.copy() if copy else adata
+    names = _resolve_genes(adata, genes, "This may be slow for large datasets.")
+    n, g = adata.n_obs, len(names)
+    logger.info(f"Computing Global Moran's I: {n:,} cells, {g} genes, k={n_neighbors}, permutations={n_permutations}")
+
+    if use_existing_graph and "spatial_connectivities" in adata.obsp:
+        logger.info("Using existing spatial connectivity graph (use_existing_graph=True)")
+        graph = _existing_graph(adata, device)
+    else:
+        graph = spatial_neighbors(adata, n_neighbors, radius, spatial_key, device=device, write=write_graph)
+
+    std = _standardize(adata, layer, names, device)
+    num, den, lag, _ = engine.lag_moran(graph, std.Z, g, want_lag=n_permutations > 0)
+    s0, s1, s2 = engine.graph_moments(graph)
+    scale = (float(n) / s0) / den  # I = scale * Σ z·lag ; NaN for zero-variance genes, as 0/0 upstream
+    I_dev = num * scale
+
+    expected_I = -1 / (n - 1)
+    var_norm = (n * n * s1 - n * s2 + 3.0 * s0 * s0) / ((n - 1.0) * (n + 1.0) * s0 * s0) - 1.0 / (n - 1.0) ** 2
+    I = I_dev.cpu().numpy()
+
+    extra = {}
+    if n_permutations > 0:
+        source = _pick_perm_source(perm_source, n, n_permutations)
+        null = MoranNull(g, std.Z.device)
+        lo, hi = dist_util.my_slice(n_permutations)
+        moran_graph_rows_null(std.Z, lag, g, scale, I_dev, n_permutations, seed, source, null, (lo, hi))
+        dist_util.all_reduce_null(null)
+        c = null.cnt_ge.cpu().numpy()
+        c = np.where(n_permutations - c < c, n_permutations - c, c)
+        p_value = (c + 1) / (n_permutations + 1)
+        mean_sim = (null.sum / n_permutations).cpu().numpy()
+        extra["var_sim"] = (null.sumsq / n_permutations).cpu().numpy() - mean_sim**2
+        extra["perm_source"] = source
+    else:
+        with np.errstate(invalid="ignore"):
+            zn = (I - expected_I) / np.sqrt(var_norm)
+        p_value = np.where(zn > 0, 1.0 - ndtr(zn), ndtr(zn))
+
+    if var_norm > 0:
+        z_score = (I - expected_I) / np.sqrt(var_norm)
+    else:
+        z_score = np.zeros_like(I)
+
+    adata.uns[key_added] = pd.DataFrame(
+        {
+            "gene": names,
+            "I": I.astype(np.float64),
+            "expected_I": np.full(g, expected_I, dtype=np.float64),
+            "z_score": np.asarray(z_score, dtype=np.float64),
+            "p_value": np.asarray(p_value, dtype=np.float64),
+        }
+    )
+    logger.info(f"Global Moran's I completed in {time.time() - t0:.1f}s")
+    update_metadata(
+        adata,
+        function_name="morans_i",
+        parameters={
+            "genes": names[:10] if len(names) > 10 else names,
+            "n_genes": g,
+            "n_neighbors": n_neighbors,
+            "n_permutations": n_permutations,
+            "use_existing_graph": use_existing_graph,
+            "seed": seed,
+            "backend": "b200",
+        },
+        outputs={"uns": key_added},
+    )
+    return adata
+
+
+# --------------------------------------------------------------------------------------------------
+# local Moran's I
+# --------------------------------------------------------------------------------------------------
+
+
+def local_morans_i(
+    adata,
+    genes: Optional[Union[str, List[str]]] = None,
+    layer: Optional[str] = None,
+    spatial_key: str = "spatial",
+    n_neighbors: int = 6,
+    n_permutations: int = 10,
+    fdr_correction: Literal["bonferroni", "fdr_bh", "none"] = "fdr_bh",
+    alpha: float = 0.05,
+    seed: int = 0,
+    batch_size: int = 100,
+    key_added: str = "local_morans",
+    copy: bool = False,
+    *,
+    perm_source: str = "auto",
+    device="cuda",
+):
+    """Local Moran's I (LISA), API and outputs of [R autocorrelation.py:656-983].  The null permutes
+    VALUES and re-applies W (gather-SpMM kernel); one permutation stream is shared across gene
+    batches exactly like the reference, so results depend on ``batch_size`` the same way."""
+    t0 = time.time()
+    _check_spatial(adata, spatial_key)
+    _check_counts(n_neighbors, n_permutations)
+    if fdr_correction not in ["bonferroni", "fdr_bh", "none"]:
+        raise ValueError(f"Invalid fdr_correction: '{fdr_correction}'. Must be 'bonferroni', 'fdr_bh', or 'none'.")
+    adata = adata.copy() if copy else adata
+    names = _resolve_genes(adata, genes, "This may be slow and memory-intensive.")
+    n, g = adata.n_obs, len(names)
+    logger.info(f"Computing Local Moran's I: {n:,} cells, {g} genes, k={n_neighbors}, permutations={n_permutations}")
+
+    graph = _build_knn(adata, spatial_key, n_neighbors, device)
+    X = _expression(adata, layer)
+    pos_all = np.asarray([adata.var_names.get_loc(x) for x in names], dtype=np.int64)
+
+    local_I = np.zeros((n, g), dtype=np.float32)
+    z_values = np.zeros((n, g), dtype=np.float32)
+    lag_values = np.zeros((n, g), dtype=np.float32)
+    p_values = np.ones((n, g), dtype=np.float32)
+    zero_mask = np.zeros(g, dtype=bool)
+
+    source = _pick_perm_source(perm_source, n, n_permutations) if n_permutations > 0 else "none"
+    rng = np.random.default_rng(seed)
+    n_batches = (g + batch_size - 1) // batch_size
+    logger.info(f"Processing {g} genes in {n_batches} batches")
+    for b in range(n_batches):
+        s, e = b * batch_size, min((b + 1) * batch_size, g)
+        gb = e - s
+        Xd, cols = engine.expression_to_device(X, pos_all[s:e], device)
+        std = engine.zscore_dense(Xd, cols=cols)
+        _, _, lag, loc = engine.lag_moran(graph, std.Z, gb, want_lag=True, want_local=True)
+        zero_mask[s:e] = std.zero_var.cpu().numpy().astype(bool)
+        z_values[:, s:e] = std.Z[:, :gb].cpu().numpy()
+        lag_values[:, s:e] = lag[:, :gb].cpu().numpy()
+        local_I[:, s:e] = loc[:, :gb].cpu().numpy()
+        if n_permutations > 0:
+            cnt = torch.zeros(std.Z.shape, dtype=torch.int32, device=std.Z.device)
+            if source == "philox":
+                engine.perm_null_values(graph, std.Z, gb, n_permutations, seed=seed, perm_offset=b * n_permutations,
+                                        cell_obs=loc, cell_cnt=cnt)
+            else:
+                for _, idx in _replay_chunks(rng, n, n_permutations, std.Z.device):
+                    engine.perm_null_values(graph, std.Z, gb, idx.shape[0], perm_idx=idx, cell_obs=loc, cell_cnt=cnt)
+            p_values[:, s:e] = ((cnt[:, :gb].cpu().numpy() + 1) / (n_permutations + 1)).astype(np.float32)
+
+    zero_genes = [names[i] for i in np.where(zero_mask)[0]]
+    if zero_mask.any():
+        logger.warning(f"{int(zero_mask.sum())} genes have zero variance and will be skipped: {zero_genes[:5]}")
+        local_I[:, zero_mask] = 0.0
+        z_values[:, zero_mask] = 0.0
+        lag_values[:, zero_mask] = 0.0
+        p_values[:, zero_mask] = 1.0
+
+    if n_permutations > 0:
+        p_adj = np.ones_like(p_values)
+        for j in range(g):
+            p_adj[:, j] = _fdr(p_values[:, j], fdr_correction)
+        quadrants = _classify_quadrants(z_values, lag_values, p_adj, alpha)
+    else:
+        logger.warning(
+            "n_permutations=0: Quadrants classified by z/lag signs only, "
+            "without significance filtering. Consider n_permutations>=99 for p-values."
+        )
+        p_adj = p_values
+        quadrants = _classify_quadrants(z_values, lag_values, p_values=None, alpha=alpha)
+
+    adata.obsm[f"{key_added}_I"] = local_I
+    adata.obsm[f"{key_added}_z"] = z_values
+    adata.obsm[f"{key_added}_lag"] = lag_values
+    adata.obsm[f"{key_added}_p"] = p_values
+    adata.obsm[f"{key_added}_p_adj"] = p_adj
+    adata.obsm[f"{key_added}_quadrant"] = quadrants
+    elapsed = time.time() - t0
+    adata.uns[f"{key_added}_params"] = {
+        "genes": names,
+        "n_neighbors": n_neighbors,
+        "n_permutations": n_permutations,
+        "fdr_correction": fdr_correction,
+        "alpha": alpha,
+        "n_cells": n,
+        "n_genes": g,
+        "seed": seed,
+        "computation_time_seconds": elapsed,
+        "zero_variance_genes": zero_genes,
+    }
+    n_sig = (quadrants != 0).sum(axis=0)
+    logger.info(f"Local Moran's I completed in {elapsed:.1f}s. Significant cells per gene: min={n_sig.min()}, max={n_sig.max()}")
+    update_metadata(
+        adata,
+        function_name="local_morans_i",
+        parameters={
+            "genes": names[:10] if len(names) > 10 else names,
+            "n_genes": g,
+            "n_neighbors": n_neighbors,
+            "n_permutations": n_permutations,
+            "fdr_correction": fdr_correction,
+            "alpha": alpha,
+            "seed": seed,
+        },
+        outputs={
+            "obsm_I": f"{key_added}_I",
+            "obsm_z": f"{key_added}_z",
+            "obsm_lag": f"{key_added}_lag",
+            "obsm_p": f"{key_added}_p",
+            "obsm_p_adj": f"{key_added}_p_adj",
+            "obsm_quadrant": f"{key_added}_quadrant",
+            "uns_params": f"{key_added}_params",
+        },
+    )
+    return adata
+
+
+# --------------------------------------------------------------------------------------------------
+# Lee's L
+# --------------------------------------------------------------------------------------------------
+
+
+def _normalize_pairs(gene_pairs):
+    single = False
+    if isinstance(gene_pairs, tuple) and len(gene_pairs) == 2 and isinstance(gene_pairs[0], str):
+        gene_pairs, single = [gene_pairs], True
+    return list(gene_pairs), single
+
+
+class _PairEngine:
+    """Standardises the unique genes of a pair list once and evaluates pairs on the device."""
+
+    def __init__(self, adata, layer, pairs, graph, device) -> None:
+        self.uniq = list(dict.fromkeys(x for pr in pairs for x in pr))
+        self.col = {name: j for j, name in enumerate(self.uniq)}
+        self.std = _standardize(adata, layer, self.uniq, device)
+        self.zero = self.std.zero_var.cpu().numpy().astype(bool)
+        self.graph = graph
+        self.n = self.std.Z.shape[0]
+        self.identity = torch.arange(self.n, dtype=torch.int32, device=self.std.Z.device).reshape(1, -1)
+
+    def column(self, name: str) -> torch.Tensor:
+        """Gene column as its own [n, 8] padded matrix (kernel operand)."""
+        out = torch.zeros((self.n, engine.padded_ld(1)), dtype=torch.float32, device=self.std.Z.device)
+        out[:, 0] = self.std.Z[:, self.col[name]]
+        return out
+
+    def is_zero(self, name: str) -> bool:
+        return bool(self.zero[self.col[name]])
+
+    def observed(self, zx: torch.Tensor, zy: torch.Tensor):
+        """(L, lag_y[n], L_local[n]) with L_local = z_x ∘ (W z_y) [R autocorrelation.py:307-315]."""
+        _, _, lag, _ = engine.lag_moran(self.graph, zy, 1, want_lag=True)
+        sims = engine.perm_null_values(self.graph, zy, 1, 1, Zx=zx, perm_idx=self.identity)
+        return float(sims[0, 0].item()), lag, zx * lag
+
+
+def lees_l(
+    adata,
+    gene_pairs: Union[Tuple[str, str], List[Tuple[str, str]]],
+    layer: Optional[str] = None,
+    spatial_key: str = "spatial",
+    n_neighbors: int = 6,
+    n_permutations: int = 199,
+    seed: int = 0,
+    *,
+    perm_source: str = "auto",
+    device="cuda",
+) -> Union[dict, List[dict]]:
+    """Global Lee's L per gene pair, API of [R autocorrelation.py:991-1163]: ``L = Σ z_x·(W z_y)``
+    (unnormalised, asymmetric), two-tailed permutation p-value with only ``z_y`` permuted; one RNG
+    stream is shared across pairs in order.  Pure: does not touch ``adata``."""
+    _check_spatial(adata, spatial_key)
+    _check_counts(n_neighbors, n_permutations)
+    pairs, single = _normalize_pairs(gene_pairs)
+    missing = set(x for pr in pairs for x in pr) - set(adata.var_names)
+    if missing:
+        raise ValueError(f"Genes not found in adata.var_names: {list(missing)}")
+    n = adata.n_obs
+    logger.info(f"Computing Global Lee's L: {n:,} cells, {len(pairs)} pair(s), k={n_neighbors}, permutations={n_permutations}")
+    t0 = time.time()
+    graph = _build_knn(adata, spatial_key, n_neighbors, device)
+    pe = _PairEngine(adata, layer, pairs, graph, device)
+    source = _pick_perm_source(perm_source, n, n_permutations) if n_permutations > 0 else "none"
+    rng = np.random.default_rng(seed)
+    results = []
+    for j, (gx, gy) in enumerate(pairs):
+        if pe.is_zero(gx) or pe.is_zero(gy):
+            logger.warning(f"Gene pair ({gx}, {gy}) has zero variance gene - setting L to 0")
+            results.append({"gene_x": gx, "gene_y": gy, "L": 0.0, "p_value": 1.0})
+            continue
+        zx, zy = pe.column(gx), pe.column(gy)
+        L, _, _ = pe.observed(zx, zy)
+        p_value = 1.0
+        if n_permutations > 0:
+            extreme = 0
+            if source == "philox":
+                sims = engine.perm_null_values(graph, zy, 1, n_permutations, Zx=zx, seed=seed, perm_offset=j * n_permutations)
+                extreme = int((sims[:, 0].abs() >= abs(L)).sum().item())
+            else:
+                for _, idx in _replay_chunks(rng, n, n_permutations, zy.device):
+                    sims = engine.perm_null_values(graph, zy, 1, idx.shape[0], Zx=zx, perm_idx=idx)
+                    extreme += int((sims[:, 0].abs() >= abs(L)).sum().item())
+            p_value = float((extreme + 1) / (n_permutations + 1))
+        results.append({"gene_x": gx, "gene_y": gy, "L": L, "p_value": p_value})
+    logger.info(f"Global Lee's L completed in {time.time() - t0:.1f}s")
+    return results[0] if single else results
+
+
+def lees_l_matrix(
+    adata,
+    genes: Optional[List[str]] = None,
+    layer: Optional[str] = None,
+    spatial_key: str = "spatial",
+    n_neighbors: int = 6,
+    *,
+    variant: Literal["reference", "lee2001"] = "reference",
+    key_added: Optional[str] = None,
+    impl: int = 0,
+    device="cuda",
+) -> pd.DataFrame:
+    """Lee's L for ALL ordered gene pairs in one dense contraction (replaces the reference's
+    G(G-1)/2-iteration Python loop over :func:`lees_l` / ``lees_l_local(genes=...)``).
+
+    ``variant="reference"``: ``L = Zᵀ(WZ)`` — entry (x, y) equals ``lees_l(adata, (x, y))["L"]``.
+    ``variant="lee2001"``:  ``L = (WZ)ᵀ(WZ)/N`` — the textbook statistic (symmetric)."""
+    _check_spatial(adata, spatial_key)
+    if n_neighbors < 1:
+        raise ValueError(f"n_neighbors must be >= 1, got {n_neighbors}")
+    names = _resolve_genes(adata, genes, "") if genes is not None else list(adata.var_names)
+    graph = _build_knn(adata, spatial_key, n_neighbors, device)
+    std = _standardize(adata, layer, names, device)
+    g = len(names)
+    _, _, lag, _ = engine.lag_moran(graph, std.Z, g, want_lag=True)
+    if variant == "reference":
+        Lm = engine.lee_gemm(std.Z, lag, g, impl=impl)
+    elif variant == "lee2001":
+        Lm = engine.lee_gemm(lag, lag, g, impl=impl) / float(adata.n_obs)
+    else:
+        raise ValueError(f"variant must be 'reference' or 'lee2001', got '{variant}'")
+    df = pd.DataFrame(Lm.cpu().numpy(), index=names, columns=names)
+    if key_added is not None:
+        adata.uns[key_added] = df
+    return df
+
+
+def lees_l_local(
+    adata,
+    gene_pairs: Optional[Union[Tuple[str, str], List[Tuple[str, str]]]] = None,
+    genes: Optional[List[str]] = None,
+    layer: Optional[str] = None,
+    spatial_key: str = "spatial",
+    n_neighbors: int = 6,
+    n_permutations: int = 199,
+    compute_cell_pvalues: bool = False,
+    significance_filter: bool = False,
+    alpha: float = 0.05,
+    seed: int = 0,
+    copy: bool = False,
+    *,
+    perm_source: str = "auto",
+    device="cuda",
+):
+    """Local Lee's L, API and outputs of [R autocorrelation.py:1171-1479]."""
+    t0 = time.time()
+    if gene_pairs is None and genes is None:
+        raise ValueError(
+            "Must provide either 'gene_pairs' or 'genes' parameter. "
+            "Example: gene_pairs=('CD8A', 'GZMB') or genes=['CD8A', 'GZMB', 'FOXP3']"
+        )
+    _check_spatial(adata, spatial_key)
+    _check_counts(n_neighbors, n_permutations)
+    if significance_filter and not compute_cell_pvalues:
+        raise ValueError("significance_filter=True requires compute_cell_pvalues=True")
+    if genes is not None:
+        logger.warning(
+            f"All-pairs mode: {len(genes)} genes = {len(genes) * (len(genes) - 1) // 2} pairs. "
+            "This may take a very long time for large gene sets. "
+            "Consider using explicit gene_pairs for better performance."
+        )
+        pairs = list(combinations(genes, 2))
+    else:
+        pairs, _ = _normalize_pairs(gene_pairs)
+    missing = set(x for pr in pairs for x in pr) - set(adata.var_names)
+    if missing:
+        raise ValueError(f"Genes not found in adata.var_names: {list(missing)}")
+    adata = adata.copy() if copy else adata
+    n = adata.n_obs
+    logger.info(f"Computing Local Lee's L: {n:,} cells, {len(pairs)} pair(s), k={n_neighbors}, permutations={n_permutations}")
+
+    graph = _build_knn(adata, spatial_key, n_neighbors, device)
+    pe = _PairEngine(adata, layer, pairs, graph, device)
+    if pe.zero.any():
+        logger.warning(f"Genes with zero variance: {set(np.asarray(pe.uniq)[pe.zero])}")
+    # per pair the reference draws P permutations for the global test and, when requested, P more
+    # for the per-cell test, all from one stream [R autocorrelation.py:1367, 1394-1408]
+    per_pair_draws = n_permutations * (2 if compute_cell_pvalues else 1)
+    source = _pick_perm_source(perm_source, n, per_pair_draws * max(len(pairs), 1)) if n_permutations > 0 else "none"
+    rng = np.random.default_rng(seed)
+    cats = ["NS", "HH", "LL", "HL", "LH"]
+
+    for j, (gx, gy) in enumerate(pairs):
+        key = f"{gx}_{gy}"
+        if pe.is_zero(gx) or pe.is_zero(gy):
+            adata.obs[f"{key}_lees_l"] = np.zeros(n, dtype=np.float32)
+            adata.obs[f"{key}_quadrant"] = pd.Categorical(["NS"] * n, categories=cats)
+            adata.uns[f"{key}_lees_l_params"] = {
+                "gene_x": gx, "gene_y": gy, "global_L": 0.0, "global_pvalue": 1.0,
+                "n_neighbors": n_neighbors, "zero_variance": True,
+            }
+            continue
+        zx, zy = pe.column(gx), pe.column(gy)
+        L, lag, loc = pe.observed(zx, zy)
+        global_p = 1.0
+        cell_p = np.ones(n, dtype=np.float32)
+        if n_permutations > 0:
+            extreme = 0
+            cnt = torch.zeros(zy.shape, dtype=torch.int32, device=zy.device) if compute_cell_pvalues else None
+            if source == "philox":
+                base = j * per_pair_draws
+                sims = engine.perm_null_values(graph, zy, 1, n_permutations, Zx=zx, seed=seed, perm_offset=base)
+                extreme = int((sims[:, 0].abs() >= abs(L)).sum().item())
+                if compute_cell_pvalues:
+                    engine.perm_null_values(graph, zy, 1, n_permutations, Zx=zx, seed=seed, perm_offset=base + n_permutations,
+                                            cell_obs=loc, cell_cnt=cnt)
+            else:
+                for _, idx in _replay_chunks(rng, n, n_permutations, zy.device):
+                    sims = engine.perm_null_values(graph, zy, 1, idx.shape[0], Zx=zx, perm_idx=idx)
+                    extreme += int((sims[:, 0].abs() >= abs(L)).sum().item())
+                if compute_cell_pvalues:
+                    for _, idx in _replay_chunks(rng, n, n_permutations, zy.device):
+                        engine.perm_null_values(graph, zy, 1, idx.shape[0], Zx=zx, perm_idx=idx, cell_obs=loc, cell_cnt=cnt)
+            global_p = float((extreme + 1) / (n_permutations + 1))
+            if compute_cell_pvalues:
+                cell_p = ((cnt[:, 0].cpu().numpy() + 1) / (n_permutations + 1)).astype(np.float32)
+        elif compute_cell_pvalues:
+            logger.warning("compute_cell_pvalues=True but n_permutations=0; p-values will be 1.0")
+
+        zx_h = zx[:, 0].cpu().numpy()
+        lag_h = lag[:, 0].cpu().numpy()
+        quad = _classify_quadrants(zx_h, lag_h, p_values=cell_p if significance_filter else None, alpha=alpha)
+        labels = [QUADRANT_LABELS[q] for q in quad]
+        adata.obs[f"{key}_lees_l"] = loc[:, 0].cpu().numpy().astype(np.float32)
+        adata.obs[f"{key}_quadrant"] = pd.Categorical(labels, categories=cats)
+        adata.obs[f"{key}_pvalue"] = cell_p.astype(np.float32)
+        counts = {c: 0 for c in cats}
+        for c, v in zip(*np.unique(quad, return_counts=True)):
+            counts[QUADRANT_LABELS[int(c)]] = int(v)
+        adata.uns[f"{key}_lees_l_params"] = {
+            "gene_x": gx, "gene_y": gy, "global_L": L, "global_pvalue": global_p,
+            "n_neighbors": n_neighbors, "n_permutations": n_permutations,
+            "compute_cell_pvalues": compute_cell_pvalues, "significance_filter": significance_filter,
+            "alpha": alpha, "quadrant_counts": counts,
+        }
+
+    logger.info(f"Local Lee's L completed in {time.time() - t0:.1f}s for {len(pairs)} pair(s)")
+    pair_keys = [f"{gx}_{gy}" for gx, gy in pairs]
+    update_metadata(
+        adata,
+        function_name="lees_l_local",
+        parameters={
+            "gene_pairs": [(gx, gy) for gx, gy in pairs[:10]],
+            "n_pairs": len(pairs),
+            "n_neighbors": n_neighbors,
+            "n_permutations": n_permutations,
+            "compute_cell_pvalues": compute_cell_pvalues,
+            "significance_filter": significance_filter,
+            "alpha": alpha,
+            "seed": seed,
+        },
+        outputs={
+            "obs_keys": [f"{k}_lees_l" for k in pair_keys[:5]],
+            "uns_keys": [f"{k}_lees_l_params" for k in pair_keys[:5]],
+        },
+    )
+    return adata

@@ -1,0 +1,428 @@
+"""GPU parity tests: CUDA path (through the C ABI) vs the CPU oracle and the reference goldens.
+
+Bars: bit-exact for indices / counts / p-values under replayed permutations; FP32 statistics within
+``|a-b| <= 1e-5*|b| + floor`` of the FP64 oracle (floor stated per test)."""
+
+import os
+
+import numpy as np
+import pandas as pd
+import pytest
+import torch
+from scipy import sparse
+
+from oracle import restate as R
+from tests.golden import inputs
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def eng():
+    if not torch.cuda.is_available():
+        pytest.skip("needs a CUDA device")
+    from spatialcore_b200 import engine
+
+    return engine
+
+
+@pytest.fixture(scope="module")
+def api(eng):
+    from spatialcore_b200 import spatial
+
+    return spatial
+
+
+@pytest.fixture(scope="module")
+def g0(golden_dir):
+    coords, X = inputs.g0()
+    return coords, X, np.load(os.path.join(golden_dir, "ref_g0.npz"))
+
+
+def _adata(X, coords, **kw):
+    from spatialcore_b200 import AnnDataLite
+
+    return AnnDataLite(X, obsm={"spatial": coords}, **kw)
+
+
+# ---------------------------------------------------------------------------------------------
+# graphs
+# ---------------------------------------------------------------------------------------------
+
+
+def test_knn_matches_reference_goldens(eng, g0, golden_dir):
+    coords, _, ref = g0
+    for k in (6, 15):
+        graph, _, _ = eng.knn_graph(coords, k, want_dist=True)
+        assert np.array_equal(graph.indices.cpu().numpy().ravel(), ref[f"W_k{k}_indices"])
+        _, dist = R.knn_canonical(coords, k)
+        assert np.array_equal(graph.dist.cpu().numpy(), dist)  # FP64 distances bit-identical
+    graph, _, _ = eng.knn_graph(coords, 6, include_self=True)
+    assert np.array_equal(graph.indices.cpu().numpy().ravel(), ref["W_k6_self_indices"])
+    refc = np.load(os.path.join(golden_dir, "ref_knn_clustered.npz"))
+    cc = inputs.clustered(4000, seed=11)
+    for k in (6, 15, 30, 50):
+        graph, _, _ = eng.knn_graph(cc, k)
+        assert np.array_equal(graph.indices.cpu().numpy().ravel(), refc[f"W_k{k}_indices"]), k
+
+
+@pytest.mark.parametrize("k", [1, 4, 9, 33, 64, 100])
+def test_knn_ties_duplicates_and_wide_k(eng, k):
+    for coords in (inputs.lattice(23, 17), inputs.with_duplicates(700, 3), inputs.clustered(1500, 4)):
+        if k >= coords.shape[0]:
+            continue
+        graph, _, _ = eng.knn_graph(coords, k, want_dist=True)
+        idx, dist = R.knn_bruteforce(coords, k)
+        assert np.array_equal(graph.indices.cpu().numpy(), idx)
+        assert np.array_equal(graph.dist.cpu().numpy(), dist)
+
+
+def test_knn_degenerate_geometry(eng):
+    rng = np.random.default_rng(0)
+    line = np.stack([rng.uniform(0, 10, 500), np.full(500, 3.0)], axis=1)  # collinear
+    same = np.concatenate([np.zeros((40, 2)), rng.uniform(0, 1, (60, 2))])  # 40 identical points
+    far = np.concatenate([rng.uniform(0, 1, (300, 2)), rng.uniform(1e5, 1e5 + 1, (300, 2))])  # big empty gap
+    for coords in (line, same, far):
+        graph, _, _ = eng.knn_graph(coords, 7)
+        idx, _ = R.knn_bruteforce(coords, 7)
+        assert np.array_equal(graph.indices.cpu().numpy(), idx)
+
+
+def test_knn_errors(eng):
+    c = np.random.default_rng(0).uniform(0, 1, (10, 2))
+    with pytest.raises(ValueError, match="k must be < number of cells"):
+        eng.knn_graph(c, 10)
+    with pytest.raises(ValueError, match="n_neighbors must be >= 1"):
+        eng.knn_graph(c, 0)
+
+
+def test_radius_graph_matches_oracle(eng):
+    coords = inputs.clustered(5000, seed=2)
+    for r in (3.0, 12.0, 40.0):
+        graph, _ = eng.radius_graph(coords, r, want_dist=True)
+        indptr, indices, dist = R.radius_graph(coords, r)
+        assert np.array_equal(graph.indptr.cpu().numpy(), indptr)
+        assert np.array_equal(graph.indices.cpu().numpy(), indices)
+        assert np.array_equal(graph.dist.cpu().numpy(), dist)
+    # inclusive boundary on a lattice: neighbours at distance exactly r are kept
+    lat = inputs.lattice(20, 20)
+    graph, _ = eng.radius_graph(lat, 1.0)
+    indptr, indices, _ = R.radius_graph(lat, 1.0)
+    assert np.array_equal(graph.indptr.cpu().numpy(), indptr)
+    assert np.array_equal(graph.indices.cpu().numpy(), indices)
+    assert int(graph.indptr[-1]) == 2 * (19 * 20) * 2
+
+
+def test_graph_moments_golden(eng, g0):
+    coords, _, _ = g0
+    graph, _, _ = eng.knn_graph(coords, 6)
+    s0, s1, s2 = eng.graph_moments(graph)
+    adj, _ = R.spatial_neighbors(coords, k=6)
+    e0, e1, e2 = R.graph_moments(R.row_normalize(adj))
+    np.testing.assert_allclose([s0, s1, s2], [e0, e1, e2], rtol=1e-12)
+    np.testing.assert_allclose([s0, s1, s2], [10000.0, 3038.6111111, 40903.1666667], rtol=1e-9)
+    # radius graph (variable degree, empty rows) and explicit weights
+    cc = inputs.clustered(3000, seed=8)
+    graph, _ = eng.radius_graph(cc, 9.0)
+    adj, _ = R.spatial_neighbors(cc, radius=9.0)
+    np.testing.assert_allclose(eng.graph_moments(graph), R.graph_moments(R.row_normalize(adj)), rtol=1e-12)
+
+
+# ---------------------------------------------------------------------------------------------
+# standardisation
+# ---------------------------------------------------------------------------------------------
+
+
+def test_zscore_dense_sparse_subset(eng):
+    rng = np.random.default_rng(1)
+    X = np.log1p(rng.poisson(0.6, (3001, 37))).astype(np.float64)
+    X[:, 5] = 2.5  # zero variance, non-zero constant
+    X[:, 11] = 0.0
+    Zr, mean, std, zero = R.zscore(X)
+    for arr in (X.astype(np.float32), X):
+        s = eng.zscore_dense(torch.from_numpy(arr).cuda())
+        np.testing.assert_allclose(s.mean.cpu().numpy(), arr.astype(np.float64).mean(0), rtol=1e-12, atol=1e-14)
+        np.testing.assert_allclose(s.std.cpu().numpy(), arr.astype(np.float64).std(0), rtol=1e-10, atol=1e-14)
+        assert np.array_equal(s.zero_var.cpu().numpy().astype(bool), zero)
+        Zq, _, _, _ = R.zscore(arr)
+        np.testing.assert_allclose(s.Z[:, :37].cpu().numpy(), Zq, rtol=2e-7, atol=1e-7)
+        assert torch.all(s.Z[:, 37:] == 0)
+    cols = np.array([30, 2, 5, 17, 2])
+    Xd, c = eng.expression_to_device(X.astype(np.float32), cols)
+    s = eng.zscore_dense(Xd, cols=c)
+    np.testing.assert_allclose(s.Z[:, :5].cpu().numpy(), Zr[:, cols], rtol=2e-7, atol=1e-7)
+    for fmt in (sparse.csr_matrix, sparse.csc_matrix):
+        for sel in (None, cols, np.array([4, 9, 20])):
+            Xd, c = eng.expression_to_device(fmt(X.astype(np.float32)), sel)
+            s = eng.zscore_dense(Xd, cols=c)
+            want = Zr if sel is None else Zr[:, sel]
+            np.testing.assert_allclose(s.Z[:, : want.shape[1]].cpu().numpy(), want, rtol=2e-7, atol=1e-7)
+
+
+# ---------------------------------------------------------------------------------------------
+# Moran's I and the graph-row null
+# ---------------------------------------------------------------------------------------------
+
+
+def _moran_device(eng, coords, X, k):
+    graph, _, _ = eng.knn_graph(coords, k)
+    std = eng.zscore_dense(torch.from_numpy(X).cuda())
+    num, den, lag, _ = eng.lag_moran(graph, std.Z, X.shape[1])
+    return graph, std, num, den, lag
+
+
+def test_morans_i_statistic(eng, g0):
+    coords, X, _ = g0
+    graph, std, num, den, lag = _moran_device(eng, coords, X, 6)
+    I = (num / den).cpu().numpy()  # N/S0 = 1 for a row-standardised kNN graph
+    t = R.morans_i_table(coords, X, k=6, n_perms=0)
+    assert np.all(np.abs(I - t["I"]) <= 1e-5 * np.abs(t["I"]) + 1e-7)
+    np.testing.assert_allclose(I[:3], [-0.003001858001485166, -0.0038586272813623985, 0.0010727504543280996], rtol=1e-5, atol=1e-7)
+    # lag against scipy
+    W = R.build_spatial_weights(coords, 6).astype(np.float64)
+    Z, _, _, _ = R.zscore(X)
+    np.testing.assert_allclose(lag[:, :50].cpu().numpy(), W @ Z, rtol=1e-5, atol=2e-6)
+
+
+def test_graph_rows_null_replay_counts_identical(eng, g0):
+    coords, X, _ = g0
+    n, g = X.shape
+    graph, std, num, den, lag = _moran_device(eng, coords, X, 6)
+    perms = R.squidpy_perm_indices(n, 99, 0)
+    t = R.morans_i_table(coords, X, k=6, n_perms=99, seed=0)
+    sims = eng.perm_null_graph_rows(std.Z, lag, g, 99, perm_idx=torch.from_numpy(perms.astype(np.int32)).cuda())
+    sims = (sims / den).cpu().numpy()
+    np.testing.assert_allclose(sims, t["sims"], rtol=1e-5, atol=2e-7)
+    I = (num / den).cpu().numpy()
+    cnt = (sims >= I[None, :]).sum(0)
+    assert np.array_equal(cnt, t["count_ge"])
+    assert np.array_equal(R.pval_sim_folded(I, sims)[:3], [0.32, 0.21, 0.38])
+    # identity permutation reproduces the observed statistic exactly
+    ident = torch.arange(n, dtype=torch.int32, device="cuda").reshape(1, -1)
+    s1 = eng.perm_null_graph_rows(std.Z, lag, g, 1, perm_idx=ident)
+    np.testing.assert_allclose(s1[0].cpu().numpy(), num.cpu().numpy(), rtol=1e-13)
+
+
+def test_philox_device_matches_host_mirror(eng, g0):
+    from spatialcore_b200 import philox
+
+    coords, X, _ = g0
+    n, g = X.shape
+    for m in (1, 2, 7, 1000, 4097, 100_000):
+        dev = eng.philox_permutation(99, 5, m).cpu().numpy()
+        assert np.array_equal(dev, philox.permutation(99, 5, m))
+        assert np.array_equal(np.sort(dev), np.arange(m))
+    graph, std, num, den, lag = _moran_device(eng, coords, X, 6)
+    P = 21
+    sims_dev = eng.perm_null_graph_rows(std.Z, lag, g, P, seed=1234, perm_offset=3)
+    host = np.stack([philox.permutation(1234, 3 + p, n) for p in range(P)])
+    sims_rep = eng.perm_null_graph_rows(std.Z, lag, g, P, perm_idx=torch.from_numpy(host).cuda())
+    assert torch.equal(sims_dev, sims_rep)  # same kernel arithmetic, same indices -> bitwise equal
+    # and against the oracle driven by the mirrored permutations
+    gN = R.row_normalize(R.spatial_neighbors(coords, k=6)[0])
+    ref = R.morans_i_perms_graph_rows(gN, X, host)
+    np.testing.assert_allclose((sims_dev / den).cpu().numpy(), ref, rtol=1e-5, atol=2e-7)
+
+
+def test_morans_i_api_end_to_end(api, g0):
+    coords, X, _ = g0
+    names = [f"g{i}" for i in range(X.shape[1])]
+    a = _adata(X, coords, var_names=names)
+    sel = ["g7", "g0", "g1", "g2", "g49"]
+    out = api.morans_i(a, genes=sel, n_neighbors=6, n_permutations=99, seed=0, perm_source="replay")
+    assert out is a
+    df = a.uns["morans_i"]
+    assert list(df.columns) == ["gene", "I", "expected_I", "z_score", "p_value"]
+    assert df["gene"].tolist() == sel
+    idx = [names.index(s) for s in sel]
+    t = R.morans_i_table(coords, X[:, idx], k=6, n_perms=99, seed=0)
+    assert np.all(np.abs(df["I"].to_numpy() - t["I"]) <= 1e-5 * np.abs(t["I"]) + 1e-7)
+    assert np.array_equal(df["p_value"].to_numpy(), t["p_value"])  # replayed permutations: identical
+    np.testing.assert_allclose(df["z_score"].to_numpy(), t["z_score"], rtol=1e-4, atol=1e-5)
+    assert df["expected_I"].iloc[0] == -1 / (X.shape[0] - 1)
+    # squidpy-style side effects
+    adj, dst = R.spatial_neighbors(coords, k=6)
+    assert (a.obsp["spatial_connectivities"] != adj).nnz == 0 and a.obsp["spatial_connectivities"].dtype == np.float64
+    assert (a.obsp["spatial_distances"] != dst).nnz == 0
+    assert a.uns["spatial_neighbors"]["params"]["n_neighbors"] == 6
+    op = a.uns["spatialcore_metadata"]["operations"][-1]
+    assert op["function"] == "morans_i" and op["parameters"]["backend"] == "b200" and op["outputs"] == {"uns": "morans_i"}
+    # no permutations -> analytic p-value; copy=True leaves the input untouched
+    b = _adata(X, coords, var_names=names)
+    c = api.morans_i(b, genes=sel, n_permutations=0, copy=True)
+    assert "morans_i" not in b.uns and c is not b
+    np.testing.assert_allclose(c.uns["morans_i"]["p_value"].to_numpy(), t["pval_norm"], rtol=1e-4, atol=1e-6)
+    # existing graph (here: a radius graph, variable degree)
+    adj_r, _ = R.spatial_neighbors(coords, radius=25.0)
+    d = _adata(X, coords, var_names=names)
+    d.obsp["spatial_connectivities"] = adj_r
+    api.morans_i(d, genes=sel, n_permutations=19, seed=2, use_existing_graph=True, perm_source="replay")
+    tr = R.morans_i_table(coords, X[:, idx], n_perms=19, seed=2, adj=adj_r)
+    dfr = d.uns["morans_i"]
+    assert np.all(np.abs(dfr["I"].to_numpy() - tr["I"]) <= 1e-5 * np.abs(tr["I"]) + 1e-7)
+    assert np.array_equal(dfr["p_value"].to_numpy(), tr["p_value"])
+    np.testing.assert_allclose(dfr["z_score"].to_numpy(), tr["z_score"], rtol=1e-4, atol=1e-5)
+    # radius keyword builds the same graph on the device
+    e = _adata(X, coords, var_names=names)
+    api.morans_i(e, genes=sel, n_permutations=19, seed=2, radius=25.0, perm_source="replay")
+    assert np.array_equal(e.uns["morans_i"]["p_value"].to_numpy(), tr["p_value"])
+    assert (e.obsp["spatial_connectivities"] != adj_r).nnz == 0
+
+
+def test_morans_i_api_errors(api, g0):
+    coords, X, _ = g0
+    a = _adata(X[:100], coords[:100])
+    with pytest.raises(ValueError, match=r"adata.obsm\['nope'\] not found"):
+        api.morans_i(a, spatial_key="nope")
+    with pytest.raises(ValueError, match="n_neighbors must be >= 1, got 0"):
+        api.morans_i(a, n_neighbors=0)
+    with pytest.raises(ValueError, match="n_permutations must be >= 0, got -1"):
+        api.morans_i(a, n_permutations=-1)
+    with pytest.raises(ValueError, match="Genes not found in adata.var_names"):
+        api.morans_i(a, genes=["zzz"])
+    with pytest.raises(ValueError, match="Invalid fdr_correction"):
+        api.local_morans_i(a, fdr_correction="bogus")
+    with pytest.raises(ValueError, match="Must provide either 'gene_pairs' or 'genes'"):
+        api.lees_l_local(a)
+    with pytest.raises(ValueError, match="significance_filter=True requires compute_cell_pvalues=True"):
+        api.lees_l_local(a, gene_pairs=("g0", "g1"), significance_filter=True)
+
+
+# ---------------------------------------------------------------------------------------------
+# value-permuting null: Lee's L and local statistics (reference-own code, pinned by goldens)
+# ---------------------------------------------------------------------------------------------
+
+
+def test_lees_l_matches_reference(api, g0):
+    coords, X, ref = g0
+    a = _adata(X.astype(np.float64), coords)
+    pairs = [("g0", "g1"), ("g1", "g0"), ("g0", "g0"), ("g3", "g7")]
+    res = api.lees_l(a, pairs, n_neighbors=6, n_permutations=99, seed=0, perm_source="replay")
+    L = np.array([r["L"] for r in res])
+    p = np.array([r["p_value"] for r in res])
+    assert np.all(np.abs(L - ref["lee_f64_L"]) <= 1e-5 * np.abs(ref["lee_f64_L"]) + 1e-4)
+    assert np.array_equal(p, ref["lee_f64_p"])
+    assert [r["gene_x"] for r in res] == [x for x, _ in pairs]
+    single = api.lees_l(a, ("g0", "g1"), n_permutations=0)
+    assert isinstance(single, dict) and single["p_value"] == 1.0
+    assert "spatialcore_metadata" not in a.uns  # lees_l is pure
+
+
+def test_lees_l_zero_variance_and_continuous(api, golden_dir):
+    ref = np.load(os.path.join(golden_dir, "ref_g0.npz"))
+    coords, X = inputs.g0_continuous()
+    a = _adata(X, coords)
+    res = api.lees_l(a, [("g0", "g1"), ("g1", "g0"), ("g5", "g5")], n_permutations=99, seed=0, perm_source="replay")
+    L = np.array([r["L"] for r in res])
+    assert np.all(np.abs(L - ref["leec_L"]) <= 1e-5 * np.abs(ref["leec_L"]) + 1e-4)
+    assert np.array_equal([r["p_value"] for r in res], ref["leec_p"])
+    Xz = X.copy()
+    Xz[:, 2] = 1.0
+    r = api.lees_l(_adata(Xz, coords), [("g2", "g1"), ("g0", "g1")], n_permutations=9, seed=0, perm_source="replay")
+    assert r[0] == {"gene_x": "g2", "gene_y": "g1", "L": 0.0, "p_value": 1.0}
+
+
+def test_local_morans_i_matches_reference(api, golden_dir):
+    ref = np.load(os.path.join(golden_dir, "ref_g0.npz"))
+    coords, X = inputs.g0_continuous()
+    a = _adata(X, coords)
+    api.local_morans_i(a, genes=["g0", "g1", "g2"], n_neighbors=6, n_permutations=99, seed=0, perm_source="replay")
+    I, z, lag, p = (a.obsm[f"local_morans_{s}"] for s in ("I", "z", "lag", "p"))
+    assert I.dtype == np.float32 and a.obsm["local_morans_quadrant"].dtype == np.int8
+    np.testing.assert_allclose(I, ref["lmc_I"], rtol=5e-5, atol=2e-6)
+    np.testing.assert_allclose(z, ref["lmc_z"], rtol=5e-6, atol=1e-6)
+    np.testing.assert_allclose(lag, ref["lmc_lag"], rtol=5e-5, atol=2e-6)
+    mism = p != ref["lmc_p"]
+    assert mism.mean() < 2e-4, f"per-cell p-value flips: {mism.sum()} of {mism.size}"
+    q = a.obsm["local_morans_quadrant"]
+    assert (q != ref["lmc_quadrant"]).mean() < 2e-4
+    prm = a.uns["local_morans_params"]
+    assert prm["genes"] == ["g0", "g1", "g2"] and prm["n_cells"] == 10000 and prm["zero_variance_genes"] == []
+    assert a.uns["spatialcore_metadata"]["operations"][-1]["function"] == "local_morans_i"
+    # batch_size changes the permutation stream exactly like the reference (2nd batch continues it)
+    b = _adata(X, coords)
+    api.local_morans_i(b, genes=["g0", "g1", "g2"], n_permutations=99, seed=0, batch_size=2, perm_source="replay")
+    assert np.array_equal(b.obsm["local_morans_p"][:, :2], p[:, :2])
+    assert (b.obsm["local_morans_p"][:, 2] != p[:, 2]).mean() > 0.3
+    # n_permutations = 0: sign-only quadrants
+    c = _adata(X, coords)
+    api.local_morans_i(c, genes=["g0"], n_permutations=0)
+    assert np.array_equal(c.obsm["local_morans_quadrant"][:, 0], R.quadrants(z[:, 0], lag[:, 0]))
+    assert np.all(c.obsm["local_morans_p"] == 1)
+
+
+def test_lees_l_local_matches_reference(api, golden_dir):
+    ref = np.load(os.path.join(golden_dir, "ref_g0.npz"))
+    coords, X = inputs.g0_continuous()
+    a = _adata(X, coords)
+    api.lees_l_local(a, gene_pairs=[("g0", "g1"), ("g2", "g3")], n_neighbors=6, n_permutations=19,
+                     compute_cell_pvalues=True, significance_filter=True, alpha=0.2, seed=0, perm_source="replay")
+    for key in ("g0_g1", "g2_g3"):
+        np.testing.assert_allclose(a.obs[f"{key}_lees_l"].to_numpy(), ref[f"llc_{key}_L"], rtol=5e-5, atol=2e-6)
+        assert (a.obs[f"{key}_pvalue"].to_numpy() != ref[f"llc_{key}_p"]).mean() < 2e-4
+        assert (a.obs[f"{key}_quadrant"].cat.codes.to_numpy() != ref[f"llc_{key}_q"]).mean() < 2e-4
+        prm = a.uns[f"{key}_lees_l_params"]
+        assert abs(prm["global_L"] - ref[f"llc_{key}_global"][0]) <= 1e-5 * abs(ref[f"llc_{key}_global"][0]) + 1e-4
+        assert prm["global_pvalue"] == ref[f"llc_{key}_global"][1]
+        assert sum(prm["quadrant_counts"].values()) == 10000
+    assert a.obs["g0_g1_quadrant"].cat.categories.tolist() == ["NS", "HH", "LL", "HL", "LH"]
+
+
+def test_lee_matrix_all_pairs(api, eng, g0):
+    coords, X, ref = g0
+    a = _adata(X, coords)
+    df = api.lees_l_matrix(a, n_neighbors=6)
+    W = R.build_spatial_weights(coords, 6).astype(np.float64)
+    Z, _, _, _ = R.zscore(X)
+    want = R.lees_l_all_pairs(Z, W)
+    got = df.to_numpy()
+    assert np.all(np.abs(got - want) <= 1e-5 * np.abs(want) + 1e-3)  # values are O(sqrt(N))..O(N)
+    np.testing.assert_allclose([got[0, 1], got[1, 0], got[0, 0]], ref["lee_f64_L"][:3], rtol=1e-5)
+    assert abs(got[0, 1] - got[1, 0]) > 1.0  # not symmetric
+    t = R.morans_i_table(coords, X, k=6, n_perms=0)
+    np.testing.assert_allclose(np.diag(got), X.shape[0] * t["I"], rtol=1e-4, atol=1e-3)  # L[x,x] = N·I[x]
+    sym = api.lees_l_matrix(a, n_neighbors=6, variant="lee2001").to_numpy()
+    lagZ = W @ Z
+    np.testing.assert_allclose(sym, lagZ.T @ lagZ / X.shape[0], rtol=1e-5, atol=1e-6)
+
+
+# ---------------------------------------------------------------------------------------------
+# neighbourhood composition
+# ---------------------------------------------------------------------------------------------
+
+
+def test_neighborhood_profile_bit_identical(api, golden_dir):
+    ref = np.load(os.path.join(golden_dir, "ref_nbhd.npz"))
+    coords, labels = inputs.nbhd()
+
+    def run(**kw):
+        a = _adata(np.zeros((coords.shape[0], 1), np.float32), coords,
+                   obs=pd.DataFrame({"ct": pd.Categorical([f"t{c:02d}" for c in labels])}))
+        api.compute_neighborhood_profile(a, "ct", **kw)
+        return a
+
+    a = run(method="knn", k=5)
+    assert a.obsm["neighborhood_profile"].dtype == np.float32
+    assert np.array_equal(a.obsm["neighborhood_profile"], ref["knn5_norm"])
+    assert a.uns["neighborhood_profile_celltypes"] == ref["celltypes"].tolist()
+    assert np.array_equal(run(method="knn", k=30).obsm["neighborhood_profile"], ref["knn30_norm"])
+    assert np.array_equal(run(method="knn", k=30, normalize=False).obsm["neighborhood_profile"], ref["knn30_raw"])
+    assert np.array_equal(run(method="radius", radius=inputs.NBHD_RADIUS, normalize=False).obsm["neighborhood_profile"], ref["radius_raw"])
+    assert np.array_equal(run(method="radius", radius=inputs.NBHD_RADIUS).obsm["neighborhood_profile"], ref["radius_norm"])
+    with pytest.raises(ValueError, match="cells have empty neighborhood profiles"):
+        run(method="radius", radius=0.5)
+    with pytest.raises(ValueError, match="'radius' must be provided"):
+        run(method="radius")
+    with pytest.raises(ValueError, match="k must be < number of cells"):
+        run(method="knn", k=6000)
+    with pytest.raises(ValueError, match="Invalid method"):
+        run(method="ball")
+
+
+def test_nbhd_counts_from_graph(eng):
+    coords, labels = inputs.nbhd()
+    graph, _, fused = eng.knn_graph(coords, 12, labels=torch.from_numpy(labels.astype(np.int32)).cuda(), n_types=8)
+    sep = eng.nbhd_counts(graph, torch.from_numpy(labels.astype(np.int32)).cuda(), 8)
+    assert torch.equal(fused, sep)
+    want = R.neighborhood_profile(coords, labels, 8, k=12, normalize=False)
+    assert np.array_equal(sep.cpu().numpy(), want)
