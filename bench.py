@@ -1,0 +1,433 @@
+#!/usr/bin/env python
+"""Headline benchmark: gene-permutations/s of global Moran's I (graph-row permutation null, the
+null behind ``morans_i``) including the neighbour-graph build, on synthetic CosMx/Xenium-shaped data.
+
+    python bench.py --gpus 1 --steps 3 --warmup 3                 # our arm (default workload C4)
+    python bench.py --impl reference --gpus 1 --steps 2 --warmup 1  # reference CPU arm
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 \
+        --master-port P bench.py --gpus N ...
+
+One "step" = one pass of the whole hot path over the workload: graph build -> z-score -> lag +
+Moran statistic -> graph moments -> P permutations -> per-gene p-values.  ``value`` times it with
+inputs resident in HBM (CUDA events, max over ranks); ``e2e`` times the public API
+``spatialcore_b200.spatial.morans_i`` on HOST arrays (pinned), H2D/D2H inside the timed region.
+Multi-GPU: gene blocks are sharded over ranks (strong scaling of the fixed workload), one
+all-gather of per-gene results at the end.  Prints ONE JSON line on rank 0.
+"""
+
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+WORKLOADS = {
+    # name: cells, genes, graph, permutations, extent, coordinate generator
+    "C4": dict(n=5_000_000, g=1000, graph="radius", degree=20.0, k=None, perms=999, extent=120_000.0, coords="uniform",
+               desc="CosMx-scale 5M cells x 1000 genes, radius graph (mean degree ~20), Moran's I, 999 permutations"),
+    "C2": dict(n=500_000, g=400, graph="knn", degree=None, k=15, perms=999, extent=10_000.0, coords="mixture",
+               desc="Xenium-scale 500k cells x 400 genes, kNN k=15, Moran's I, 999 permutations"),
+    "C1": dict(n=10_000, g=50, graph="knn", degree=None, k=6, perms=99, extent=1_000.0, coords="uniform",
+               desc="10k cells x 50 genes, kNN k=6, Moran's I, 99 permutations"),
+}
+METRIC = "gene-perms/sec Moran's I (graph build + statistic + permutation null)"
+UNIT = "gene-perms/s"
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default=os.environ.get("SC_BENCH_WORKLOAD", "C4"), choices=list(WORKLOADS))
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--seed", type=int, default=3)
+    return ap.parse_args()
+
+
+def make_coords(w, seed):
+    from spatialcore_b200 import synthetic
+
+    if w["coords"] == "uniform":
+        return synthetic.coords_uniform(w["n"], w["extent"], seed)
+    return synthetic.coords_mixture(w["n"], w["extent"], seed)
+
+
+def workload_radius(w):
+    from spatialcore_b200 import synthetic
+
+    return synthetic.radius_for_mean_degree(w["n"], w["extent"], w["degree"]) if w["graph"] == "radius" else None
+
+
+# ------------------------------------------------------------------------------------------------
+# clocks
+# ------------------------------------------------------------------------------------------------
+
+
+class ClockSampler:
+    FIELDS = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+              "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.gpu = gpu_index
+        self.samples = []
+        self.proc = None
+        self.thread = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", "-i", str(self.gpu), f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits", "-lms", "200"],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+        except OSError:
+            self.proc = None
+            return
+        self.thread = threading.Thread(target=self._read, daemon=True)
+        self.thread.start()
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.samples.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+        sm, smax, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for s in self.samples:
+            parts = [p.strip() for p in s.split(",")]
+            if len(parts) < 6:
+                continue
+            try:
+                sm.append(float(parts[0]))
+                smax.append(float(parts[1]))
+            except ValueError:
+                continue
+            for nm, val in zip(names, parts[2:6]):
+                if val.lower().startswith("active"):
+                    reasons.add(nm)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(smax) if smax else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------------------
+# our arm
+# ------------------------------------------------------------------------------------------------
+
+
+def device_step(engine, ac, coords_dev, X_dev, w, radius, seed, events=None):
+    """One pass of the hot path with inputs resident in HBM.  Returns (I, p_value) device tensors."""
+    import torch
+
+    def mark(name):
+        if events is not None:
+            ev = torch.cuda.Event(enable_timing=True)
+            ev.record()
+            events.append((name, ev))
+
+    n, g = X_dev.shape
+    P = w["perms"]
+    mark("start")
+    if radius is not None:
+        graph, _ = engine.radius_graph(coords_dev, radius, device=coords_dev.device)
+    else:
+        graph, _, _ = engine.knn_graph(coords_dev, w["k"], device=coords_dev.device)
+    mark("graph")
+    std = engine.zscore_dense(X_dev)
+    mark("zscore")
+    num, den, lag, _ = engine.lag_moran(graph, std.Z, g, want_lag=True)
+    mark("lag")
+    s0, s1, s2 = engine.graph_moments(graph)
+    mark("moments")
+    scale = (float(n) / s0) / den
+    I = num * scale
+    null = ac.MoranNull(g, X_dev.device)
+    ac.moran_graph_rows_null(std.Z, lag, g, scale, I, P, seed, "philox", null, (0, P))
+    mark("perms")
+    c = torch.minimum(null.cnt_ge, P - null.cnt_ge)
+    p_value = (c + 1).double() / (P + 1)
+    return I, p_value
+
+
+def run_b200(args):
+    import torch
+    import torch.distributed as dist
+
+    from spatialcore_b200 import AnnDataLite, engine, spatial, synthetic
+    from spatialcore_b200 import distributed as dist_util
+    from spatialcore_b200.spatial import autocorrelation as ac
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise RuntimeError("bench.py (impl b200) needs a CUDA device; there is no CPU path")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    w = WORKLOADS[args.workload]
+    n, g_total, P = w["n"], w["g"], w["perms"]
+    g_lo, g_hi = dist_util.block_slice(g_total, rank, world)
+    g = g_hi - g_lo
+    radius = workload_radius(w)
+
+    coords = make_coords(w, args.seed)
+    coords_dev = torch.from_numpy(coords).to(dev)
+    X_dev = synthetic.expression_device(coords, g, seed=args.seed * 1000 + rank, device=dev)
+    torch.cuda.synchronize()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def gather_results(I, p):
+        if world > 1:
+            sizes = [dist_util.block_slice(g_total, r, world) for r in range(world)]
+            pad = max(hi - lo for lo, hi in sizes)
+            buf = torch.zeros(2, pad, dtype=torch.float64, device=dev)
+            buf[0, : I.numel()] = I
+            buf[1, : p.numel()] = p
+            out = [torch.empty_like(buf) for _ in range(world)]
+            dist.all_gather(out, buf)
+            I = torch.cat([o[0, : hi - lo] for o, (lo, hi) in zip(out, sizes)])
+            p = torch.cat([o[1, : hi - lo] for o, (lo, hi) in zip(out, sizes)])
+        return I.cpu().numpy(), p.cpu().numpy()
+
+    # ---------------- device-resident leg -------------------------------------------------------
+    for _ in range(args.warmup):
+        I, p = device_step(engine, ac, coords_dev, X_dev, w, radius, args.seed)
+        gather_results(I, p)
+    sampler = ClockSampler(local_rank)
+    barrier()
+    sampler.start()
+    launches0 = engine.launches()
+    phase_ms = {}
+    t_start = torch.cuda.Event(enable_timing=True)
+    t_end = torch.cuda.Event(enable_timing=True)
+    t_start.record()
+    for _ in range(args.steps):
+        events = []
+        I, p = device_step(engine, ac, coords_dev, X_dev, w, radius, args.seed, events)
+        I_h, p_h = gather_results(I, p)
+        torch.cuda.synchronize()
+        for (_, a), (name, b) in zip(events[:-1], events[1:]):
+            phase_ms[name] = phase_ms.get(name, 0.0) + a.elapsed_time(b) / args.steps
+    t_end.record()
+    barrier()
+    clocks = sampler.stop()
+    launches = engine.launches() - launches0
+    ms = t_start.elapsed_time(t_end)
+    t = torch.tensor([ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_per_step = float(t.item()) / args.steps
+    value = g_total * P / (ms_per_step / 1e3)
+
+    # roofline of the dominant kernel (perm_rows_kernel): algorithmic bytes per launch / launch time.
+    # per gene-perm 4N(1+1/P) bytes; one launch covers PB permutations x g genes.
+    PB = 8
+    n_launch = (P + PB - 1) // PB
+    perm_ms = phase_ms.get("perms", float("nan"))
+    bytes_per_launch = 4.0 * n * (1.0 + 1.0 / P) * g * (P / n_launch)
+    achieved = bytes_per_launch / (perm_ms / 1e3 / n_launch) / 1e9
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except OSError:
+        pass
+    peak = float(peaks.get("hbm_gbs", 6650.0))
+    roofline = {"bound": "hbm", "kernel": "perm_rows_kernel<8,double>", "achieved": round(achieved, 1), "peak": peak,
+                "peak_source": "MEASURED_PEAKS.json hbm_gbs (burst copy)" if peaks else "fallback 6650 GB/s",
+                "unit": "GB/s", "frac": round(achieved / peak, 4), "traffic": None,
+                "launch_ms": round(perm_ms / n_launch, 4), "perms_per_launch": PB,
+                "bytes_per_launch": bytes_per_launch}
+
+    # ---------------- end-to-end leg through the public API, host buffers ------------------------
+    e2e = None
+    if not args.no_e2e:
+        X_host = torch.empty((n, g), dtype=torch.float32, pin_memory=True)
+        X_host.copy_(X_dev)
+        del X_dev
+        torch.cuda.empty_cache()
+        coords_host = torch.empty((n, 2), dtype=torch.float64, pin_memory=True)
+        coords_host.copy_(torch.from_numpy(coords))
+        Xn, cn = X_host.numpy(), coords_host.numpy()
+        names = [f"g{i}" for i in range(g_lo, g_hi)]
+
+        def e2e_step():
+            adata = AnnDataLite(Xn, obsm={"spatial": cn}, var_names=names)
+            spatial.morans_i(adata, n_neighbors=w["k"] or 6, n_permutations=P, seed=args.seed, radius=radius,
+                             perm_source="philox", write_graph=False, shard="none", device=dev)
+            df = adata.uns["morans_i"]
+            return torch.from_numpy(df["I"].to_numpy()).to(dev), torch.from_numpy(df["p_value"].to_numpy()).to(dev)
+
+        import logging
+
+        logging.getLogger("spatialcore").setLevel(logging.WARNING)
+        for _ in range(max(1, min(args.warmup, 3))):
+            gather_results(*e2e_step())
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            gather_results(*e2e_step())
+        barrier()
+        dt = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(dt, op=dist.ReduceOp.MAX)
+        e2e_s = float(dt.item()) / args.steps
+        e2e = {"value": round(g_total * P / e2e_s, 1), "unit": UNIT, "ms_per_step": round(e2e_s * 1e3, 2),
+               "h2d_bytes_per_step": int(Xn.nbytes + cn.nbytes), "d2h_bytes_per_step": int(2 * 8 * g + 3 * 8),
+               "api": "spatialcore_b200.spatial.morans_i(adata[numpy, pinned host]) per rank + all_gather"}
+        X_dev = None
+
+    # ---------------- CPU baseline on a bounded sample (rank 0, single-GPU runs only) --------------
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu:
+        cpu = cpu_baseline_sample(w, coords, radius, args.seed)
+
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": round(value, 1), "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": round(ms_per_step, 3), "higher_is_better": True, "scaling": "strong",
+            "vs_baseline": None, "dtype": "f32 storage, f64 accumulation", "data": "synthetic",
+            "config": {"workload": f"{args.workload}: {w['desc']}", "n_cells": n, "n_genes": g_total, "n_permutations": P,
+                       "graph": w["graph"], "radius": radius, "k": w["k"], "null": "graph_rows (squidpy semantics)",
+                       "perm_source": "philox (on-device bijection)", "sharding": f"gene blocks over {world} rank(s)",
+                       "l2": "inputs (Z, lag: 4*N*G bytes each) far larger than the 126 MB L2; no flush needed"},
+            "phases_ms": {k: round(v, 3) for k, v in phase_ms.items()},
+            "knn_build_ms": round(phase_ms.get("graph", float("nan")), 3),
+            "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "e2e": e2e, "cpu_baseline": cpu,
+            "check": {"I_mean": float(np.nanmean(I_h)), "p_min": float(np.nanmin(p_h)), "n_sig_0.01": int((p_h <= 0.01).sum())},
+        }
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+# ------------------------------------------------------------------------------------------------
+# CPU arm: the reference's own CPU path (sklearn graph + the squidpy/scanpy Moran loop, ported in
+# oracle/moran_port.c because squidpy is not installable here) on a bounded sample
+# ------------------------------------------------------------------------------------------------
+
+
+def cpu_graph(w, coords, radius):
+    """Neighbour graph the way the reference path builds it (squidpy -> sklearn NearestNeighbors)."""
+    from scipy import sparse
+    from sklearn.neighbors import NearestNeighbors
+
+    t0 = time.perf_counter()
+    if radius is not None:
+        nn = NearestNeighbors(radius=radius, n_jobs=-1).fit(coords)
+        adj = nn.radius_neighbors_graph(mode="connectivity").tocsr()
+    else:
+        nn = NearestNeighbors(n_neighbors=w["k"], n_jobs=-1).fit(coords)
+        adj = nn.kneighbors_graph(mode="connectivity").tocsr()
+    dt = time.perf_counter() - t0
+    adj = adj.astype(np.float64)
+    rs = np.asarray(adj.sum(axis=1)).ravel()
+    rs[rs == 0] = 1.0
+    adj.data /= np.repeat(rs, np.diff(adj.indptr))
+    return sparse.csr_matrix(adj), dt
+
+
+def cpu_expression(coords, g, seed):
+    rng = np.random.default_rng(seed)
+    return np.log1p(rng.poisson(0.4, (g, coords.shape[0]))).astype(np.float64)  # (G, N) like squidpy's vals
+
+
+def cpu_sample_plan(w):
+    """Genes x permutations of the bounded CPU sample: ~1.5e10 gather-FMAs (10-30 s on 8-64 cores)."""
+    nnz = w["n"] * (w["degree"] or w["k"])
+    budget = 1.5e10
+    gene_perms = max(4, int(budget / nnz))
+    g = int(min(w["g"], max(4, min(64, gene_perms // 2))))
+    p = int(max(1, min(w["perms"], gene_perms // g)))
+    return g, p
+
+
+def cpu_baseline_sample(w, coords, radius, seed, graph=None):
+    from oracle import port, restate
+
+    g_cpu, p_cpu = cpu_sample_plan(w)
+    n = w["n"]
+    graph_s = None
+    if graph is None:
+        graph, graph_s = cpu_graph(w, coords, radius)
+    vals = cpu_expression(coords, g_cpu, seed)
+    perms = restate.squidpy_perm_indices(n, p_cpu, seed).astype(np.int32)
+    port.morans_i(graph, vals[:1, : n], None)  # touch pages / thread pool
+    t0 = time.perf_counter()
+    port.morans_i(graph, vals, perms)
+    dt = time.perf_counter() - t0
+    value = g_cpu * p_cpu / dt
+    return {"value": round(value, 2), "unit": UNIT, "cores": port.threads(), "kind": "port",
+            "sample": f"full N={n} cells, {g_cpu} genes x {p_cpu} permutations (+1 observed pass), "
+                      f"oracle/moran_port.c (OpenMP over genes, CSR row gather per permutation)",
+            "seconds": round(dt, 2), "graph_build_s": None if graph_s is None else round(graph_s, 2),
+            "graph_build": "sklearn NearestNeighbors (squidpy's call), n_jobs=-1"}
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from oracle import port
+
+    w = WORKLOADS[args.workload]
+    coords = make_coords(w, args.seed)
+    radius = workload_radius(w)
+    graph, graph_s = cpu_graph(w, coords, radius)
+    samples = []
+    for i in range(args.warmup + args.steps):
+        r = cpu_baseline_sample(w, coords, radius, args.seed + i, graph=graph)
+        if i >= args.warmup:
+            samples.append(r)
+    value = float(np.mean([s["value"] for s in samples]))
+    secs = float(np.mean([s["seconds"] for s in samples]))
+    cpu = dict(samples[-1], value=round(value, 2), graph_build_s=round(graph_s, 2), kind="port")
+    line = {
+        "impl": "reference", "metric": METRIC, "value": round(value, 2), "unit": UNIT, "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(secs * 1e3, 2), "higher_is_better": True,
+        "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": f"{args.workload}: {w['desc']}", "n_cells": w["n"], "n_genes": w["g"],
+                   "n_permutations": w["perms"], "graph": w["graph"], "radius": radius, "k": w["k"],
+                   "null": "graph_rows (squidpy semantics)",
+                   "note": "CPU reference path: sklearn graph build (timed once, graph_build_s) + the squidpy/scanpy "
+                           "Moran permutation loop as ported in oracle/moran_port.c (squidpy itself is not installable "
+                           "offline); each step is a bounded sample, throughput is per gene-permutation"},
+        "cpu_baseline": cpu,
+        "e2e": {"value": round(value, 2), "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "cores": port.threads(),
+    }
+    print(json.dumps(line))
+
+
+def main():
+    args = parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_b200(args)
+
+
+if __name__ == "__main__":
+    main()

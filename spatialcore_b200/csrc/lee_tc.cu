@@ -5,7 +5,7 @@
 namespace sc {
 bool lee_tc_supported(int64_t, int, int64_t, int64_t) { return false; }
 size_t lee_tc_extra_workspace_bytes(int64_t, int) { return 0; }
-int lee_tc_launch(const float*, int64_t, const float*, int64_t, int64_t, int, const LeePlan&, float*,
+int lee_tc_launch(const float*, int64_t, const float*, int64_t, int64_t, int, const LeePlan&, double*,
                   void*, cudaStream_t) {
   set_error("tcgen05 Lee kernel not built");
   return SC_ERR_UNSUPPORTED;

@@ -48,3 +48,20 @@ def all_reduce_null(null) -> None:
         packed = null.packed().contiguous()
         dist.all_reduce(packed, op=dist.ReduceOp.SUM)
         null.unpack(packed)
+
+
+def all_gather_columns(local, total_cols: int, device):
+    """Gene-block sharding: every rank contributes ``local`` (numpy [rows, its block]); returns the
+    concatenation over ranks in block order (numpy [rows, total_cols])."""
+    import numpy as np
+
+    rank, ws = world()
+    if ws == 1:
+        return local
+    sizes = [block_slice(total_cols, r, ws) for r in range(ws)]
+    pad = max(hi - lo for lo, hi in sizes)
+    buf = torch.zeros((local.shape[0], pad), dtype=torch.float64, device=device)
+    buf[:, : local.shape[1]] = torch.from_numpy(np.ascontiguousarray(local)).to(device)
+    out = [torch.empty_like(buf) for _ in range(ws)]
+    dist.all_gather(out, buf)
+    return torch.cat([o[:, : hi - lo] for o, (lo, hi) in zip(out, sizes)], dim=1).cpu().numpy()

@@ -274,20 +274,41 @@ def morans_i(
     perm_source: str = "auto",
     radius: Optional[float] = None,
     write_graph: bool = True,
+    shard: str = "auto",
     device="cuda",
 ):
     """Global Moran's I with the squidpy permutation null, API of [R autocorrelation.py:421-648].
 
     Writes ``adata.uns[key_added]`` (DataFrame ``gene, I, expected_I, z_score, p_value`` in input gene
-    order), the squidpy graph slots, and a metadata entry.  With ``torch.distributed`` initialised
-    the permutations are sharded over ranks and the per-gene null summaries all-reduced."""
+    order), the squidpy graph slots, and a metadata entry.
+
+    With ``torch.distributed`` initialised, ``shard`` picks the multi-GPU partition: ``"genes"``
+    (each rank standardises and tests its own gene block, per-gene results all-gathered),
+    ``"perms"`` (every rank holds all genes and runs a block of the permutations, null summaries
+    all-reduced), ``"none"`` (ranks work independently), ``"auto"`` = genes when there are at least
+    8 genes per rank, else perms."""
     t0 = time.time()
     _check_spatial(adata, spatial_key)
     _check_counts(n_neighbors, n_permutations)
+    if shard not in ("auto", "genes", "perms", "none"):
+        raise ValueError(f"shard must be 'auto', 'genes', 'perms' or 'none', got '{shard}'")
     adata = adata.copy() if copy else adata
-    names = _resolve_genes(adata, genes, "This may be slow for large datasets.")
-    n, g = adata.n_obs, len(names)
-    logger.info(f"Computing Global Moran's I: {n:,} cells, {g} genes, k={n_neighbors}, permutations={n_permutations}")
+    all_names = _resolve_genes(adata, genes, "This may be slow for large datasets.")
+    n = adata.n_obs
+    logger.info(f"Computing Global Moran's I: {n:,} cells, {len(all_names)} genes, k={n_neighbors}, permutations={n_permutations}")
+    rank, world = dist_util.world()
+    if world == 1 or shard == "none":
+        mode = "none"
+    elif shard == "auto":
+        mode = "genes" if len(all_names) >= 8 * world else "perms"
+    else:
+        mode = shard
+    if mode == "genes":
+        g_lo, g_hi = dist_util.block_slice(len(all_names), rank, world)
+        names = all_names[g_lo:g_hi]
+    else:
+        names = all_names
+    g = len(names)
 
     if use_existing_graph and "spatial_connectivities" in adata.obsp:
         logger.info("Using existing spatial connectivity graph (use_existing_graph=True)")
@@ -309,9 +330,10 @@ def morans_i(
     if n_permutations > 0:
         source = _pick_perm_source(perm_source, n, n_permutations)
         null = MoranNull(g, std.Z.device)
-        lo, hi = dist_util.my_slice(n_permutations)
+        lo, hi = dist_util.my_slice(n_permutations) if mode == "perms" else (0, n_permutations)
         moran_graph_rows_null(std.Z, lag, g, scale, I_dev, n_permutations, seed, source, null, (lo, hi))
-        dist_util.all_reduce_null(null)
+        if mode == "perms":
+            dist_util.all_reduce_null(null)
         c = null.cnt_ge.cpu().numpy()
         c = np.where(n_permutations - c < c, n_permutations - c, c)
         p_value = (c + 1) / (n_permutations + 1)
@@ -327,6 +349,11 @@ def morans_i(
         z_score = (I - expected_I) / np.sqrt(var_norm)
     else:
         z_score = np.zeros_like(I)
+
+    if mode == "genes":
+        cols = dist_util.all_gather_columns(np.stack([I, z_score, p_value]).astype(np.float64), len(all_names), std.Z.device)
+        I, z_score, p_value = cols[0], cols[1], cols[2]
+        names, g = all_names, len(all_names)
 
     adata.uns[key_added] = pd.DataFrame(
         {
