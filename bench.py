@@ -244,7 +244,7 @@ def run_b200(args):
 
     # roofline of the dominant kernel (perm_rows_kernel): algorithmic bytes per launch / launch time.
     # per gene-perm 4N(1+1/P) bytes; one launch covers PB permutations x g genes.
-    PB = 8
+    PB = 16  # permutations per launch of the default kernel variant (bulk16)
     n_launch = (P + PB - 1) // PB
     perm_ms = phase_ms.get("perms", float("nan"))
     bytes_per_launch = 4.0 * n * (1.0 + 1.0 / P) * g * (P / n_launch)
@@ -255,7 +255,7 @@ def run_b200(args):
     except OSError:
         pass
     peak = float(peaks.get("hbm_gbs", 6650.0))
-    roofline = {"bound": "hbm", "kernel": "perm_rows_kernel<8,double>", "achieved": round(achieved, 1), "peak": peak,
+    roofline = {"bound": "hbm", "kernel": "perm_rows_bulk_kernel<16> (cp.async.bulk gather pipeline, FP64 accumulate)", "achieved": round(achieved, 1), "peak": peak,
                 "peak_source": "MEASURED_PEAKS.json hbm_gbs (burst copy)" if peaks else "fallback 6650 GB/s",
                 "unit": "GB/s", "frac": round(achieved / peak, 4), "traffic": None,
                 "launch_ms": round(perm_ms / n_launch, 4), "perms_per_launch": PB,

@@ -2,13 +2,14 @@
 // (the per-pair statistic of autocorrelation.py:307-315 evaluated for every (x, y) at once).
 //
 // K (= cells) is huge and M = N = genes is small, so the contraction is split along K: every CTA
-// owns one K-range of one 128x128 output tile.  FP32 accumulation runs only over sub-chunks of
-// kLeeSubChunk cells; each finished sub-chunk is folded into the CTA's FP64 partial tile, and a
-// second kernel sums the partial tiles per output element in FP64 in fixed order.  The rounding
-// error of the contraction then stays near the FP32 rounding of the inputs themselves
-// (~1e-5 * sqrt(N) absolute), independent of N.
+// owns one K-range of one 128x128 output tile and writes an FP64 partial tile; a second kernel sums
+// the partial tiles per output element in FP64 in fixed order (bitwise reproducible).
 //
-// This file holds the CUDA-core FP32 kernel (impl 1).  The tcgen05 3xTF32 kernel (impl 2) lives in
+// Accuracy note: the reference sums with numpy's pairwise reduction, good to ~1e-7 relative.  FP32
+// accumulation over K (even in 512-cell sub-chunks folded into FP64) measured 4.7e-4 absolute error
+// at N = 10k on entries of magnitude ~20, so the exact path accumulates in FP64.
+//
+// This file holds the CUDA-core FP64-accumulating kernel (impl 1).  The tcgen05 3xTF32 kernel (impl 2) lives in
 // lee_tc.cu and shares the split-K partial layout and the reduction kernel.
 #include "common.cuh"
 #include "lee.cuh"
@@ -16,98 +17,91 @@
 namespace sc {
 
 constexpr int kTile = 128;   // output tile edge
-constexpr int kKStep = 16;   // cells per shared-memory stage
+constexpr int kKStep = 8;    // cells per shared-memory stage
 
-// 256 threads, each owns an 8x8 block of the 128x128 tile.
+// 256 threads, each owns an 8x8 block of the 128x128 tile.  Operands are widened to FP64 once, when
+// they are staged in shared memory; the inner loop is pure DFMA (B200: ~37 TFLOP/s FP64), so the
+// result carries only the FP32 rounding of the inputs.
 __global__ void __launch_bounds__(256)
-lee_simt_kernel(const float* __restrict__ A, int64_t lda, const float* __restrict__ B, int64_t ldb,
-                int64_t n, int g, int64_t chunk, double* __restrict__ partial, int64_t ldt) {
-  __shared__ __align__(16) float As[2][kKStep][kTile];
-  __shared__ __align__(16) float Bs[2][kKStep][kTile];
+lee_f64_kernel(const float* __restrict__ A, int64_t lda, const float* __restrict__ B, int64_t ldb,
+               int64_t n, int g, int64_t chunk, double* __restrict__ partial, int64_t ldt) {
+  __shared__ __align__(16) double As[2][kKStep][kTile];
+  __shared__ __align__(16) double Bs[2][kKStep][kTile];
   const int m0 = blockIdx.y * kTile, n0 = blockIdx.x * kTile;
   const int64_t k_begin = (int64_t)blockIdx.z * chunk;
   const int64_t k_end = min(n, k_begin + chunk);
   const int tid = threadIdx.x;
   const int tx = tid & 15, ty = tid >> 4;  // 16 x 16 thread grid
 
-  // loader mapping: 16 rows x 128 cols = 512 float4 per operand, 2 per thread
-  const int lrow = tid >> 5;          // 0..7 (+8)
+  // loader mapping: 8 rows x 128 cols = 256 float4 per operand, one per thread
+  const int lrow = tid >> 5;          // 0..7
   const int lcol = (tid & 31) * 4;    // 0..124
 
-  float acc[8][8];
+  double acc[8][8];
 #pragma unroll
   for (int i = 0; i < 8; ++i)
 #pragma unroll
-    for (int j = 0; j < 8; ++j) acc[i][j] = 0.f;
+    for (int j = 0; j < 8; ++j) acc[i][j] = 0.0;
 
-  // partial[z][m][n] (FP64), m/n padded to ldt; this CTA is the only writer of its tile
-  double* P = partial + (int64_t)blockIdx.z * ldt * ldt;
-  auto flush = [&](bool first) {
-#pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      int m = m0 + (i < 4 ? ty * 4 + i : 64 + ty * 4 + (i - 4));
-#pragma unroll
-      for (int jh = 0; jh < 2; ++jh) {
-        double* dst = P + (int64_t)m * ldt + n0 + jh * 64 + tx * 4;
-        double2 lo = make_double2(0, 0), hi = make_double2(0, 0);
-        if (!first) {
-          lo = *reinterpret_cast<double2*>(dst);
-          hi = *reinterpret_cast<double2*>(dst + 2);
-        }
-        lo.x += (double)acc[i][jh * 4 + 0]; lo.y += (double)acc[i][jh * 4 + 1];
-        hi.x += (double)acc[i][jh * 4 + 2]; hi.y += (double)acc[i][jh * 4 + 3];
-        *reinterpret_cast<double2*>(dst) = lo;
-        *reinterpret_cast<double2*>(dst + 2) = hi;
-#pragma unroll
-        for (int c = 0; c < 4; ++c) acc[i][jh * 4 + c] = 0.f;
-      }
+  float4 va, vb;
+  auto fetch = [&](int64_t k0) {
+    const int64_t kk = k0 + lrow;
+    va = make_float4(0.f, 0.f, 0.f, 0.f);
+    vb = va;
+    if (kk < k_end) {
+      if (m0 + lcol < lda) va = ldg4(A + kk * lda + m0 + lcol);
+      if (n0 + lcol < ldb) vb = ldg4(B + kk * ldb + n0 + lcol);
     }
   };
-
-  auto load_stage = [&](int buf, int64_t k0) {
-#pragma unroll
-    for (int h = 0; h < 2; ++h) {
-      int r = lrow + 8 * h;
-      int64_t kk = k0 + r;
-      float4 va = make_float4(0.f, 0.f, 0.f, 0.f), vb = va;
-      if (kk < k_end) {
-        if (m0 + lcol < lda) va = ldg4(A + kk * lda + m0 + lcol);
-        if (n0 + lcol < ldb) vb = ldg4(B + kk * ldb + n0 + lcol);
-      }
-      *reinterpret_cast<float4*>(&As[buf][r][lcol]) = va;
-      *reinterpret_cast<float4*>(&Bs[buf][r][lcol]) = vb;
-    }
+  auto stash = [&](int buf) {
+    double2* pa = reinterpret_cast<double2*>(&As[buf][lrow][lcol]);
+    double2* pb = reinterpret_cast<double2*>(&Bs[buf][lrow][lcol]);
+    pa[0] = make_double2((double)va.x, (double)va.y);
+    pa[1] = make_double2((double)va.z, (double)va.w);
+    pb[0] = make_double2((double)vb.x, (double)vb.y);
+    pb[1] = make_double2((double)vb.z, (double)vb.w);
   };
 
   int buf = 0;
-  bool flushed = false;
-  if (k_begin < k_end) load_stage(0, k_begin);
+  if (k_begin < k_end) { fetch(k_begin); stash(0); }
   __syncthreads();
   for (int64_t k0 = k_begin; k0 < k_end; k0 += kKStep) {
-    if (k0 + kKStep < k_end) load_stage(buf ^ 1, k0 + kKStep);
+    const bool more = k0 + kKStep < k_end;
+    if (more) fetch(k0 + kKStep);  // global loads in flight during the DFMA block
 #pragma unroll
     for (int kk = 0; kk < kKStep; ++kk) {
-      float a[8], b[8];
-      float4 a0 = *reinterpret_cast<const float4*>(&As[buf][kk][ty * 4]);
-      float4 a1 = *reinterpret_cast<const float4*>(&As[buf][kk][64 + ty * 4]);
-      float4 b0 = *reinterpret_cast<const float4*>(&Bs[buf][kk][tx * 4]);
-      float4 b1 = *reinterpret_cast<const float4*>(&Bs[buf][kk][64 + tx * 4]);
-      a[0] = a0.x; a[1] = a0.y; a[2] = a0.z; a[3] = a0.w; a[4] = a1.x; a[5] = a1.y; a[6] = a1.z; a[7] = a1.w;
-      b[0] = b0.x; b[1] = b0.y; b[2] = b0.z; b[3] = b0.w; b[4] = b1.x; b[5] = b1.y; b[6] = b1.z; b[7] = b1.w;
+      double a[8], b[8];
+      const double2* pa0 = reinterpret_cast<const double2*>(&As[buf][kk][ty * 4]);
+      const double2* pa1 = reinterpret_cast<const double2*>(&As[buf][kk][64 + ty * 4]);
+      const double2* pb0 = reinterpret_cast<const double2*>(&Bs[buf][kk][tx * 4]);
+      const double2* pb1 = reinterpret_cast<const double2*>(&Bs[buf][kk][64 + tx * 4]);
+      double2 t;
+      t = pa0[0]; a[0] = t.x; a[1] = t.y; t = pa0[1]; a[2] = t.x; a[3] = t.y;
+      t = pa1[0]; a[4] = t.x; a[5] = t.y; t = pa1[1]; a[6] = t.x; a[7] = t.y;
+      t = pb0[0]; b[0] = t.x; b[1] = t.y; t = pb0[1]; b[2] = t.x; b[3] = t.y;
+      t = pb1[0]; b[4] = t.x; b[5] = t.y; t = pb1[1]; b[6] = t.x; b[7] = t.y;
 #pragma unroll
       for (int i = 0; i < 8; ++i)
 #pragma unroll
-        for (int j = 0; j < 8; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+        for (int j = 0; j < 8; ++j) acc[i][j] = fma(a[i], b[j], acc[i][j]);
     }
+    if (more) stash(buf ^ 1);
     __syncthreads();
     buf ^= 1;
-    const int64_t done = k0 + kKStep - k_begin;
-    if (done % kLeeSubChunk == 0 && k0 + kKStep < k_end) {
-      flush(!flushed);
-      flushed = true;
+  }
+
+  // partial[z][m][n] (FP64), m/n padded to ldt; this CTA is the only writer of its tile
+  double* P = partial + (int64_t)blockIdx.z * ldt * ldt;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    int m = m0 + (i < 4 ? ty * 4 + i : 64 + ty * 4 + (i - 4));
+#pragma unroll
+    for (int jh = 0; jh < 2; ++jh) {
+      double* dst = P + (int64_t)m * ldt + n0 + jh * 64 + tx * 4;
+      *reinterpret_cast<double2*>(dst) = make_double2(acc[i][jh * 4 + 0], acc[i][jh * 4 + 1]);
+      *reinterpret_cast<double2*>(dst + 2) = make_double2(acc[i][jh * 4 + 2], acc[i][jh * 4 + 3]);
     }
   }
-  flush(!flushed);
 }
 
 __global__ void lee_reduce_kernel(const double* __restrict__ partial, int splits, int64_t ldt, int g,
@@ -131,7 +125,7 @@ LeePlan lee_plan(int64_t n, int g) {
   if (splits > kLeeMaxSplits) splits = kLeeMaxSplits;
   if (splits < 1) splits = 1;
   p.chunk = (n + splits - 1) / splits;
-  p.chunk = (int64_t)align_up((size_t)p.chunk, 64);
+  p.chunk = (int64_t)align_up((size_t)p.chunk, 64);  // multiple of every kernel's K step
   p.splits = (int)((n + p.chunk - 1) / p.chunk);
   return p;
 }
@@ -173,7 +167,7 @@ extern "C" int sc_lee_gemm(const float* A, int64_t lda, const float* B, int64_t 
     if (rc) return rc;
   } else {
     dim3 grid(p.ldt / kTile, p.ldt / kTile, p.splits);
-    lee_simt_kernel<<<grid, 256, 0, st>>>(A, lda, B, ldb, n, g, p.chunk, partial, p.ldt);
+    lee_f64_kernel<<<grid, 256, 0, st>>>(A, lda, B, ldb, n, g, p.chunk, partial, p.ldt);
     SC_LAUNCH_OK();
   }
   return lee_reduce(partial, p, g, L, ldl, st);

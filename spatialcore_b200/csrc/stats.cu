@@ -322,6 +322,193 @@ perm_rows_kernel(const float* __restrict__ A, int64_t lda, const float* __restri
   }
 }
 
+
+// ------------------------------------------------------------------------------------------------
+// graph-row null, bulk-async pipeline (the production kernel)
+//
+// The gather `B[π_p(i), :]` moves whole rows (ld*4 contiguous bytes) from random places in HBM.
+// Holding those loads in registers caps the bytes in flight per SM well below what HBM3e needs
+// (Little: ~6.5 TB/s x ~1 us = ~45 KB per SM just to break even).  Here one producer warp resolves
+// the permutation indices and issues one `cp.async.bulk` (TMA 1-D bulk copy, SASS UBLKCP) per row
+// into a shared-memory ring of `stages` stages, completion tracked by mbarrier transaction counts;
+// eight consumer warps read the staged rows conflict-free and accumulate in FP64.  In-flight bytes
+// per SM = (stages-1) x rows-per-stage x (PB+1) x ld x 4, i.e. 100-200 KB.
+// ------------------------------------------------------------------------------------------------
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+  return (uint32_t)__cvta_generic_to_shared(p);
+}
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "WAIT_%=:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra DONE_%=;\n"
+      "bra WAIT_%=;\n"
+      "DONE_%=:\n"
+      "}\n" ::"r"(smem_u32(bar)),
+      "r"(parity)
+      : "memory");
+}
+// global -> shared bulk copy (bytes % 16 == 0, both addresses 16-byte aligned), completes on `bar`
+__device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src_gmem, uint32_t bytes,
+                                         uint64_t* bar, uint64_t policy) {
+  asm volatile(
+      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;" ::"r"(
+          smem_u32(dst_smem)),
+      "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar)), "l"(policy)
+      : "memory");
+}
+__device__ __forceinline__ uint64_t policy_evict_first() {
+  uint64_t pol;
+  asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+  return pol;
+}
+
+constexpr int kBulkConsumerWarps = 8;
+constexpr int kBulkProducerWarps = 4;  // one warpgroup; producer w owns pipeline iterations it = w (mod 4)
+constexpr int kBulkThreads = (kBulkConsumerWarps + kBulkProducerWarps) * 32;
+constexpr int kBulkMaxStages = 8;
+
+template <int PB>
+__global__ void __launch_bounds__(kBulkThreads, 1)
+perm_rows_bulk_kernel(const float* __restrict__ A, int64_t lda, const float* __restrict__ B,
+                      int64_t ldb, int64_t n, int cols /*floats per staged row segment*/,
+                      const __grid_constant__ PermBatch pb, double* __restrict__ partial,
+                      int64_t ldp, int wpr, int stages, int n_producers) {
+  extern __shared__ __align__(128) unsigned char dyn_smem[];
+  __shared__ uint64_t full_bar[kBulkMaxStages], empty_bar[kBulkMaxStages];
+  __shared__ uint32_t s_keys[kMaxPermBatch][kFeistelRounds];
+  __shared__ double sh[kStatWarps * 32 * 4];
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int rpp = kBulkConsumerWarps / wpr;
+  const int count = pb.count;
+  const uint32_t row_bytes = (uint32_t)cols * 4u;
+  const uint32_t unit_bytes = (uint32_t)(PB + 1) * row_bytes;
+  const uint32_t stage_bytes = (uint32_t)rpp * unit_bytes;
+  const int64_t col0 = (int64_t)blockIdx.y * 1024;  // first column of this CTA's column block
+  const int64_t n_groups = (n + rpp - 1) / rpp;
+
+  for (int t = threadIdx.x; t < kMaxPermBatch * kFeistelRounds; t += blockDim.x)
+    s_keys[t / kFeistelRounds][t % kFeistelRounds] = pb.keys[t / kFeistelRounds][t % kFeistelRounds];
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < stages; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], kBulkConsumerWarps);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+
+  if (warp >= kBulkConsumerWarps) {
+    // ===== producer warps: permutation lookup + bulk copies =====================================
+    // The Feistel evaluation is a ~1000-cycle dependent chain per stage; up to four warps
+    // interleave the pipeline iterations so index generation never paces the copies.
+    // INVARIANT: n_producers divides stages, so a given stage is always refilled by the same warp,
+    // strictly one phase after its own previous fill.  (With rotating owners a fast warp could reach
+    // a stage two phases early and the 1-bit mbarrier parity test would let it through.)
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");
+    const uint64_t pol = policy_evict_first();
+    const int pw = warp - kBulkConsumerWarps;
+    int it = pw;
+    for (int64_t grp = blockIdx.x + (int64_t)pw * gridDim.x; pw < n_producers && grp < n_groups;
+         grp += (int64_t)n_producers * gridDim.x, it += n_producers) {
+      const int stage = it % stages;
+      const uint32_t phase = (uint32_t)(it / stages) & 1u;
+      mbar_wait(&empty_bar[stage], phase ^ 1u);
+      const int64_t row0 = grp * rpp;
+      const int nslots = (int)min((int64_t)rpp, n - row0);
+      const int per_slot = count + 1;
+      if (lane == 0) mbar_expect_tx(&full_bar[stage], (uint32_t)(nslots * per_slot) * row_bytes);
+      __syncwarp();
+      unsigned char* sbase = dyn_smem + (size_t)stage * stage_bytes;
+      for (int j = lane; j < nslots * per_slot; j += 32) {
+        const int slot = j / per_slot;
+        const int p = j - slot * per_slot - 1;  // -1: the streamed A row
+        const int64_t row = row0 + slot;
+        const float* src;
+        if (p < 0) {
+          src = A + row * lda + col0;
+        } else {
+          const int64_t srow = perm_lookup(pb, s_keys, p, row, n);
+          src = B + srow * ldb + col0;
+        }
+        bulk_g2s(sbase + (size_t)slot * unit_bytes + (size_t)(p + 1) * row_bytes, src, row_bytes,
+                 &full_bar[stage], pol);
+      }
+    }
+  } else {
+    // ===== consumer warps ========================================================================
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 208;");
+    const int slot = warp / wpr;
+    const int c4 = ((warp % wpr) * 32 + lane) * 4;  // column within the staged row segment
+    const bool active = c4 < cols;
+    double acc[PB][4];
+#pragma unroll
+    for (int p = 0; p < PB; ++p)
+#pragma unroll
+      for (int c = 0; c < 4; ++c) acc[p][c] = 0.0;
+
+    int it = 0;
+    for (int64_t grp = blockIdx.x; grp < n_groups; grp += gridDim.x, ++it) {
+      const int stage = it % stages;
+      const uint32_t phase = (uint32_t)(it / stages) & 1u;
+      mbar_wait(&full_bar[stage], phase);
+      const int64_t row = grp * rpp + slot;
+      if (active && row < n) {
+        const float* u = reinterpret_cast<const float*>(dyn_smem + (size_t)stage * stage_bytes +
+                                                        (size_t)slot * unit_bytes) + c4;
+        const float4 a = *reinterpret_cast<const float4*>(u);
+        const double ax = a.x, ay = a.y, az = a.z, aw = a.w;
+#pragma unroll
+        for (int p = 0; p < PB; ++p) {
+          if (p < count) {
+            const float4 v = *reinterpret_cast<const float4*>(u + (size_t)(p + 1) * cols);
+            acc[p][0] = fma(ax, (double)v.x, acc[p][0]);
+            acc[p][1] = fma(ay, (double)v.y, acc[p][1]);
+            acc[p][2] = fma(az, (double)v.z, acc[p][2]);
+            acc[p][3] = fma(aw, (double)v.w, acc[p][3]);
+          }
+        }
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&empty_bar[stage]);
+    }
+
+    // reduce over row slots among the 256 consumer threads (named barrier 1), write partials
+#pragma unroll
+    for (int p = 0; p < PB; ++p) {
+      asm volatile("bar.sync 1, 256;" ::: "memory");
+      if (slot > 0) {
+#pragma unroll
+        for (int c = 0; c < 4; ++c) sh[(warp * 32 + lane) * 4 + c] = acc[p][c];
+      }
+      asm volatile("bar.sync 1, 256;" ::: "memory");
+      if (slot == 0 && active && p < count) {
+        double v4[4] = {acc[p][0], acc[p][1], acc[p][2], acc[p][3]};
+        for (int w2 = warp + wpr; w2 < kBulkConsumerWarps; w2 += wpr)
+#pragma unroll
+          for (int c = 0; c < 4; ++c) v4[c] += sh[(w2 * 32 + lane) * 4 + c];
+        double* dst = partial + ((int64_t)blockIdx.x * PB + p) * ldp + col0 + c4;
+#pragma unroll
+        for (int c = 0; c < 4; ++c) dst[c] = v4[c];
+      }
+    }
+  }
+}
+
 // ------------------------------------------------------------------------------------------------
 // value-permuting null (gather-SpMM):
 //   sims[p,c] = Σ_i S_p[i,c] · Σ_j w_ij Zy[π_p(j),c],  S_p[i] = Zx ? Zx[i] : Zy[π_p(i)]
@@ -637,10 +824,56 @@ static int launch_perm_rows(const float* A, int64_t lda, const float* B, int64_t
   return SC_OK;
 }
 
-// Tunable from the host for experiments: SC_PERM_ROWS_VARIANT = "8d" | "16d" | "16f" | "8f"
+
+template <int PB>
+static int launch_perm_rows_bulk(const float* A, int64_t lda, const float* B, int64_t ldb,
+                                 int64_t n, int g, int source, const int32_t* perm_idx,
+                                 uint64_t seed, int64_t perm_offset, int n_perms, double* sims,
+                                 double* partial, cudaStream_t st) {
+  RowGeom rg = row_geom(lda);
+  const int by = (int)((lda + 1023) / 1024);
+  // every column block stages the same number of floats per row (the last block may be narrower:
+  // it is handled as a separate launch geometry only when lda is not a multiple of 1024 and by > 1)
+  if (by > 1 && lda % 1024 != 0) return SC_ERR_UNSUPPORTED;
+  const int cols = (int)(by > 1 ? 1024 : lda);
+  const size_t stage_bytes = (size_t)rg.rpp * (PB + 1) * cols * 4;
+  int max_smem = 0, dev = 0;
+  SC_CUDA_OK(cudaGetDevice(&dev));
+  SC_CUDA_OK(cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
+  const size_t budget = (size_t)max_smem - 12 * 1024;  // static smem (barriers, keys, reduction)
+  int stages = (int)(budget / stage_bytes);
+  if (stages > kBulkMaxStages) stages = kBulkMaxStages;
+  if (stages < 2) return SC_ERR_UNSUPPORTED;
+  // producers must divide stages (see the kernel's invariant): prefer 4 warps, then 3, then 2
+  int n_producers = stages >= 4 ? 4 : stages;
+  stages = stages / n_producers * n_producers;
+  const size_t dyn = (size_t)stages * stage_bytes;
+  SC_CUDA_OK(cudaFuncSetAttribute(perm_rows_bulk_kernel<PB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn));
+  int bx = sm_count();
+  int64_t n_groups = (n + rg.rpp - 1) / rg.rpp;
+  if (bx > n_groups) bx = (int)n_groups;
+  if (by > 1) bx = bx / by > 0 ? bx / by : 1;
+  for (int p0 = 0; p0 < n_perms; p0 += PB) {
+    int count = n_perms - p0 < PB ? n_perms - p0 : PB;
+    PermBatch pb;
+    fill_batch(&pb, source, perm_idx, seed, perm_offset + p0, p0, count, n);
+    perm_rows_bulk_kernel<PB><<<dim3(bx, by), kBulkThreads, dyn, st>>>(A, lda, B, ldb, n, cols, pb, partial, lda, rg.wpr, stages, n_producers);
+    SC_LAUNCH_OK();
+    reduce_partials_kernel<<<dim3((g + 127) / 128, count), 128, 0, st>>>(partial, bx, PB, lda, g, sims + (int64_t)p0 * g, g);
+    SC_LAUNCH_OK();
+  }
+  return SC_OK;
+}
+
+// Tunable from the host for experiments: SC_PERM_ROWS_VARIANT =
+//   "bulk16" (default) | "bulk8" : bulk-async shared-memory pipeline, 16 / 8 permutations per pass
+//   "8d" | "16d" | "16f" | "8f" | "4d" : register-staged gather kernel (PB, accumulator type)
 static int perm_rows_variant() {
   const char* v = getenv("SC_PERM_ROWS_VARIANT");
-  if (!v) return 0;
+  if (!v) return 11;
+  if (!strcmp(v, "bulk8")) return 10;
+  if (!strcmp(v, "bulk16")) return 11;
+  if (!strcmp(v, "8d")) return 0;
   if (!strcmp(v, "16d")) return 1;
   if (!strcmp(v, "16f")) return 2;
   if (!strcmp(v, "8f")) return 3;
@@ -662,7 +895,15 @@ extern "C" int sc_perm_null_graph_rows(const float* A, int64_t lda, const float*
                "sc_perm_null_graph_rows: lda/ldb must be multiples of 4, g <= lda <= round_up(g,32), ldb >= lda");
   if (ws_bytes < sc_perm_null_workspace_bytes(n, g)) { set_error("sc_perm_null_graph_rows: workspace too small"); return SC_ERR_WORKSPACE; }
   double* partial = static_cast<double*>(ws);
-  switch (perm_rows_variant()) {
+  int variant = perm_rows_variant();
+  if (variant >= 10) {
+    rc = variant == 11
+             ? launch_perm_rows_bulk<16>(A, lda, B, ldb, n, g, source, perm_idx, seed, perm_offset, n_perms, sims, partial, st)
+             : launch_perm_rows_bulk<8>(A, lda, B, ldb, n, g, source, perm_idx, seed, perm_offset, n_perms, sims, partial, st);
+    if (rc != SC_ERR_UNSUPPORTED) return rc;
+    variant = 0;  // geometry the pipeline does not cover: register-staged kernel
+  }
+  switch (variant) {
     case 1: return launch_perm_rows<16, double>(A, lda, B, ldb, n, g, source, perm_idx, seed, perm_offset, n_perms, sims, partial, st);
     case 2: return launch_perm_rows<16, float>(A, lda, B, ldb, n, g, source, perm_idx, seed, perm_offset, n_perms, sims, partial, st);
     case 3: return launch_perm_rows<8, float>(A, lda, B, ldb, n, g, source, perm_idx, seed, perm_offset, n_perms, sims, partial, st);

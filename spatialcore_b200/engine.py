@@ -403,7 +403,7 @@ def perm_null_graph_rows(A: torch.Tensor, B: torch.Tensor, g: int, n_perms: int,
                                   int(perm_offset), int(n_perms), _ptr(sims), _ptr(ws), ws.numel(), _stream()),
         "sc_perm_null_graph_rows",
     )
-    _count(2 * ((n_perms + 7) // 8))
+    _count(2 * ((n_perms + 15) // 16))
     return sims
 
 

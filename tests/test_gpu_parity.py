@@ -222,6 +222,34 @@ def test_graph_rows_null_replay_counts_identical(eng, g0):
     np.testing.assert_allclose(s1[0].cpu().numpy(), num.cpu().numpy(), rtol=1e-13)
 
 
+@pytest.mark.parametrize("shape", [(3000, 7), (20011, 50), (9000, 260), (4000, 1000), (1500, 1030), (900, 2048)])
+def test_graph_rows_kernel_variants_agree(eng, shape, monkeypatch):
+    """The bulk-async pipeline and the register-staged kernels compute the same sums (FP64
+    accumulation of identical FP32 products; only the summation order differs), on every geometry:
+    1/2/4/8 warps per row, several column blocks, ragged last permutation batch."""
+    n, g = shape
+    rng = np.random.default_rng(n + g)
+    A = torch.zeros((n, eng.padded_ld(g)), dtype=torch.float32, device="cuda")
+    B = torch.zeros_like(A)
+    A[:, :g] = torch.from_numpy(rng.normal(size=(n, g)).astype(np.float32)).cuda()
+    B[:, :g] = torch.from_numpy(rng.normal(size=(n, g)).astype(np.float32)).cuda()
+    P = 19
+    perms = np.stack([rng.permutation(n) for _ in range(P)]).astype(np.int32)
+    want = np.stack([(A[:, :g].double().cpu().numpy() * B[:, :g].double().cpu().numpy()[pm]).sum(0) for pm in perms])
+    pidx = torch.from_numpy(perms).cuda()
+    outs = {}
+    for variant in ("bulk8", "bulk16", "8d", "16f"):
+        monkeypatch.setenv("SC_PERM_ROWS_VARIANT", variant)
+        outs[variant] = eng.perm_null_graph_rows(A, B, g, P, perm_idx=pidx).cpu().numpy()
+        tol = 2e-4 if variant.endswith("f") else 1e-9
+        np.testing.assert_allclose(outs[variant], want, rtol=0, atol=tol * np.sqrt(n)), variant
+    monkeypatch.setenv("SC_PERM_ROWS_VARIANT", "bulk8")
+    s1 = eng.perm_null_graph_rows(A, B, g, P, seed=5, perm_offset=2)
+    monkeypatch.setenv("SC_PERM_ROWS_VARIANT", "8d")
+    s2 = eng.perm_null_graph_rows(A, B, g, P, seed=5, perm_offset=2)
+    np.testing.assert_allclose(s1.cpu().numpy(), s2.cpu().numpy(), rtol=0, atol=1e-9 * np.sqrt(n))
+
+
 def test_philox_device_matches_host_mirror(eng, g0):
     from spatialcore_b200 import philox
 
