@@ -1,0 +1,127 @@
+"""CPU-only checks of the drop-in boundary: the C-ABI library loads, exports every symbol that
+include/sc_b200.h declares, the ctypes table matches the header, argument validation and the host
+permutation export work without a GPU, and the product never imports the oracle."""
+
+import ctypes as C
+import os
+import re
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _header_functions():
+    text = open(os.path.join(ROOT, "include", "sc_b200.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return re.findall(r"SC_API\s+[\w\s\*]+?\b(sc_\w+)\s*\(", text)
+
+
+def test_library_exports_every_declared_symbol():
+    from spatialcore_b200 import _lib
+
+    assert os.path.exists(_lib.LIB_PATH), "run __graft_entry__.build() first"
+    names = _header_functions()
+    assert len(names) >= 24
+    handle = C.CDLL(_lib.LIB_PATH)
+    for name in names:
+        assert hasattr(handle, name), f"{name} declared in sc_b200.h but not exported"
+    assert sorted(names) == sorted(_lib.SIGNATURES), "ctypes table and header disagree"
+
+
+def test_ctypes_arity_matches_header():
+    from spatialcore_b200 import _lib
+
+    text = open(os.path.join(ROOT, "include", "sc_b200.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    for name, (_, args) in _lib.SIGNATURES.items():
+        m = re.search(r"\b" + name + r"\s*\(([^)]*)\)", text)
+        assert m, name
+        params = [p for p in m.group(1).split(",") if p.strip() and p.strip() != "void"]
+        assert len(params) == len(args), f"{name}: header has {len(params)} parameters, ctypes {len(args)}"
+
+
+def test_version_error_channel_and_argument_validation_without_gpu():
+    from spatialcore_b200 import _lib
+
+    L = _lib.lib()
+    assert L.sc_version() >= 100
+    # workspace queries are pure host arithmetic
+    assert L.sc_grid_knn_workspace_bytes(1_000_000, 15) > 1_000_000 * 4 * 4
+    assert L.sc_perm_null_workspace_bytes(5_000_000, 1000) > 0
+    assert L.sc_lee_gemm_workspace_bytes(200_000, 1000) >= 1024 * 1024 * 8
+    # invalid arguments are rejected before any CUDA call, with a message
+    rc = L.sc_grid_knn(None, 10, 3, 0, None, None, None, None, 0, None, None, 0, None)
+    assert rc == -1 and b"null" in L.sc_last_error()
+    with pytest.raises(ValueError):
+        _lib.check(rc, "sc_grid_knn")
+    rc = L.sc_philox_permutation_host(1, 0, 0, None)
+    assert rc == -1
+
+
+def test_philox_host_export_is_a_bijection_and_matches_python_mirror():
+    from spatialcore_b200 import _lib, philox
+
+    L = _lib.lib()
+    for n in (1, 2, 3, 17, 1024, 1025, 65_537, 300_000):
+        out = np.empty(n, dtype=np.int32)
+        assert L.sc_philox_permutation_host(42, 9, n, out.ctypes.data) == 0
+        assert np.array_equal(np.sort(out), np.arange(n))
+        assert np.array_equal(out, philox.permutation(42, 9, n))
+    a = philox.permutation(1, 0, 5000)
+    b = philox.permutation(1, 1, 5000)
+    c = philox.permutation(2, 0, 5000)
+    assert (a != b).mean() > 0.99 and (a != c).mean() > 0.99
+
+
+def test_philox_permutations_are_statistically_uniform():
+    """position uniformity (chi-square), fixed-point count ~ Poisson(1), and the
+    permutation statistic Σ x_i y_π(i) has the moments of a uniform random permutation."""
+    from spatialcore_b200 import philox
+
+    n, P = 2000, 400
+    perms = np.stack([philox.permutation(7, p, n) for p in range(P)])
+    # where does element 0..9 land? 20 equal bins, P draws each
+    for i in range(10):
+        hist = np.bincount(perms[:, i] * 20 // n, minlength=20)
+        chi2 = ((hist - P / 20) ** 2 / (P / 20)).sum()
+        assert chi2 < 50.0, (i, chi2)  # 19 dof: P(chi2 > 50) ~ 1e-4
+    fixed = (perms == np.arange(n)[None, :]).sum(1)
+    assert 0.7 < fixed.mean() < 1.3
+    rng = np.random.default_rng(0)
+    x, y = rng.normal(size=n), rng.normal(size=n)
+    stat = (x[None, :] * y[perms]).sum(1)
+    mu = n * x.mean() * y.mean()
+    var = (n - 1) * x.var(ddof=1) * y.var(ddof=1) * (n - 1) / n  # exact permutation variance
+    assert abs(stat.mean() - mu) < 4 * np.sqrt(var / P)
+    assert 0.8 < stat.var() / var < 1.25
+    # consecutive permutations are uncorrelated
+    r = np.corrcoef(perms[:-1, :50].ravel(), perms[1:, :50].ravel())[0, 1]
+    assert abs(r) < 0.02
+
+
+def test_product_never_imports_the_oracle():
+    pkg = os.path.join(ROOT, "spatialcore_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                src = open(os.path.join(dirpath, f)).read()
+                assert not re.search(r"^\s*(from|import)\s+oracle\b", src, flags=re.M), f
+                assert "moran_port" not in src and "oracle.restate" not in src, f
+
+
+def test_no_cpu_fallback_when_cuda_is_missing():
+    import torch
+
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    from spatialcore_b200 import AnnDataLite, spatial
+
+    a = AnnDataLite(np.zeros((30, 3), np.float32), obsm={"spatial": np.random.default_rng(0).uniform(size=(30, 2))})
+    with pytest.raises(Exception) as ei:
+        spatial.morans_i(a, n_permutations=0)
+    assert "nvidia" in str(ei.value).lower() or "cuda" in str(ei.value).lower()
+    # argument errors still surface first, exactly like the reference
+    with pytest.raises(ValueError, match="n_neighbors must be >= 1"):
+        spatial.morans_i(a, n_neighbors=0)

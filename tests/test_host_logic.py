@@ -1,0 +1,178 @@
+"""CPU-only tests of the host-side logic: AnnData duck type, metadata log, FDR / quadrant helpers,
+permutation-source selection, replay chunking, the C port of the CPU baseline, and the multi-rank
+sharding + reduction path on the gloo backend (world_size 2)."""
+
+import os
+import socket
+import sys
+
+import numpy as np
+import pandas as pd
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from oracle import restate as R
+from tests.golden import inputs
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_anndata_lite_protocol():
+    from spatialcore_b200 import AnnDataLite
+
+    X = np.arange(12, dtype=np.float32).reshape(4, 3)
+    a = AnnDataLite(X, obsm={"spatial": np.zeros((4, 2))}, var_names=["a", "b", "c"])
+    assert a.n_obs == 4 and a.n_vars == 3 and a.shape == (4, 3)
+    sub = a[:, ["c", "a"]]
+    assert np.array_equal(sub.X, X[:, [2, 0]]) and list(sub.var_names) == ["c", "a"]
+    b = a.copy()
+    b.uns["k"] = 1
+    b.X[0, 0] = 99
+    assert "k" not in a.uns and a.X[0, 0] == 0
+    with pytest.raises(ValueError):
+        AnnDataLite(X, var_names=["a"])
+
+
+def test_metadata_log_matches_reference_schema():
+    from spatialcore_b200 import AnnDataLite
+    from spatialcore_b200.core import update_metadata
+
+    a = AnnDataLite(np.zeros((2, 2), np.float32))
+    update_metadata(a, "morans_i", {"genes": ("g0", "g1"), "seed": 0, "obj": object(), "nested": {"x": 1.5}}, {"uns": "morans_i"})
+    update_metadata(a, "lees_l_local", {"n_pairs": 2})
+    meta = a.uns["spatialcore_metadata"]
+    assert set(meta) == {"created", "operations"} and len(meta["operations"]) == 2
+    op = meta["operations"][0]
+    assert set(op) == {"timestamp", "function", "parameters", "outputs"}
+    assert op["parameters"] == {"genes": ["g0", "g1"], "seed": 0, "obj": "object", "nested": {"x": 1.5}}
+    assert "outputs" not in meta["operations"][1]
+
+
+def test_fdr_and_quadrants_match_oracle():
+    from spatialcore_b200.spatial import autocorrelation as ac
+
+    rng = np.random.default_rng(0)
+    p = rng.uniform(size=500)
+    p[:20] = 0.001
+    np.testing.assert_array_equal(ac._fdr(p, "fdr_bh"), R.bh_adjust(p))
+    np.testing.assert_array_equal(ac._fdr(p, "bonferroni"), np.clip(p * 500, 0, 1))
+    np.testing.assert_array_equal(ac._fdr(p, "none"), p)
+    assert ac._fdr(np.zeros(0), "fdr_bh").size == 0
+    with pytest.raises(ValueError, match="Unknown FDR method"):
+        ac._fdr(p, "holm")
+    z, lag = rng.normal(size=(50, 3)), rng.normal(size=(50, 3))
+    z[0, 0] = 0.0
+    pa = rng.uniform(size=(50, 3))
+    np.testing.assert_array_equal(ac._classify_quadrants(z, lag, pa, 0.3), R.quadrants(z, lag, pa, 0.3))
+    assert ac._classify_quadrants(z, lag)[0, 0] == 0
+
+
+def test_perm_source_selection_and_replay_stream():
+    from spatialcore_b200.spatial import autocorrelation as ac
+
+    assert ac._pick_perm_source("auto", 10_000, 99) == "replay"
+    assert ac._pick_perm_source("auto", 5_000_000, 999) == "philox"
+    assert ac._pick_perm_source("philox", 10, 1) == "philox"
+    with pytest.raises(ValueError):
+        ac._pick_perm_source("numpy", 10, 1)
+    # chunks reproduce numpy's draw order exactly, whatever the chunking
+    old = ac._REPLAY_CHUNK_ELEMS
+    try:
+        ac._REPLAY_CHUNK_ELEMS = 2500  # 2 permutations of 1000 per chunk
+        got = torch.cat([c for _, c in ac._replay_chunks(np.random.default_rng(5), 1000, 7, "cpu")]).numpy()
+    finally:
+        ac._REPLAY_CHUNK_ELEMS = old
+    rng = np.random.default_rng(5)
+    want = np.stack([rng.permutation(1000) for _ in range(7)])
+    np.testing.assert_array_equal(got, want)
+
+
+def test_block_slice_partitions():
+    from spatialcore_b200.distributed import block_slice
+
+    for total in (0, 1, 7, 999, 1000):
+        for ws in (1, 2, 3, 8):
+            parts = [block_slice(total, r, ws) for r in range(ws)]
+            assert parts[0][0] == 0 and parts[-1][1] == total
+            assert all(a[1] == b[0] for a, b in zip(parts, parts[1:]))
+            sizes = [hi - lo for lo, hi in parts]
+            assert max(sizes) - min(sizes) <= 1
+
+
+def test_cpu_port_matches_restatement():
+    from oracle import port
+
+    coords, X = inputs.g0()
+    adj, _ = R.spatial_neighbors(coords[:3000], k=6)
+    g = R.row_normalize(adj)
+    perms = R.squidpy_perm_indices(3000, 5, 1)
+    score, sims = port.morans_i(g, X[:3000, :7].T.astype(np.float64), perms.astype(np.int32))
+    np.testing.assert_allclose(score, R.morans_i_stat(g, X[:3000, :7]), rtol=1e-12)
+    np.testing.assert_allclose(sims, R.morans_i_perms_graph_rows(g, X[:3000, :7], perms), rtol=1e-11)
+    # radius graph (ragged rows, empty rows)
+    adj, _ = R.spatial_neighbors(coords[:3000], radius=12.0)
+    g = R.row_normalize(adj)
+    score, sims = port.morans_i(g, X[:3000, :4].T.astype(np.float64), perms.astype(np.int32))
+    np.testing.assert_allclose(sims, R.morans_i_perms_graph_rows(g, X[:3000, :4], perms), rtol=1e-11)
+    assert port.threads() >= 1
+
+
+# ---------------------------------------------------------------------------------------------
+# multi-rank path on gloo (world_size 2): the same sharding / reduction code the GPU ranks run
+# ---------------------------------------------------------------------------------------------
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _worker(rank, world, port_no, out_dir):
+    sys.path.insert(0, ROOT)
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port_no)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from spatialcore_b200 import distributed as du
+    from spatialcore_b200.spatial.autocorrelation import MoranNull
+
+    G, P = 11, 37
+    rng = np.random.default_rng(0)
+    sims = rng.normal(size=(P, G))
+    obs = rng.normal(size=G) * 0.5
+    # --- permutation sharding: every rank folds its block, one all-reduce of the [4, G] summary
+    lo, hi = du.my_slice(P)
+    null = MoranNull(G, "cpu")
+    blk = torch.from_numpy(sims[lo:hi])
+    null.cnt_ge += (blk >= torch.from_numpy(obs)).sum(0)
+    null.cnt_abs_ge += (blk.abs() >= torch.from_numpy(obs).abs()).sum(0)
+    null.sum += blk.sum(0)
+    null.sumsq += (blk * blk).sum(0)
+    du.all_reduce_null(null)
+    # --- gene sharding: every rank owns a gene block, one all-gather of per-gene columns
+    glo, ghi = du.block_slice(G, rank, world)
+    local = np.stack([obs[glo:ghi], obs[glo:ghi] * 2])
+    gathered = du.all_gather_columns(local, G, "cpu")
+    np.savez(os.path.join(out_dir, f"r{rank}.npz"), cnt=null.cnt_ge.numpy(), cabs=null.cnt_abs_ge.numpy(),
+             s=null.sum.numpy(), ss=null.sumsq.numpy(), gathered=gathered, slice=np.array([lo, hi]))
+    dist.destroy_process_group()
+
+
+def test_two_rank_sharding_and_reduction_gloo(tmp_path):
+    world = 2
+    mp.spawn(_worker, args=(world, _free_port(), str(tmp_path)), nprocs=world, join=True)
+    rng = np.random.default_rng(0)
+    sims = rng.normal(size=(37, 11))
+    obs = rng.normal(size=11) * 0.5
+    r0, r1 = (np.load(tmp_path / f"r{r}.npz") for r in range(2))
+    assert r0["slice"].tolist() == [0, 19] and r1["slice"].tolist() == [19, 37]
+    for r in (r0, r1):
+        np.testing.assert_array_equal(r["cnt"], (sims >= obs).sum(0))
+        np.testing.assert_array_equal(r["cabs"], (np.abs(sims) >= np.abs(obs)).sum(0))
+        np.testing.assert_allclose(r["s"], sims.sum(0), rtol=1e-12)
+        np.testing.assert_allclose(r["ss"], (sims**2).sum(0), rtol=1e-12)
+        np.testing.assert_array_equal(r["gathered"], np.stack([obs, obs * 2]))
