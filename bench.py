@@ -11,8 +11,9 @@ One "step" = one pass of the whole hot path over the workload: graph build -> z-
 Moran statistic -> graph moments -> P permutations -> per-gene p-values.  ``value`` times it with
 inputs resident in HBM (CUDA events, max over ranks); ``e2e`` times the public API
 ``spatialcore_b200.spatial.morans_i`` on HOST arrays (pinned), H2D/D2H inside the timed region.
-Multi-GPU: gene blocks are sharded over ranks (strong scaling of the fixed workload), one
-all-gather of per-gene results at the end.  Prints ONE JSON line on rank 0.
+Multi-GPU (strong scaling of the fixed workload): ranks form gene blocks (>= 500 genes each) x
+permutation groups; one all-reduce of the [4, G] null summary inside a gene block and one all-gather
+of per-gene results at the end.  Prints ONE JSON line on rank 0.
 """
 
 from __future__ import annotations
@@ -132,7 +133,7 @@ class ClockSampler:
 # ------------------------------------------------------------------------------------------------
 
 
-def device_step(engine, ac, coords_dev, X_dev, w, radius, seed, events=None):
+def device_step(engine, ac, coords_dev, X_dev, w, radius, seed, events=None, perm_range=None, group=None):
     """One pass of the hot path with inputs resident in HBM.  Returns (I, p_value) device tensors."""
     import torch
 
@@ -159,8 +160,12 @@ def device_step(engine, ac, coords_dev, X_dev, w, radius, seed, events=None):
     scale = (float(n) / s0) / den
     I = num * scale
     null = ac.MoranNull(g, X_dev.device)
-    ac.moran_graph_rows_null(std.Z, lag, g, scale, I, P, seed, "philox", null, (0, P))
+    ac.moran_graph_rows_null(std.Z, lag, g, scale, I, P, seed, "philox", null, perm_range or (0, P))
     mark("perms")
+    if group is not None:
+        from spatialcore_b200 import distributed as dist_util
+
+        dist_util.all_reduce_null(null, group)  # [4, G_block] FP64 over the ranks sharing this gene block
     c = torch.minimum(null.cnt_ge, P - null.cnt_ge)
     p_value = (c + 1).double() / (P + 1)
     return I, p_value
@@ -185,13 +190,24 @@ def run_b200(args):
         dist.init_process_group("nccl", device_id=dev)
     w = WORKLOADS[args.workload]
     n, g_total, P = w["n"], w["g"], w["perms"]
-    g_lo, g_hi = dist_util.block_slice(g_total, rank, world)
+    # hybrid partition: gene blocks (>= 500 genes each, so matrix rows stay wide) x permutation groups
+    n_gene_groups = dist_util.gene_groups_for(g_total, world)
+    n_perm_groups = world // n_gene_groups
+    gi, pi = rank // n_perm_groups, rank % n_perm_groups
+    g_lo, g_hi = dist_util.block_slice(g_total, gi, n_gene_groups)
     g = g_hi - g_lo
+    perm_range = dist_util.block_slice(P, pi, n_perm_groups)
+    group = None
+    if world > 1:
+        for j in range(n_gene_groups):  # every rank creates every sub-group, in the same order
+            grp = dist.new_group(list(range(j * n_perm_groups, (j + 1) * n_perm_groups)))
+            if j == gi:
+                group = grp
     radius = workload_radius(w)
 
     coords = make_coords(w, args.seed)
     coords_dev = torch.from_numpy(coords).to(dev)
-    X_dev = synthetic.expression_device(coords, g, seed=args.seed * 1000 + rank, device=dev)
+    X_dev = synthetic.expression_device(coords, g, seed=args.seed * 1000 + gi, device=dev)
     torch.cuda.synchronize()
 
     def barrier():
@@ -200,21 +216,23 @@ def run_b200(args):
         torch.cuda.synchronize()
 
     def gather_results(I, p):
+        """Per-gene results of every gene block -> full table on every rank (one all-gather)."""
         if world > 1:
-            sizes = [dist_util.block_slice(g_total, r, world) for r in range(world)]
+            sizes = [dist_util.block_slice(g_total, j, n_gene_groups) for j in range(n_gene_groups)]
             pad = max(hi - lo for lo, hi in sizes)
             buf = torch.zeros(2, pad, dtype=torch.float64, device=dev)
             buf[0, : I.numel()] = I
             buf[1, : p.numel()] = p
             out = [torch.empty_like(buf) for _ in range(world)]
             dist.all_gather(out, buf)
-            I = torch.cat([o[0, : hi - lo] for o, (lo, hi) in zip(out, sizes)])
-            p = torch.cat([o[1, : hi - lo] for o, (lo, hi) in zip(out, sizes)])
+            firsts = [out[j * n_perm_groups] for j in range(n_gene_groups)]  # one rank per gene block
+            I = torch.cat([o[0, : hi - lo] for o, (lo, hi) in zip(firsts, sizes)])
+            p = torch.cat([o[1, : hi - lo] for o, (lo, hi) in zip(firsts, sizes)])
         return I.cpu().numpy(), p.cpu().numpy()
 
     # ---------------- device-resident leg -------------------------------------------------------
     for _ in range(args.warmup):
-        I, p = device_step(engine, ac, coords_dev, X_dev, w, radius, args.seed)
+        I, p = device_step(engine, ac, coords_dev, X_dev, w, radius, args.seed, None, perm_range, group)
         gather_results(I, p)
     sampler = ClockSampler(local_rank)
     barrier()
@@ -226,7 +244,7 @@ def run_b200(args):
     t_start.record()
     for _ in range(args.steps):
         events = []
-        I, p = device_step(engine, ac, coords_dev, X_dev, w, radius, args.seed, events)
+        I, p = device_step(engine, ac, coords_dev, X_dev, w, radius, args.seed, events, perm_range, group)
         I_h, p_h = gather_results(I, p)
         torch.cuda.synchronize()
         for (_, a), (name, b) in zip(events[:-1], events[1:]):
@@ -245,9 +263,10 @@ def run_b200(args):
     # roofline of the dominant kernel (perm_rows_kernel): algorithmic bytes per launch / launch time.
     # per gene-perm 4N(1+1/P) bytes; one launch covers PB permutations x g genes.
     PB = 16  # permutations per launch of the default kernel variant (bulk16)
-    n_launch = (P + PB - 1) // PB
+    my_perms = perm_range[1] - perm_range[0]
+    n_launch = (my_perms + PB - 1) // PB
     perm_ms = phase_ms.get("perms", float("nan"))
-    bytes_per_launch = 4.0 * n * (1.0 + 1.0 / P) * g * (P / n_launch)
+    bytes_per_launch = 4.0 * n * (1.0 + 1.0 / P) * g * (my_perms / n_launch)
     achieved = bytes_per_launch / (perm_ms / 1e3 / n_launch) / 1e9
     peaks = {}
     try:
@@ -276,7 +295,8 @@ def run_b200(args):
         def e2e_step():
             adata = AnnDataLite(Xn, obsm={"spatial": cn}, var_names=names)
             spatial.morans_i(adata, n_neighbors=w["k"] or 6, n_permutations=P, seed=args.seed, radius=radius,
-                             perm_source="philox", write_graph=False, shard="none", device=dev)
+                             perm_source="philox", write_graph=False, shard="perms" if group is not None else "none",
+                             group=group, device=dev)
             df = adata.uns["morans_i"]
             return torch.from_numpy(df["I"].to_numpy()).to(dev), torch.from_numpy(df["p_value"].to_numpy()).to(dev)
 
@@ -311,7 +331,7 @@ def run_b200(args):
             "vs_baseline": None, "dtype": "f32 storage, f64 accumulation", "data": "synthetic",
             "config": {"workload": f"{args.workload}: {w['desc']}", "n_cells": n, "n_genes": g_total, "n_permutations": P,
                        "graph": w["graph"], "radius": radius, "k": w["k"], "null": "graph_rows (squidpy semantics)",
-                       "perm_source": "philox (on-device bijection)", "sharding": f"gene blocks over {world} rank(s)",
+                       "perm_source": "philox (on-device bijection)", "sharding": f"{n_gene_groups} gene block(s) x {n_perm_groups} permutation group(s) over {world} rank(s)",
                        "l2": "inputs (Z, lag: 4*N*G bytes each) far larger than the 126 MB L2; no flush needed"},
             "phases_ms": {k: round(v, 3) for k, v in phase_ms.items()},
             "knn_build_ms": round(phase_ms.get("graph", float("nan")), 3),
@@ -367,6 +387,7 @@ def cpu_sample_plan(w):
 def cpu_baseline_sample(w, coords, radius, seed, graph=None):
     from oracle import port, restate
 
+    port.use_all_cores()
     g_cpu, p_cpu = cpu_sample_plan(w)
     n = w["n"]
     graph_s = None

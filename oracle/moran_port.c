@@ -19,6 +19,15 @@
 #include <omp.h>
 #endif
 
+/* torchrun exports OMP_NUM_THREADS=1; the CPU arm asks for all host cores explicitly */
+void moran_port_set_threads(int n) {
+#ifdef _OPENMP
+  if (n > 0) omp_set_num_threads(n);
+#else
+  (void)n;
+#endif
+}
+
 int moran_port_threads(void) {
 #ifdef _OPENMP
   return omp_get_max_threads();

@@ -19,7 +19,19 @@ def lib():
         _lib.moran_port_run.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_int64,
                                         C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p]
         _lib.moran_port_threads.restype = C.c_int
+        _lib.moran_port_set_threads.argtypes = [C.c_int]
+        _lib.moran_port_set_threads.restype = None
     return _lib
+
+
+def use_all_cores() -> int:
+    """Use every core this process may run on (ignores OMP_NUM_THREADS, which torchrun sets to 1)."""
+    try:
+        n = len(os.sched_getaffinity(0))
+    except AttributeError:
+        n = os.cpu_count() or 1
+    lib().moran_port_set_threads(n)
+    return threads()
 
 
 def threads() -> int:

@@ -134,36 +134,51 @@ __host__ __device__ __forceinline__ uint32_t mix32(uint32_t x) {
   return x;
 }
 
-// Alternating unbalanced Feistel network on m = bl + br bits (bl = m/2, br = m - bl), kFeistelRounds
-// (even) rounds, cycle-walked into [0, n).  A bijection of [0, n) for every key set.
+// Generalised (group-operation) Feistel network on Z_a x Z_b with b = 2^s ~ sqrt(n) and
+// a = ceil(n / b): the domain a*b exceeds n by less than b, so cycle-walking into [0, n) almost
+// never iterates (acceptance >= 1 - b/n) and warps do not diverge.  State (L, R); even rounds map
+// (Z_a, Z_b) -> (Z_b, Z_a) with R' = (L + F(R)) mod a, odd rounds map back with R' = (L + F(R)) mod b.
+// kFeistelRounds (even) rounds; a bijection of [0, a*b) for every key set.
 struct PermDomain {
   uint32_t n;
-  uint32_t bl, br;  // bit widths of the left / right halves
+  uint32_t a;  // size of the "high" factor
+  uint32_t s;  // log2 of the "low" factor b
 };
 
 __host__ __device__ __forceinline__ PermDomain make_perm_domain(uint32_t n) {
-  uint32_t m = 2;
-  while (m < 32 && (1ull << m) < (uint64_t)n) ++m;
+  uint32_t bits = 1;
+  while (bits < 32 && (1ull << bits) < (uint64_t)n) ++bits;  // bits = ceil(log2 n), >= 1
   PermDomain d;
   d.n = n;
-  d.bl = m / 2;
-  d.br = m - d.bl;
+  d.s = (bits + 1) / 2;
+  d.a = (uint32_t)(((uint64_t)n + (1ull << d.s) - 1) >> d.s);
+  if (d.a == 0) d.a = 1;
   return d;
+}
+
+__host__ __device__ __forceinline__ uint32_t mulhi32(uint32_t x, uint32_t y) {
+  return (uint32_t)(((uint64_t)x * (uint64_t)y) >> 32);
 }
 
 __host__ __device__ __forceinline__ uint32_t feistel_once(uint32_t v, const PermDomain& d,
                                                           const uint32_t* keys) {
-  uint32_t wl = d.bl, wr = d.br;
-  uint32_t L = v >> wr, R = v & ((1u << wr) - 1u);
+  const uint32_t bmask = (1u << d.s) - 1u;
+  uint32_t L = v >> d.s, R = v & bmask;  // L in Z_a, R in Z_b
 #pragma unroll
-  for (int r = 0; r < kFeistelRounds; ++r) {
-    uint32_t f = mix32(R * 0x9E3779B1u + keys[r]) & ((1u << wl) - 1u);
-    uint32_t nR = L ^ f;  // wl bits
-    L = R;                // wr bits
-    R = nR;
-    uint32_t t = wl; wl = wr; wr = t;
+  for (int r = 0; r < kFeistelRounds; r += 2) {
+    // (Z_a, Z_b) -> (Z_b, Z_a)
+    uint32_t f = mulhi32(mix32(R * 0x9E3779B1u + keys[r]), d.a);  // uniform in [0, a)
+    uint32_t t = L + f;
+    if (t >= d.a) t -= d.a;
+    L = R;
+    R = t;
+    // (Z_b, Z_a) -> (Z_a, Z_b)
+    uint32_t f2 = mix32(R * 0x9E3779B1u + keys[r + 1]) >> (32u - d.s);  // uniform in [0, b)
+    uint32_t t2 = (L + f2) & bmask;
+    L = R;
+    R = t2;
   }
-  return (L << wr) | R;
+  return (L << d.s) | R;
 }
 
 __host__ __device__ __forceinline__ uint32_t perm_apply(uint32_t i, const PermDomain& d,

@@ -5,7 +5,9 @@ matrices, runs a contiguous block of the P permutations and the per-gene null su
 (count_ge, count_abs_ge, Σsim, Σsim²; a [4, G] FP64 tensor, 32 KB at G = 1000) are summed with ONE
 all-reduce (NCCL over NVLink on GPUs, gloo in the CPU tests).  Philox permutations are addressed by
 their global index, so the result does not depend on the world size.  There is no other exchange
-on this path, hence no fused compute+collective kernel.
+on this path, hence no fused compute+collective kernel.  Gene blocks are the other natural partition
+(each rank owns G/W genes end to end, one all-gather of per-gene vectors); ``gene_groups_for`` picks
+the hybrid of the two that keeps matrix rows wide.
 """
 
 from __future__ import annotations
@@ -16,9 +18,9 @@ import torch
 import torch.distributed as dist
 
 
-def world() -> Tuple[int, int]:
+def world(group=None) -> Tuple[int, int]:
     if dist.is_available() and dist.is_initialized():
-        return dist.get_rank(), dist.get_world_size()
+        return dist.get_rank(group), dist.get_world_size(group)
     return 0, 1
 
 
@@ -29,33 +31,37 @@ def block_slice(total: int, rank: int, world_size: int) -> Tuple[int, int]:
     return lo, lo + base + (1 if rank < rem else 0)
 
 
-def my_slice(total: int) -> Tuple[int, int]:
-    rank, ws = world()
+def my_slice(total: int, group=None) -> Tuple[int, int]:
+    rank, ws = world(group)
     return block_slice(total, rank, ws)
 
 
-def all_reduce_packed(t: torch.Tensor) -> torch.Tensor:
-    _, ws = world()
-    if ws > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.SUM)
-    return t
+def gene_groups_for(n_genes: int, world_size: int, min_genes: int = 500) -> int:
+    """Hybrid partition: the largest divisor d of the world size that keeps >= ``min_genes`` genes per
+    block (rows of the N x G matrices stay wide enough for the gather kernel to run at HBM speed);
+    the remaining factor world/d shards the permutations."""
+    best = 1
+    for d in range(1, world_size + 1):
+        if world_size % d == 0 and n_genes // d >= min_genes:
+            best = d
+    return best
 
 
-def all_reduce_null(null) -> None:
-    """Sum a ``MoranNull`` over ranks (counts travel as exact FP64 integers)."""
-    _, ws = world()
+def all_reduce_null(null, group=None) -> None:
+    """Sum a ``MoranNull`` over the ranks of ``group`` (counts travel as exact FP64 integers)."""
+    _, ws = world(group)
     if ws > 1:
         packed = null.packed().contiguous()
-        dist.all_reduce(packed, op=dist.ReduceOp.SUM)
+        dist.all_reduce(packed, op=dist.ReduceOp.SUM, group=group)
         null.unpack(packed)
 
 
-def all_gather_columns(local, total_cols: int, device):
+def all_gather_columns(local, total_cols: int, device, group=None):
     """Gene-block sharding: every rank contributes ``local`` (numpy [rows, its block]); returns the
     concatenation over ranks in block order (numpy [rows, total_cols])."""
     import numpy as np
 
-    rank, ws = world()
+    rank, ws = world(group)
     if ws == 1:
         return local
     sizes = [block_slice(total_cols, r, ws) for r in range(ws)]
@@ -63,5 +69,5 @@ def all_gather_columns(local, total_cols: int, device):
     buf = torch.zeros((local.shape[0], pad), dtype=torch.float64, device=device)
     buf[:, : local.shape[1]] = torch.from_numpy(np.ascontiguousarray(local)).to(device)
     out = [torch.empty_like(buf) for _ in range(ws)]
-    dist.all_gather(out, buf)
+    dist.all_gather(out, buf, group=group)
     return torch.cat([o[:, : hi - lo] for o, (lo, hi) in zip(out, sizes)], dim=1).cpu().numpy()

@@ -1,9 +1,10 @@
 """Host mirror of the device permutation generator (``csrc/common.cuh``).
 
-Permutation ``p`` under ``seed`` is a keyed bijection of ``[0, n)``: eight rounds of an alternating
-unbalanced Feistel network on ``m = ceil(log2 n)`` bits (murmur3-finalizer round function), round
-keys drawn from Philox4x32-10 with counter ``(p_lo, p_hi, block, 0x5C0B200)`` and key
-``(seed_lo, seed_hi)``, cycle-walked into range.  No index array is ever stored on the device; this
+Permutation ``p`` under ``seed`` is a keyed bijection of ``[0, n)``: eight rounds of a generalised
+Feistel network on ``Z_a x Z_b`` (``b = 2^s ~ sqrt(n)``, ``a = ceil(n/b)``, additive combine,
+murmur3-finalizer round function), round keys drawn from Philox4x32-10 with counter
+``(p_lo, p_hi, block, 0x5C0B200)`` and key ``(seed_lo, seed_hi)``, cycle-walked into range (the
+domain exceeds ``n`` by less than ``b``, so the walk almost never iterates).  No index array is ever stored on the device; this
 numpy implementation reproduces it bit for bit so a Philox-mode run can be replayed on the CPU
 oracle (``tests/``) or exported.
 """
@@ -50,32 +51,40 @@ def _mix32(x: np.ndarray) -> np.ndarray:
     return x
 
 
-def _domain_bits(n: int):
-    m = 2
-    while m < 32 and (1 << m) < n:
-        m += 1
-    bl = m // 2
-    return bl, m - bl
+def _domain(n: int):
+    """(a, s): Z_a x Z_{2^s} with 2^s ~ sqrt(n) and a = ceil(n / 2^s)."""
+    bits = 1
+    while bits < 32 and (1 << bits) < n:
+        bits += 1
+    s = (bits + 1) // 2
+    a = max(1, (n + (1 << s) - 1) >> s)
+    return a, s
 
 
-def _feistel_once(v: np.ndarray, bl: int, br: int, keys) -> np.ndarray:
-    wl, wr = bl, br
-    L = v >> np.uint64(wr)
-    R = v & np.uint64((1 << wr) - 1)
-    for r in range(FEISTEL_ROUNDS):
-        f = _mix32((R * np.uint64(0x9E3779B1) + np.uint64(keys[r])) & _M32) & np.uint64((1 << wl) - 1)
-        L, R = R, L ^ f
-        wl, wr = wr, wl
-    return (L << np.uint64(wr)) | R
+def _feistel_once(v: np.ndarray, a: int, s: int, keys) -> np.ndarray:
+    bmask = np.uint64((1 << s) - 1)
+    L = v >> np.uint64(s)
+    R = v & bmask
+    for r in range(0, FEISTEL_ROUNDS, 2):
+        h = _mix32((R * np.uint64(0x9E3779B1) + np.uint64(keys[r])) & _M32)
+        f = (h * np.uint64(a)) >> np.uint64(32)
+        t = L + f
+        t = np.where(t >= a, t - np.uint64(a), t)
+        L, R = R, t
+        h2 = _mix32((R * np.uint64(0x9E3779B1) + np.uint64(keys[r + 1])) & _M32)
+        f2 = h2 >> np.uint64(32 - s)
+        t2 = (L + f2) & bmask
+        L, R = R, t2
+    return (L << np.uint64(s)) | R
 
 
 def permutation(seed: int, perm_index: int, n: int) -> np.ndarray:
     """π_p as an int32 array: ``out[i] = π_p(i)`` — identical to ``sc_philox_permutation``."""
     keys = round_keys(seed, perm_index)
-    bl, br = _domain_bits(n)
-    v = _feistel_once(np.arange(n, dtype=np.uint64), bl, br, keys)
+    a, s = _domain(n)
+    v = _feistel_once(np.arange(n, dtype=np.uint64), a, s, keys)
     bad = v >= n
     while bad.any():
-        v[bad] = _feistel_once(v[bad], bl, br, keys)
+        v[bad] = _feistel_once(v[bad], a, s, keys)
         bad = v >= n
     return v.astype(np.int32)

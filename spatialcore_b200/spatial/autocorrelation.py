@@ -275,6 +275,7 @@ def morans_i(
     radius: Optional[float] = None,
     write_graph: bool = True,
     shard: str = "auto",
+    group=None,
     device="cuda",
 ):
     """Global Moran's I with the squidpy permutation null, API of [R autocorrelation.py:421-648].
@@ -296,11 +297,11 @@ def morans_i(
     all_names = _resolve_genes(adata, genes, "This may be slow for large datasets.")
     n = adata.n_obs
     logger.info(f"Computing Global Moran's I: {n:,} cells, {len(all_names)} genes, k={n_neighbors}, permutations={n_permutations}")
-    rank, world = dist_util.world()
+    rank, world = dist_util.world(group)
     if world == 1 or shard == "none":
         mode = "none"
     elif shard == "auto":
-        mode = "genes" if len(all_names) >= 8 * world else "perms"
+        mode = "genes" if len(all_names) >= 500 * world else "perms"
     else:
         mode = shard
     if mode == "genes":
@@ -330,10 +331,10 @@ def morans_i(
     if n_permutations > 0:
         source = _pick_perm_source(perm_source, n, n_permutations)
         null = MoranNull(g, std.Z.device)
-        lo, hi = dist_util.my_slice(n_permutations) if mode == "perms" else (0, n_permutations)
+        lo, hi = dist_util.my_slice(n_permutations, group) if mode == "perms" else (0, n_permutations)
         moran_graph_rows_null(std.Z, lag, g, scale, I_dev, n_permutations, seed, source, null, (lo, hi))
         if mode == "perms":
-            dist_util.all_reduce_null(null)
+            dist_util.all_reduce_null(null, group)
         c = null.cnt_ge.cpu().numpy()
         c = np.where(n_permutations - c < c, n_permutations - c, c)
         p_value = (c + 1) / (n_permutations + 1)
@@ -351,7 +352,7 @@ def morans_i(
         z_score = np.zeros_like(I)
 
     if mode == "genes":
-        cols = dist_util.all_gather_columns(np.stack([I, z_score, p_value]).astype(np.float64), len(all_names), std.Z.device)
+        cols = dist_util.all_gather_columns(np.stack([I, z_score, p_value]).astype(np.float64), len(all_names), std.Z.device, group)
         I, z_score, p_value = cols[0], cols[1], cols[2]
         names, g = all_names, len(all_names)
 
