@@ -179,6 +179,9 @@ def run_b200(args):
     from spatialcore_b200 import distributed as dist_util
     from spatialcore_b200.spatial import autocorrelation as ac
 
+    import logging
+
+    logging.getLogger("spatialcore").setLevel(logging.ERROR)  # the reference logger writes to stdout
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -298,11 +301,9 @@ def run_b200(args):
                              perm_source="philox", write_graph=False, shard="perms" if group is not None else "none",
                              group=group, device=dev)
             df = adata.uns["morans_i"]
-            return torch.from_numpy(df["I"].to_numpy()).to(dev), torch.from_numpy(df["p_value"].to_numpy()).to(dev)
+            return (torch.from_numpy(df["I"].to_numpy(copy=True)).to(dev),
+                    torch.from_numpy(df["p_value"].to_numpy(copy=True)).to(dev))
 
-        import logging
-
-        logging.getLogger("spatialcore").setLevel(logging.WARNING)
         for _ in range(max(1, min(args.warmup, 3))):
             gather_results(*e2e_step())
         barrier()
@@ -443,6 +444,7 @@ def run_reference(args):
 
 
 def main():
+    os.environ.setdefault("NCCL_DEBUG", "WARN")  # keep stdout to the single JSON line
     args = parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -186,9 +186,11 @@ SC_API int sc_null_accumulate(const double* sims, int n_perms, int g, const doub
 
 /* ---------------------------------------------------------------------------------------------
  * Lee's L for all ordered gene pairs: L[x, y] = Σ_i A[i, x] · B[i, y]  (A = Z, B = W Z), i.e. the
- * matrix of autocorrelation.py:307-315 over every pair.  Tensor cores (tcgen05, 3xTF32, FP32
- * accumulation in TMEM) when available for the shape, otherwise an FP32 CUDA-core kernel.
- * L f32[g, ldl].  impl: 0 = auto, 1 = CUDA-core FP32, 2 = tcgen05 3xTF32.
+ * matrix of autocorrelation.py:307-315 over every pair.
+ * impl 1 (and 0 = default): CUDA-core kernel, FP64 accumulation (exact up to input rounding).
+ * impl 2: tensor cores — tcgen05.mma kind::tf32 with 3xTF32 operand splitting, FP32 accumulation in
+ *         TMEM per 1024-cell chunk, chunks summed in FP64 (~1e-6 of the matrix scale sqrt(n)).
+ * L f32[g, ldl].
  * ------------------------------------------------------------------------------------------- */
 SC_API size_t sc_lee_gemm_workspace_bytes(int64_t n, int g);
 SC_API int sc_lee_gemm(const float* A, int64_t lda, const float* B, int64_t ldb, int64_t n, int g,

@@ -1,0 +1,91 @@
+"""Secondary measurements (one GPU): graph builds, neighbourhood composition, Lee's L contraction,
+value-permuting null, lag kernel, local Moran API.  Prints one JSON object."""
+import json, os, sys, time
+import numpy as np, torch
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from spatialcore_b200 import AnnDataLite, engine as eng, spatial, synthetic
+import logging; logging.getLogger("spatialcore").setLevel(logging.ERROR)
+
+only = set(sys.argv[1].split(",")) if len(sys.argv) > 1 else None
+def want(name): return only is None or name in only
+
+def timed(fn, reps=3, warm=1):
+    for _ in range(warm): fn()
+    torch.cuda.synchronize()
+    ts = []
+    for _ in range(reps):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(); fn(); e1.record(); torch.cuda.synchronize()
+        ts.append(e0.elapsed_time(e1))
+    return float(np.median(ts))
+
+out = {}
+if want("graphs"):
+    for name, n, ext, k, gen in (("C2_knn15_500k", 500_000, 1e4, 15, "mixture"), ("C5_knn30_2M", 2_000_000, 2e4, 30, "mixture"),
+                                 ("knn15_5M", 5_000_000, 1.2e5, 15, "uniform"), ("knn6_5M", 5_000_000, 1.2e5, 6, "uniform")):
+        c = synthetic.coords_mixture(n, ext, 4) if gen == "mixture" else synthetic.coords_uniform(n, ext, 4)
+        cd = torch.from_numpy(c).cuda()
+        out[name + "_ms"] = timed(lambda: eng.knn_graph(cd, k))
+        out[name + "_with_dist_ms"] = timed(lambda: eng.knn_graph(cd, k, want_dist=True))
+    c = synthetic.coords_uniform(5_000_000, 1.2e5, 3); cd = torch.from_numpy(c).cuda()
+    r = synthetic.radius_for_mean_degree(5_000_000, 1.2e5, 20.0)
+    out["C4_radius_5M_deg20_ms"] = timed(lambda: eng.radius_graph(cd, r))
+    g, _ = eng.radius_graph(cd, r); out["C4_radius_nnz"] = g.nnz
+    del cd, g
+
+if want("nbhd"):
+    n = 2_000_000
+    c = synthetic.coords_mixture(n, 2e4, 4); lab = synthetic.patchy_labels(c, 30, 5)
+    cd = torch.from_numpy(c).cuda(); ld = torch.from_numpy(lab).cuda()
+    def nb():
+        _, _, prof = eng.knn_graph(cd, 30, labels=ld, n_types=30, want_idx=False)
+        eng.profile_normalize(prof, True)
+    out["C5_nbhd_knn30_2M_T30_fused_ms"] = timed(nb)
+    a = AnnDataLite(np.zeros((n, 1), np.float32), obsm={"spatial": c})
+    import pandas as pd
+    a.obs = pd.DataFrame({"ct": pd.Categorical.from_codes(lab, [f"t{i:02d}" for i in range(30)])})
+    t0 = time.perf_counter(); spatial.compute_neighborhood_profile(a, "ct", k=30); out["C5_nbhd_api_e2e_s"] = time.perf_counter() - t0
+    t0 = time.perf_counter(); spatial.compute_neighborhood_profile(a, "ct", k=30); out["C5_nbhd_api_e2e_s_2nd"] = time.perf_counter() - t0
+    del cd, ld
+
+if want("lee"):
+    n, g = 200_000, 1000
+    c = synthetic.coords_mixture(n, 6e3, 2); cd = torch.from_numpy(c).cuda()
+    X = synthetic.expression_device(c, g, 2)
+    graph, _, _ = eng.knn_graph(cd, 6)
+    std = eng.zscore_dense(X); _, _, lag, _ = eng.lag_moran(graph, std.Z, g)
+    for impl in (1, 2):
+        try:
+            ms = timed(lambda: eng.lee_gemm(std.Z, lag, g, impl=impl))
+            out[f"C3_lee_gemm_impl{impl}_ms"] = ms
+            out[f"C3_lee_gemm_impl{impl}_useful_tflops"] = 2.0 * n * g * g / (ms / 1e3) / 1e12
+        except Exception as e:
+            out[f"C3_lee_gemm_impl{impl}"] = "unavailable: " + str(e)[:80]
+    L = eng.lee_gemm(std.Z, lag, g, impl=1)
+    ref = (std.Z[:, :g].double().T @ lag[:, :g].double())
+    out["C3_lee_impl1_max_abs_err_vs_fp64_torch"] = float((L.double() - ref).abs().max())
+    del X, std, lag
+
+if want("values"):
+    for name, n, g, k, ext in (("C2", 500_000, 400, 15, 1e4), ("C1x", 100_000, 50, 6, 3e3)):
+        c = synthetic.coords_mixture(n, ext, 1); cd = torch.from_numpy(c).cuda()
+        X = synthetic.expression_device(c, g, 1)
+        graph, _, _ = eng.knn_graph(cd, k)
+        std = eng.zscore_dense(X)
+        out[f"{name}_lag_moran_ms"] = timed(lambda: eng.lag_moran(graph, std.Z, g))
+        P = 8
+        ms = timed(lambda: eng.perm_null_values(graph, std.Z, g, P, seed=1), reps=2)
+        out[f"{name}_values_null_gene_perms_per_s"] = g * P / (ms / 1e3)
+        out[f"{name}_values_null_ms_per_perm"] = ms / P
+        ms = timed(lambda: eng.perm_null_graph_rows(std.Z, eng.lag_moran(graph, std.Z, g)[2], g, 64, seed=1), reps=2)
+        out[f"{name}_graph_rows_null_gene_perms_per_s_incl_lag"] = g * 64 / (ms / 1e3)
+        del X, std
+
+if want("local"):
+    n, g = 200_000, 20
+    c = synthetic.coords_mixture(n, 6e3, 1)
+    X = synthetic.expression_device(c, g, 1).cpu().numpy()
+    a = AnnDataLite(X, obsm={"spatial": c})
+    for src in ("philox", "replay"):
+        t0 = time.perf_counter(); spatial.local_morans_i(a, n_permutations=99, perm_source=src); out[f"local_morans_200k_x20_P99_{src}_s"] = time.perf_counter() - t0
+print(json.dumps(out, indent=1))

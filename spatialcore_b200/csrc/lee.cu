@@ -159,12 +159,11 @@ extern "C" int sc_lee_gemm(const float* A, int64_t lda, const float* B, int64_t 
   if (ws_bytes < sc_lee_gemm_workspace_bytes(n, g)) { set_error("sc_lee_gemm: workspace too small"); return SC_ERR_WORKSPACE; }
   LeePlan p = lee_plan(n, g);
   double* partial = static_cast<double*>(ws);
-  if (impl == 0) impl = lee_tc_supported(n, g, lda, ldb) ? 2 : 1;
+  if (impl == 0) impl = 1;  // exact FP64 accumulation by default; tensor cores (3xTF32) on request
   if (impl == 2) {
     if (!lee_tc_supported(n, g, lda, ldb)) { set_error("sc_lee_gemm: tcgen05 path unsupported for this shape"); return SC_ERR_UNSUPPORTED; }
     char* extra = static_cast<char*>(ws) + align_up(sizeof(double) * (size_t)p.splits * p.ldt * p.ldt, 256);
-    int rc = lee_tc_launch(A, lda, B, ldb, n, g, p, partial, extra, st);
-    if (rc) return rc;
+    return lee_tc_launch(A, lda, B, ldb, n, g, p, partial, extra, L, ldl, st);
   } else {
     dim3 grid(p.ldt / kTile, p.ldt / kTile, p.splits);
     lee_f64_kernel<<<grid, 256, 0, st>>>(A, lda, B, ldb, n, g, p.chunk, partial, p.ldt);

@@ -19,7 +19,9 @@ int lee_reduce(const double* partial, const LeePlan& p, int g, float* L, int64_t
 
 bool lee_tc_supported(int64_t n, int g, int64_t lda, int64_t ldb);
 size_t lee_tc_extra_workspace_bytes(int64_t n, int g);
+// Runs split + tcgen05 contraction + FP64 reduction and writes L (f32 [g, ldl]).
 int lee_tc_launch(const float* A, int64_t lda, const float* B, int64_t ldb, int64_t n, int g,
-                  const LeePlan& p, double* partial, void* extra_ws, cudaStream_t st);
+                  const LeePlan& p, double* partial, void* extra_ws, float* L, int64_t ldl,
+                  cudaStream_t st);
 
 }  // namespace sc

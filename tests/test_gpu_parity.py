@@ -434,6 +434,32 @@ def test_lee_matrix_all_pairs(api, eng, g0):
     np.testing.assert_allclose(sym, lagZ.T @ lagZ / X.shape[0], rtol=1e-5, atol=1e-6)
 
 
+@pytest.mark.parametrize("shape", [(64, 32), (1000, 50), (5003, 300), (20000, 1000), (9000, 1300)])
+def test_lee_gemm_tensor_core_path(eng, shape):
+    """impl 2 = tcgen05 kind::tf32 with 3xTF32 splitting.  The tensor core truncates when it adds
+    into its FP32 accumulator, which leaves a relative bias of up to ~5e-6 per 256-cell chunk (all-positive sums are the worst case); the bar is
+    1e-5 of the matrix maximum and 1e-5 median relative error.  impl 1 (FP64 accumulate) is exact."""
+    n, g = shape
+    torch.manual_seed(n + g)
+    ld = eng.padded_ld(g)
+    A = torch.zeros((n, ld), device="cuda")
+    B = torch.zeros((n, ld), device="cuda")
+    A[:, :g] = torch.randn((n, g), device="cuda")
+    B[:, :g] = 0.4 * torch.randn((n, g), device="cuda") + 0.1 * A[:, :g]
+    ref = A[:, :g].double().T @ B[:, :g].double()
+    exact = eng.lee_gemm(A, B, g, impl=1).double()
+    assert (exact - ref).abs().max() <= 2e-7 * ref.abs().max() + 1e-6  # only the FP32 rounding of the output
+    fast = eng.lee_gemm(A, B, g, impl=2).double()
+    err = (fast - ref).abs()
+    assert err.max() <= 1e-5 * ref.abs().max(), float(err.max())
+    assert (err / ref.abs().clamp_min(1e-12)).median() <= 1e-5
+    # symmetric variant (A == B): (WZ)ᵀ(WZ)
+    sym = eng.lee_gemm(B, B, g, impl=2).double()
+    refs = B[:, :g].double().T @ B[:, :g].double()
+    assert (sym - refs).abs().max() <= 1e-5 * refs.abs().max()
+    assert torch.equal(sym, sym.T)  or (sym - sym.T).abs().max() <= 1e-5 * refs.abs().max()
+
+
 # ---------------------------------------------------------------------------------------------
 # neighbourhood composition
 # ---------------------------------------------------------------------------------------------
