@@ -151,9 +151,12 @@ def device_step(engine, ac, coords_dev, X_dev, w, radius, seed, events=None, per
     else:
         graph, _, _ = engine.knn_graph(coords_dev, w["k"], device=coords_dev.device)
     mark("graph")
-    std = engine.zscore_dense(X_dev)
+    co = engine.spatial_order(coords_dev, device=coords_dev.device)
+    graph_s = engine.relabel_graph(graph, co)
+    mark("reorder")
+    std = engine.zscore_dense(X_dev, rows=co.order)
     mark("zscore")
-    num, den, lag, _ = engine.lag_moran(graph, std.Z, g, want_lag=True)
+    num, den, lag, _ = engine.lag_moran(graph_s, std.Z, g, want_lag=True)
     mark("lag")
     s0, s1, s2 = engine.graph_moments(graph)
     mark("moments")
@@ -181,7 +184,11 @@ def run_b200(args):
 
     import logging
 
-    logging.getLogger("spatialcore").setLevel(logging.ERROR)  # the reference logger writes to stdout
+    sc_log = logging.getLogger("spatialcore")  # the reference logger writes to stdout: keep stdout to the JSON line
+    sc_log.setLevel(logging.ERROR)
+    for h in sc_log.handlers:
+        if isinstance(h, logging.StreamHandler):
+            h.setStream(sys.stderr)
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))

@@ -85,6 +85,22 @@ SC_API int sc_grid_radius_fill(const double* coords, int64_t n, double r, const 
                         int32_t* indices, double* dist, void* scratch, size_t scratch_bytes,
                         void* ws, size_t ws_bytes, sc_stream_t stream);
 
+/* Spatial (grid) ordering of the cells: order_out i32[n] = original id of the cell at sorted position
+ * a; rank_out i32[n] or NULL = its inverse.  The statistics are sums over cells, so the library may
+ * hold Z / lag / the graph in this order: a row's neighbours are then close in memory. */
+SC_API size_t sc_spatial_order_workspace_bytes(int64_t n);
+SC_API int sc_spatial_order(const double* coords, int64_t n, int32_t* order_out, int32_t* rank_out,
+                            void* ws, size_t ws_bytes, sc_stream_t stream);
+
+/* Relabel a column-sorted CSR graph into that order: output row a = input row order[a], columns
+ * mapped through rank and re-sorted.  out_indptr i32[n+1] (CSR input only), out_indices i32[nnz],
+ * out_weights f32[nnz] iff weights != NULL. */
+SC_API size_t sc_graph_relabel_workspace_bytes(int64_t n);
+SC_API int sc_graph_relabel(const int32_t* indptr, const int32_t* indices, const float* weights,
+                            int64_t n, int k_fixed, const int32_t* order, const int32_t* rank,
+                            int32_t* out_indptr, int32_t* out_indices, float* out_weights, void* ws,
+                            size_t ws_bytes, sc_stream_t stream);
+
 /* Neighbourhood composition from an existing CSR graph (k_fixed>0 and indptr==NULL: every row has
  * k_fixed entries).  profile f32[n,n_types] raw counts. */
 SC_API int sc_nbhd_counts(const int32_t* indptr, const int32_t* indices, int64_t n, int k_fixed,
@@ -168,6 +184,22 @@ SC_API int sc_perm_null_values(const int32_t* indptr, const int32_t* indices, co
                         int64_t perm_offset, int n_perms, double* sims, const float* cell_obs,
                         int32_t* cell_cnt, int64_t ldc, void* ws, size_t ws_bytes,
                         sc_stream_t stream);
+
+/* Workspace for sc_perm_null_values: sc_perm_null_workspace_bytes plus, for wide matrices, room for
+ * one permuted copy of Zy (the materialised variant; a smaller workspace selects the register-gather
+ * kernel). */
+SC_API size_t sc_perm_null_values_workspace_bytes(int64_t n, int g);
+
+/* dst[a, 0:cols) = src[rows[a], 0:cols): put per-cell matrices into / out of the spatial order.
+ * cols, lds, ldd multiples of 4. */
+SC_API int sc_gather_rows(const float* src, int64_t lds, int64_t n, int64_t cols, const int32_t* rows,
+                          float* dst, int64_t ldd, sc_stream_t stream);
+
+/* Re-express replayed permutations of cell ids on sorted positions:
+ * out[p, a] = rank[perm_idx[p, order[a]]], so that Σ_a A_s[a]·B_s[out[p,a]] = Σ_i A[i]·B[perm_idx[p,i]]
+ * for A_s[a] = A[order[a]].  perm_idx, out i32[n_perms, n] (must not alias). */
+SC_API int sc_perm_conjugate(const int32_t* perm_idx, int64_t n, int n_perms, const int32_t* order,
+                             const int32_t* rank, int32_t* out, sc_stream_t stream);
 
 /* Materialise Philox permutation `perm_index` of [0,n) into out i32[n] (tests, replay export). */
 SC_API int sc_philox_permutation(uint64_t seed, int64_t perm_index, int64_t n, int32_t* out,

@@ -41,6 +41,13 @@ SIGNATURES = {
     "sc_perm_null_workspace_bytes": (_sz, [_i64, _i32]),
     "sc_perm_null_graph_rows": (_i32, [_vp, _i64, _vp, _i64, _i64, _i32, _i32, _vp, _u64, _i64, _i32, _vp, _vp, _sz, _vp]),
     "sc_perm_null_values": (_i32, [_vp, _vp, _vp, _i64, _i32, _vp, _vp, _i64, _i32, _i32, _vp, _u64, _i64, _i32, _vp, _vp, _vp, _i64, _vp, _sz, _vp]),
+    "sc_perm_null_values_workspace_bytes": (_sz, [_i64, _i32]),
+    "sc_gather_rows": (_i32, [_vp, _i64, _i64, _i64, _vp, _vp, _i64, _vp]),
+    "sc_perm_conjugate": (_i32, [_vp, _i64, _i32, _vp, _vp, _vp, _vp]),
+    "sc_spatial_order_workspace_bytes": (_sz, [_i64]),
+    "sc_spatial_order": (_i32, [_vp, _i64, _vp, _vp, _vp, _sz, _vp]),
+    "sc_graph_relabel_workspace_bytes": (_sz, [_i64]),
+    "sc_graph_relabel": (_i32, [_vp, _vp, _vp, _i64, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
     "sc_philox_permutation": (_i32, [_u64, _i64, _i64, _vp, _vp]),
     "sc_philox_permutation_host": (_i32, [_u64, _i64, _i64, _vp]),
     "sc_null_accumulate": (_i32, [_vp, _i32, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),

@@ -93,16 +93,29 @@ __device__ __forceinline__ int cell_coord(double v, double v0, double inv_h, int
   return min(max(c, 0), nmax - 1);
 }
 
+__device__ __forceinline__ uint32_t spread_bits16(uint32_t v) {
+  v &= 0xFFFFu;
+  v = (v | (v << 8)) & 0x00FF00FFu;
+  v = (v | (v << 4)) & 0x0F0F0F0Fu;
+  v = (v | (v << 2)) & 0x33333333u;
+  v = (v | (v << 1)) & 0x55555555u;
+  return v;
+}
+
+// morton: key = Z-order code of the cell (used only to produce a spatially compact ordering; the
+// query kernels need the row-major key so that a cell-row segment is one contiguous range).
 __global__ void assign_cells_kernel(const double* __restrict__ coords, int64_t n,
                                     const GridParams* __restrict__ gp, int32_t* __restrict__ keys,
-                                    int32_t* __restrict__ vals) {
+                                    int32_t* __restrict__ vals, int morton) {
   GridParams g = *gp;
+  const bool zorder = morton && g.nx <= 32768 && g.ny <= 32768;
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n;
        i += (int64_t)gridDim.x * blockDim.x) {
     double2 p = reinterpret_cast<const double2*>(coords)[i];
     int cx = cell_coord(p.x, g.x0, g.inv_h, g.nx);
     int cy = cell_coord(p.y, g.y0, g.inv_h, g.ny);
-    keys[i] = cy * g.nx + cx;
+    keys[i] = zorder ? (int32_t)(spread_bits16((uint32_t)cx) | (spread_bits16((uint32_t)cy) << 1))
+                     : cy * g.nx + cx;
     vals[i] = (int32_t)i;
   }
 }
@@ -149,8 +162,7 @@ static int key_bits(int max_cells) {
 static size_t binning_cub_bytes(int64_t n, int max_cells) {
   size_t bytes = 0;
   cub::DeviceRadixSort::SortPairs(nullptr, bytes, (const int32_t*)nullptr, (int32_t*)nullptr,
-                                  (const int32_t*)nullptr, (int32_t*)nullptr, (int)n, 0,
-                                  key_bits(max_cells));
+                                  (const int32_t*)nullptr, (int32_t*)nullptr, (int)n, 0, 31);
   size_t scan = 0;
   cub::DeviceScan::ExclusiveSum(nullptr, scan, (const int32_t*)nullptr, (int32_t*)nullptr,
                                 (int)(n + 1));
@@ -188,7 +200,7 @@ static bool carve_binning(Arena& a, int64_t n, Binning* b) {
 }
 
 static int run_binning(const double* coords, int64_t n, double pts_per_cell, double h_fixed,
-                       const Binning& b, cudaStream_t st) {
+                       const Binning& b, cudaStream_t st, bool order_only = false) {
   int blocks = (int)((n + 255) / 256);
   if (blocks > 148 * 8) blocks = 148 * 8;
   bbox_partial_kernel<<<kBboxBlocks, 256, 0, st>>>(coords, n, b.partial);
@@ -196,11 +208,12 @@ static int run_binning(const double* coords, int64_t n, double pts_per_cell, dou
   grid_setup_kernel<<<1, 1, 0, st>>>(b.partial, kBboxBlocks, n, pts_per_cell, h_fixed, b.max_cells,
                                      b.gp);
   SC_LAUNCH_OK();
-  assign_cells_kernel<<<blocks, 256, 0, st>>>(coords, n, b.gp, b.keys, b.vals);
+  assign_cells_kernel<<<blocks, 256, 0, st>>>(coords, n, b.gp, b.keys, b.vals, order_only ? 1 : 0);
   SC_LAUNCH_OK();
   size_t bytes = b.cub_bytes;
   SC_CUDA_OK(cub::DeviceRadixSort::SortPairs(b.cub_tmp, bytes, b.keys, b.keys_sorted, b.vals,
-                                             b.order, (int)n, 0, key_bits(b.max_cells), st));
+                                             b.order, (int)n, 0, order_only ? 31 : key_bits(b.max_cells), st));
+  if (order_only) return SC_OK;  // Z-order keys: no cell table
   cell_bounds_kernel<<<blocks, 256, 0, st>>>(b.keys_sorted, n, b.gp, b.cell_start);
   SC_LAUNCH_OK();
   gather_coords_kernel<<<blocks, 256, 0, st>>>(coords, b.order, n, b.xs, b.ys);
@@ -622,6 +635,59 @@ __global__ void moments_final_kernel(const double* __restrict__ p01, const doubl
   out[0] = s0; out[1] = s1; out[2] = s2;
 }
 
+
+// ------------------------------------------------------------------------------------------------
+// spatial (grid) order and graph relabelling
+//
+// The statistics are sums over cells, invariant under any relabelling of the cells.  Storing Z / lag
+// in grid order makes a row's neighbours close in memory, so the lag SpMM reads them from L1/L2
+// instead of HBM.  order[a] = original id of the cell at sorted position a; rank = its inverse.
+// ------------------------------------------------------------------------------------------------
+
+__global__ void invert_order_kernel(const int32_t* __restrict__ order, int64_t n,
+                                    int32_t* __restrict__ rank) {
+  for (int64_t a = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; a < n;
+       a += (int64_t)gridDim.x * blockDim.x)
+    rank[order[a]] = (int32_t)a;
+}
+
+__global__ void gather_degrees_kernel(const int32_t* __restrict__ indptr,
+                                      const int32_t* __restrict__ order, int64_t n,
+                                      int32_t* __restrict__ out) {
+  for (int64_t a = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; a <= n;
+       a += (int64_t)gridDim.x * blockDim.x) {
+    if (a == n) { out[a] = 0; continue; }
+    int i = order[a];
+    out[a] = indptr[i + 1] - indptr[i];
+  }
+}
+
+// warp per output row a (= original row order[a]): map columns through rank, rank-sort within the
+// row, write (weights follow their edge).
+__global__ void __launch_bounds__(256)
+relabel_rows_kernel(const int32_t* __restrict__ indptr, const int32_t* __restrict__ indices,
+                    const float* __restrict__ weights, int64_t n, int k_fixed,
+                    const int32_t* __restrict__ order, const int32_t* __restrict__ rank,
+                    const int32_t* __restrict__ out_indptr, int32_t* __restrict__ out_indices,
+                    float* __restrict__ out_weights) {
+  const int lane = threadIdx.x & 31;
+  const int64_t warps = (int64_t)gridDim.x * (blockDim.x >> 5);
+  for (int64_t a = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); a < n; a += warps) {
+    const int64_t i = order[a];
+    const int64_t sb = indptr ? indptr[i] : i * k_fixed;
+    const int64_t se = indptr ? indptr[i + 1] : sb + k_fixed;
+    const int64_t db = out_indptr ? out_indptr[a] : a * k_fixed;
+    const int deg = (int)(se - sb);
+    for (int e = lane; e < deg; e += 32) {
+      const int mine = rank[indices[sb + e]];
+      int rk = 0;
+      for (int j = 0; j < deg; ++j) rk += rank[indices[sb + j]] < mine;
+      out_indices[db + rk] = mine;
+      if (out_weights) out_weights[db + rk] = weights[sb + e];
+    }
+  }
+}
+
 constexpr int kMomentBlocks = 592;
 
 }  // namespace sc
@@ -681,6 +747,63 @@ extern "C" int sc_grid_knn(const double* coords, int64_t n, int k, int include_s
   else if (k <= 64) SC_KNN_LAUNCH(2);
   else SC_KNN_LAUNCH(4);
 #undef SC_KNN_LAUNCH
+  SC_LAUNCH_OK();
+  return SC_OK;
+}
+
+
+extern "C" size_t sc_spatial_order_workspace_bytes(int64_t n) {
+  if (n <= 0) return 256;
+  return binning_bytes(n) + 1024;
+}
+
+extern "C" int sc_spatial_order(const double* coords, int64_t n, int32_t* order_out,
+                                int32_t* rank_out, void* ws, size_t ws_bytes, sc_stream_t stream) {
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  SC_CHECK_ARG(coords && order_out && ws, "sc_spatial_order: null argument");
+  SC_CHECK_ARG(n >= 1 && n < (1ll << 31) - 2048, "sc_spatial_order: n out of range");
+  if (ws_bytes < sc_spatial_order_workspace_bytes(n)) { set_error("sc_spatial_order: workspace too small"); return SC_ERR_WORKSPACE; }
+  Arena arena(ws, ws_bytes);
+  Binning b;
+  if (!carve_binning(arena, n, &b)) { set_error("sc_spatial_order: carve failed"); return SC_ERR_WORKSPACE; }
+  int rc = run_binning(coords, n, 8.0, 0.0, b, st, /*order_only=*/true);
+  if (rc) return rc;
+  SC_CUDA_OK(cudaMemcpyAsync(order_out, b.order, sizeof(int32_t) * n, cudaMemcpyDeviceToDevice, st));
+  if (rank_out) {
+    int blocks = (int)((n + 255) / 256 > 148 * 8 ? 148 * 8 : (n + 255) / 256);
+    invert_order_kernel<<<blocks, 256, 0, st>>>(order_out, n, rank_out);
+    SC_LAUNCH_OK();
+  }
+  return SC_OK;
+}
+
+extern "C" size_t sc_graph_relabel_workspace_bytes(int64_t n) {
+  size_t scan = 0;
+  cub::DeviceScan::ExclusiveSum(nullptr, scan, (const int32_t*)nullptr, (int32_t*)nullptr, (int)(n + 1));
+  return align_up(scan, 256) + 512;
+}
+
+extern "C" int sc_graph_relabel(const int32_t* indptr, const int32_t* indices, const float* weights,
+                                int64_t n, int k_fixed, const int32_t* order, const int32_t* rank,
+                                int32_t* out_indptr, int32_t* out_indices, float* out_weights,
+                                void* ws, size_t ws_bytes, sc_stream_t stream) {
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  SC_CHECK_ARG(indices && order && rank && out_indices, "sc_graph_relabel: null argument");
+  SC_CHECK_ARG(indptr || k_fixed > 0, "sc_graph_relabel: need indptr or k_fixed");
+  SC_CHECK_ARG(!indptr || out_indptr, "sc_graph_relabel: CSR input needs out_indptr");
+  SC_CHECK_ARG((weights == nullptr) == (out_weights == nullptr), "sc_graph_relabel: weights and out_weights go together");
+  int blocks = (int)((n + 255) / 256 > 148 * 8 ? 148 * 8 : (n + 255) / 256);
+  if (indptr) {
+    if (!ws || ws_bytes < sc_graph_relabel_workspace_bytes(n)) { set_error("sc_graph_relabel: workspace too small"); return SC_ERR_WORKSPACE; }
+    gather_degrees_kernel<<<blocks, 256, 0, st>>>(indptr, order, n, out_indptr);
+    SC_LAUNCH_OK();
+    size_t bytes = ws_bytes;
+    SC_CUDA_OK(cub::DeviceScan::ExclusiveSum(ws, bytes, out_indptr, out_indptr, (int)(n + 1), st));
+  }
+  int64_t want = (n + 7) / 8;
+  int rb = (int)(want > 148 * 16 ? 148 * 16 : (want < 1 ? 1 : want));
+  relabel_rows_kernel<<<rb, 256, 0, st>>>(indptr, indices, weights, n, k_fixed, order, rank,
+                                          indptr ? out_indptr : nullptr, out_indices, out_weights);
   SC_LAUNCH_OK();
   return SC_OK;
 }

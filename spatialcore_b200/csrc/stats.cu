@@ -182,63 +182,93 @@ __global__ void reduce_partials_kernel(const double* __restrict__ partial, int n
 // spatial lag + Moran numerator / denominator
 // ------------------------------------------------------------------------------------------------
 
+// Geometry: a CTA owns contiguous chunks of kLagChunkRows rows and one 32-gene column block
+// (8 lanes x float4 per row, 32 rows per pass).  With the cells in spatial order the neighbour rows
+// of a chunk form a small working set (~500 rows x 128 B) that stays in L1, so Z is read from HBM
+// about once instead of once per edge.  blockIdx.x = column block (fastest: the column blocks of
+// one chunk run together and share the CSR indices through L2), blockIdx.y = chunk group.
+constexpr int kLagColQuads = 8;
+constexpr int kLagRowsPerPass = kStatThreads / kLagColQuads;  // 32
+constexpr int kLagChunkRows = 256;
+
 template <bool HAS_W>
 __global__ void __launch_bounds__(kStatThreads)
-lag_moran_kernel(const int32_t* __restrict__ indptr, const int32_t* __restrict__ indices,
-                 const float* __restrict__ weights, int64_t n, int k_fixed,
-                 const float* __restrict__ Z, int64_t ldz, float* __restrict__ lag,
-                 float* __restrict__ local, int64_t ldl, double* __restrict__ partial, int wpr) {
-  __shared__ double sh[kStatWarps * 32 * 4];
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int rphase = warp / wpr, rpp = kStatWarps / wpr;
-  const int64_t col = ((int64_t)blockIdx.y * 256 + (warp % wpr) * 32 + lane) * 4;
+lag_stat_kernel(const int32_t* __restrict__ indptr, const int32_t* __restrict__ indices,
+                const float* __restrict__ weights, int64_t n, int k_fixed,
+                const float* __restrict__ Zself, const float* __restrict__ Zlag, int64_t ldz,
+                float* __restrict__ lag, float* __restrict__ local, int64_t ldl,
+                double* __restrict__ partial, const float* __restrict__ cell_obs,
+                int32_t* __restrict__ cell_cnt, int64_t ldc, int64_t n_chunks) {
+  __shared__ double sh[2][kLagRowsPerPass][kLagColQuads][4];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int q = lane & (kLagColQuads - 1);
+  const int rslot = warp * (32 / kLagColQuads) + (lane >> 3);
+  const int64_t col = ((int64_t)blockIdx.x * kLagColQuads + q) * 4;
   const bool active = col < ldz;
+  const float* Zs = Zself ? Zself : Zlag;
   double num[4] = {0, 0, 0, 0}, den[4] = {0, 0, 0, 0};
 
-  for (int64_t row = (int64_t)blockIdx.x * rpp + rphase; row < n; row += (int64_t)gridDim.x * rpp) {
-    const int64_t b = indptr ? indptr[row] : row * k_fixed;
-    const int64_t e = indptr ? indptr[row + 1] : b + k_fixed;
-    if (!active) continue;
-    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-    int64_t t = b;
-    for (; t + 4 <= e; t += 4) {
-      int j0 = indices[t], j1 = indices[t + 1], j2 = indices[t + 2], j3 = indices[t + 3];
-      float4 v0 = ldg4(Z + (int64_t)j0 * ldz + col);
-      float4 v1 = ldg4(Z + (int64_t)j1 * ldz + col);
-      float4 v2 = ldg4(Z + (int64_t)j2 * ldz + col);
-      float4 v3 = ldg4(Z + (int64_t)j3 * ldz + col);
-      float w0 = 1.f, w1 = 1.f, w2 = 1.f, w3 = 1.f;
-      if (HAS_W) { w0 = weights[t]; w1 = weights[t + 1]; w2 = weights[t + 2]; w3 = weights[t + 3]; }
-      acc.x += w0 * v0.x + w1 * v1.x + w2 * v2.x + w3 * v3.x;
-      acc.y += w0 * v0.y + w1 * v1.y + w2 * v2.y + w3 * v3.y;
-      acc.z += w0 * v0.z + w1 * v1.z + w2 * v2.z + w3 * v3.z;
-      acc.w += w0 * v0.w + w1 * v1.w + w2 * v2.w + w3 * v3.w;
+  for (int64_t chunk = blockIdx.y; chunk < n_chunks; chunk += gridDim.y) {
+    const int64_t r0 = chunk * kLagChunkRows;
+#pragma unroll 1
+    for (int pass = 0; pass < kLagChunkRows / kLagRowsPerPass; ++pass) {
+      const int64_t row = r0 + pass * kLagRowsPerPass + rslot;
+      if (row >= n || !active) continue;
+      const int64_t b = indptr ? indptr[row] : row * k_fixed;
+      const int64_t e = indptr ? indptr[row + 1] : b + k_fixed;
+      float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+      int64_t t = b;
+      for (; t + 4 <= e; t += 4) {
+        const int j0 = indices[t], j1 = indices[t + 1], j2 = indices[t + 2], j3 = indices[t + 3];
+        const float4 v0 = ldg4(Zlag + (int64_t)j0 * ldz + col);
+        const float4 v1 = ldg4(Zlag + (int64_t)j1 * ldz + col);
+        const float4 v2 = ldg4(Zlag + (int64_t)j2 * ldz + col);
+        const float4 v3 = ldg4(Zlag + (int64_t)j3 * ldz + col);
+        float w0 = 1.f, w1 = 1.f, w2 = 1.f, w3 = 1.f;
+        if (HAS_W) { w0 = weights[t]; w1 = weights[t + 1]; w2 = weights[t + 2]; w3 = weights[t + 3]; }
+        acc.x += w0 * v0.x + w1 * v1.x + w2 * v2.x + w3 * v3.x;
+        acc.y += w0 * v0.y + w1 * v1.y + w2 * v2.y + w3 * v3.y;
+        acc.z += w0 * v0.z + w1 * v1.z + w2 * v2.z + w3 * v3.z;
+        acc.w += w0 * v0.w + w1 * v1.w + w2 * v2.w + w3 * v3.w;
+      }
+      for (; t < e; ++t) {
+        const float4 v = ldg4(Zlag + (int64_t)indices[t] * ldz + col);
+        const float w = HAS_W ? weights[t] : 1.f;
+        acc.x += w * v.x; acc.y += w * v.y; acc.z += w * v.z; acc.w += w * v.w;
+      }
+      if (!HAS_W) {
+        const float inv = (e > b) ? 1.f / (float)(e - b) : 0.f;
+        acc.x *= inv; acc.y *= inv; acc.z *= inv; acc.w *= inv;
+      }
+      const float4 z = ldg4(Zs + row * ldz + col);
+      const float4 loc = make_float4(z.x * acc.x, z.y * acc.y, z.z * acc.z, z.w * acc.w);
+      if (lag) *reinterpret_cast<float4*>(lag + row * ldl + col) = acc;
+      if (local) *reinterpret_cast<float4*>(local + row * ldl + col) = loc;
+      if (cell_cnt) {
+        const float4 o = ldg4(cell_obs + row * ldc + col);
+        int4* cp = reinterpret_cast<int4*>(cell_cnt + row * ldc + col);
+        int4 c = *cp;
+        c.x += fabsf(loc.x) >= fabsf(o.x); c.y += fabsf(loc.y) >= fabsf(o.y);
+        c.z += fabsf(loc.z) >= fabsf(o.z); c.w += fabsf(loc.w) >= fabsf(o.w);
+        *cp = c;
+      }
+      num[0] += (double)z.x * (double)acc.x; den[0] += (double)z.x * (double)z.x;
+      num[1] += (double)z.y * (double)acc.y; den[1] += (double)z.y * (double)z.y;
+      num[2] += (double)z.z * (double)acc.z; den[2] += (double)z.z * (double)z.z;
+      num[3] += (double)z.w * (double)acc.w; den[3] += (double)z.w * (double)z.w;
     }
-    for (; t < e; ++t) {
-      float4 v = ldg4(Z + (int64_t)indices[t] * ldz + col);
-      float w = HAS_W ? weights[t] : 1.f;
-      acc.x += w * v.x; acc.y += w * v.y; acc.z += w * v.z; acc.w += w * v.w;
-    }
-    if (!HAS_W) {
-      float inv = (e > b) ? 1.f / (float)(e - b) : 0.f;
-      acc.x *= inv; acc.y *= inv; acc.z *= inv; acc.w *= inv;
-    }
-    const float4 z = ldg4(Z + row * ldz + col);
-    if (lag) *reinterpret_cast<float4*>(lag + row * ldl + col) = acc;
-    if (local)
-      *reinterpret_cast<float4*>(local + row * ldl + col) =
-          make_float4(z.x * acc.x, z.y * acc.y, z.z * acc.z, z.w * acc.w);
-    num[0] += (double)z.x * (double)acc.x; den[0] += (double)z.x * (double)z.x;
-    num[1] += (double)z.y * (double)acc.y; den[1] += (double)z.y * (double)z.y;
-    num[2] += (double)z.z * (double)acc.z; den[2] += (double)z.z * (double)z.z;
-    num[3] += (double)z.w * (double)acc.w; den[3] += (double)z.w * (double)z.w;
   }
-  reduce_row_phases(num, wpr, sh);
-  reduce_row_phases(den, wpr, sh);
-  if (rphase == 0 && active) {
-    double* p = partial + ((int64_t)blockIdx.x * 2) * ldz + col;
 #pragma unroll
-    for (int c = 0; c < 4; ++c) { p[c] = num[c]; p[ldz + c] = den[c]; }
+  for (int c = 0; c < 4; ++c) { sh[0][rslot][q][c] = num[c]; sh[1][rslot][q][c] = den[c]; }
+  __syncthreads();
+  if (rslot == 0 && active) {
+    double* p = partial + ((int64_t)blockIdx.y * 2) * ldz + col;
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+      double a = 0, d = 0;
+      for (int r = 0; r < kLagRowsPerPass; ++r) { a += sh[0][r][q][c]; d += sh[1][r][q][c]; }
+      p[c] = a; p[ldz + c] = d;
+    }
   }
 }
 
@@ -616,6 +646,54 @@ perm_values_kernel(const int32_t* __restrict__ indptr, const int32_t* __restrict
   }
 }
 
+// out[a, :] = Z[π(a), :]  (materialised permuted copy for the value-permuting null).  Warp per row;
+// lane 0 resolves the index once.
+__global__ void __launch_bounds__(256)
+permute_rows_kernel(const float* __restrict__ Z, int64_t ld, int64_t n,
+                    const __grid_constant__ PermBatch pb, float* __restrict__ out) {
+  __shared__ uint32_t s_keys[kMaxPermBatch][kFeistelRounds];
+  for (int t = threadIdx.x; t < kMaxPermBatch * kFeistelRounds; t += blockDim.x)
+    s_keys[t / kFeistelRounds][t % kFeistelRounds] = pb.keys[t / kFeistelRounds][t % kFeistelRounds];
+  __syncthreads();
+  const int lane = threadIdx.x & 31;
+  const int64_t warps = (int64_t)gridDim.x * (blockDim.x >> 5);
+  const int64_t Q = ld / 4;
+  for (int64_t a = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); a < n; a += warps) {
+    int src = 0;
+    if (lane == 0) src = perm_lookup(pb, s_keys, 0, a, n);
+    src = __shfl_sync(kFull, src, 0);
+    const float4* in = reinterpret_cast<const float4*>(Z + (int64_t)src * ld);
+    float4* o = reinterpret_cast<float4*>(out + a * ld);
+    for (int64_t qq = lane; qq < Q; qq += 32) o[qq] = __ldg(in + qq);
+  }
+}
+
+// dst[a, 0:cols) = src[rows[a], 0:cols)  (cols % 4 == 0).  Warp per row.
+__global__ void __launch_bounds__(256)
+gather_rows_kernel(const float* __restrict__ src, int64_t lds, int64_t n, int64_t cols,
+                   const int32_t* __restrict__ rows, float* __restrict__ dst, int64_t ldd) {
+  const int lane = threadIdx.x & 31;
+  const int64_t warps = (int64_t)gridDim.x * (blockDim.x >> 5);
+  const int64_t Q = cols / 4;
+  for (int64_t a = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); a < n; a += warps) {
+    const float4* in = reinterpret_cast<const float4*>(src + (int64_t)rows[a] * lds);
+    float4* o = reinterpret_cast<float4*>(dst + a * ldd);
+    for (int64_t qq = lane; qq < Q; qq += 32) o[qq] = __ldg(in + qq);
+  }
+}
+
+// out[p, a] = rank[perm[p, order[a]]]: a permutation of cell ids re-expressed on sorted positions.
+__global__ void perm_conjugate_kernel(const int32_t* __restrict__ perm, int64_t n, int n_perms,
+                                      const int32_t* __restrict__ order,
+                                      const int32_t* __restrict__ rank, int32_t* __restrict__ out) {
+  const int64_t total = n * n_perms;
+  for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < total;
+       t += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t p = t / n, a = t - p * n;
+    out[t] = rank[perm[p * n + order[a]]];
+  }
+}
+
 __global__ void philox_permutation_kernel(PermDomain dom, const __grid_constant__ PermBatch pb,
                                           int32_t* __restrict__ out) {
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < dom.n;
@@ -668,6 +746,28 @@ static void fill_batch(PermBatch* pb, int source, const int32_t* perm_idx, uint6
 }
 
 constexpr int kMaxStatBlocks = 148 * 8;
+
+// Launch lag_stat_kernel; *by_out = number of partial rows written ([by][2][ldz] doubles).
+static int launch_lag_stat(const int32_t* indptr, const int32_t* indices, const float* weights,
+                           int64_t n, int k_fixed, const float* Zself, const float* Zlag, int64_t ldz,
+                           float* lag, float* local, int64_t ldl, double* partial,
+                           const float* cell_obs, int32_t* cell_cnt, int64_t ldc, int* by_out,
+                           cudaStream_t st) {
+  const int bx = (int)((ldz / 4 + kLagColQuads - 1) / kLagColQuads);
+  const int64_t n_chunks = (n + kLagChunkRows - 1) / kLagChunkRows;
+  int64_t by = ((int64_t)sm_count() * 8 + bx - 1) / bx;
+  if (by > n_chunks) by = n_chunks;
+  if (by > kMaxStatBlocks) by = kMaxStatBlocks;
+  if (by < 1) by = 1;
+  dim3 grid(bx, (unsigned)by);
+  if (weights)
+    lag_stat_kernel<true><<<grid, kStatThreads, 0, st>>>(indptr, indices, weights, n, k_fixed, Zself, Zlag, ldz, lag, local, ldl, partial, cell_obs, cell_cnt, ldc, n_chunks);
+  else
+    lag_stat_kernel<false><<<grid, kStatThreads, 0, st>>>(indptr, indices, weights, n, k_fixed, Zself, Zlag, ldz, lag, local, ldl, partial, cell_obs, cell_cnt, ldc, n_chunks);
+  SC_LAUNCH_OK();
+  *by_out = (int)by;
+  return SC_OK;
+}
 
 }  // namespace sc
 
@@ -764,20 +864,12 @@ extern "C" int sc_csr_lag_moran(const int32_t* indptr, const int32_t* indices,
                "sc_csr_lag_moran: ldz must be a multiple of 4 in [g, round_up(g,32)]");
   SC_CHECK_ARG((!lag && !local) || (ldl % 4 == 0 && ldl >= ldz), "sc_csr_lag_moran: ldl must be a multiple of 4 and >= ldz");
   if (ws_bytes < sc_csr_lag_moran_workspace_bytes(n, g)) { set_error("sc_csr_lag_moran: workspace too small"); return SC_ERR_WORKSPACE; }
-  RowGeom rg = row_geom(ldz);
-  const void* kern = weights ? (const void*)lag_moran_kernel<true> : (const void*)lag_moran_kernel<false>;
-  int bx = persistent_blocks(kern, kStatThreads, 0);
-  int64_t max_bx = (n + rg.rpp - 1) / rg.rpp;
-  if (bx > max_bx) bx = (int)max_bx;
-  if (bx > kMaxStatBlocks) bx = kMaxStatBlocks;
-  int by = (int)((ldz / 4 + 255) / 256);
   double* partial = static_cast<double*>(ws);
-  dim3 grid(bx, by);
-  if (weights)
-    lag_moran_kernel<true><<<grid, kStatThreads, 0, st>>>(indptr, indices, weights, n, k_fixed, Z, ldz, lag, local, ldl, partial, rg.wpr);
-  else
-    lag_moran_kernel<false><<<grid, kStatThreads, 0, st>>>(indptr, indices, weights, n, k_fixed, Z, ldz, lag, local, ldl, partial, rg.wpr);
-  SC_LAUNCH_OK();
+  int by = 0;
+  int rc = launch_lag_stat(indptr, indices, weights, n, k_fixed, nullptr, Z, ldz, lag, local, ldl, partial,
+                           nullptr, nullptr, 0, &by, st);
+  if (rc) return rc;
+  const int bx = by;
   // partial rows: [block][0]=num, [block][1]=den  -> view as (nblocks, rows=2, ldp=ldz)
   reduce_partials_kernel<<<dim3((g + 127) / 128, 1), 128, 0, st>>>(partial, bx, 2, ldz, g, num, g);
   SC_LAUNCH_OK();
@@ -938,6 +1030,42 @@ static int launch_perm_values(const int32_t* indptr, const int32_t* indices, con
   return SC_OK;
 }
 
+// Wide matrices: materialise Zp = Zy[π_p(.)] (one streaming row gather) and run the lag kernel on it.
+// With the cells in spatial order the lag kernel reads Zp about once, so a permutation costs ~12·N·ld
+// bytes of HBM traffic instead of (k+1) random row gathers per cell.
+constexpr int kValuesMaterializeMinLd = 32;
+
+extern "C" size_t sc_perm_null_values_workspace_bytes(int64_t n, int g) {
+  size_t base = sc_perm_null_workspace_bytes(n, g);
+  if (max_ld(g) >= (size_t)kValuesMaterializeMinLd && n > 0)
+    base += align_up(sizeof(float) * (size_t)n * max_ld(g), 256);
+  return base;
+}
+
+static int launch_perm_values_materialised(const int32_t* indptr, const int32_t* indices,
+                                           const float* weights, int64_t n, int k_fixed,
+                                           const float* Zx, const float* Zy, int64_t ldz, int g,
+                                           int source, const int32_t* perm_idx, uint64_t seed,
+                                           int64_t perm_offset, int n_perms, double* sims,
+                                           const float* cell_obs, int32_t* cell_cnt, int64_t ldc,
+                                           double* partial, float* Zp, cudaStream_t st) {
+  int64_t want = (n + 7) / 8;
+  const int pblocks = (int)(want > sm_count() * 16 ? sm_count() * 16 : (want < 1 ? 1 : want));
+  for (int p = 0; p < n_perms; ++p) {
+    PermBatch pb;
+    fill_batch(&pb, source, perm_idx, seed, perm_offset + p, p, 1, n);
+    permute_rows_kernel<<<pblocks, 256, 0, st>>>(Zy, ldz, n, pb, Zp);
+    SC_LAUNCH_OK();
+    int by = 0;
+    int rc = launch_lag_stat(indptr, indices, weights, n, k_fixed, Zx, Zp, ldz, nullptr, nullptr, 0,
+                             partial, cell_obs, cell_cnt, ldc, &by, st);
+    if (rc) return rc;
+    reduce_partials_kernel<<<dim3((g + 127) / 128, 1), 128, 0, st>>>(partial, by, 2, ldz, g, sims + (int64_t)p * g, g);
+    SC_LAUNCH_OK();
+  }
+  return SC_OK;
+}
+
 extern "C" int sc_perm_null_values(const int32_t* indptr, const int32_t* indices,
                                    const float* weights, int64_t n, int k_fixed, const float* Zx,
                                    const float* Zy, int64_t ldz, int g, int source,
@@ -956,9 +1084,45 @@ extern "C" int sc_perm_null_values(const int32_t* indptr, const int32_t* indices
   SC_CHECK_ARG(!cell_cnt || (ldc % 4 == 0 && ldc >= ldz), "sc_perm_null_values: ldc must be a multiple of 4 and >= ldz");
   if (ws_bytes < sc_perm_null_workspace_bytes(n, g)) { set_error("sc_perm_null_values: workspace too small"); return SC_ERR_WORKSPACE; }
   double* partial = static_cast<double*>(ws);
+  const size_t base = sc_perm_null_workspace_bytes(n, g);
+  const size_t zp_bytes = align_up(sizeof(float) * (size_t)n * (size_t)ldz, 256);
+  const char* force = getenv("SC_PERM_VALUES_VARIANT");  // "gather" forces the register-gather kernel
+  const bool allow = !(force && !strcmp(force, "gather"));
+  if (allow && ldz >= kValuesMaterializeMinLd && ws_bytes >= base + zp_bytes) {
+    float* Zp = reinterpret_cast<float*>(static_cast<char*>(ws) + base);
+    return launch_perm_values_materialised(indptr, indices, weights, n, k_fixed, Zx, Zy, ldz, g, source,
+                                           perm_idx, seed, perm_offset, n_perms, sims, cell_obs,
+                                           cell_cnt, ldc, partial, Zp, st);
+  }
   if (weights)
     return launch_perm_values<4, true>(indptr, indices, weights, n, k_fixed, Zx, Zy, ldz, g, source, perm_idx, seed, perm_offset, n_perms, sims, cell_obs, cell_cnt, ldc, partial, st);
   return launch_perm_values<4, false>(indptr, indices, weights, n, k_fixed, Zx, Zy, ldz, g, source, perm_idx, seed, perm_offset, n_perms, sims, cell_obs, cell_cnt, ldc, partial, st);
+}
+
+extern "C" int sc_gather_rows(const float* src, int64_t lds, int64_t n, int64_t cols,
+                              const int32_t* rows, float* dst, int64_t ldd, sc_stream_t stream) {
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  SC_CHECK_ARG(src && rows && dst, "sc_gather_rows: null argument");
+  SC_CHECK_ARG(n >= 1 && cols >= 4 && cols % 4 == 0 && lds >= cols && ldd >= cols && lds % 4 == 0 && ldd % 4 == 0,
+               "sc_gather_rows: cols, lds, ldd must be multiples of 4 with lds, ldd >= cols");
+  int64_t want = (n + 7) / 8;
+  int blocks = (int)(want > sm_count() * 16 ? sm_count() * 16 : want);
+  gather_rows_kernel<<<blocks, 256, 0, st>>>(src, lds, n, cols, rows, dst, ldd);
+  SC_LAUNCH_OK();
+  return SC_OK;
+}
+
+extern "C" int sc_perm_conjugate(const int32_t* perm_idx, int64_t n, int n_perms,
+                                 const int32_t* order, const int32_t* rank, int32_t* out,
+                                 sc_stream_t stream) {
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  SC_CHECK_ARG(perm_idx && order && rank && out && perm_idx != out, "sc_perm_conjugate: null or aliased argument");
+  SC_CHECK_ARG(n >= 1 && n_perms >= 1, "sc_perm_conjugate: empty input");
+  int64_t want = (n * n_perms + 255) / 256;
+  int blocks = (int)(want > sm_count() * 16 ? sm_count() * 16 : want);
+  perm_conjugate_kernel<<<blocks, 256, 0, st>>>(perm_idx, n, n_perms, order, rank, out);
+  SC_LAUNCH_OK();
+  return SC_OK;
 }
 
 extern "C" int sc_philox_permutation(uint64_t seed, int64_t perm_index, int64_t n, int32_t* out,

@@ -195,6 +195,70 @@ def radius_graph(
     return DeviceGraph(n=n, indices=indices, indptr=indptr, dist=dist), profile
 
 
+@dataclass
+class CellOrder:
+    """A spatially compact (Z-order) relabelling of the cells.  ``order[a]`` = original id of the cell
+    at sorted position ``a``; ``rank`` is the inverse.  Every statistic on this path is a sum over
+    cells, so Z / lag / the graph may be held in this order; a row's neighbours are then close in
+    memory and the lag kernel reads Z about once instead of once per edge."""
+
+    order: torch.Tensor  # int32 [n]
+    rank: torch.Tensor  # int32 [n]
+
+
+def spatial_order(coords, device="cuda") -> CellOrder:
+    """``sc_spatial_order``: Z-order curve over a uniform grid of the coordinates."""
+    c = _coords_tensor(coords, device)
+    n = c.shape[0]
+    L = _lib.lib()
+    order = torch.empty(n, dtype=torch.int32, device=c.device)
+    rank = torch.empty(n, dtype=torch.int32, device=c.device)
+    ws = _workspace(L.sc_spatial_order_workspace_bytes(n), c.device)
+    check(L.sc_spatial_order(_ptr(c), n, _ptr(order), _ptr(rank), _ptr(ws), ws.numel(), _stream()), "sc_spatial_order")
+    _count(6)
+    return CellOrder(order=order, rank=rank)
+
+
+def relabel_graph(graph: DeviceGraph, co: CellOrder) -> DeviceGraph:
+    """``sc_graph_relabel``: the same graph on sorted positions (rows permuted, columns mapped and
+    re-sorted; weights follow their edges)."""
+    L = _lib.lib()
+    dev = graph.indices.device
+    out_idx = torch.empty_like(graph.indices)
+    out_ptr = torch.empty_like(graph.indptr) if graph.indptr is not None else None
+    out_w = torch.empty_like(graph.weights) if graph.weights is not None else None
+    ws = _workspace(L.sc_graph_relabel_workspace_bytes(graph.n), dev)
+    check(
+        L.sc_graph_relabel(_ptr(graph.indptr), _ptr(graph.indices), _ptr(graph.weights), graph.n, int(graph.k_fixed),
+                           _ptr(co.order), _ptr(co.rank), _ptr(out_ptr), _ptr(out_idx), _ptr(out_w), _ptr(ws), ws.numel(),
+                           _stream()),
+        "sc_graph_relabel",
+    )
+    _count(3 if graph.indptr is not None else 1)
+    return DeviceGraph(n=graph.n, indices=out_idx, indptr=out_ptr, k_fixed=graph.k_fixed, weights=out_w)
+
+
+def gather_rows(src: torch.Tensor, rows: torch.Tensor) -> torch.Tensor:
+    """``sc_gather_rows``: ``dst[a] = src[rows[a]]`` for a float32 [n, ld] matrix (ld % 4 == 0)."""
+    _require_cuda(src, "src")
+    L = _lib.lib()
+    n, ld = src.shape
+    dst = torch.empty_like(src)
+    check(L.sc_gather_rows(_ptr(src), src.stride(0), n, ld, _ptr(rows), _ptr(dst), ld, _stream()), "sc_gather_rows")
+    _count()
+    return dst
+
+
+def conjugate_perms(perm_idx: torch.Tensor, co: CellOrder) -> torch.Tensor:
+    """``sc_perm_conjugate``: replayed permutations of cell ids -> permutations of sorted positions."""
+    L = _lib.lib()
+    P, n = perm_idx.shape
+    out = torch.empty_like(perm_idx)
+    check(L.sc_perm_conjugate(_ptr(perm_idx), n, P, _ptr(co.order), _ptr(co.rank), _ptr(out), _stream()), "sc_perm_conjugate")
+    _count()
+    return out
+
+
 def graph_from_scipy(adj, device="cuda", use_weights: bool = False) -> DeviceGraph:
     """Upload an existing scipy CSR connectivity matrix (``use_existing_graph`` path)."""
     from scipy import sparse
@@ -415,7 +479,7 @@ def perm_null_values(graph: DeviceGraph, Zy: torch.Tensor, g: int, n_perms: int,
     n, ld = Zy.shape
     source, pidx = _perm_source(perm_idx, n, n_perms)
     sims = torch.empty((n_perms, g), dtype=torch.float64, device=Zy.device)
-    ws = _workspace(L.sc_perm_null_workspace_bytes(n, g), Zy.device)
+    ws = _workspace(L.sc_perm_null_values_workspace_bytes(n, g), Zy.device)
     ldc = cell_cnt.shape[1] if cell_cnt is not None else 0
     check(
         L.sc_perm_null_values(_ptr(graph.indptr), _ptr(graph.indices), _ptr(graph.weights), n, int(graph.k_fixed),
@@ -424,7 +488,7 @@ def perm_null_values(graph: DeviceGraph, Zy: torch.Tensor, g: int, n_perms: int,
                               _stream()),
         "sc_perm_null_values",
     )
-    _count(2 * ((n_perms + 3) // 4))
+    _count(3 * n_perms if ld >= 32 else 2 * ((n_perms + 3) // 4))
     return sims
 
 

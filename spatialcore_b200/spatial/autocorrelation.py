@@ -82,9 +82,11 @@ def _gene_positions(adata, names: List[str]) -> Optional[np.ndarray]:
     return pos
 
 
-def _standardize(adata, layer, names: List[str], device) -> engine.Standardized:
+def _standardize(adata, layer, names: List[str], device, rows: Optional[torch.Tensor] = None) -> engine.Standardized:
+    """z-scored expression of ``names`` on the device; ``rows`` (a ``CellOrder.order``) writes the
+    matrix in spatial order."""
     Xd, cols = engine.expression_to_device(_expression(adata, layer), _gene_positions(adata, names), device)
-    return engine.zscore_dense(Xd, cols=cols)
+    return engine.zscore_dense(Xd, cols=cols, rows=rows)
 
 
 def _pick_perm_source(perm_source: str, n: int, n_perms: int) -> str:
@@ -228,10 +230,12 @@ class MoranNull:
 
 def moran_graph_rows_null(Z: torch.Tensor, lag: torch.Tensor, g: int, scale: torch.Tensor, obs: torch.Tensor,
                           n_perms: int, seed: int, source: str, null: MoranNull, perm_range: Tuple[int, int],
-                          keep_sims: bool = False):
+                          keep_sims: bool = False, cell_order: Optional[engine.CellOrder] = None):
     """Run permutations ``perm_range`` of the graph-row null and fold them into ``null``.
     Philox permutations are addressed by global index, so any partition of ``[0, P)`` over ranks
-    or batches yields the same counts."""
+    or batches yields the same counts.  ``cell_order``: Z and lag are stored in that order; replayed
+    permutations (of cell ids) are re-expressed on sorted positions, Philox permutations act on the
+    stored positions directly."""
     n = Z.shape[0]
     first, last = perm_range
     sims_all = []
@@ -252,6 +256,8 @@ def moran_graph_rows_null(Z: torch.Tensor, lag: torch.Tensor, g: int, scale: tor
         for _ in range(first):
             rng.permutation(n)
         for _, idx in _replay_chunks(rng, n, last - first, Z.device):
+            if cell_order is not None:
+                idx = engine.conjugate_perms(idx, cell_order)
             sims = engine.perm_null_graph_rows(Z, lag, g, idx.shape[0], perm_idx=idx)
             engine.null_accumulate(sims, scale, obs, null.cnt_ge, null.cnt_abs_ge, null.sum, null.sumsq)
             if keep_sims:
@@ -317,8 +323,11 @@ def morans_i(
     else:
         graph = spatial_neighbors(adata, n_neighbors, radius, spatial_key, device=device, write=write_graph)
 
-    std = _standardize(adata, layer, names, device)
-    num, den, lag, _ = engine.lag_moran(graph, std.Z, g, want_lag=n_permutations > 0)
+    # cells are held in spatial (Z-curve) order on the device: every quantity below is a sum over cells
+    co = engine.spatial_order(adata.obsm[spatial_key], device=device)
+    graph_s = engine.relabel_graph(graph, co)
+    std = _standardize(adata, layer, names, device, rows=co.order)
+    num, den, lag, _ = engine.lag_moran(graph_s, std.Z, g, want_lag=n_permutations > 0)
     s0, s1, s2 = engine.graph_moments(graph)
     scale = (float(n) / s0) / den  # I = scale * Σ z·lag ; NaN for zero-variance genes, as 0/0 upstream
     I_dev = num * scale
@@ -332,7 +341,7 @@ def morans_i(
         source = _pick_perm_source(perm_source, n, n_permutations)
         null = MoranNull(g, std.Z.device)
         lo, hi = dist_util.my_slice(n_permutations, group) if mode == "perms" else (0, n_permutations)
-        moran_graph_rows_null(std.Z, lag, g, scale, I_dev, n_permutations, seed, source, null, (lo, hi))
+        moran_graph_rows_null(std.Z, lag, g, scale, I_dev, n_permutations, seed, source, null, (lo, hi), cell_order=co)
         if mode == "perms":
             dist_util.all_reduce_null(null, group)
         c = null.cnt_ge.cpu().numpy()
@@ -419,6 +428,8 @@ def local_morans_i(
     logger.info(f"Computing Local Moran's I: {n:,} cells, {g} genes, k={n_neighbors}, permutations={n_permutations}")
 
     graph = _build_knn(adata, spatial_key, n_neighbors, device)
+    co = engine.spatial_order(adata.obsm[spatial_key], device=device)
+    graph = engine.relabel_graph(graph, co)  # device work runs on sorted positions; outputs are un-sorted below
     X = _expression(adata, layer)
     pos_all = np.asarray([adata.var_names.get_loc(x) for x in names], dtype=np.int64)
 
@@ -436,12 +447,12 @@ def local_morans_i(
         s, e = b * batch_size, min((b + 1) * batch_size, g)
         gb = e - s
         Xd, cols = engine.expression_to_device(X, pos_all[s:e], device)
-        std = engine.zscore_dense(Xd, cols=cols)
+        std = engine.zscore_dense(Xd, cols=cols, rows=co.order)
         _, _, lag, loc = engine.lag_moran(graph, std.Z, gb, want_lag=True, want_local=True)
         zero_mask[s:e] = std.zero_var.cpu().numpy().astype(bool)
-        z_values[:, s:e] = std.Z[:, :gb].cpu().numpy()
-        lag_values[:, s:e] = lag[:, :gb].cpu().numpy()
-        local_I[:, s:e] = loc[:, :gb].cpu().numpy()
+        z_values[:, s:e] = engine.gather_rows(std.Z, co.rank)[:, :gb].cpu().numpy()
+        lag_values[:, s:e] = engine.gather_rows(lag, co.rank)[:, :gb].cpu().numpy()
+        local_I[:, s:e] = engine.gather_rows(loc, co.rank)[:, :gb].cpu().numpy()
         if n_permutations > 0:
             cnt = torch.zeros(std.Z.shape, dtype=torch.int32, device=std.Z.device)
             if source == "philox":
@@ -449,7 +460,9 @@ def local_morans_i(
                                         cell_obs=loc, cell_cnt=cnt)
             else:
                 for _, idx in _replay_chunks(rng, n, n_permutations, std.Z.device):
+                    idx = engine.conjugate_perms(idx, co)
                     engine.perm_null_values(graph, std.Z, gb, idx.shape[0], perm_idx=idx, cell_obs=loc, cell_cnt=cnt)
+            cnt = engine.gather_rows(cnt.view(torch.float32), co.rank).view(torch.int32)  # bit-preserving row move
             p_values[:, s:e] = ((cnt[:, :gb].cpu().numpy() + 1) / (n_permutations + 1)).astype(np.float32)
 
     zero_genes = [names[i] for i in np.where(zero_mask)[0]]
@@ -633,7 +646,9 @@ def lees_l_matrix(
         raise ValueError(f"n_neighbors must be >= 1, got {n_neighbors}")
     names = _resolve_genes(adata, genes, "") if genes is not None else list(adata.var_names)
     graph = _build_knn(adata, spatial_key, n_neighbors, device)
-    std = _standardize(adata, layer, names, device)
+    co = engine.spatial_order(adata.obsm[spatial_key], device=device)
+    graph = engine.relabel_graph(graph, co)
+    std = _standardize(adata, layer, names, device, rows=co.order)
     g = len(names)
     _, _, lag, _ = engine.lag_moran(graph, std.Z, g, want_lag=True)
     if variant == "reference":

@@ -500,3 +500,107 @@ def test_nbhd_counts_from_graph(eng):
     assert torch.equal(fused, sep)
     want = R.neighborhood_profile(coords, labels, 8, k=12, normalize=False)
     assert np.array_equal(sep.cpu().numpy(), want)
+
+
+# ---------------------------------------------------------------------------------------------
+# spatial order: relabelled graph / matrices give the same statistics
+# ---------------------------------------------------------------------------------------------
+
+
+@pytest.mark.parametrize("kind", ["knn", "radius", "weighted"])
+def test_spatial_order_and_graph_relabel(eng, kind):
+    rng = np.random.default_rng(11)
+    n = 6011
+    coords = np.concatenate([rng.uniform(0, 300, (n - 2000, 2)), rng.normal(150, 5, (2000, 2))])
+    cd = torch.from_numpy(coords).cuda()
+    co = eng.spatial_order(cd)
+    order, rank = co.order.cpu().numpy(), co.rank.cpu().numpy()
+    assert np.array_equal(np.sort(order), np.arange(n))
+    assert np.array_equal(rank[order], np.arange(n))
+    # spatially compact: consecutive sorted cells are close (median step far below the extent)
+    step = np.linalg.norm(np.diff(coords[order], axis=0), axis=1)
+    assert np.median(step) < 10.0
+    if kind == "knn":
+        graph, _, _ = eng.knn_graph(cd, 7)
+    else:
+        graph, _ = eng.radius_graph(cd, 6.0)
+        assert (np.diff(graph.indptr.cpu().numpy()) == 0).any()  # some empty rows survive relabelling
+    A = graph.to_scipy("ones", np.float64)
+    if kind == "weighted":
+        A.data = rng.uniform(0.5, 2.0, A.nnz)
+        graph = eng.graph_from_scipy(A, use_weights=True)
+    gs = eng.relabel_graph(graph, co)
+    B = sparse.csr_matrix(
+        (np.ones(gs.nnz) if gs.weights is None else gs.weights.cpu().numpy().astype(np.float64),
+         gs.indices.reshape(-1).cpu().numpy(), gs.indptr_tensor().cpu().numpy()), shape=(n, n))
+    want = sparse.csr_matrix(A.astype(np.float32).astype(np.float64))[order][:, order]
+    want.sort_indices()
+    B2 = B.copy(); B2.sort_indices()
+    assert np.array_equal(B.indices, B2.indices), "relabelled rows are not column-sorted"
+    assert np.array_equal(want.indptr, B.indptr) and np.array_equal(want.indices, B.indices)
+    np.testing.assert_array_equal(want.data, B.data)
+
+
+def test_statistics_invariant_under_spatial_order(eng, g0):
+    coords, X, _ = g0
+    n, g = X.shape
+    cd = torch.from_numpy(coords).cuda()
+    Xd = torch.from_numpy(X).cuda()
+    graph, _, _ = eng.knn_graph(cd, 6)
+    co = eng.spatial_order(cd)
+    gs = eng.relabel_graph(graph, co)
+    su, ss = eng.zscore_dense(Xd), eng.zscore_dense(Xd, rows=co.order)
+    assert torch.equal(ss.Z, su.Z[co.order.long()])
+    assert torch.equal(eng.gather_rows(ss.Z, co.rank), su.Z)
+    nu, du, lag_u, loc_u = eng.lag_moran(graph, su.Z, g, want_local=True)
+    ns, ds, lag_s, loc_s = eng.lag_moran(gs, ss.Z, g, want_local=True)
+    np.testing.assert_allclose(ns.cpu().numpy(), nu.cpu().numpy(), rtol=0, atol=5e-5)  # FP32 lag rounded in a different neighbour order
+    np.testing.assert_allclose(ds.cpu().numpy(), du.cpu().numpy(), rtol=1e-13)
+    # per-cell lag: same neighbours, summed in a different order (FP32)
+    np.testing.assert_allclose(eng.gather_rows(lag_s, co.rank).cpu().numpy(), lag_u.cpu().numpy(), rtol=0, atol=2e-6)
+    # replayed permutations of cell ids, conjugated onto sorted positions
+    perms = np.stack([np.random.default_rng(5).permutation(n) for _ in range(1)] + [R.squidpy_perm_indices(n, 20, 0)[j] for j in range(20)]).astype(np.int32)
+    pidx = torch.from_numpy(perms).cuda()
+    sims_u = eng.perm_null_graph_rows(su.Z, lag_u, g, len(perms), perm_idx=pidx)
+    sims_s = eng.perm_null_graph_rows(ss.Z, lag_s, g, len(perms), perm_idx=eng.conjugate_perms(pidx, co))
+    np.testing.assert_allclose(sims_s.cpu().numpy(), sims_u.cpu().numpy(), rtol=0, atol=5e-4)  # sums of ~1e4 O(1) terms, FP32 lag rounding
+
+
+@pytest.mark.parametrize("shape,k", [((5003, 40), 6), ((3001, 130), 9)])
+def test_values_null_materialised_matches_gather_kernel(eng, shape, k, monkeypatch):
+    """Wide matrices take the materialise-then-lag variant; it must agree with the register-gather
+    kernel (identical FP32 products, different summation order) and with a numpy FP64 evaluation."""
+    n, g = shape
+    rng = np.random.default_rng(n)
+    coords = rng.uniform(0, 100, (n, 2))
+    Xc = rng.normal(size=(n, g)).astype(np.float32)
+    cd = torch.from_numpy(coords).cuda()
+    graph, _, _ = eng.knn_graph(cd, k)
+    std = eng.zscore_dense(torch.from_numpy(Xc).cuda())
+    P = 5
+    perms = np.stack([rng.permutation(n) for _ in range(P)]).astype(np.int32)
+    pidx = torch.from_numpy(perms).cuda()
+    _, _, _, loc = eng.lag_moran(graph, std.Z, g, want_lag=False, want_local=True)
+    res = {}
+    for variant in ("gather", "materialised"):
+        if variant == "gather":
+            monkeypatch.setenv("SC_PERM_VALUES_VARIANT", "gather")
+        else:
+            monkeypatch.delenv("SC_PERM_VALUES_VARIANT", raising=False)
+        cnt = torch.zeros(std.Z.shape, dtype=torch.int32, device="cuda")
+        sims = eng.perm_null_values(graph, std.Z, g, P, perm_idx=pidx, cell_obs=loc, cell_cnt=cnt)
+        sims_ph = eng.perm_null_values(graph, std.Z, g, 3, seed=9, perm_offset=4)
+        res[variant] = (sims.cpu().numpy(), cnt[:, :g].cpu().numpy(), sims_ph.cpu().numpy())
+    W = graph.to_scipy("weights", np.float64)
+    Z = std.Z[:, :g].double().cpu().numpy()
+    want = np.stack([(Z[pm] * (W @ Z[pm])).sum(0) for pm in perms])
+    for variant, (sims, cnt, sims_ph) in res.items():
+        np.testing.assert_allclose(sims, want, rtol=0, atol=2e-5 * np.sqrt(n)), variant
+    np.testing.assert_allclose(res["gather"][2], res["materialised"][2], rtol=0, atol=2e-5 * np.sqrt(n))
+    # per-cell exceedance counts: identical except where |local_p| ties |obs| to FP32 rounding
+    diff = res["gather"][1] != res["materialised"][1]
+    assert diff.mean() < 1e-4, diff.mean()
+    # Lee form (x fixed, only y permuted) on the wide path
+    sims_lee = eng.perm_null_values(graph, std.Z, g, P, Zx=std.Z, perm_idx=pidx).cpu().numpy()
+    want_lee = np.stack([(Z * (W @ Z[pm])).sum(0) for pm in perms])
+    np.testing.assert_allclose(sims_lee, want_lee, rtol=0, atol=2e-5 * np.sqrt(n))
