@@ -81,6 +81,16 @@ if want("lag"):
     num_s, den_s, _, _ = eng.lag_moran(gs, std.Z, g, want_lag=False)
     out["lag_num_rel_diff_user_vs_spatial"] = float(((num_s - num_u).abs() / num_u.abs().clamp_min(1e-30)).max())
 
+if want("lagsweep"):
+    sweep = {}
+    for vec in (1, 2):
+        for chunk in (64, 128, 256, 512):
+            os.environ["SC_LAG_VEC"], os.environ["SC_LAG_CHUNK"] = str(vec), str(chunk)
+            sweep[f"vec{vec}_chunk{chunk}"] = [round(timed(lambda: eng.lag_moran(gs, std.Z, g)), 3),
+                                               round(timed(lambda: eng.lag_moran(gs, std.Z, g, want_lag=False)), 3)]
+    del os.environ["SC_LAG_VEC"], os.environ["SC_LAG_CHUNK"]
+    out["lag_sweep_ms_[with_lag,stat_only]"] = sweep
+
 if want("values"):
     k1 = nnz / n + 1.0
     P = 4

@@ -32,9 +32,7 @@ class AnnDataLite:
     ) -> None:
         self.X = X
         n_obs, n_vars = X.shape
-        if obs is None:
-            obs = pd.DataFrame(index=pd.RangeIndex(n_obs).astype(str))
-        self.obs = obs
+        self._obs = obs  # built on first access: a 5 M-row string index costs ~1 s and most calls never read it
         if var_names is None:
             var_names = [f"g{i}" for i in range(n_vars)]
         self.var_names = pd.Index(list(var_names))
@@ -45,6 +43,16 @@ class AnnDataLite:
         self.obsp = dict(obsp) if obsp else {}
         self.uns = dict(uns) if uns else {}
         self.layers = dict(layers) if layers else {}
+
+    @property
+    def obs(self) -> pd.DataFrame:
+        if self._obs is None:
+            self._obs = pd.DataFrame(index=pd.RangeIndex(self.X.shape[0]).astype(str))
+        return self._obs
+
+    @obs.setter
+    def obs(self, value: pd.DataFrame) -> None:
+        self._obs = value
 
     @property
     def n_obs(self) -> int:

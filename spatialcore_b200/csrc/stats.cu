@@ -112,6 +112,99 @@ zscore_write_kernel(const T* __restrict__ X, int64_t n, int64_t ldx, int g,
   }
 }
 
+// ---- fast path: dense FP32 input, all columns, 16-byte aligned rows --------------------------------
+// A thread owns one column quad (float4) and walks the rows; a CTA is QW quads wide (QW a power of
+// two <= 256) and 256/QW rows deep per pass, so every warp request is a contiguous >= 128-byte run
+// and the per-column constants stay in registers.
+
+__global__ void __launch_bounds__(256)
+colstats4_kernel(const float* __restrict__ X, int64_t n, int64_t ldx, int g, int qw_log2,
+                 double* __restrict__ partial) {
+  __shared__ double sh[8][256];
+  const int qw = 1 << qw_log2;
+  const int qx = threadIdx.x & (qw - 1), ry = threadIdx.x >> qw_log2, rpc = 256 >> qw_log2;
+  const int col = (blockIdx.x * qw + qx) * 4;
+  const bool active = col < g;  // g % 4 may be non-zero: the caller guarantees ldx >= round_up(g,4)
+  double s[4] = {0, 0, 0, 0}, ss[4] = {0, 0, 0, 0};
+  if (active) {
+    const float4 sh4 = ldg4(X + col);
+    const double shift[4] = {(double)sh4.x, (double)sh4.y, (double)sh4.z, (double)sh4.w};
+    const int64_t step = (int64_t)gridDim.y * rpc;
+    int64_t r = (int64_t)blockIdx.y * rpc + ry;
+    const float* p = X + col;
+    for (; r + 3 * step < n; r += 4 * step) {
+      const float4 a = ld_stream4(p + r * ldx);
+      const float4 b = ld_stream4(p + (r + step) * ldx);
+      const float4 c = ld_stream4(p + (r + 2 * step) * ldx);
+      const float4 d = ld_stream4(p + (r + 3 * step) * ldx);
+      const float4 q[4] = {a, b, c, d};
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const double v0 = (double)q[u].x - shift[0], v1 = (double)q[u].y - shift[1];
+        const double v2 = (double)q[u].z - shift[2], v3 = (double)q[u].w - shift[3];
+        s[0] += v0; ss[0] = fma(v0, v0, ss[0]);
+        s[1] += v1; ss[1] = fma(v1, v1, ss[1]);
+        s[2] += v2; ss[2] = fma(v2, v2, ss[2]);
+        s[3] += v3; ss[3] = fma(v3, v3, ss[3]);
+      }
+    }
+    for (; r < n; r += step) {
+      const float4 a = ld_stream4(p + r * ldx);
+      const double v0 = (double)a.x - shift[0], v1 = (double)a.y - shift[1];
+      const double v2 = (double)a.z - shift[2], v3 = (double)a.w - shift[3];
+      s[0] += v0; ss[0] = fma(v0, v0, ss[0]);
+      s[1] += v1; ss[1] = fma(v1, v1, ss[1]);
+      s[2] += v2; ss[2] = fma(v2, v2, ss[2]);
+      s[3] += v3; ss[3] = fma(v3, v3, ss[3]);
+    }
+  }
+#pragma unroll
+  for (int c = 0; c < 4; ++c) { sh[c][threadIdx.x] = s[c]; sh[4 + c][threadIdx.x] = ss[c]; }
+  __syncthreads();
+  if (ry == 0 && active) {
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+      if (col + c >= g) break;
+      double a = 0, b = 0;
+      for (int r2 = 0; r2 < rpc; ++r2) { a += sh[c][r2 * qw + qx]; b += sh[4 + c][r2 * qw + qx]; }
+      double* dst = partial + ((int64_t)blockIdx.y * g + col + c) * 2;
+      dst[0] = a; dst[1] = b;
+    }
+  }
+}
+
+__global__ void __launch_bounds__(256)
+zscore_write4_kernel(const float* __restrict__ X, int64_t n, int64_t ldx, int g,
+                     const int32_t* __restrict__ rows, const double* __restrict__ mean,
+                     const double* __restrict__ std, const uint8_t* __restrict__ zero_var,
+                     float* __restrict__ Z, int64_t ldz, int qw_log2) {
+  const int qw = 1 << qw_log2;
+  const int qx = threadIdx.x & (qw - 1), ry = threadIdx.x >> qw_log2, rpc = 256 >> qw_log2;
+  const int col = (blockIdx.x * qw + qx) * 4;
+  if (col >= ldz) return;
+  double m[4], inv[4];
+  bool live[4];
+#pragma unroll
+  for (int c = 0; c < 4; ++c) {
+    live[c] = col + c < g && !zero_var[col + c];  // padding / zero-variance columns -> exactly 0
+    m[c] = live[c] ? mean[col + c] : 0.0;
+    inv[c] = live[c] ? 1.0 / std[col + c] : 0.0;
+  }
+  const bool in_x = col < g;  // a quad entirely in the padding has nothing to read
+  const int64_t step = (int64_t)gridDim.y * rpc;
+  for (int64_t a = (int64_t)blockIdx.y * rpc + ry; a < n; a += step) {
+    const int64_t src = rows ? rows[a] : a;
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (in_x) v = ld_stream4(X + src * ldx + col);
+    float4 o;
+    o.x = live[0] ? (float)(((double)v.x - m[0]) * inv[0]) : 0.f;
+    o.y = live[1] ? (float)(((double)v.y - m[1]) * inv[1]) : 0.f;
+    o.z = live[2] ? (float)(((double)v.z - m[2]) * inv[2]) : 0.f;
+    o.w = live[3] ? (float)(((double)v.w - m[3]) * inv[3]) : 0.f;
+    *reinterpret_cast<float4*>(Z + a * ldz + col) = o;
+  }
+}
+
 template <typename T>
 __global__ void __launch_bounds__(256)
 csr_densify_kernel(const int64_t* __restrict__ indptr, const int32_t* __restrict__ indices,
@@ -182,92 +275,137 @@ __global__ void reduce_partials_kernel(const double* __restrict__ partial, int n
 // spatial lag + Moran numerator / denominator
 // ------------------------------------------------------------------------------------------------
 
-// Geometry: a CTA owns contiguous chunks of kLagChunkRows rows and one 32-gene column block
-// (8 lanes x float4 per row, 32 rows per pass).  With the cells in spatial order the neighbour rows
-// of a chunk form a small working set (~500 rows x 128 B) that stays in L1, so Z is read from HBM
-// about once instead of once per edge.  blockIdx.x = column block (fastest: the column blocks of
-// one chunk run together and share the CSR indices through L2), blockIdx.y = chunk group.
+// Geometry: a CTA owns contiguous chunks of `chunk_rows` rows and one column block of 32*VEC genes
+// (8 lanes x VEC float4 per row, 32 rows per pass).  With the cells in spatial order the neighbour
+// rows of a chunk form a small working set (~1.7x the chunk) that stays in L1, so Z is read from HBM
+// about once instead of once per edge.  blockIdx.x = column block (fastest: the column blocks of one
+// chunk run together and share the CSR indices through L2), blockIdx.y = chunk group.
+//
+// The kernel is bound by L1 wavefronts and instruction issue, not HBM (one FADD/FFMA per 4 gathered
+// bytes), so the inner loop is kept lean: 32-bit edge counters, one IMAD.WIDE per gathered row, the
+// second float4 of a VEC=2 thread at a constant +128 B.  The Moran sums stay FP64 sums of the exact
+// FP32 products (identical arithmetic to the permutation kernels, so the identity permutation
+// reproduces the observed statistic to round-off).
 constexpr int kLagColQuads = 8;
 constexpr int kLagRowsPerPass = kStatThreads / kLagColQuads;  // 32
-constexpr int kLagChunkRows = 256;
 
-template <bool HAS_W>
-__global__ void __launch_bounds__(kStatThreads)
+__device__ __forceinline__ float4 ldg4_row(const char* base, int j, uint32_t ld_bytes) {
+  return __ldg(reinterpret_cast<const float4*>(base + (uint64_t)(uint32_t)j * ld_bytes));
+}
+__device__ __forceinline__ void fma4(float4& a, float w, const float4& v) {
+  a.x += w * v.x; a.y += w * v.y; a.z += w * v.z; a.w += w * v.w;
+}
+
+template <bool HAS_W, int VEC>
+__global__ void __launch_bounds__(kStatThreads, 2)
 lag_stat_kernel(const int32_t* __restrict__ indptr, const int32_t* __restrict__ indices,
                 const float* __restrict__ weights, int64_t n, int k_fixed,
                 const float* __restrict__ Zself, const float* __restrict__ Zlag, int64_t ldz,
                 float* __restrict__ lag, float* __restrict__ local, int64_t ldl,
                 double* __restrict__ partial, const float* __restrict__ cell_obs,
-                int32_t* __restrict__ cell_cnt, int64_t ldc, int64_t n_chunks) {
-  __shared__ double sh[2][kLagRowsPerPass][kLagColQuads][4];
+                int32_t* __restrict__ cell_cnt, int64_t ldc, int64_t n_chunks, int chunk_rows) {
+  __shared__ double sh[VEC][2][kLagRowsPerPass][kLagColQuads][4];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int q = lane & (kLagColQuads - 1);
   const int rslot = warp * (32 / kLagColQuads) + (lane >> 3);
-  const int64_t col = ((int64_t)blockIdx.x * kLagColQuads + q) * 4;
-  const bool active = col < ldz;
+  const int64_t col = ((int64_t)blockIdx.x * kLagColQuads * VEC + q) * 4;
+  bool active[VEC];
+#pragma unroll
+  for (int v = 0; v < VEC; ++v) active[v] = col + 32 * v < ldz;
   const float* Zs = Zself ? Zself : Zlag;
-  double num[4] = {0, 0, 0, 0}, den[4] = {0, 0, 0, 0};
+  const char* zbase = reinterpret_cast<const char*>(Zlag + col);
+  const uint32_t ldzb = (uint32_t)ldz * 4u;
+  double num[VEC][4], den[VEC][4];  // FP64 sums of the exact FP32 products, as in the permutation kernels
+#pragma unroll
+  for (int v = 0; v < VEC; ++v)
+#pragma unroll
+    for (int c = 0; c < 4; ++c) { num[v][c] = 0; den[v][c] = 0; }
 
   for (int64_t chunk = blockIdx.y; chunk < n_chunks; chunk += gridDim.y) {
-    const int64_t r0 = chunk * kLagChunkRows;
+    const int64_t r0 = chunk * chunk_rows;
 #pragma unroll 1
-    for (int pass = 0; pass < kLagChunkRows / kLagRowsPerPass; ++pass) {
-      const int64_t row = r0 + pass * kLagRowsPerPass + rslot;
-      if (row >= n || !active) continue;
-      const int64_t b = indptr ? indptr[row] : row * k_fixed;
-      const int64_t e = indptr ? indptr[row + 1] : b + k_fixed;
-      float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-      int64_t t = b;
-      for (; t + 4 <= e; t += 4) {
-        const int j0 = indices[t], j1 = indices[t + 1], j2 = indices[t + 2], j3 = indices[t + 3];
-        const float4 v0 = ldg4(Zlag + (int64_t)j0 * ldz + col);
-        const float4 v1 = ldg4(Zlag + (int64_t)j1 * ldz + col);
-        const float4 v2 = ldg4(Zlag + (int64_t)j2 * ldz + col);
-        const float4 v3 = ldg4(Zlag + (int64_t)j3 * ldz + col);
+    for (int pass = 0; pass < chunk_rows; pass += kLagRowsPerPass) {
+      const int64_t row = r0 + pass + rslot;
+      if (row >= n || !active[0]) continue;
+      int64_t b;
+      int deg;
+      if (indptr) { b = indptr[row]; deg = indptr[row + 1] - (int)b; } else { b = row * k_fixed; deg = k_fixed; }
+      const int32_t* __restrict__ ip = indices + b;
+      const float* __restrict__ wp = HAS_W ? weights + b : nullptr;
+      float4 acc[VEC];
+#pragma unroll
+      for (int v = 0; v < VEC; ++v) acc[v] = make_float4(0.f, 0.f, 0.f, 0.f);
+      int t = 0;
+#pragma unroll 1
+      for (; t + 4 <= deg; t += 4) {
+        const int j0 = ip[t], j1 = ip[t + 1], j2 = ip[t + 2], j3 = ip[t + 3];
         float w0 = 1.f, w1 = 1.f, w2 = 1.f, w3 = 1.f;
-        if (HAS_W) { w0 = weights[t]; w1 = weights[t + 1]; w2 = weights[t + 2]; w3 = weights[t + 3]; }
-        acc.x += w0 * v0.x + w1 * v1.x + w2 * v2.x + w3 * v3.x;
-        acc.y += w0 * v0.y + w1 * v1.y + w2 * v2.y + w3 * v3.y;
-        acc.z += w0 * v0.z + w1 * v1.z + w2 * v2.z + w3 * v3.z;
-        acc.w += w0 * v0.w + w1 * v1.w + w2 * v2.w + w3 * v3.w;
+        if (HAS_W) { w0 = wp[t]; w1 = wp[t + 1]; w2 = wp[t + 2]; w3 = wp[t + 3]; }
+#pragma unroll
+        for (int v = 0; v < VEC; ++v) {
+          if (v > 0 && !active[v]) continue;
+          const float4 v0 = ldg4_row(zbase + 128 * v, j0, ldzb);
+          const float4 v1 = ldg4_row(zbase + 128 * v, j1, ldzb);
+          const float4 v2 = ldg4_row(zbase + 128 * v, j2, ldzb);
+          const float4 v3 = ldg4_row(zbase + 128 * v, j3, ldzb);
+          acc[v].x += w0 * v0.x + w1 * v1.x + w2 * v2.x + w3 * v3.x;
+          acc[v].y += w0 * v0.y + w1 * v1.y + w2 * v2.y + w3 * v3.y;
+          acc[v].z += w0 * v0.z + w1 * v1.z + w2 * v2.z + w3 * v3.z;
+          acc[v].w += w0 * v0.w + w1 * v1.w + w2 * v2.w + w3 * v3.w;
+        }
       }
-      for (; t < e; ++t) {
-        const float4 v = ldg4(Zlag + (int64_t)indices[t] * ldz + col);
-        const float w = HAS_W ? weights[t] : 1.f;
-        acc.x += w * v.x; acc.y += w * v.y; acc.z += w * v.z; acc.w += w * v.w;
+#pragma unroll 1
+      for (; t < deg; ++t) {
+        const int j = ip[t];
+        const float w = HAS_W ? wp[t] : 1.f;
+#pragma unroll
+        for (int v = 0; v < VEC; ++v) {
+          if (v > 0 && !active[v]) continue;
+          fma4(acc[v], w, ldg4_row(zbase + 128 * v, j, ldzb));
+        }
       }
-      if (!HAS_W) {
-        const float inv = (e > b) ? 1.f / (float)(e - b) : 0.f;
-        acc.x *= inv; acc.y *= inv; acc.z *= inv; acc.w *= inv;
+      const float inv = HAS_W ? 1.f : ((deg > 0) ? 1.f / (float)deg : 0.f);
+#pragma unroll
+      for (int v = 0; v < VEC; ++v) {
+        if (v > 0 && !active[v]) continue;
+        if (!HAS_W) { acc[v].x *= inv; acc[v].y *= inv; acc[v].z *= inv; acc[v].w *= inv; }
+        const int64_t c = col + 32 * v;
+        const float4 z = ldg4(Zs + row * ldz + c);
+        const float4 loc = make_float4(z.x * acc[v].x, z.y * acc[v].y, z.z * acc[v].z, z.w * acc[v].w);
+        if (lag) *reinterpret_cast<float4*>(lag + row * ldl + c) = acc[v];
+        if (local) *reinterpret_cast<float4*>(local + row * ldl + c) = loc;
+        if (cell_cnt) {
+          const float4 o = ldg4(cell_obs + row * ldc + c);
+          int4* cp = reinterpret_cast<int4*>(cell_cnt + row * ldc + c);
+          int4 cc = *cp;
+          cc.x += fabsf(loc.x) >= fabsf(o.x); cc.y += fabsf(loc.y) >= fabsf(o.y);
+          cc.z += fabsf(loc.z) >= fabsf(o.z); cc.w += fabsf(loc.w) >= fabsf(o.w);
+          *cp = cc;
+        }
+        const double zx = z.x, zy = z.y, zz = z.z, zw = z.w;
+        num[v][0] = fma(zx, (double)acc[v].x, num[v][0]); den[v][0] = fma(zx, zx, den[v][0]);
+        num[v][1] = fma(zy, (double)acc[v].y, num[v][1]); den[v][1] = fma(zy, zy, den[v][1]);
+        num[v][2] = fma(zz, (double)acc[v].z, num[v][2]); den[v][2] = fma(zz, zz, den[v][2]);
+        num[v][3] = fma(zw, (double)acc[v].w, num[v][3]); den[v][3] = fma(zw, zw, den[v][3]);
       }
-      const float4 z = ldg4(Zs + row * ldz + col);
-      const float4 loc = make_float4(z.x * acc.x, z.y * acc.y, z.z * acc.z, z.w * acc.w);
-      if (lag) *reinterpret_cast<float4*>(lag + row * ldl + col) = acc;
-      if (local) *reinterpret_cast<float4*>(local + row * ldl + col) = loc;
-      if (cell_cnt) {
-        const float4 o = ldg4(cell_obs + row * ldc + col);
-        int4* cp = reinterpret_cast<int4*>(cell_cnt + row * ldc + col);
-        int4 c = *cp;
-        c.x += fabsf(loc.x) >= fabsf(o.x); c.y += fabsf(loc.y) >= fabsf(o.y);
-        c.z += fabsf(loc.z) >= fabsf(o.z); c.w += fabsf(loc.w) >= fabsf(o.w);
-        *cp = c;
-      }
-      num[0] += (double)z.x * (double)acc.x; den[0] += (double)z.x * (double)z.x;
-      num[1] += (double)z.y * (double)acc.y; den[1] += (double)z.y * (double)z.y;
-      num[2] += (double)z.z * (double)acc.z; den[2] += (double)z.z * (double)z.z;
-      num[3] += (double)z.w * (double)acc.w; den[3] += (double)z.w * (double)z.w;
     }
   }
 #pragma unroll
-  for (int c = 0; c < 4; ++c) { sh[0][rslot][q][c] = num[c]; sh[1][rslot][q][c] = den[c]; }
-  __syncthreads();
-  if (rslot == 0 && active) {
-    double* p = partial + ((int64_t)blockIdx.y * 2) * ldz + col;
+  for (int v = 0; v < VEC; ++v)
 #pragma unroll
-    for (int c = 0; c < 4; ++c) {
-      double a = 0, d = 0;
-      for (int r = 0; r < kLagRowsPerPass; ++r) { a += sh[0][r][q][c]; d += sh[1][r][q][c]; }
-      p[c] = a; p[ldz + c] = d;
+    for (int c = 0; c < 4; ++c) { sh[v][0][rslot][q][c] = num[v][c]; sh[v][1][rslot][q][c] = den[v][c]; }
+  __syncthreads();
+#pragma unroll
+  for (int v = 0; v < VEC; ++v) {
+    if (rslot == 0 && active[v]) {
+      double* p = partial + ((int64_t)blockIdx.y * 2) * ldz + col + 32 * v;
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        double a = 0, d = 0;
+#pragma unroll 4
+        for (int r = 0; r < kLagRowsPerPass; ++r) { a += sh[v][0][r][q][c]; d += sh[v][1][r][q][c]; }
+        p[c] = a; p[ldz + c] = d;
+      }
     }
   }
 }
@@ -748,22 +886,41 @@ static void fill_batch(PermBatch* pb, int source, const int32_t* perm_idx, uint6
 constexpr int kMaxStatBlocks = 148 * 8;
 
 // Launch lag_stat_kernel; *by_out = number of partial rows written ([by][2][ldz] doubles).
+// SC_LAG_VEC (1|2) and SC_LAG_CHUNK (multiple of 32) override the geometry for experiments.
+template <bool HAS_W, int VEC>
+static void launch_lag_stat_t(dim3 grid, cudaStream_t st, const int32_t* indptr, const int32_t* indices,
+                              const float* weights, int64_t n, int k_fixed, const float* Zself,
+                              const float* Zlag, int64_t ldz, float* lag, float* local, int64_t ldl,
+                              double* partial, const float* cell_obs, int32_t* cell_cnt, int64_t ldc,
+                              int64_t n_chunks, int chunk_rows) {
+  lag_stat_kernel<HAS_W, VEC><<<grid, kStatThreads, 0, st>>>(indptr, indices, weights, n, k_fixed, Zself, Zlag, ldz, lag,
+                                                             local, ldl, partial, cell_obs, cell_cnt, ldc, n_chunks,
+                                                             chunk_rows);
+}
+
 static int launch_lag_stat(const int32_t* indptr, const int32_t* indices, const float* weights,
                            int64_t n, int k_fixed, const float* Zself, const float* Zlag, int64_t ldz,
                            float* lag, float* local, int64_t ldl, double* partial,
                            const float* cell_obs, int32_t* cell_cnt, int64_t ldc, int* by_out,
                            cudaStream_t st) {
-  const int bx = (int)((ldz / 4 + kLagColQuads - 1) / kLagColQuads);
-  const int64_t n_chunks = (n + kLagChunkRows - 1) / kLagChunkRows;
+  // measured on B200 (C4, 5 M x 1000, degree 20): VEC=1 / 512-row chunks 32 ms, VEC=2 / 128 36 ms
+  int vec = 1;
+  int chunk_rows = 512;
+  while (chunk_rows > 64 && ((n + chunk_rows - 1) / chunk_rows) * ((ldz + 31) / 32) < 4 * (int64_t)sm_count()) chunk_rows /= 2;
+  if (const char* e = getenv("SC_LAG_VEC")) { int v = atoi(e); if (v == 1 || v == 2) vec = v; }
+  if (const char* e = getenv("SC_LAG_CHUNK")) { int v = atoi(e); if (v >= 32 && v % 32 == 0 && v <= 4096) chunk_rows = v; }
+  const int colblk = 32 * vec;
+  const int bx = (int)((ldz + colblk - 1) / colblk);
+  const int64_t n_chunks = (n + chunk_rows - 1) / chunk_rows;
   int64_t by = ((int64_t)sm_count() * 8 + bx - 1) / bx;
   if (by > n_chunks) by = n_chunks;
   if (by > kMaxStatBlocks) by = kMaxStatBlocks;
   if (by < 1) by = 1;
   dim3 grid(bx, (unsigned)by);
-  if (weights)
-    lag_stat_kernel<true><<<grid, kStatThreads, 0, st>>>(indptr, indices, weights, n, k_fixed, Zself, Zlag, ldz, lag, local, ldl, partial, cell_obs, cell_cnt, ldc, n_chunks);
-  else
-    lag_stat_kernel<false><<<grid, kStatThreads, 0, st>>>(indptr, indices, weights, n, k_fixed, Zself, Zlag, ldz, lag, local, ldl, partial, cell_obs, cell_cnt, ldc, n_chunks);
+#define SC_LAG_ARGS grid, st, indptr, indices, weights, n, k_fixed, Zself, Zlag, ldz, lag, local, ldl, partial, cell_obs, cell_cnt, ldc, n_chunks, chunk_rows
+  if (weights) { if (vec == 2) launch_lag_stat_t<true, 2>(SC_LAG_ARGS); else launch_lag_stat_t<true, 1>(SC_LAG_ARGS); }
+  else         { if (vec == 2) launch_lag_stat_t<false, 2>(SC_LAG_ARGS); else launch_lag_stat_t<false, 1>(SC_LAG_ARGS); }
+#undef SC_LAG_ARGS
   SC_LAUNCH_OK();
   *by_out = (int)by;
   return SC_OK;
@@ -786,6 +943,40 @@ template <typename T>
 static int zscore_impl(const T* X, int64_t n, int64_t ldx, int g, const int32_t* cols,
                        const int32_t* rows, float* Z, int64_t ldz, double* mean, double* std,
                        uint8_t* zero_var, double* partial, cudaStream_t st) {
+  // fast path: FP32, all columns, rows readable as float4 up to round_up(g,4)
+  const bool fast = sizeof(T) == 4 && !cols && ldx % 4 == 0 && ldx >= (g + 3) / 4 * 4 &&
+                    (reinterpret_cast<uintptr_t>(X) & 15) == 0 && !getenv("SC_ZSCORE_GENERIC");
+  if (fast) {
+    const int quads = (g + 3) / 4;
+    int qw_log2 = 0;
+    while ((1 << qw_log2) < quads && qw_log2 < 8) ++qw_log2;
+    const int qw = 1 << qw_log2, rpc = 256 >> qw_log2;
+    const int bx = (quads + qw - 1) / qw;
+    int64_t by = ((int64_t)sm_count() * 8 + bx - 1) / bx;
+    const int64_t max_by = (n + rpc - 1) / rpc;
+    if (by > max_by) by = max_by;
+    if (by * bx > kMaxStatBlocks) by = kMaxStatBlocks / bx;
+    if (by < 1) by = 1;
+    const float* Xf = reinterpret_cast<const float*>(X);
+    colstats4_kernel<<<dim3(bx, (unsigned)by), 256, 0, st>>>(Xf, n, ldx, g, qw_log2, partial);
+    SC_LAUNCH_OK();
+    colstats_final_kernel<T><<<(g + 127) / 128, 128, 0, st>>>(X, n, g, cols, partial, (int)by, mean, std, zero_var);
+    SC_LAUNCH_OK();
+    if (Z) {
+      const int zquads = (int)(ldz / 4);
+      int zq_log2 = 0;
+      while ((1 << zq_log2) < zquads && zq_log2 < 8) ++zq_log2;
+      const int zqw = 1 << zq_log2, zrpc = 256 >> zq_log2;
+      const int zbx = (zquads + zqw - 1) / zqw;
+      int64_t zby = ((int64_t)sm_count() * 16 + zbx - 1) / zbx;
+      const int64_t zmax = (n + zrpc - 1) / zrpc;
+      if (zby > zmax) zby = zmax;
+      if (zby > 65535) zby = 65535;
+      zscore_write4_kernel<<<dim3(zbx, (unsigned)zby), 256, 0, st>>>(Xf, n, ldx, g, rows, mean, std, zero_var, Z, ldz, zq_log2);
+      SC_LAUNCH_OK();
+    }
+    return SC_OK;
+  }
   int tiles = (g + 127) / 128;
   int groups = (sm_count() * 8 + tiles - 1) / tiles;
   int64_t max_groups = (n + 1) / 2;

@@ -159,6 +159,30 @@ def test_zscore_dense_sparse_subset(eng):
             np.testing.assert_allclose(s.Z[:, : want.shape[1]].cpu().numpy(), want, rtol=2e-7, atol=1e-7)
 
 
+@pytest.mark.parametrize("shape", [(4001, 1000), (777, 64), (2500, 20), (300, 2052), (9, 8)])
+def test_zscore_vector_path_matches_generic_and_numpy(eng, shape, monkeypatch):
+    """FP32 matrices whose rows are float4-readable take the vectorised kernels (thread per column
+    quad); they must agree with the generic kernels and with numpy FP64, with and without a row map."""
+    n, g = shape
+    rng = np.random.default_rng(g)
+    X = np.log1p(rng.poisson(0.7, (n, g))).astype(np.float32)
+    X[:, g // 2] = 1.25  # zero variance
+    Xd = torch.from_numpy(X).cuda()
+    rows = torch.from_numpy(rng.permutation(n).astype(np.int32)).cuda()
+    fast = eng.zscore_dense(Xd, rows=rows)
+    monkeypatch.setenv("SC_ZSCORE_GENERIC", "1")
+    slow = eng.zscore_dense(Xd, rows=rows)
+    monkeypatch.delenv("SC_ZSCORE_GENERIC")
+    Zq, mean, std, zero = R.zscore(X)
+    for s in (fast, slow):
+        np.testing.assert_allclose(s.mean.cpu().numpy(), mean, rtol=1e-12, atol=1e-14)
+        np.testing.assert_allclose(s.std.cpu().numpy(), std, rtol=1e-10, atol=1e-14)
+        assert np.array_equal(s.zero_var.cpu().numpy().astype(bool), zero)
+        np.testing.assert_allclose(s.Z[:, :g].cpu().numpy(), Zq[rows.cpu().numpy()], rtol=2e-7, atol=1e-7)
+        assert torch.all(s.Z[:, g:] == 0) and torch.all(s.Z[:, g // 2] == 0)
+    np.testing.assert_allclose(fast.Z.cpu().numpy(), slow.Z.cpu().numpy(), rtol=0, atol=1.2e-7)  # x/std vs x*(1/std)
+
+
 # ---------------------------------------------------------------------------------------------
 # Moran's I and the graph-row null
 # ---------------------------------------------------------------------------------------------
