@@ -134,6 +134,13 @@ SC_API int sc_zscore(const void* X, int dtype, int64_t n, int64_t ldx, int g, co
               const int32_t* rows, float* Z, int64_t ldz, double* mean, double* std,
               uint8_t* zero_var, void* ws, size_t ws_bytes, sc_stream_t stream);
 
+/* Second half of sc_zscore on its own: write Z from GIVEN per-gene mean / std / zero_var (device
+ * arrays).  Lets several devices standardise row blocks of one matrix with moments combined across
+ * them (row-sharded ingest; spatialcore_b200/distributed.py). */
+SC_API int sc_zscore_apply(const void* X, int dtype, int64_t n, int64_t ldx, int g, const int32_t* cols,
+                           const int32_t* rows, const double* mean, const double* std,
+                           const uint8_t* zero_var, float* Z, int64_t ldz, sc_stream_t stream);
+
 /* Scatter CSR expression (indptr i64[n+1], indices i32, data of `dtype`) into dense f32 [n, ldo]
  * (zero-filled first).  colmap i32[n_cols_x] or NULL: source column -> output column, -1 = drop. */
 SC_API int sc_csr_densify(const int64_t* indptr, const int32_t* indices, const void* data, int dtype,

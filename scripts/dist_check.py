@@ -24,6 +24,16 @@ for mode in ("genes", "perms"):
     np.testing.assert_allclose(got["I"].to_numpy(), ref["I"].to_numpy(), rtol=1e-12)
     np.testing.assert_allclose(got["z_score"].to_numpy(), ref["z_score"].to_numpy(), rtol=1e-12)
     if rank == 0: print("shard=%s ok on %d ranks" % (mode, dist.get_world_size()), flush=True)
+# row-sharded ingest: pooled moments differ in the last FP64 bit -> Z agrees to FP32 rounding
+sh = spatial.morans_i(AnnDataLite(X, obsm={"spatial": coords}), n_permutations=101, seed=4, perm_source="philox",
+                      shard="perms", ingest="sharded", device=dev).uns["morans_i"]
+np.testing.assert_allclose(sh["I"].to_numpy(), ref["I"].to_numpy(), rtol=1e-6, atol=1e-9)
+assert (sh["p_value"].to_numpy() != ref["p_value"].to_numpy()).mean() <= 0.03
+Xc = X.copy(); Xc[:, 5] = 0.75  # zero-variance gene must pool to exactly zero variance
+shc = spatial.morans_i(AnnDataLite(Xc, obsm={"spatial": coords}), n_permutations=9, seed=4, perm_source="philox",
+                       shard="perms", ingest="sharded", device=dev).uns["morans_i"]
+assert np.isnan(shc["I"].to_numpy()[5]) and np.isfinite(np.delete(shc["I"].to_numpy(), 5)).all()
+if rank == 0: print("ingest=sharded ok", flush=True)
 rep = spatial.morans_i(AnnDataLite(X, obsm={"spatial": coords}), n_permutations=33, seed=4, perm_source="replay",
                        shard="perms", device=dev).uns["morans_i"]
 one = spatial.morans_i(AnnDataLite(X, obsm={"spatial": coords}), n_permutations=33, seed=4, perm_source="replay",

@@ -1016,6 +1016,41 @@ extern "C" int sc_zscore(const void* X, int dtype, int64_t n, int64_t ldx, int g
   return zscore_impl<double>(static_cast<const double*>(X), n, ldx, g, cols, rows, Z, ldz, mean, std, zero_var, partial, st);
 }
 
+extern "C" int sc_zscore_apply(const void* X, int dtype, int64_t n, int64_t ldx, int g,
+                               const int32_t* cols, const int32_t* rows, const double* mean,
+                               const double* std, const uint8_t* zero_var, float* Z, int64_t ldz,
+                               sc_stream_t stream) {
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  SC_CHECK_ARG(X && mean && std && zero_var && Z, "sc_zscore_apply: null argument");
+  SC_CHECK_ARG(n >= 1 && g >= 1, "sc_zscore_apply: empty matrix (%lld x %d)", (long long)n, g);
+  SC_CHECK_ARG(ldz % 4 == 0 && ldz >= g, "sc_zscore_apply: ldz=%lld must be a multiple of 4 and >= g", (long long)ldz);
+  SC_CHECK_ARG(dtype == SC_F32 || dtype == SC_F64, "sc_zscore_apply: bad dtype %d", dtype);
+  const bool fast = dtype == SC_F32 && !cols && ldx % 4 == 0 && ldx >= (g + 3) / 4 * 4 &&
+                    (reinterpret_cast<uintptr_t>(X) & 15) == 0;
+  if (fast) {
+    const int zquads = (int)(ldz / 4);
+    int zq_log2 = 0;
+    while ((1 << zq_log2) < zquads && zq_log2 < 8) ++zq_log2;
+    const int zqw = 1 << zq_log2, zrpc = 256 >> zq_log2;
+    const int zbx = (zquads + zqw - 1) / zqw;
+    int64_t zby = ((int64_t)sm_count() * 16 + zbx - 1) / zbx;
+    const int64_t zmax = (n + zrpc - 1) / zrpc;
+    if (zby > zmax) zby = zmax;
+    if (zby > 65535) zby = 65535;
+    zscore_write4_kernel<<<dim3(zbx, (unsigned)zby), 256, 0, st>>>(static_cast<const float*>(X), n, ldx, g, rows, mean, std, zero_var, Z, ldz, zq_log2);
+  } else {
+    int64_t total = n * (ldz / 4);
+    int64_t want = (total + 255) / 256;
+    int blocks = (int)(want > sm_count() * 16 ? sm_count() * 16 : (want < 1 ? 1 : want));
+    if (dtype == SC_F32)
+      zscore_write_kernel<float><<<blocks, 256, 0, st>>>(static_cast<const float*>(X), n, ldx, g, cols, rows, mean, std, zero_var, Z, ldz);
+    else
+      zscore_write_kernel<double><<<blocks, 256, 0, st>>>(static_cast<const double*>(X), n, ldx, g, cols, rows, mean, std, zero_var, Z, ldz);
+  }
+  SC_LAUNCH_OK();
+  return SC_OK;
+}
+
 extern "C" int sc_csr_densify(const int64_t* indptr, const int32_t* indices, const void* data,
                               int dtype, int64_t n, const int32_t* colmap, int g_out, float* out,
                               int64_t ldo, sc_stream_t stream) {

@@ -47,6 +47,34 @@ def gene_groups_for(n_genes: int, world_size: int, min_genes: int = 500) -> int:
     return best
 
 
+def combine_moments(counts, means, stds):
+    """Pool per-block (count, mean, population std) of each gene into the moments of the whole
+    matrix (Chan et al. pairwise update, FP64 numpy).  Inputs are [B], [B, G], [B, G].
+    Differences are taken against block 0's mean so that a column that is constant everywhere pools
+    to variance exactly 0 (it must be flagged zero-variance, not divided by 1e-17)."""
+    import numpy as np
+
+    counts = np.asarray(counts, dtype=np.float64).reshape(-1, 1)
+    means = np.asarray(means, dtype=np.float64)
+    stds = np.asarray(stds, dtype=np.float64)
+    total = counts.sum()
+    delta0 = means - means[0:1]
+    mean = means[0] + (counts * delta0).sum(0) / total
+    m2 = (counts * stds * stds).sum(0) + (counts * (means - mean[None, :]) ** 2).sum(0)
+    const = np.all(stds == 0, axis=0) & np.all(delta0 == 0, axis=0)
+    var = np.where(const, 0.0, m2 / total)
+    std = np.sqrt(var)
+    return mean, std, (std == 0)
+
+
+def row_block(n: int, rank: int, world_size: int) -> Tuple[int, int, int]:
+    """Equal-sized row blocks for ``all_gather_into_tensor``: returns ``(rows_per_rank, lo, hi)``;
+    the last blocks may be short or empty."""
+    per = (n + world_size - 1) // world_size
+    lo = min(n, rank * per)
+    return per, lo, min(n, lo + per)
+
+
 def all_reduce_null(null, group=None) -> None:
     """Sum a ``MoranNull`` over the ranks of ``group`` (counts travel as exact FP64 integers)."""
     _, ws = world(group)

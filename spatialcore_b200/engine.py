@@ -355,6 +355,33 @@ def zscore_dense(X: torch.Tensor, cols: Optional[torch.Tensor] = None, rows: Opt
     return Standardized(Z=Z, g=g, mean=mean, std=std, zero_var=zero)
 
 
+def zscore_apply(X: torch.Tensor, mean: torch.Tensor, std: torch.Tensor, zero_var: torch.Tensor,
+                 cols: Optional[torch.Tensor] = None, rows: Optional[torch.Tensor] = None,
+                 out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """``sc_zscore_apply``: z-score ``X`` with GIVEN per-gene moments (row-sharded ingest: the moments
+    were combined over the ranks).  ``out`` may be a row slice of a larger [*, ld] buffer."""
+    _require_cuda(X, "X")
+    if X.dtype not in (torch.float32, torch.float64):
+        X = X.to(torch.float32)
+    if X.stride(1) != 1:
+        X = X.contiguous()
+    n = int(rows.numel()) if rows is not None else X.shape[0]
+    g = int(cols.numel()) if cols is not None else X.shape[1]
+    ld = padded_ld(g)
+    L = _lib.lib()
+    if out is None:
+        out = torch.empty((n, ld), dtype=torch.float32, device=X.device)
+    if out.shape != (n, ld) or out.stride(1) != 1 or out.stride(0) != ld or out.dtype != torch.float32:
+        raise ValueError("zscore_apply: out must be a float32 [n, padded_ld(g)] row-contiguous tensor")
+    check(
+        L.sc_zscore_apply(_ptr(X), SC_F32 if X.dtype == torch.float32 else SC_F64, n, X.stride(0), g, _ptr(cols),
+                          _ptr(rows), _ptr(mean), _ptr(std), _ptr(zero_var), _ptr(out), ld, _stream()),
+        "sc_zscore_apply",
+    )
+    _count()
+    return out
+
+
 def densify_csr(indptr: torch.Tensor, indices: torch.Tensor, data: torch.Tensor, n: int, n_cols: int,
                 colmap: Optional[torch.Tensor], g_out: int) -> torch.Tensor:
     """``sc_csr_densify``: CSR expression -> dense float32 [n, padded_ld(g_out)] on the device."""
