@@ -158,7 +158,7 @@ def device_step(engine, ac, coords_dev, X_dev, w, radius, seed, events=None, per
     mark("zscore")
     num, den, lag, _ = engine.lag_moran(graph_s, std.Z, g, want_lag=True)
     mark("lag")
-    s0, s1, s2 = engine.graph_moments(graph)
+    s0, s1, s2 = engine.graph_moments(graph_s)  # label-invariant; reverse-edge lookups are local in spatial order
     mark("moments")
     scale = (float(n) / s0) / den
     I = num * scale
@@ -286,9 +286,19 @@ def run_b200(args):
     except OSError:
         pass
     peak = float(peaks.get("hbm_gbs", 6650.0))
+    # DRAM bytes per launch of the same kernel at the same geometry, from the committed ncu --set full
+    # capture (profiles/); None for geometries that were not captured
+    traffic = None
+    try:
+        cap = json.load(open(os.path.join(ROOT, "profiles", "r01b_perm_rows_bulk16_c4_ncu.json")))
+        if args.workload == "C4" and g == 1000 and my_perms >= PB:
+            traffic = cap["traffic_bytes_per_launch"] * (my_perms / n_launch) / PB
+    except (OSError, KeyError, ValueError):
+        pass
     roofline = {"bound": "hbm", "kernel": "perm_rows_bulk_kernel<16> (cp.async.bulk gather pipeline, FP64 accumulate)", "achieved": round(achieved, 1), "peak": peak,
                 "peak_source": "MEASURED_PEAKS.json hbm_gbs (burst copy)" if peaks else "fallback 6650 GB/s",
-                "unit": "GB/s", "frac": round(achieved / peak, 4), "traffic": None,
+                "unit": "GB/s", "frac": round(achieved / peak, 4), "traffic": traffic,
+                "traffic_source": "ncu dram__bytes_read.sum + dram__bytes_write.sum of a full 16-permutation launch (profiles/r01b_perm_rows_bulk16_c4_ncu.json), scaled to the mean permutations per launch" if traffic else None,
                 "launch_ms": round(perm_ms / n_launch, 4), "perms_per_launch": PB,
                 "bytes_per_launch": bytes_per_launch}
 

@@ -377,7 +377,7 @@ def morans_i(
     else:
         std = _standardize(adata, layer, names, device, rows=co.order)
     num, den, lag, _ = engine.lag_moran(graph_s, std.Z, g, want_lag=n_permutations > 0)
-    s0, s1, s2 = engine.graph_moments(graph)
+    s0, s1, s2 = engine.graph_moments(graph_s)  # s0, s1, s2 do not depend on the labelling of the cells
     scale = (float(n) / s0) / den  # I = scale * Σ z·lag ; NaN for zero-variance genes, as 0/0 upstream
     I_dev = num * scale
 
