@@ -83,12 +83,14 @@ if want("lag"):
 
 if want("lagsweep"):
     sweep = {}
-    for vec in (1, 2):
-        for chunk in (64, 128, 256, 512):
-            os.environ["SC_LAG_VEC"], os.environ["SC_LAG_CHUNK"] = str(vec), str(chunk)
-            sweep[f"vec{vec}_chunk{chunk}"] = [round(timed(lambda: eng.lag_moran(gs, std.Z, g)), 3),
-                                               round(timed(lambda: eng.lag_moran(gs, std.Z, g, want_lag=False)), 3)]
-    del os.environ["SC_LAG_VEC"], os.environ["SC_LAG_CHUNK"]
+    for variant, vecs, chunks in (("tile", (1,), (256, 512, 1024)), ("l1", (1, 2), (128, 512))):
+        os.environ["SC_LAG_VARIANT"] = variant
+        for vec in vecs:
+            for chunk in chunks:
+                os.environ["SC_LAG_VEC"], os.environ["SC_LAG_CHUNK"] = str(vec), str(chunk)
+                sweep[f"{variant}_vec{vec}_chunk{chunk}"] = [round(timed(lambda: eng.lag_moran(gs, std.Z, g)), 3),
+                                                             round(timed(lambda: eng.lag_moran(gs, std.Z, g, want_lag=False)), 3)]
+    del os.environ["SC_LAG_VEC"], os.environ["SC_LAG_CHUNK"], os.environ["SC_LAG_VARIANT"]
     out["lag_sweep_ms_[with_lag,stat_only]"] = sweep
 
 if want("values"):

@@ -410,6 +410,115 @@ lag_stat_kernel(const int32_t* __restrict__ indptr, const int32_t* __restrict__ 
   }
 }
 
+// ---- lag through shared memory ---------------------------------------------------------------------
+// In spatial order ~87 % of a row's neighbours lie inside its own 512-row chunk (measured on uniform
+// 2-D points at degree 20).  The chunk's own rows are contiguous, so the CTA stages them once
+// (cp.async, 128 B per row) and serves in-chunk neighbours from shared memory (LDS: 128 B/clk/SM)
+// while only the halo goes through L1 (LDG: ~70 B/clk/SM, 2 cycles per extra line).  Same arithmetic,
+// same summation order as lag_stat_kernel.
+__device__ __forceinline__ void cp_async16(void* smem, const void* gmem) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(smem)), "l"(gmem) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+
+template <bool HAS_W>
+__global__ void __launch_bounds__(kStatThreads, 3)
+lag_stat_tile_kernel(const int32_t* __restrict__ indptr, const int32_t* __restrict__ indices,
+                     const float* __restrict__ weights, int64_t n, int k_fixed,
+                     const float* __restrict__ Zself, const float* __restrict__ Zlag, int64_t ldz,
+                     float* __restrict__ lag, float* __restrict__ local, int64_t ldl,
+                     double* __restrict__ partial, const float* __restrict__ cell_obs,
+                     int32_t* __restrict__ cell_cnt, int64_t ldc, int64_t n_chunks, int chunk_rows) {
+  extern __shared__ __align__(128) unsigned char lag_smem[];
+  float4* tile = reinterpret_cast<float4*>(lag_smem);  // [chunk_rows][8] float4
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int q = lane & (kLagColQuads - 1);
+  const int rslot = warp * (32 / kLagColQuads) + (lane >> 3);
+  const int64_t col = ((int64_t)blockIdx.x * kLagColQuads + q) * 4;
+  const bool active = col < ldz;
+  const char* zbase = reinterpret_cast<const char*>(Zlag + col);
+  const uint32_t ldzb = (uint32_t)ldz * 4u;
+  double num[4] = {0, 0, 0, 0}, den[4] = {0, 0, 0, 0};
+
+  for (int64_t chunk = blockIdx.y; chunk < n_chunks; chunk += gridDim.y) {
+    const int r0 = (int)(chunk * chunk_rows);
+    const int rows_here = (int)min((int64_t)chunk_rows, n - r0);
+    __syncthreads();  // previous chunk's readers are done with the tile
+    if (active)
+      for (int r = rslot; r < rows_here; r += kLagRowsPerPass)
+        cp_async16(&tile[r * kLagColQuads + q], zbase + (uint64_t)(uint32_t)(r0 + r) * ldzb);
+    cp_async_wait_all();
+    __syncthreads();
+#pragma unroll 1
+    for (int pass = 0; pass < rows_here; pass += kLagRowsPerPass) {
+      const int lrow = pass + rslot;
+      if (lrow >= rows_here || !active) continue;
+      const int64_t row = (int64_t)r0 + lrow;
+      int64_t b;
+      int deg;
+      if (indptr) { b = indptr[row]; deg = indptr[row + 1] - (int)b; } else { b = row * k_fixed; deg = k_fixed; }
+      const int32_t* __restrict__ ip = indices + b;
+      const float* __restrict__ wp = HAS_W ? weights + b : nullptr;
+      float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+      auto fetch = [&](int j) -> float4 {
+        const uint32_t off = (uint32_t)(j - r0);
+        if (off < (uint32_t)rows_here) return tile[off * kLagColQuads + q];
+        return ldg4_row(zbase, j, ldzb);
+      };
+      int t = 0;
+#pragma unroll 1
+      for (; t + 4 <= deg; t += 4) {
+        const int j0 = ip[t], j1 = ip[t + 1], j2 = ip[t + 2], j3 = ip[t + 3];
+        float w0 = 1.f, w1 = 1.f, w2 = 1.f, w3 = 1.f;
+        if (HAS_W) { w0 = wp[t]; w1 = wp[t + 1]; w2 = wp[t + 2]; w3 = wp[t + 3]; }
+        const float4 v0 = fetch(j0), v1 = fetch(j1), v2 = fetch(j2), v3 = fetch(j3);
+        acc.x += w0 * v0.x + w1 * v1.x + w2 * v2.x + w3 * v3.x;
+        acc.y += w0 * v0.y + w1 * v1.y + w2 * v2.y + w3 * v3.y;
+        acc.z += w0 * v0.z + w1 * v1.z + w2 * v2.z + w3 * v3.z;
+        acc.w += w0 * v0.w + w1 * v1.w + w2 * v2.w + w3 * v3.w;
+      }
+#pragma unroll 1
+      for (; t < deg; ++t) fma4(acc, HAS_W ? wp[t] : 1.f, fetch(ip[t]));
+      if (!HAS_W) {
+        const float inv = (deg > 0) ? 1.f / (float)deg : 0.f;
+        acc.x *= inv; acc.y *= inv; acc.z *= inv; acc.w *= inv;
+      }
+      const float4 z = Zself ? ldg4(Zself + row * ldz + col) : tile[lrow * kLagColQuads + q];
+      const float4 loc = make_float4(z.x * acc.x, z.y * acc.y, z.z * acc.z, z.w * acc.w);
+      if (lag) *reinterpret_cast<float4*>(lag + row * ldl + col) = acc;
+      if (local) *reinterpret_cast<float4*>(local + row * ldl + col) = loc;
+      if (cell_cnt) {
+        const float4 o = ldg4(cell_obs + row * ldc + col);
+        int4* cp = reinterpret_cast<int4*>(cell_cnt + row * ldc + col);
+        int4 cc = *cp;
+        cc.x += fabsf(loc.x) >= fabsf(o.x); cc.y += fabsf(loc.y) >= fabsf(o.y);
+        cc.z += fabsf(loc.z) >= fabsf(o.z); cc.w += fabsf(loc.w) >= fabsf(o.w);
+        *cp = cc;
+      }
+      const double zx = z.x, zy = z.y, zz = z.z, zw = z.w;
+      num[0] = fma(zx, (double)acc.x, num[0]); den[0] = fma(zx, zx, den[0]);
+      num[1] = fma(zy, (double)acc.y, num[1]); den[1] = fma(zy, zy, den[1]);
+      num[2] = fma(zz, (double)acc.z, num[2]); den[2] = fma(zz, zz, den[2]);
+      num[3] = fma(zw, (double)acc.w, num[3]); den[3] = fma(zw, zw, den[3]);
+    }
+  }
+  __syncthreads();
+  double (*sh)[kLagRowsPerPass][kLagColQuads][4] = reinterpret_cast<double (*)[kLagRowsPerPass][kLagColQuads][4]>(lag_smem);
+#pragma unroll
+  for (int c = 0; c < 4; ++c) { sh[0][rslot][q][c] = num[c]; sh[1][rslot][q][c] = den[c]; }
+  __syncthreads();
+  if (rslot == 0 && active) {
+    double* p = partial + ((int64_t)blockIdx.y * 2) * ldz + col;
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+      double a = 0, d = 0;
+#pragma unroll 4
+      for (int r = 0; r < kLagRowsPerPass; ++r) { a += sh[0][r][q][c]; d += sh[1][r][q][c]; }
+      p[c] = a; p[ldz + c] = d;
+    }
+  }
+}
+
 // ------------------------------------------------------------------------------------------------
 // permutation sources
 // ------------------------------------------------------------------------------------------------
@@ -909,6 +1018,13 @@ static int launch_lag_stat(const int32_t* indptr, const int32_t* indices, const 
   while (chunk_rows > 64 && ((n + chunk_rows - 1) / chunk_rows) * ((ldz + 31) / 32) < 4 * (int64_t)sm_count()) chunk_rows /= 2;
   if (const char* e = getenv("SC_LAG_VEC")) { int v = atoi(e); if (v == 1 || v == 2) vec = v; }
   if (const char* e = getenv("SC_LAG_CHUNK")) { int v = atoi(e); if (v >= 32 && v % 32 == 0 && v <= 4096) chunk_rows = v; }
+  // SC_LAG_VARIANT=tile selects the shared-memory variant.  Measured on B200: it wins on C2 (kNN k=15,
+  // 500 k x 400: 1.22 vs 1.44 ms) and loses on C4 (radius, 5 M x 1000: 42 vs 33 ms) -- both variants
+  // are bound by exposed L1-miss latency (ncu: long-scoreboard stalls, 41-56 % issue utilisation), and
+  // the tile's 64 KB per CTA costs a quarter of the resident warps.  Default: the L1 variant.
+  const char* variant = getenv("SC_LAG_VARIANT");
+  const bool tile = ldz >= 32 && variant && !strcmp(variant, "tile");
+  if (tile) vec = 1;
   const int colblk = 32 * vec;
   const int bx = (int)((ldz + colblk - 1) / colblk);
   const int64_t n_chunks = (n + chunk_rows - 1) / chunk_rows;
@@ -917,6 +1033,20 @@ static int launch_lag_stat(const int32_t* indptr, const int32_t* indices, const 
   if (by > kMaxStatBlocks) by = kMaxStatBlocks;
   if (by < 1) by = 1;
   dim3 grid(bx, (unsigned)by);
+  if (tile) {
+    size_t dyn = (size_t)chunk_rows * kLagColQuads * sizeof(float4);
+    if (dyn < sizeof(double) * 2 * kLagRowsPerPass * kLagColQuads * 4) dyn = sizeof(double) * 2 * kLagRowsPerPass * kLagColQuads * 4;
+    if (weights) {
+      SC_CUDA_OK(cudaFuncSetAttribute(lag_stat_tile_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn));
+      lag_stat_tile_kernel<true><<<grid, kStatThreads, dyn, st>>>(indptr, indices, weights, n, k_fixed, Zself, Zlag, ldz, lag, local, ldl, partial, cell_obs, cell_cnt, ldc, n_chunks, chunk_rows);
+    } else {
+      SC_CUDA_OK(cudaFuncSetAttribute(lag_stat_tile_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn));
+      lag_stat_tile_kernel<false><<<grid, kStatThreads, dyn, st>>>(indptr, indices, weights, n, k_fixed, Zself, Zlag, ldz, lag, local, ldl, partial, cell_obs, cell_cnt, ldc, n_chunks, chunk_rows);
+    }
+    SC_LAUNCH_OK();
+    *by_out = (int)by;
+    return SC_OK;
+  }
 #define SC_LAG_ARGS grid, st, indptr, indices, weights, n, k_fixed, Zself, Zlag, ldz, lag, local, ldl, partial, cell_obs, cell_cnt, ldc, n_chunks, chunk_rows
   if (weights) { if (vec == 2) launch_lag_stat_t<true, 2>(SC_LAG_ARGS); else launch_lag_stat_t<true, 1>(SC_LAG_ARGS); }
   else         { if (vec == 2) launch_lag_stat_t<false, 2>(SC_LAG_ARGS); else launch_lag_stat_t<false, 1>(SC_LAG_ARGS); }
