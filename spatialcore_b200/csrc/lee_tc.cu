@@ -8,13 +8,22 @@
 // Layout trick: both operands are cell-major [cells][genes], i.e. "MN-major" for this product.
 // For 32-bit MN-major operands the tensor core accepts exactly one shared-memory layout,
 // SWIZZLE_128B_BASE32B: rows of 128 B (32 genes), 32-byte chunks XOR-swizzled with (row mod 4),
-// atoms of 4 K-rows.  A TMA box of (32 genes x 8 cells x atoms) with CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B
-// lands in that layout directly: K groups (4 cells) SBO = 512 B apart, gene atoms LBO = 1024 B
-// apart — no transpose of Z or lag is ever made.
+// atoms of 4 K-rows.  A TMA box of (32 genes x 8 cells) with CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B
+// lands as one such atom: K groups (4 cells) SBO = 512 B apart, gene atoms LBO = 1024 B apart --
+// no transpose of Z or lag is ever made, and genes beyond the matrix width are zero-filled by TMA.
 //
-// Work decomposition: CTA = one 128 x 256 output tile x one chunk of kLeeTcChunk cells.  The FP32
-// tile of each chunk is written to a partial buffer; the chunks are summed in FP64 afterwards.
-// Warp roles: 0 = TMA producer, 1 = TMEM allocator + MMA issuer, 2..5 = epilogue (TMEM -> global).
+// The hi/lo split is fused: TMA brings the RAW FP32 tiles of Z and lag, the epilogue warps (idle
+// between accumulator drains) rewrite each staged element in place as hi and store lo next to it
+// (an element-wise map, so the swizzled layout is irrelevant), fence the generic->async proxy and
+// release the stage to the MMA warp.  No split copies of the operands exist in HBM.
+//
+// Work decomposition: CTA = one 128 x 256 output tile x a span of consecutive `chunk`-cell chunks.
+// The tensor core truncates when it adds into its FP32 accumulator, so a chunk is kept short (256
+// cells = 96 accumulate steps); chunks alternate between two 256-column TMEM accumulators, and while
+// the MMA warp fills one the eight epilogue warps drain the other into FP32 REGISTER accumulators
+// (round-to-nearest adds).  One FP32 tile per CTA goes to a small partial buffer ([splits] tiles,
+// ~40 MB instead of one tile per chunk = 3.3 GB at C3) and the splits are summed in FP64.
+// Warp roles: 0 = TMA producer, 1 = TMEM allocator + MMA issuer, 2..9 = epilogue.
 #include <cuda.h>
 #include <cudaTypedefs.h>
 
@@ -27,8 +36,9 @@ namespace sc {
 constexpr int kTcM = 128;      // UMMA M (genes x)
 constexpr int kTcN = 256;      // UMMA N (genes y)
 constexpr int kTcK = 8;        // cells per stage = one tf32 UMMA K step
-constexpr int kTcStages = 4;
-constexpr int kTcThreads = 192;
+constexpr int kTcStages = 8;
+constexpr int kTcThreads = 320;
+constexpr int kTcEpiWarps = 8;
 constexpr uint32_t kTcABytes = kTcM * kTcK * 4;  // 4 KB per hi / lo
 constexpr uint32_t kTcBBytes = kTcN * kTcK * 4;  // 8 KB per hi / lo
 constexpr uint32_t kTcStageBytes = 2 * kTcABytes + 2 * kTcBBytes;  // 24 KB
@@ -57,12 +67,11 @@ __device__ __forceinline__ void tc_mbar_wait(uint64_t* bar, uint32_t parity) {
       "r"(parity)
       : "memory");
 }
-__device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* map, int c0, int c1, int c2,
-                                            uint64_t* bar) {
+__device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, int c0, int c1, uint64_t* bar) {
   asm volatile(
-      "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];" ::"r"(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(
           tc_smem_u32(dst)),
-      "l"(map), "r"(tc_smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
+      "l"(map), "r"(tc_smem_u32(bar)), "r"(c0), "r"(c1)
       : "memory");
 }
 
@@ -100,19 +109,23 @@ __device__ __forceinline__ void umma_commit(uint64_t* bar) {
                : "memory");
 }
 
-__global__ void __launch_bounds__(kTcThreads)
-lee_tc_kernel(const __grid_constant__ CUtensorMap map_ahi, const __grid_constant__ CUtensorMap map_alo,
-              const __grid_constant__ CUtensorMap map_bhi, const __grid_constant__ CUtensorMap map_blo,
-              int64_t n, int64_t chunk, float* __restrict__ partial, int64_t ldt) {
+__device__ __forceinline__ void tc_mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(tc_smem_u32(bar)) : "memory");
+}
+
+__global__ void __launch_bounds__(kTcThreads, 1)
+lee_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
+              int64_t n, int64_t chunk, int chunks_per_cta, float* __restrict__ partial, int64_t ldt) {
   extern __shared__ __align__(1024) unsigned char tc_smem[];
-  __shared__ uint64_t full_bar[kTcStages], empty_bar[kTcStages], tmem_full_bar;
+  __shared__ uint64_t full_bar[kTcStages], split_bar[kTcStages], empty_bar[kTcStages];
+  __shared__ uint64_t tmem_full_bar[2], tmem_empty_bar[2];
   __shared__ uint32_t tmem_base_slot;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int n0 = blockIdx.x * kTcN, m0 = blockIdx.y * kTcM;
-  const int64_t k_begin = (int64_t)blockIdx.z * chunk;
-  const int64_t k_end = min(n, k_begin + chunk);
-  const int k_steps = (int)((k_end - k_begin + kTcK - 1) / kTcK);
+  const int64_t cta_begin = (int64_t)blockIdx.z * chunks_per_cta * chunk;
+  const int64_t cta_end = min(n, cta_begin + (int64_t)chunks_per_cta * chunk);
+  const int n_chunks = cta_end > cta_begin ? (int)((cta_end - cta_begin + chunk - 1) / chunk) : 0;
 
   // dynamic smem is only guaranteed 16-byte aligned by the runtime: align the ring to 1024 B by hand
   const uint32_t raw = tc_smem_u32(tc_smem);
@@ -120,14 +133,18 @@ lee_tc_kernel(const __grid_constant__ CUtensorMap map_ahi, const __grid_constant
   unsigned char* ring_ptr = tc_smem + (ring - raw);
 
   if (threadIdx.x == 0) {
-    for (int s = 0; s < kTcStages; ++s) { tc_mbar_init(&full_bar[s], 1); tc_mbar_init(&empty_bar[s], 1); }
-    tc_mbar_init(&tmem_full_bar, 1);
+    for (int s = 0; s < kTcStages; ++s) {
+      tc_mbar_init(&full_bar[s], 1);
+      tc_mbar_init(&split_bar[s], kTcEpiWarps / 2);
+      tc_mbar_init(&empty_bar[s], 1);
+    }
+    for (int b = 0; b < 2; ++b) { tc_mbar_init(&tmem_full_bar[b], 1); tc_mbar_init(&tmem_empty_bar[b], kTcEpiWarps); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(
                      tc_smem_u32(&tmem_base_slot)),
-                 "n"(kTcN)
+                 "n"(2 * kTcN)
                  : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
@@ -137,100 +154,135 @@ lee_tc_kernel(const __grid_constant__ CUtensorMap map_ahi, const __grid_constant
   const uint32_t tmem_d = tmem_base_slot;
 
   if (warp == 0) {
-    // ===== TMA producer =====
+    // ===== TMA producer: raw FP32 tiles, one continuous stream of K steps over the CTA's chunks =====
     if (lane == 0) {
-      for (int it = 0; it < k_steps; ++it) {
+      const int total_steps = (int)((cta_end - cta_begin + kTcK - 1) / kTcK);
+      for (int it = 0; it < total_steps; ++it) {
         const int s = it % kTcStages;
         const uint32_t ph = (uint32_t)(it / kTcStages) & 1u;
         tc_mbar_wait(&empty_bar[s], ph ^ 1u);
-        tc_mbar_expect_tx(&full_bar[s], kTcStageBytes);
+        tc_mbar_expect_tx(&full_bar[s], kTcABytes + kTcBBytes);
         unsigned char* st = ring_ptr + (size_t)s * kTcStageBytes;
-        const int cell = (int)(k_begin + (int64_t)it * kTcK);
-        tma_load_3d(st, &map_ahi, 0, cell, m0 / 32, &full_bar[s]);
-        tma_load_3d(st + kTcABytes, &map_alo, 0, cell, m0 / 32, &full_bar[s]);
-        tma_load_3d(st + 2 * kTcABytes, &map_bhi, 0, cell, n0 / 32, &full_bar[s]);
-        tma_load_3d(st + 2 * kTcABytes + kTcBBytes, &map_blo, 0, cell, n0 / 32, &full_bar[s]);
+        const int cell = (int)(cta_begin + (int64_t)it * kTcK);
+#pragma unroll
+        for (int a = 0; a < kTcM / 32; ++a) tma_load_2d(st + a * 1024, &map_a, m0 + 32 * a, cell, &full_bar[s]);
+#pragma unroll
+        for (int a = 0; a < kTcN / 32; ++a)
+          tma_load_2d(st + 2 * kTcABytes + a * 1024, &map_b, n0 + 32 * a, cell, &full_bar[s]);
       }
     }
   } else if (warp == 1) {
     // ===== MMA issuer (one elected lane) =====
     if (lane == 0) {
-      for (int it = 0; it < k_steps; ++it) {
-        const int s = it % kTcStages;
-        const uint32_t ph = (uint32_t)(it / kTcStages) & 1u;
-        tc_mbar_wait(&full_bar[s], ph);
+      int it = 0;
+      for (int c = 0; c < n_chunks; ++c) {
+        const int buf = c & 1;
+        tc_mbar_wait(&tmem_empty_bar[buf], (((uint32_t)c >> 1) & 1u) ^ 1u);  // epilogue drained this accumulator
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        const uint32_t base = ring + (uint32_t)s * kTcStageBytes;
-        const uint64_t ahi = umma_desc_mn_sw128(base, 1024, 512);
-        const uint64_t alo = umma_desc_mn_sw128(base + kTcABytes, 1024, 512);
-        const uint64_t bhi = umma_desc_mn_sw128(base + 2 * kTcABytes, 1024, 512);
-        const uint64_t blo = umma_desc_mn_sw128(base + 2 * kTcABytes + kTcBBytes, 1024, 512);
-        umma_tf32(tmem_d, alo, bhi, it > 0 ? 1u : 0u);  // small terms first
-        umma_tf32(tmem_d, ahi, blo, 1u);
-        umma_tf32(tmem_d, ahi, bhi, 1u);
-        umma_commit(&empty_bar[s]);  // frees the stage when these MMAs have read it
+        const int64_t kb = cta_begin + (int64_t)c * chunk;
+        const int steps = (int)((min(cta_end, kb + chunk) - kb + kTcK - 1) / kTcK);
+        const uint32_t acc = tmem_d + (uint32_t)(buf * kTcN);
+        for (int ks = 0; ks < steps; ++ks, ++it) {
+          const int s = it % kTcStages;
+          const uint32_t ph = (uint32_t)(it / kTcStages) & 1u;
+          tc_mbar_wait(&split_bar[s], ph);
+          asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+          const uint32_t base = ring + (uint32_t)s * kTcStageBytes;
+          const uint64_t ahi = umma_desc_mn_sw128(base, 1024, 512);
+          const uint64_t alo = umma_desc_mn_sw128(base + kTcABytes, 1024, 512);
+          const uint64_t bhi = umma_desc_mn_sw128(base + 2 * kTcABytes, 1024, 512);
+          const uint64_t blo = umma_desc_mn_sw128(base + 2 * kTcABytes + kTcBBytes, 1024, 512);
+          umma_tf32(acc, alo, bhi, ks > 0 ? 1u : 0u);  // small terms first
+          umma_tf32(acc, ahi, blo, 1u);
+          umma_tf32(acc, ahi, bhi, 1u);
+          umma_commit(&empty_bar[s]);  // frees the stage when these MMAs have read it
+        }
+        umma_commit(&tmem_full_bar[buf]);  // this chunk's accumulator is complete
       }
-      umma_commit(&tmem_full_bar);   // accumulator complete
     }
   } else {
-    // ===== epilogue: TMEM -> registers -> FP32 partial tile =====
-    tc_mbar_wait(&tmem_full_bar, 0);
-    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-    const int lane_grp = warp & 3;               // TMEM lanes this warp may touch: 32*lane_grp ..
-    const int row = m0 + lane_grp * 32 + lane;   // output row (gene x)
-    float* dst = partial + ((int64_t)blockIdx.z * ldt + row) * ldt + n0;
-#pragma unroll 1
-    for (int c = 0; c < kTcN / 32; ++c) {
-      uint32_t v[32];
-      const uint32_t taddr = tmem_d + ((uint32_t)(lane_grp * 32) << 16) + (uint32_t)(c * 32);
-      asm volatile(
-          "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-          "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,"
-          "%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
-          : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
-            "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]),
-            "=r"(v[15]), "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]),
-            "=r"(v[22]), "=r"(v[23]), "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]),
-            "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
-          : "r"(taddr));
-      asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+    // ===== split + epilogue warps =====
+    const int ew = warp - 2, et = threadIdx.x - 64;   // 0..7, 0..255
+    const int lane_grp = warp & 3;               // TMEM lanes this warp may touch: 32*(warp % 4) ..
+    const int half = ew >> 2;                    // column half (128 of the 256 accumulator columns)
+    float acc[128];
 #pragma unroll
-      for (int j = 0; j < 32; j += 4)
-        *reinterpret_cast<float4*>(dst + c * 32 + j) =
-            make_float4(__uint_as_float(v[j]), __uint_as_float(v[j + 1]), __uint_as_float(v[j + 2]),
-                        __uint_as_float(v[j + 3]));
+    for (int j = 0; j < 128; ++j) acc[j] = 0.f;
+
+    // drain chunk c's accumulator into the register tile (round-to-nearest FP32 adds)
+    auto drain = [&](int c) {
+      const int buf = c & 1;
+      tc_mbar_wait(&tmem_full_bar[buf], ((uint32_t)c >> 1) & 1u);
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        uint32_t v[32];
+        const uint32_t taddr = tmem_d + ((uint32_t)(lane_grp * 32) << 16) + (uint32_t)(buf * kTcN + half * 128 + q * 32);
+        asm volatile(
+            "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+            "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,"
+            "%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+            : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+              "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]),
+              "=r"(v[15]), "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]),
+              "=r"(v[22]), "=r"(v[23]), "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]),
+              "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+            : "r"(taddr));
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+        for (int j = 0; j < 32; ++j) acc[q * 32 + j] += __uint_as_float(v[j]);
+      }
+      asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+      __syncwarp();
+      if (lane == 0) tc_mbar_arrive(&tmem_empty_bar[buf]);
+    };
+
+    int it = 0;
+    for (int c = 0; c < n_chunks; ++c) {
+      const int64_t kb = cta_begin + (int64_t)c * chunk;
+      const int steps = (int)((min(cta_end, kb + chunk) - kb + kTcK - 1) / kTcK);
+      for (int ks = 0; ks < steps; ++ks, ++it) {
+        // split stage `it`: 768 float4 (A 256, B 512), in place hi + separate lo.  The two column
+        // halves of the epilogue (4 warps each) take alternate stages, so two stages are in flight.
+        if (((it ^ half) & 1) == 0) {
+        const int s = it % kTcStages;
+        tc_mbar_wait(&full_bar[s], (uint32_t)(it / kTcStages) & 1u);
+        unsigned char* st = ring_ptr + (size_t)s * kTcStageBytes;
+#pragma unroll
+        for (int u = 0; u < 6; ++u) {
+          const int idx = (et & 127) + u * 128;
+          unsigned char* hp = idx < 256 ? st + idx * 16 : st + 2 * kTcABytes + (idx - 256) * 16;
+          unsigned char* lp = hp + (idx < 256 ? kTcABytes : kTcBBytes);
+          const float4 x = *reinterpret_cast<const float4*>(hp);
+          float4 h, l;
+          h.x = __uint_as_float(__float_as_uint(x.x) & 0xFFFFE000u); l.x = x.x - h.x;
+          h.y = __uint_as_float(__float_as_uint(x.y) & 0xFFFFE000u); l.y = x.y - h.y;
+          h.z = __uint_as_float(__float_as_uint(x.z) & 0xFFFFE000u); l.z = x.z - h.z;
+          h.w = __uint_as_float(__float_as_uint(x.w) & 0xFFFFE000u); l.w = x.w - h.w;
+          *reinterpret_cast<float4*>(hp) = h;
+          *reinterpret_cast<float4*>(lp) = l;
+        }
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic writes -> visible to UMMA / TMA
+        __syncwarp();
+        if (lane == 0) tc_mbar_arrive(&split_bar[s]);
+        }
+        // the previous chunk's MMAs have retired by now: drain it while this chunk computes
+        if (c > 0 && ks == (steps > 4 ? 4 : steps - 1)) drain(c - 1);
+      }
     }
+    if (n_chunks > 0) drain(n_chunks - 1);
+    const int row = m0 + lane_grp * 32 + lane;   // output row (gene x)
+    float* dst = partial + ((int64_t)blockIdx.z * ldt + row) * ldt + n0 + half * 128;
+#pragma unroll
+    for (int j = 0; j < 128; j += 4)
+      *reinterpret_cast<float4*>(dst + j) = make_float4(acc[j], acc[j + 1], acc[j + 2], acc[j + 3]);
   }
 
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
   if (warp == 1) {
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_d), "n"(kTcN) : "memory");
-  }
-}
-
-// hi = x with the low 13 mantissa bits cleared (a TF32 value), lo = x - hi; zero padding to ldt.
-__global__ void __launch_bounds__(256)
-lee_split_kernel(const float* __restrict__ X, int64_t ldx, int64_t n, int g, int64_t ldt,
-                 float* __restrict__ hi, float* __restrict__ lo) {
-  const int64_t Q = ldt / 4;
-  const int64_t total = n * Q;
-  for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < total;
-       t += (int64_t)gridDim.x * blockDim.x) {
-    const int64_t r = t / Q;
-    const int c = (int)(t - r * Q) * 4;
-    float4 x = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (c + 3 < ldx) x = ldg4(X + r * ldx + c);
-    float xs[4] = {x.x, x.y, x.z, x.w}, h[4], l[4];
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      float v = (c + j < g) ? xs[j] : 0.f;
-      h[j] = __uint_as_float(__float_as_uint(v) & 0xFFFFE000u);
-      l[j] = v - h[j];
-    }
-    *reinterpret_cast<float4*>(hi + r * ldt + c) = make_float4(h[0], h[1], h[2], h[3]);
-    *reinterpret_cast<float4*>(lo + r * ldt + c) = make_float4(l[0], l[1], l[2], l[3]);
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_d), "n"(2 * kTcN) : "memory");
   }
 }
 
@@ -245,9 +297,11 @@ __global__ void lee_tc_reduce_kernel(const float* __restrict__ partial, int chun
 }
 
 struct TcPlan {
-  int64_t ldt;    // genes padded to a multiple of 256
-  int64_t chunk;  // cells per CTA (multiple of 8)
-  int chunks;
+  int64_t ldt;         // genes padded to a multiple of 256
+  int64_t chunk;       // cells per TMEM accumulation (multiple of 8)
+  int chunks;          // over all cells
+  int chunks_per_cta;  // consecutive chunks one CTA folds in registers
+  int splits;          // CTAs along the cell dimension = partial tiles
 };
 
 static TcPlan tc_plan(int64_t n, int g) {
@@ -258,9 +312,16 @@ static TcPlan tc_plan(int64_t n, int g) {
   // accurate but write more partial tiles.  SC_LEE_TC_CHUNK overrides (multiple of 8).
   int64_t chunk = 256;
   if (const char* e = getenv("SC_LEE_TC_CHUNK")) { long v = atol(e); if (v >= 8) chunk = (v + 7) / 8 * 8; }
-  while ((n + chunk - 1) / chunk > kLeeTcMaxChunks) chunk *= 2;
   p.chunk = chunk;
   p.chunks = (int)((n + chunk - 1) / chunk);
+  // one CTA per SM (512 TMEM columns): ~2 waves of CTAs over the (tiles x splits) grid
+  const int tiles = (int)((p.ldt / kTcN) * (p.ldt / kTcM));
+  int splits = (2 * sm_count()) / tiles;  // floor: a partial third wave would leave most SMs idle at the end
+  if (splits > p.chunks) splits = p.chunks;
+  if (splits > kLeeTcMaxChunks) splits = kLeeTcMaxChunks;
+  if (splits < 1) splits = 1;
+  p.chunks_per_cta = (p.chunks + splits - 1) / splits;
+  p.splits = (p.chunks + p.chunks_per_cta - 1) / p.chunks_per_cta;
   return p;
 }
 
@@ -276,16 +337,17 @@ static PFN_cuTensorMapEncodeTiled_v12000 get_encode() {
   return fn;
 }
 
-// 3-D view of a cell-major [n][ldt] FP32 matrix: (32 genes, n cells, ldt/32 gene groups); box
-// (32, 8, atoms) lands as `atoms` MN-major SW128_32B gene atoms, 1024 B apart (2 K groups each).
-static int make_map(CUtensorMap* map, const float* base, int64_t n, int64_t ldt, int atoms) {
+// 2-D view of a cell-major [n][ld] FP32 matrix: (ld genes, n cells); a box of (32 genes, 8 cells)
+// lands as one MN-major SW128_32B atom (1024 B, two 4-cell K groups).  Genes >= ld and cells >= n are
+// out of bounds for the map and arrive as zeros.
+static int make_map(CUtensorMap* map, const float* base, int64_t n, int64_t ld) {
   PFN_cuTensorMapEncodeTiled_v12000 enc = get_encode();
   if (!enc) { set_error("cuTensorMapEncodeTiled entry point not available"); return SC_ERR_CUDA; }
-  cuuint64_t dims[3] = {32, (cuuint64_t)n, (cuuint64_t)(ldt / 32)};
-  cuuint64_t strides[2] = {(cuuint64_t)ldt * 4, 128};
-  cuuint32_t box[3] = {32, (cuuint32_t)kTcK, (cuuint32_t)atoms};
-  cuuint32_t estr[3] = {1, 1, 1};
-  CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(base), dims, strides, box, estr,
+  cuuint64_t dims[2] = {(cuuint64_t)ld, (cuuint64_t)n};
+  cuuint64_t strides[1] = {(cuuint64_t)ld * 4};
+  cuuint32_t box[2] = {32, (cuuint32_t)kTcK};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), dims, strides, box, estr,
                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B,
                    CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled failed with CUresult %d", (int)r); return SC_ERR_CUDA; }
@@ -293,55 +355,39 @@ static int make_map(CUtensorMap* map, const float* base, int64_t n, int64_t ldt,
 }
 
 bool lee_tc_supported(int64_t n, int g, int64_t lda, int64_t ldb) {
-  (void)lda; (void)ldb;
-  return n >= 8 && g >= 1 && g <= 8192 && get_encode() != nullptr;
+  // TMA: row pitch a multiple of 16 bytes (base alignment is checked at launch)
+  return n >= 8 && g >= 1 && g <= 8192 && lda % 4 == 0 && ldb % 4 == 0 && get_encode() != nullptr;
 }
 
 size_t lee_tc_extra_workspace_bytes(int64_t n, int g) {
   if (n < 1 || g < 1) return 0;
   TcPlan p = tc_plan(n, g);
-  size_t split = 4 * align_up(sizeof(float) * (size_t)n * (size_t)p.ldt, 1024);
-  size_t part = align_up(sizeof(float) * (size_t)p.chunks * (size_t)p.ldt * (size_t)p.ldt, 1024);
-  return split + part + 4096;
+  return align_up(sizeof(float) * (size_t)p.splits * (size_t)p.ldt * (size_t)p.ldt, 1024) + 4096;
 }
 
 int lee_tc_launch(const float* A, int64_t lda, const float* B, int64_t ldb, int64_t n, int g,
                   const LeePlan&, double*, void* extra_ws, float* L, int64_t ldl, cudaStream_t st) {
   TcPlan p = tc_plan(n, g);
+  if ((reinterpret_cast<uintptr_t>(A) & 15) || (reinterpret_cast<uintptr_t>(B) & 15)) {
+    set_error("sc_lee_gemm: tcgen05 path needs 16-byte aligned operands");
+    return SC_ERR_UNSUPPORTED;
+  }
   char* w = static_cast<char*>(extra_ws);
   w = reinterpret_cast<char*>(align_up(reinterpret_cast<size_t>(w), 1024));
-  const size_t mat = align_up(sizeof(float) * (size_t)n * (size_t)p.ldt, 1024);
-  float* ahi = reinterpret_cast<float*>(w);
-  float* alo = reinterpret_cast<float*>(w + mat);
-  float* bhi = reinterpret_cast<float*>(w + 2 * mat);
-  float* blo = reinterpret_cast<float*>(w + 3 * mat);
-  float* partial = reinterpret_cast<float*>(w + 4 * mat);
-
-  int64_t total = n * (p.ldt / 4);
-  int blocks = (int)((total + 255) / 256 > 148 * 16 ? 148 * 16 : (total + 255) / 256);
-  lee_split_kernel<<<blocks, 256, 0, st>>>(A, lda, n, g, p.ldt, ahi, alo);
-  SC_LAUNCH_OK();
-  if (B == A) {
-    bhi = ahi; blo = alo;
-  } else {
-    lee_split_kernel<<<blocks, 256, 0, st>>>(B, ldb, n, g, p.ldt, bhi, blo);
-    SC_LAUNCH_OK();
-  }
-  CUtensorMap mah, mal, mbh, mbl;
+  float* partial = reinterpret_cast<float*>(w);
+  CUtensorMap ma, mb;
   int rc;
-  if ((rc = make_map(&mah, ahi, n, p.ldt, kTcM / 32))) return rc;
-  if ((rc = make_map(&mal, alo, n, p.ldt, kTcM / 32))) return rc;
-  if ((rc = make_map(&mbh, bhi, n, p.ldt, kTcN / 32))) return rc;
-  if ((rc = make_map(&mbl, blo, n, p.ldt, kTcN / 32))) return rc;
+  if ((rc = make_map(&ma, A, n, lda))) return rc;
+  if ((rc = make_map(&mb, B, n, ldb))) return rc;
 
   const size_t dyn = (size_t)kTcStages * kTcStageBytes + 1024;
   SC_CUDA_OK(cudaFuncSetAttribute(lee_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn));
-  dim3 grid((unsigned)(p.ldt / kTcN), (unsigned)(p.ldt / kTcM), (unsigned)p.chunks);
-  lee_tc_kernel<<<grid, kTcThreads, dyn, st>>>(mah, mal, mbh, mbl, n, p.chunk, partial, p.ldt);
+  dim3 grid((unsigned)(p.ldt / kTcN), (unsigned)(p.ldt / kTcM), (unsigned)p.splits);
+  lee_tc_kernel<<<grid, kTcThreads, dyn, st>>>(ma, mb, n, p.chunk, p.chunks_per_cta, partial, p.ldt);
   SC_LAUNCH_OK();
   dim3 blk(32, 8);
   dim3 grd((g + 31) / 32, (g + 7) / 8);
-  lee_tc_reduce_kernel<<<grd, blk, 0, st>>>(partial, p.chunks, p.ldt, g, L, ldl);
+  lee_tc_reduce_kernel<<<grd, blk, 0, st>>>(partial, p.splits, p.ldt, g, L, ldl);
   SC_LAUNCH_OK();
   return SC_OK;
 }
