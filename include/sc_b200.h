@@ -235,6 +235,35 @@ SC_API size_t sc_lee_gemm_workspace_bytes(int64_t n, int g);
 SC_API int sc_lee_gemm(const float* A, int64_t lda, const float* B, int64_t ldb, int64_t n, int g,
                 float* L, int64_t ldl, int impl, void* ws, size_t ws_bytes, sc_stream_t stream);
 
+/* ---------------------------------------------------------------------------------------------
+ * K-means on the neighbourhood-profile matrix (identify_niches, neighborhoods.py:299-522; replaces
+ * sklearn.cluster.KMeans: k-means++ seeding + Lloyd iterations).  X f32[n, ldx], d <= 128 features,
+ * k <= 64 centres, k*d <= 2048.
+ *
+ * sc_kmeans_assign: one Lloyd pass.  labels i32[n] IN/OUT (the previous labels are compared to count
+ * changes; fill with -1 before the first pass); mind f32[n] or NULL = squared distance to the chosen
+ * centre; out f64[k*d + k + 2] = per-centre feature sums [k][d], member counts [k], inertia
+ * (sum of min squared distances), number of rows whose label changed.  Nearest centre by FP32
+ * squared differences, first minimum wins (numpy argmin).
+ * ------------------------------------------------------------------------------------------- */
+SC_API size_t sc_kmeans_workspace_bytes(int64_t n, int d, int k);
+SC_API int sc_kmeans_assign(const float* X, int64_t n, int64_t ldx, int d, const float* centers, int k,
+                            int32_t* labels, float* mind, double* out, void* ws, size_t ws_bytes,
+                            sc_stream_t stream);
+
+/* k-means++ seeding.  cand i32[n_cand] (device) are row indices of candidate centres;
+ * pot_out f64[n_cand] = sum_i min(mind_in[i], ||x_i - x_cand||^2) (mind_in NULL: plain sum).
+ * commit >= 0: also store min(mind_in, distance to candidate `commit`) into mind_out f32[n]. */
+SC_API int sc_kmeans_pp_potential(const float* X, int64_t n, int64_t ldx, int d, const int32_t* cand,
+                                  int n_cand, const float* mind_in, float* mind_out, int commit,
+                                  double* pot_out, void* ws, size_t ws_bytes, sc_stream_t stream);
+
+/* D^2 sampling: idx_out[l] = searchsorted(cumsum_f64(mind), vals[l], side="left") clipped to n-1
+ * (vals f64[n_vals] on the device, n_vals <= 16). */
+SC_API size_t sc_kmeans_pp_sample_workspace_bytes(int64_t n);
+SC_API int sc_kmeans_pp_sample(const float* mind, int64_t n, const double* vals, int n_vals,
+                               int32_t* idx_out, void* ws, size_t ws_bytes, sc_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

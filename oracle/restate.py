@@ -371,3 +371,47 @@ def neighborhood_profile(coords, labels: np.ndarray, n_types: int, k=None, radiu
     if normalize:
         prof = prof / rs[:, None]
     return prof
+
+
+# --------------------------------------------------------------------------------------
+# niches (k-means on the profile matrix)
+# --------------------------------------------------------------------------------------
+
+
+def identify_niches(profiles: np.ndarray, n_niches: int, random_state: int = 0, n_init: int = 10, max_iter: int = 300):
+    """[R spatial/neighborhoods.py:441-466]: the reference's exact call,
+    ``KMeans(n_clusters, init="k-means++", n_init, max_iter, random_state).fit_predict(profiles)``
+    (scikit-learn is the third-party dependency behind this row and is installed on both the build
+    container and the GPU box).  Returns ``(labels, centroids, inertia)``."""
+    from sklearn.cluster import KMeans
+
+    km = KMeans(n_clusters=n_niches, init="k-means++", n_init=n_init, max_iter=max_iter, random_state=random_state)
+    labels = km.fit_predict(profiles)
+    return labels.astype(np.int32), km.cluster_centers_, float(km.inertia_)
+
+
+def kmeans_lloyd_from(profiles: np.ndarray, centers: np.ndarray, max_iter: int = 300):
+    """Lloyd iterations from given centres (``KMeans(init=centers, n_init=1)``): isolates the
+    iteration from the random seeding, so labels / centres are comparable exactly."""
+    from sklearn.cluster import KMeans
+
+    km = KMeans(n_clusters=centers.shape[0], init=np.asarray(centers), n_init=1, max_iter=max_iter)
+    labels = km.fit_predict(profiles)
+    return labels.astype(np.int32), km.cluster_centers_, float(km.inertia_), int(km.n_iter_)
+
+
+def adjusted_rand_index(a: np.ndarray, b: np.ndarray) -> float:
+    """Hubert-Arabie adjusted Rand index of two labelings (for clustering parity)."""
+    a = np.asarray(a)
+    b = np.asarray(b)
+    _, ai = np.unique(a, return_inverse=True)
+    _, bi = np.unique(b, return_inverse=True)
+    cont = np.zeros((ai.max() + 1, bi.max() + 1), dtype=np.int64)
+    np.add.at(cont, (ai, bi), 1)
+    comb = lambda x: x * (x - 1) / 2.0  # noqa: E731
+    s_ij = comb(cont).sum()
+    s_a = comb(cont.sum(1)).sum()
+    s_b = comb(cont.sum(0)).sum()
+    tot = comb(a.size)
+    expected = s_a * s_b / tot
+    return float((s_ij - expected) / (0.5 * (s_a + s_b) - expected))

@@ -48,6 +48,30 @@ if want("nbhd"):
     t0 = time.perf_counter(); spatial.compute_neighborhood_profile(a, "ct", k=30); out["C5_nbhd_api_e2e_s_2nd"] = time.perf_counter() - t0
     del cd, ld
 
+if want("niches"):
+    # C5: 2 M cells x 30 types, k=30 profiles -> 8 niches (n_init=10, max_iter=300 like the reference default)
+    n = 2_000_000
+    c = synthetic.coords_mixture(n, 2e4, 4); lab = synthetic.patchy_labels(c, 30, 5)
+    cd = torch.from_numpy(c).cuda(); ld = torch.from_numpy(lab).cuda()
+    _, _, prof = eng.knn_graph(cd, 30, labels=ld, n_types=30, want_idx=False)
+    eng.profile_normalize(prof, True)
+    from spatialcore_b200.spatial import niches
+    torch.cuda.synchronize(); t0 = time.perf_counter()
+    labels, cent, inertia, n_iter = niches.kmeans_fit(prof, 8, 10, 300, 0)
+    torch.cuda.synchronize(); out["C5_niches_kmeans_2M_x30_k8_ninit10_s"] = time.perf_counter() - t0
+    out["C5_niches_inertia"] = inertia
+    km = eng.KMeansDevice(prof, 8)
+    ms = timed(lambda: km.assign(cent))
+    out["C5_kmeans_assign_pass_ms"] = ms
+    out["C5_kmeans_assign_pass_GBps"] = (4.0 * n * 30 + 8.0 * n) / (ms / 1e3) / 1e9
+    from sklearn.cluster import KMeans
+    ph = prof.cpu().numpy()
+    sub = ph[:: 10]
+    t0 = time.perf_counter(); km_cpu = KMeans(n_clusters=8, init="k-means++", n_init=10, max_iter=300, random_state=0).fit(sub)
+    out["cpu_sklearn_kmeans_200k_sample_s"] = time.perf_counter() - t0
+    out["cpu_sklearn_cores"] = os.cpu_count()
+    del cd, ld, prof
+
 if want("lee"):
     n, g = 200_000, 1000
     c = synthetic.coords_mixture(n, 6e3, 2); cd = torch.from_numpy(c).cuda()

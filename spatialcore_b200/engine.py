@@ -551,3 +551,80 @@ def lee_gemm(A: torch.Tensor, B: torch.Tensor, g: int, impl: int = 0) -> torch.T
     )
     _count(2)
     return out
+
+
+# --------------------------------------------------------------------------------------------------
+# k-means on neighbourhood profiles (identify_niches)
+# --------------------------------------------------------------------------------------------------
+
+
+class KMeansDevice:
+    """Device state of one k-means problem: the profile matrix, labels, distances and workspaces.
+    Every numeric step is a kernel of ``csrc/niches.cu``; the host only draws random numbers, divides
+    K x d sums by counts and tests convergence."""
+
+    def __init__(self, X: torch.Tensor, k: int) -> None:
+        _require_cuda(X, "X")
+        if X.dim() != 2:
+            raise ValueError("X must be 2-D")
+        if X.dtype != torch.float32:
+            X = X.to(torch.float32)
+        if X.stride(1) != 1:
+            X = X.contiguous()
+        self.X, self.k = X, int(k)
+        self.n, self.d = X.shape
+        dev = X.device
+        L = _lib.lib()
+        self.labels = torch.full((self.n,), -1, dtype=torch.int32, device=dev)
+        self.mind = torch.empty(self.n, dtype=torch.float32, device=dev)
+        self.mind_tmp = torch.empty(self.n, dtype=torch.float32, device=dev)
+        self.out = torch.empty(self.k * self.d + self.k + 2, dtype=torch.float64, device=dev)
+        self.ws = _workspace(L.sc_kmeans_workspace_bytes(self.n, self.d, self.k), dev)
+        self.ws_sample = _workspace(L.sc_kmeans_pp_sample_workspace_bytes(self.n), dev)
+
+    def assign(self, centers: np.ndarray, want_mind: bool = False):
+        """One Lloyd pass with ``centers`` (float32 [k, d]).  Returns (sums[k,d], counts[k], inertia,
+        n_changed) as host float64 / ints; ``self.labels`` holds the new labels."""
+        L = _lib.lib()
+        c = torch.from_numpy(np.ascontiguousarray(centers, dtype=np.float32)).to(self.X.device)
+        check(
+            L.sc_kmeans_assign(_ptr(self.X), self.n, self.X.stride(0), self.d, _ptr(c), self.k, _ptr(self.labels),
+                               _ptr(self.mind) if want_mind else None, _ptr(self.out), _ptr(self.ws), self.ws.numel(), _stream()),
+            "sc_kmeans_assign",
+        )
+        _count(2)
+        o = self.out.cpu().numpy()
+        kd = self.k * self.d
+        return o[:kd].reshape(self.k, self.d).copy(), o[kd:kd + self.k].copy(), float(o[kd + self.k]), int(round(o[kd + self.k + 1]))
+
+    def pp_potential(self, cand: np.ndarray, first: bool, commit: int = -1) -> np.ndarray:
+        """Potentials of candidate centres (row indices); ``commit`` folds that candidate into mind."""
+        L = _lib.lib()
+        c = torch.from_numpy(np.ascontiguousarray(cand, dtype=np.int32)).to(self.X.device)
+        pot = torch.empty(len(cand), dtype=torch.float64, device=self.X.device)
+        check(
+            L.sc_kmeans_pp_potential(_ptr(self.X), self.n, self.X.stride(0), self.d, _ptr(c), len(cand),
+                                     None if first else _ptr(self.mind), _ptr(self.mind_tmp), int(commit), _ptr(pot),
+                                     _ptr(self.ws), self.ws.numel(), _stream()),
+            "sc_kmeans_pp_potential",
+        )
+        _count(2)
+        if commit >= 0:
+            self.mind, self.mind_tmp = self.mind_tmp, self.mind
+        return pot.cpu().numpy()
+
+    def pp_sample(self, vals: np.ndarray) -> np.ndarray:
+        """``searchsorted(cumsum(mind), vals)``: D^2 sampling of candidate rows."""
+        L = _lib.lib()
+        v = torch.from_numpy(np.ascontiguousarray(vals, dtype=np.float64)).to(self.X.device)
+        idx = torch.empty(len(vals), dtype=torch.int32, device=self.X.device)
+        check(
+            L.sc_kmeans_pp_sample(_ptr(self.mind), self.n, _ptr(v), len(vals), _ptr(idx), _ptr(self.ws_sample),
+                                  self.ws_sample.numel(), _stream()),
+            "sc_kmeans_pp_sample",
+        )
+        _count(3)
+        return idx.cpu().numpy().astype(np.int64)
+
+    def rows(self, idx) -> np.ndarray:
+        return self.X[torch.as_tensor(np.asarray(idx, dtype=np.int64), device=self.X.device)].cpu().numpy()

@@ -61,3 +61,13 @@ def with_duplicates(n: int, seed: int):
     dup = rng.integers(0, n, n // 10)
     c[rng.integers(0, n, n // 10)] = c[dup]
     return c
+
+
+def niche_profiles(n: int = 20000, n_types: int = 12, n_niches: int = 6, seed: int = 21):
+    """Row-normalised neighbourhood profiles drawn from a mixture of ``n_niches`` Dirichlet
+    archetypes (k = 15 neighbours): overlapping clusters, FP32 like the reference's profiles."""
+    rng = np.random.default_rng(seed)
+    arche = rng.dirichlet(np.full(n_types, 0.35), n_niches)
+    which = rng.integers(0, n_niches, n)
+    counts = np.stack([rng.multinomial(15, arche[w]) for w in which]).astype(np.float32)
+    return counts / counts.sum(1, keepdims=True)

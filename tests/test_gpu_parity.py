@@ -628,3 +628,104 @@ def test_values_null_materialised_matches_gather_kernel(eng, shape, k, monkeypat
     sims_lee = eng.perm_null_values(graph, std.Z, g, P, Zx=std.Z, perm_idx=pidx).cpu().numpy()
     want_lee = np.stack([(Z * (W @ Z[pm])).sum(0) for pm in perms])
     np.testing.assert_allclose(sims_lee, want_lee, rtol=0, atol=2e-5 * np.sqrt(n))
+
+
+# ---------------------------------------------------------------------------------------------
+# niches: k-means on the profile matrix
+# ---------------------------------------------------------------------------------------------
+
+
+def test_kmeans_lloyd_matches_sklearn_from_same_centres(eng, golden_dir):
+    """Same starting centres -> the device Lloyd iteration must land on sklearn's fixed point:
+    labels identical up to near-ties (sklearn ranks by |x|^2 - 2x.c + |c|^2 in FP32), centres and
+    inertia to FP32 accuracy."""
+    from spatialcore_b200.spatial import niches
+
+    P = inputs.niche_profiles()
+    rng = np.random.default_rng(3)
+    c0 = P[rng.choice(P.shape[0], 6, replace=False)].astype(np.float32)
+    want_l, want_c, want_i, _ = R.kmeans_lloyd_from(P, c0)
+    km = eng.KMeansDevice(torch.from_numpy(P).cuda(), 6)
+    var = P.astype(np.float64).var(0).mean()
+    cent, inertia, n_iter = niches.lloyd(km, c0, 300, float(var * 1e-4))
+    labels = km.labels.cpu().numpy()
+    assert (labels != want_l).mean() < 2e-3
+    assert R.adjusted_rand_index(labels, want_l) > 0.995
+    np.testing.assert_allclose(cent, want_c, rtol=0, atol=2e-3)
+    np.testing.assert_allclose(inertia, want_i, rtol=1e-4)
+    # one assignment pass against a numpy FP64 evaluation: sums, counts, inertia, labels
+    sums, counts, inert, changed = km.assign(want_c.astype(np.float32), want_mind=True)
+    d2 = ((P[:, None, :].astype(np.float64) - want_c[None].astype(np.float64)) ** 2).sum(-1)
+    lab64 = d2.argmin(1)
+    lab = km.labels.cpu().numpy()
+    near_tie = np.sort(d2, 1)[:, 1] - np.sort(d2, 1)[:, 0] < 1e-6
+    assert np.array_equal(lab[~near_tie], lab64[~near_tie])
+    np.testing.assert_allclose(inert, d2[np.arange(len(lab)), lab].sum(), rtol=1e-6)
+    np.testing.assert_allclose(km.mind.cpu().numpy(), d2[np.arange(len(lab)), lab], rtol=2e-5, atol=1e-7)
+    for k in range(6):
+        assert counts[k] == (lab == k).sum()
+        np.testing.assert_allclose(sums[k], P[lab == k].astype(np.float64).sum(0), rtol=1e-12, atol=1e-12)
+
+
+def test_kmeans_seeding_kernels(eng):
+    """k-means++ building blocks against numpy: candidate potentials with and without commit,
+    D^2 sampling = searchsorted(cumsum)."""
+    rng = np.random.default_rng(8)
+    n, d = 7013, 9
+    X = rng.random((n, d)).astype(np.float32)
+    km = eng.KMeansDevice(torch.from_numpy(X).cuda(), 4)
+    X64 = X.astype(np.float64)
+    dist = lambda i: ((X64 - X64[i]) ** 2).sum(1)  # noqa: E731
+    pot = km.pp_potential(np.array([17]), first=True, commit=0)
+    np.testing.assert_allclose(pot[0], dist(17).sum(), rtol=1e-6)
+    np.testing.assert_allclose(km.mind.cpu().numpy(), dist(17), rtol=2e-5, atol=1e-7)
+    mind = km.mind.cpu().numpy().astype(np.float64)
+    cand = np.array([5, 999, 7012, 17, 3000])
+    pots = km.pp_potential(cand, first=False)
+    want = np.array([np.minimum(mind, dist(c)).sum() for c in cand])
+    np.testing.assert_allclose(pots, want, rtol=1e-6)
+    vals = np.array([0.0, 1e-9, 0.25, 0.5, 0.999999, 1.0, 1.5]) * mind.sum()
+    got = km.pp_sample(vals)
+    ref = np.minimum(np.searchsorted(np.cumsum(mind), vals), n - 1)
+    assert np.abs(got - ref).max() <= 1  # cumsum order differs in the last FP64 bit
+    assert got[-1] == n - 1 and got[0] == ref[0]
+    km.pp_potential(cand[1:2], first=False, commit=0)
+    np.testing.assert_allclose(km.mind.cpu().numpy(), np.minimum(mind, dist(999)), rtol=2e-5, atol=1e-7)
+
+
+def test_identify_niches_matches_reference(api, golden_dir):
+    """Full drop-in against the frozen output of the unmodified reference: same partition (ARI),
+    inertia within 0.1 %, schema and error behaviour of [R neighborhoods.py:299-522]."""
+    g = np.load(os.path.join(golden_dir, "ref_niches.npz"))
+    prof = {"nbhd": np.load(os.path.join(golden_dir, "ref_nbhd.npz"))["knn30_norm"], "dirichlet": inputs.niche_profiles()}
+    for tag, P in prof.items():
+        k = int(g[f"{tag}_k"])
+        a = _adata(np.zeros((P.shape[0], 1), np.float32), np.zeros((P.shape[0], 2)))
+        a.obsm["neighborhood_profile"] = P
+        api.identify_niches(a, n_niches=k, random_state=0)
+        codes = a.obs["niche"].cat.codes.to_numpy()
+        assert list(a.obs["niche"].cat.categories) == [f"niche_{i + 1}" for i in range(k)]
+        inertia = a.uns["niche_params"]["inertia"]
+        assert inertia <= float(g[f"{tag}_inertia"]) * 1.001, (tag, inertia, float(g[f"{tag}_inertia"]))
+        assert R.adjusted_rand_index(codes, g[f"{tag}_labels"]) > 0.97, tag
+        assert a.uns["niche_centroids"].shape == (k, P.shape[1]) and a.uns["niche_centroids"].dtype == np.float32
+        assert a.uns["niche_params"]["n_niches"] == k and a.uns["niche_params"]["method"] == "kmeans"
+        assert a.uns["spatialcore_metadata"]["operations"][-1]["function"] == "identify_niches"
+        # deterministic in random_state
+        b = _adata(np.zeros((P.shape[0], 1), np.float32), np.zeros((P.shape[0], 2)))
+        b.obsm["neighborhood_profile"] = P
+        api.identify_niches(b, n_niches=k, random_state=0)
+        assert np.array_equal(b.obs["niche"].cat.codes.to_numpy(), codes)
+    a = _adata(np.zeros((50, 1), np.float32), np.zeros((50, 2)))
+    with pytest.raises(ValueError, match="not found. Run compute_neighborhood_profile"):
+        api.identify_niches(a, n_niches=3)
+    a.obsm["neighborhood_profile"] = np.abs(np.random.default_rng(0).normal(size=(50, 4))).astype(np.float32)
+    with pytest.raises(ValueError, match="Invalid method"):
+        api.identify_niches(a, n_niches=3, method="dbscan")
+    with pytest.raises(ValueError, match="n_niches must be >= 2"):
+        api.identify_niches(a, n_niches=1)
+    with pytest.raises(ValueError, match="cannot exceed number of cells"):
+        api.identify_niches(a, n_niches=51)
+    a.obsm["neighborhood_profile"][7] = 0
+    with pytest.raises(ValueError, match="1 cells have empty neighborhood profiles"):
+        api.identify_niches(a, n_niches=3)
