@@ -83,15 +83,21 @@ if want("lag"):
 
 if want("lagsweep"):
     sweep = {}
-    for variant, vecs, chunks in (("tile", (1,), (256, 512, 1024)), ("l1", (1, 2), (128, 512))):
-        os.environ["SC_LAG_VARIANT"] = variant
-        for vec in vecs:
-            for chunk in chunks:
-                os.environ["SC_LAG_VEC"], os.environ["SC_LAG_CHUNK"] = str(vec), str(chunk)
-                sweep[f"{variant}_vec{vec}_chunk{chunk}"] = [round(timed(lambda: eng.lag_moran(gs, std.Z, g)), 3),
-                                                             round(timed(lambda: eng.lag_moran(gs, std.Z, g, want_lag=False)), 3)]
-    del os.environ["SC_LAG_VEC"], os.environ["SC_LAG_CHUNK"], os.environ["SC_LAG_VARIANT"]
+    for unr in (4, 8, 16):
+        for chunk in (256, 512, 1024):
+            os.environ["SC_LAG_UNR"], os.environ["SC_LAG_CHUNK"] = str(unr), str(chunk)
+            sweep[f"unr{unr}_chunk{chunk}"] = [round(timed(lambda: eng.lag_moran(gs, std.Z, g)), 3),
+                                               round(timed(lambda: eng.lag_moran(gs, std.Z, g, want_lag=False)), 3)]
+    del os.environ["SC_LAG_UNR"], os.environ["SC_LAG_CHUNK"]
     out["lag_sweep_ms_[with_lag,stat_only]"] = sweep
+
+if want("lagocc"):
+    occ = {}
+    for pad in (0, 40, 60, 100):
+        os.environ["SC_LAG_PAD_KB"] = str(pad)
+        occ[f"pad{pad}KB"] = round(timed(lambda: eng.lag_moran(gs, std.Z, g)), 3)
+    del os.environ["SC_LAG_PAD_KB"]
+    out["lag_ms_vs_smem_pad(occupancy)"] = occ
 
 if want("values"):
     k1 = nnz / n + 1.0

@@ -275,18 +275,19 @@ __global__ void reduce_partials_kernel(const double* __restrict__ partial, int n
 // spatial lag + Moran numerator / denominator
 // ------------------------------------------------------------------------------------------------
 
-// Geometry: a CTA owns contiguous chunks of `chunk_rows` rows and one column block of 32*VEC genes
-// (8 lanes x VEC float4 per row, 32 rows per pass).  With the cells in spatial order the neighbour
+// Geometry: a CTA owns contiguous chunks of `chunk_rows` rows and one column block of 32 genes
+// (8 lanes x float4 per row, 32 rows per pass).  With the cells in spatial order the neighbour
 // rows of a chunk form a small working set (~1.7x the chunk) that stays in L1, so Z is read from HBM
 // about once instead of once per edge.  blockIdx.x = column block (fastest: the column blocks of one
 // chunk run together and share the CSR indices through L2), blockIdx.y = chunk group.
 //
 // The kernel is bound by L1 wavefronts and instruction issue, not HBM (one FADD/FFMA per 4 gathered
-// bytes), so the inner loop is kept lean: 32-bit edge counters, one IMAD.WIDE per gathered row, the
-// second float4 of a VEC=2 thread at a constant +128 B.  The Moran sums stay FP64 sums of the exact
+// bytes), so the inner loop is kept lean: 32-bit edge counters, one IMAD.WIDE per gathered row.
+// The Moran sums stay FP64 sums of the exact
 // FP32 products (identical arithmetic to the permutation kernels, so the identity permutation
 // reproduces the observed statistic to round-off).
 constexpr int kLagColQuads = 8;
+constexpr int kLagDefaultUnr = 4;
 constexpr int kLagRowsPerPass = kStatThreads / kLagColQuads;  // 32
 
 __device__ __forceinline__ float4 ldg4_row(const char* base, int j, uint32_t ld_bytes) {
@@ -296,116 +297,111 @@ __device__ __forceinline__ void fma4(float4& a, float w, const float4& v) {
   a.x += w * v.x; a.y += w * v.y; a.z += w * v.z; a.w += w * v.w;
 }
 
-template <bool HAS_W, int VEC>
-__global__ void __launch_bounds__(kStatThreads, 2)
+// UNR = neighbour rows fetched per inner iteration (loads in flight per thread).  The kernel is bound by
+// exposed L1-miss latency (ncu: long-scoreboard stalls, time inversely proportional to resident warps),
+// and the register file caps warps x loads-in-flight, so fewer warps with deeper unrolling carry more
+// bytes in flight: UNR = 4 -> 56 registers, 32 warps/SM; 8 -> 24 warps; 16 -> 16 warps.  Measured on
+// B200 (C4 / C2, ms): UNR 4: 32.8 / 1.44, 8: 45 / 1.57, 16: 45-55 / 2.2-2.6 -- occupancy wins, so 4 is
+// the default.  (One 16-byte load for four column indices was also tried: 38 / 1.72, slower.)
+template <bool HAS_W, int UNR>
+__global__ void __launch_bounds__(kStatThreads, UNR >= 16 ? 2 : (UNR >= 8 ? 3 : 4))
 lag_stat_kernel(const int32_t* __restrict__ indptr, const int32_t* __restrict__ indices,
                 const float* __restrict__ weights, int64_t n, int k_fixed,
                 const float* __restrict__ Zself, const float* __restrict__ Zlag, int64_t ldz,
                 float* __restrict__ lag, float* __restrict__ local, int64_t ldl,
                 double* __restrict__ partial, const float* __restrict__ cell_obs,
                 int32_t* __restrict__ cell_cnt, int64_t ldc, int64_t n_chunks, int chunk_rows) {
-  __shared__ double sh[VEC][2][kLagRowsPerPass][kLagColQuads][4];
+  __shared__ double sh[2][kLagRowsPerPass][kLagColQuads][4];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int q = lane & (kLagColQuads - 1);
   const int rslot = warp * (32 / kLagColQuads) + (lane >> 3);
-  const int64_t col = ((int64_t)blockIdx.x * kLagColQuads * VEC + q) * 4;
-  bool active[VEC];
-#pragma unroll
-  for (int v = 0; v < VEC; ++v) active[v] = col + 32 * v < ldz;
+  const int64_t col = ((int64_t)blockIdx.x * kLagColQuads + q) * 4;
+  const bool active = col < ldz;
   const float* Zs = Zself ? Zself : Zlag;
   const char* zbase = reinterpret_cast<const char*>(Zlag + col);
   const uint32_t ldzb = (uint32_t)ldz * 4u;
-  double num[VEC][4], den[VEC][4];  // FP64 sums of the exact FP32 products, as in the permutation kernels
-#pragma unroll
-  for (int v = 0; v < VEC; ++v)
-#pragma unroll
-    for (int c = 0; c < 4; ++c) { num[v][c] = 0; den[v][c] = 0; }
+  double num[4] = {0, 0, 0, 0}, den[4] = {0, 0, 0, 0};  // FP64 sums of the exact FP32 products
 
   for (int64_t chunk = blockIdx.y; chunk < n_chunks; chunk += gridDim.y) {
     const int64_t r0 = chunk * chunk_rows;
 #pragma unroll 1
     for (int pass = 0; pass < chunk_rows; pass += kLagRowsPerPass) {
       const int64_t row = r0 + pass + rslot;
-      if (row >= n || !active[0]) continue;
+      if (row >= n || !active) continue;
       int64_t b;
       int deg;
       if (indptr) { b = indptr[row]; deg = indptr[row + 1] - (int)b; } else { b = row * k_fixed; deg = k_fixed; }
       const int32_t* __restrict__ ip = indices + b;
       const float* __restrict__ wp = HAS_W ? weights + b : nullptr;
-      float4 acc[VEC];
-#pragma unroll
-      for (int v = 0; v < VEC; ++v) acc[v] = make_float4(0.f, 0.f, 0.f, 0.f);
+      float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
       int t = 0;
 #pragma unroll 1
-      for (; t + 4 <= deg; t += 4) {
-        const int j0 = ip[t], j1 = ip[t + 1], j2 = ip[t + 2], j3 = ip[t + 3];
-        float w0 = 1.f, w1 = 1.f, w2 = 1.f, w3 = 1.f;
-        if (HAS_W) { w0 = wp[t]; w1 = wp[t + 1]; w2 = wp[t + 2]; w3 = wp[t + 3]; }
+      for (; t + UNR <= deg; t += UNR) {
+        int j[UNR];
+        float w[UNR];
+        float4 v[UNR];
 #pragma unroll
-        for (int v = 0; v < VEC; ++v) {
-          if (v > 0 && !active[v]) continue;
-          const float4 v0 = ldg4_row(zbase + 128 * v, j0, ldzb);
-          const float4 v1 = ldg4_row(zbase + 128 * v, j1, ldzb);
-          const float4 v2 = ldg4_row(zbase + 128 * v, j2, ldzb);
-          const float4 v3 = ldg4_row(zbase + 128 * v, j3, ldzb);
-          acc[v].x += w0 * v0.x + w1 * v1.x + w2 * v2.x + w3 * v3.x;
-          acc[v].y += w0 * v0.y + w1 * v1.y + w2 * v2.y + w3 * v3.y;
-          acc[v].z += w0 * v0.z + w1 * v1.z + w2 * v2.z + w3 * v3.z;
-          acc[v].w += w0 * v0.w + w1 * v1.w + w2 * v2.w + w3 * v3.w;
+        for (int u = 0; u < UNR; ++u) { j[u] = ip[t + u]; w[u] = HAS_W ? wp[t + u] : 1.f; }
+#pragma unroll
+        for (int u = 0; u < UNR; ++u) v[u] = ldg4_row(zbase, j[u], ldzb);
+#pragma unroll
+        for (int u = 0; u < UNR; u += 4) {  // groups of four, summed in the same order for every UNR
+          acc.x += w[u] * v[u].x + w[u + 1] * v[u + 1].x + w[u + 2] * v[u + 2].x + w[u + 3] * v[u + 3].x;
+          acc.y += w[u] * v[u].y + w[u + 1] * v[u + 1].y + w[u + 2] * v[u + 2].y + w[u + 3] * v[u + 3].y;
+          acc.z += w[u] * v[u].z + w[u + 1] * v[u + 1].z + w[u + 2] * v[u + 2].z + w[u + 3] * v[u + 3].z;
+          acc.w += w[u] * v[u].w + w[u + 1] * v[u + 1].w + w[u + 2] * v[u + 2].w + w[u + 3] * v[u + 3].w;
+        }
+      }
+      if (UNR > 4) {
+#pragma unroll 1
+        for (; t + 4 <= deg; t += 4) {
+          const int j0 = ip[t], j1 = ip[t + 1], j2 = ip[t + 2], j3 = ip[t + 3];
+          float w0 = 1.f, w1 = 1.f, w2 = 1.f, w3 = 1.f;
+          if (HAS_W) { w0 = wp[t]; w1 = wp[t + 1]; w2 = wp[t + 2]; w3 = wp[t + 3]; }
+          const float4 v0 = ldg4_row(zbase, j0, ldzb), v1 = ldg4_row(zbase, j1, ldzb);
+          const float4 v2 = ldg4_row(zbase, j2, ldzb), v3 = ldg4_row(zbase, j3, ldzb);
+          acc.x += w0 * v0.x + w1 * v1.x + w2 * v2.x + w3 * v3.x;
+          acc.y += w0 * v0.y + w1 * v1.y + w2 * v2.y + w3 * v3.y;
+          acc.z += w0 * v0.z + w1 * v1.z + w2 * v2.z + w3 * v3.z;
+          acc.w += w0 * v0.w + w1 * v1.w + w2 * v2.w + w3 * v3.w;
         }
       }
 #pragma unroll 1
-      for (; t < deg; ++t) {
-        const int j = ip[t];
-        const float w = HAS_W ? wp[t] : 1.f;
-#pragma unroll
-        for (int v = 0; v < VEC; ++v) {
-          if (v > 0 && !active[v]) continue;
-          fma4(acc[v], w, ldg4_row(zbase + 128 * v, j, ldzb));
-        }
+      for (; t < deg; ++t) fma4(acc, HAS_W ? wp[t] : 1.f, ldg4_row(zbase, ip[t], ldzb));
+      if (!HAS_W) {
+        const float inv = (deg > 0) ? 1.f / (float)deg : 0.f;
+        acc.x *= inv; acc.y *= inv; acc.z *= inv; acc.w *= inv;
       }
-      const float inv = HAS_W ? 1.f : ((deg > 0) ? 1.f / (float)deg : 0.f);
-#pragma unroll
-      for (int v = 0; v < VEC; ++v) {
-        if (v > 0 && !active[v]) continue;
-        if (!HAS_W) { acc[v].x *= inv; acc[v].y *= inv; acc[v].z *= inv; acc[v].w *= inv; }
-        const int64_t c = col + 32 * v;
-        const float4 z = ldg4(Zs + row * ldz + c);
-        const float4 loc = make_float4(z.x * acc[v].x, z.y * acc[v].y, z.z * acc[v].z, z.w * acc[v].w);
-        if (lag) *reinterpret_cast<float4*>(lag + row * ldl + c) = acc[v];
-        if (local) *reinterpret_cast<float4*>(local + row * ldl + c) = loc;
-        if (cell_cnt) {
-          const float4 o = ldg4(cell_obs + row * ldc + c);
-          int4* cp = reinterpret_cast<int4*>(cell_cnt + row * ldc + c);
-          int4 cc = *cp;
-          cc.x += fabsf(loc.x) >= fabsf(o.x); cc.y += fabsf(loc.y) >= fabsf(o.y);
-          cc.z += fabsf(loc.z) >= fabsf(o.z); cc.w += fabsf(loc.w) >= fabsf(o.w);
-          *cp = cc;
-        }
-        const double zx = z.x, zy = z.y, zz = z.z, zw = z.w;
-        num[v][0] = fma(zx, (double)acc[v].x, num[v][0]); den[v][0] = fma(zx, zx, den[v][0]);
-        num[v][1] = fma(zy, (double)acc[v].y, num[v][1]); den[v][1] = fma(zy, zy, den[v][1]);
-        num[v][2] = fma(zz, (double)acc[v].z, num[v][2]); den[v][2] = fma(zz, zz, den[v][2]);
-        num[v][3] = fma(zw, (double)acc[v].w, num[v][3]); den[v][3] = fma(zw, zw, den[v][3]);
+      const float4 z = ldg4(Zs + row * ldz + col);
+      const float4 loc = make_float4(z.x * acc.x, z.y * acc.y, z.z * acc.z, z.w * acc.w);
+      if (lag) *reinterpret_cast<float4*>(lag + row * ldl + col) = acc;
+      if (local) *reinterpret_cast<float4*>(local + row * ldl + col) = loc;
+      if (cell_cnt) {
+        const float4 o = ldg4(cell_obs + row * ldc + col);
+        int4* cp = reinterpret_cast<int4*>(cell_cnt + row * ldc + col);
+        int4 cc = *cp;
+        cc.x += fabsf(loc.x) >= fabsf(o.x); cc.y += fabsf(loc.y) >= fabsf(o.y);
+        cc.z += fabsf(loc.z) >= fabsf(o.z); cc.w += fabsf(loc.w) >= fabsf(o.w);
+        *cp = cc;
       }
+      const double zx = z.x, zy = z.y, zz = z.z, zw = z.w;
+      num[0] = fma(zx, (double)acc.x, num[0]); den[0] = fma(zx, zx, den[0]);
+      num[1] = fma(zy, (double)acc.y, num[1]); den[1] = fma(zy, zy, den[1]);
+      num[2] = fma(zz, (double)acc.z, num[2]); den[2] = fma(zz, zz, den[2]);
+      num[3] = fma(zw, (double)acc.w, num[3]); den[3] = fma(zw, zw, den[3]);
     }
   }
 #pragma unroll
-  for (int v = 0; v < VEC; ++v)
-#pragma unroll
-    for (int c = 0; c < 4; ++c) { sh[v][0][rslot][q][c] = num[v][c]; sh[v][1][rslot][q][c] = den[v][c]; }
+  for (int c = 0; c < 4; ++c) { sh[0][rslot][q][c] = num[c]; sh[1][rslot][q][c] = den[c]; }
   __syncthreads();
+  if (rslot == 0 && active) {
+    double* p = partial + ((int64_t)blockIdx.y * 2) * ldz + col;
 #pragma unroll
-  for (int v = 0; v < VEC; ++v) {
-    if (rslot == 0 && active[v]) {
-      double* p = partial + ((int64_t)blockIdx.y * 2) * ldz + col + 32 * v;
-#pragma unroll
-      for (int c = 0; c < 4; ++c) {
-        double a = 0, d = 0;
+    for (int c = 0; c < 4; ++c) {
+      double a = 0, d = 0;
 #pragma unroll 4
-        for (int r = 0; r < kLagRowsPerPass; ++r) { a += sh[v][0][r][q][c]; d += sh[v][1][r][q][c]; }
-        p[c] = a; p[ldz + c] = d;
-      }
+      for (int r = 0; r < kLagRowsPerPass; ++r) { a += sh[0][r][q][c]; d += sh[1][r][q][c]; }
+      p[c] = a; p[ldz + c] = d;
     }
   }
 }
@@ -995,14 +991,15 @@ static void fill_batch(PermBatch* pb, int source, const int32_t* perm_idx, uint6
 constexpr int kMaxStatBlocks = 148 * 8;
 
 // Launch lag_stat_kernel; *by_out = number of partial rows written ([by][2][ldz] doubles).
-// SC_LAG_VEC (1|2) and SC_LAG_CHUNK (multiple of 32) override the geometry for experiments.
-template <bool HAS_W, int VEC>
+// SC_LAG_UNR (4|8|16), SC_LAG_CHUNK (multiple of 32) and SC_LAG_VARIANT=tile override the geometry for
+// experiments.
+template <bool HAS_W, int UNR>
 static void launch_lag_stat_t(dim3 grid, cudaStream_t st, const int32_t* indptr, const int32_t* indices,
                               const float* weights, int64_t n, int k_fixed, const float* Zself,
                               const float* Zlag, int64_t ldz, float* lag, float* local, int64_t ldl,
                               double* partial, const float* cell_obs, int32_t* cell_cnt, int64_t ldc,
                               int64_t n_chunks, int chunk_rows) {
-  lag_stat_kernel<HAS_W, VEC><<<grid, kStatThreads, 0, st>>>(indptr, indices, weights, n, k_fixed, Zself, Zlag, ldz, lag,
+  lag_stat_kernel<HAS_W, UNR><<<grid, kStatThreads, 0, st>>>(indptr, indices, weights, n, k_fixed, Zself, Zlag, ldz, lag,
                                                              local, ldl, partial, cell_obs, cell_cnt, ldc, n_chunks,
                                                              chunk_rows);
 }
@@ -1012,21 +1009,17 @@ static int launch_lag_stat(const int32_t* indptr, const int32_t* indices, const 
                            float* lag, float* local, int64_t ldl, double* partial,
                            const float* cell_obs, int32_t* cell_cnt, int64_t ldc, int* by_out,
                            cudaStream_t st) {
-  // measured on B200 (C4, 5 M x 1000, degree 20): VEC=1 / 512-row chunks 32 ms, VEC=2 / 128 36 ms
-  int vec = 1;
+  int unr = kLagDefaultUnr;
   int chunk_rows = 512;
   while (chunk_rows > 64 && ((n + chunk_rows - 1) / chunk_rows) * ((ldz + 31) / 32) < 4 * (int64_t)sm_count()) chunk_rows /= 2;
-  if (const char* e = getenv("SC_LAG_VEC")) { int v = atoi(e); if (v == 1 || v == 2) vec = v; }
+  if (const char* e = getenv("SC_LAG_UNR")) { int v = atoi(e); if (v == 4 || v == 8 || v == 16) unr = v; }
   if (const char* e = getenv("SC_LAG_CHUNK")) { int v = atoi(e); if (v >= 32 && v % 32 == 0 && v <= 4096) chunk_rows = v; }
   // SC_LAG_VARIANT=tile selects the shared-memory variant.  Measured on B200: it wins on C2 (kNN k=15,
-  // 500 k x 400: 1.22 vs 1.44 ms) and loses on C4 (radius, 5 M x 1000: 42 vs 33 ms) -- both variants
-  // are bound by exposed L1-miss latency (ncu: long-scoreboard stalls, 41-56 % issue utilisation), and
-  // the tile's 64 KB per CTA costs a quarter of the resident warps.  Default: the L1 variant.
+  // 500 k x 400: 1.22 vs 1.44 ms) and loses on C4 (radius, 5 M x 1000: 42 vs 33 ms) -- the tile's 64 KB
+  // per CTA costs resident warps, and this kernel's time is inversely proportional to them.
   const char* variant = getenv("SC_LAG_VARIANT");
   const bool tile = ldz >= 32 && variant && !strcmp(variant, "tile");
-  if (tile) vec = 1;
-  const int colblk = 32 * vec;
-  const int bx = (int)((ldz + colblk - 1) / colblk);
+  const int bx = (int)((ldz + 31) / 32);
   const int64_t n_chunks = (n + chunk_rows - 1) / chunk_rows;
   int64_t by = ((int64_t)sm_count() * 8 + bx - 1) / bx;
   if (by > n_chunks) by = n_chunks;
@@ -1048,8 +1041,11 @@ static int launch_lag_stat(const int32_t* indptr, const int32_t* indices, const 
     return SC_OK;
   }
 #define SC_LAG_ARGS grid, st, indptr, indices, weights, n, k_fixed, Zself, Zlag, ldz, lag, local, ldl, partial, cell_obs, cell_cnt, ldc, n_chunks, chunk_rows
-  if (weights) { if (vec == 2) launch_lag_stat_t<true, 2>(SC_LAG_ARGS); else launch_lag_stat_t<true, 1>(SC_LAG_ARGS); }
-  else         { if (vec == 2) launch_lag_stat_t<false, 2>(SC_LAG_ARGS); else launch_lag_stat_t<false, 1>(SC_LAG_ARGS); }
+  if (weights) {
+    if (unr == 16) launch_lag_stat_t<true, 16>(SC_LAG_ARGS); else if (unr == 8) launch_lag_stat_t<true, 8>(SC_LAG_ARGS); else launch_lag_stat_t<true, 4>(SC_LAG_ARGS);
+  } else {
+    if (unr == 16) launch_lag_stat_t<false, 16>(SC_LAG_ARGS); else if (unr == 8) launch_lag_stat_t<false, 8>(SC_LAG_ARGS); else launch_lag_stat_t<false, 4>(SC_LAG_ARGS);
+  }
 #undef SC_LAG_ARGS
   SC_LAUNCH_OK();
   *by_out = (int)by;
