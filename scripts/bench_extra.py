@@ -112,4 +112,15 @@ if want("local"):
     a = AnnDataLite(X, obsm={"spatial": c})
     for src in ("philox", "replay"):
         t0 = time.perf_counter(); spatial.local_morans_i(a, n_permutations=99, perm_source=src); out[f"local_morans_200k_x20_P99_{src}_s"] = time.perf_counter() - t0
+if want("local_ref"):
+    # the one timing the reference publishes (docs/spatial/spatial_stats.md:202-215): local_morans_i on the
+    # 366 938-cell CosMx colon vignette, 5 / 10 / 20 genes, 10 permutations: ~69 / 52 / 80 s (batched call)
+    n = 366_938
+    c = synthetic.coords_mixture(n, 8e3, 9)
+    X = synthetic.expression_device(c, 20, 9).cpu().numpy()
+    for g in (5, 10, 20):
+        a = AnnDataLite(X[:, :g].copy(), obsm={"spatial": c})
+        spatial.local_morans_i(a, n_permutations=10)  # warm
+        t0 = time.perf_counter(); spatial.local_morans_i(a, n_permutations=10); out[f"local_morans_366938_x{g}_P10_s"] = time.perf_counter() - t0
+
 print(json.dumps(out, indent=1))
