@@ -101,6 +101,19 @@ SC_API int sc_graph_relabel(const int32_t* indptr, const int32_t* indices, const
                             int32_t* out_indptr, int32_t* out_indices, float* out_weights, void* ws,
                             size_t ws_bytes, sc_stream_t stream);
 
+/* Cross-set nearest neighbour: for every query point the nearest of `targets` (exact FP64 d2, ties by
+ * target index).  Replaces cKDTree(target).query(source, k=1) in calculate_domain_distances
+ * (distance.py:222-233, 359-367).  idx_out i32[n_queries] (index into targets), dist_out f64 or NULL. */
+SC_API size_t sc_cross_nn_workspace_bytes(int64_t n_targets);
+SC_API int sc_cross_nn(const double* targets, int64_t n_targets, const double* queries, int64_t n_queries,
+                       int32_t* idx_out, double* dist_out, void* ws, size_t ws_bytes, sc_stream_t stream);
+
+/* out f64[2] = { min over all pairs of |a_i - b_j|, sum over all pairs of |a_i - b_j| } (FP64, brute
+ * force).  Replaces scipy cdist(a, b).min() / .mean() (distance.py:268-270, 341-343, 392-393). */
+SC_API size_t sc_pairwise_reduce_workspace_bytes(void);
+SC_API int sc_pairwise_reduce(const double* a, int64_t na, const double* b, int64_t nb, double* out,
+                              void* ws, size_t ws_bytes, sc_stream_t stream);
+
 /* Neighbourhood composition from an existing CSR graph (k_fixed>0 and indptr==NULL: every row has
  * k_fixed entries).  profile f32[n,n_types] raw counts. */
 SC_API int sc_nbhd_counts(const int32_t* indptr, const int32_t* indices, int64_t n, int k_fixed,

@@ -415,3 +415,101 @@ def adjusted_rand_index(a: np.ndarray, b: np.ndarray) -> float:
     tot = comb(a.size)
     expected = s_a * s_b / tot
     return float((s_ij - expected) / (0.5 * (s_a + s_b) - expected))
+
+
+# --------------------------------------------------------------------------------------
+# domain distances
+# --------------------------------------------------------------------------------------
+
+
+def domain_distances(coords, src_labels, tgt_labels, source_domains, target_domains, metric="minimum",
+                     mode="both", same_column=False):
+    """[R spatial/distance.py:196-400] restated with the same third-party calls (``cKDTree.query``,
+    ``cdist``): returns ``(cell_dist float64[n] (NaN = not a source cell), cell_nearest object[n],
+    matrix float64[len(source_domains), len(target_domains)] (NaN = not computed))``.
+    ``src_labels`` / ``tgt_labels`` are object arrays with ``None`` for unlabelled cells."""
+    from scipy.spatial import cKDTree
+    from scipy.spatial.distance import cdist
+
+    coords = np.asarray(coords, dtype=np.float64)[:, :2]
+    n = coords.shape[0]
+    src_labels = np.asarray(src_labels, dtype=object)
+    tgt_labels = np.asarray(tgt_labels, dtype=object)
+    cell_d = np.full(n, np.nan)
+    cell_n = np.full(n, None, dtype=object)
+    M = np.full((len(source_domains), len(target_domains)), np.nan)
+    want_cell = mode in ("cell", "both")
+
+    def nearest_cells():
+        t_idx = np.where(np.isin(tgt_labels, target_domains))[0]
+        s_idx = np.where(np.isin(src_labels, source_domains))[0]
+        if len(t_idx) == 0 or len(s_idx) == 0:
+            return None
+        d, j = cKDTree(coords[t_idx]).query(coords[s_idx], k=1)
+        cell_d[s_idx] = d
+        cell_n[s_idx] = tgt_labels[t_idx][j]
+        return s_idx, t_idx, d, tgt_labels[t_idx][j]
+
+    if metric == "minimum" and want_cell:  # :214-271
+        r = nearest_cells()
+        if r is not None:
+            s_idx, t_idx, d, near = r
+            for a, src in enumerate(source_domains):
+                m = src_labels[s_idx] == src
+                if not m.any():
+                    continue
+                for b, tgt in enumerate(target_domains):
+                    if src == tgt and same_column:
+                        M[a, b] = 0.0
+                    elif (near[m] == tgt).any():
+                        M[a, b] = d[m][near[m] == tgt].min()
+                    elif (tgt_labels[t_idx] == tgt).any():
+                        M[a, b] = cdist(coords[s_idx][m], coords[t_idx][tgt_labels[t_idx] == tgt]).min()
+    elif metric == "centroid":  # :273-327
+        sc = {s: coords[src_labels == s].mean(0) for s in source_domains if (src_labels == s).any()}
+        tc = {t: coords[tgt_labels == t].mean(0) for t in target_domains if (tgt_labels == t).any()}
+        for a, src in enumerate(source_domains):
+            for b, tgt in enumerate(target_domains):
+                if src not in sc:
+                    continue
+                if src == tgt and same_column:
+                    M[a, b] = 0.0
+                elif tgt in tc:
+                    M[a, b] = np.linalg.norm(sc[src] - tc[tgt])
+        if want_cell:
+            for i in np.where(np.isin(src_labels, source_domains))[0]:
+                if src_labels[i] not in sc:
+                    continue
+                best, who = np.inf, None
+                for tgt, c in tc.items():
+                    if tgt == src_labels[i] and same_column:
+                        continue
+                    dd = np.linalg.norm(coords[i] - c)
+                    if dd < best:
+                        best, who = dd, tgt
+                cell_d[i], cell_n[i] = best, who
+    elif metric == "mean":  # :329-372
+        for a, src in enumerate(source_domains):
+            A = coords[src_labels == src]
+            for b, tgt in enumerate(target_domains):
+                B = coords[tgt_labels == tgt]
+                if len(A) == 0:
+                    continue
+                if src == tgt and same_column:
+                    M[a, b] = 0.0
+                elif len(B):
+                    M[a, b] = cdist(A, B).mean()
+        if want_cell:
+            nearest_cells()
+    else:  # minimum, matrix only :374-398
+        for a, src in enumerate(source_domains):
+            A = coords[src_labels == src]
+            for b, tgt in enumerate(target_domains):
+                B = coords[tgt_labels == tgt]
+                if len(A) == 0:
+                    continue
+                if src == tgt and same_column:
+                    M[a, b] = 0.0
+                elif len(B):
+                    M[a, b] = cdist(A, B).min()
+    return cell_d, cell_n, M

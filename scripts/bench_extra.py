@@ -112,6 +112,20 @@ if want("local"):
     a = AnnDataLite(X, obsm={"spatial": c})
     for src in ("philox", "replay"):
         t0 = time.perf_counter(); spatial.local_morans_i(a, n_permutations=99, perm_source=src); out[f"local_morans_200k_x20_P99_{src}_s"] = time.perf_counter() - t0
+if want("distances"):
+    # calculate_domain_distances kernels: 1-NN of 1 M source cells among 1 M target cells; min/mean over 100 k x 100 k pairs
+    rng = np.random.default_rng(2)
+    T = rng.uniform(0, 2e4, (1_000_000, 2)); Q = rng.uniform(0, 2e4, (1_000_000, 2))
+    Td, Qd = torch.from_numpy(T).cuda(), torch.from_numpy(Q).cuda()
+    out["cross_nn_1Mx1M_ms"] = timed(lambda: eng.cross_nn(Td, Qd))
+    from scipy.spatial import cKDTree
+    t0 = time.perf_counter(); cKDTree(T).query(Q, k=1); out["cpu_ckdtree_1nn_1Mx1M_1thread_s"] = time.perf_counter() - t0
+    t0 = time.perf_counter(); cKDTree(T).query(Q, k=1, workers=-1); out["cpu_ckdtree_1nn_1Mx1M_allcores_s"] = time.perf_counter() - t0
+    A, B = Td[:100_000].contiguous(), Qd[:100_000].contiguous()
+    out["pairwise_min_mean_100kx100k_ms"] = timed(lambda: eng.pairwise_reduce(A, B))
+    from scipy.spatial.distance import cdist
+    t0 = time.perf_counter(); D = cdist(T[:10_000], Q[:10_000]); D.min(); D.mean(); out["cpu_cdist_10kx10k_s"] = time.perf_counter() - t0
+
 if want("local_ref"):
     # the one timing the reference publishes (docs/spatial/spatial_stats.md:202-215): local_morans_i on the
     # 366 938-cell CosMx colon vignette, 5 / 10 / 20 genes, 10 permutations: ~69 / 52 / 80 s (batched call)

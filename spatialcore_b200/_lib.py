@@ -29,6 +29,10 @@ SIGNATURES = {
     "sc_grid_radius_workspace_bytes": (_sz, [_i64]),
     "sc_grid_radius_count": (_i32, [_vp, _i64, _f64, _vp, _vp, _vp, _i32, _vp, _vp, _sz, _vp]),
     "sc_grid_radius_fill": (_i32, [_vp, _i64, _f64, _vp, _vp, _vp, _vp, _sz, _vp, _sz, _vp]),
+    "sc_cross_nn_workspace_bytes": (_sz, [_i64]),
+    "sc_cross_nn": (_i32, [_vp, _i64, _vp, _i64, _vp, _vp, _vp, _sz, _vp]),
+    "sc_pairwise_reduce_workspace_bytes": (_sz, []),
+    "sc_pairwise_reduce": (_i32, [_vp, _i64, _vp, _i64, _vp, _vp, _sz, _vp]),
     "sc_nbhd_counts": (_i32, [_vp, _vp, _i64, _i32, _vp, _i32, _vp, _vp]),
     "sc_profile_normalize": (_i32, [_vp, _i64, _i32, _i32, _vp, _vp]),
     "sc_graph_moments_workspace_bytes": (_sz, [_i64]),

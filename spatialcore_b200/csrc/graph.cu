@@ -1025,6 +1025,114 @@ relabel_rows_kernel(const int32_t* __restrict__ indptr, const int32_t* __restric
   }
 }
 
+// ------------------------------------------------------------------------------------------------
+// cross-set nearest neighbour and pairwise distance reductions (calculate_domain_distances,
+// [R spatial/distance.py:46-449]: cKDTree.query(k=1) between labelled subsets, cdist().min()/.mean())
+// ------------------------------------------------------------------------------------------------
+
+// One thread per query point (not a member of the binned target set): ring search over the target
+// grid until the best distance clears the nearest unsearched cell.  Key (d2, target index).
+__global__ void __launch_bounds__(256)
+cross_nn_kernel(const GridParams* __restrict__ gp, const int32_t* __restrict__ cell_start,
+                const double* __restrict__ xs, const double* __restrict__ ys,
+                const int32_t* __restrict__ order, const double* __restrict__ queries, int64_t nq,
+                int32_t* __restrict__ idx_out, double* __restrict__ dist_out) {
+  const GridParams g = *gp;
+  for (int64_t q = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; q < nq;
+       q += (int64_t)gridDim.x * blockDim.x) {
+    const double2 p = reinterpret_cast<const double2*>(queries)[q];
+    const double ux = (p.x - g.x0) * g.inv_h, uy = (p.y - g.y0) * g.inv_h;
+    const int cx = min(max((int)floor(fmin(fmax(ux, -1.0), (double)g.nx)), 0), g.nx - 1);
+    const int cy = min(max((int)floor(fmin(fmax(uy, -1.0), (double)g.ny)), 0), g.ny - 1);
+    double bd = INFINITY;
+    int bi = INT_MAX;
+    auto scan = [&](int b, int e) {
+      for (int s = b; s < e; ++s) {
+        const double d2 = sq_dist(p.x, p.y, xs[s], ys[s]);
+        const int id = order[s];
+        if (cand_less(d2, id, bd, bi)) { bd = d2; bi = id; }
+      }
+    };
+    scan(cell_start[cy * g.nx + cx], cell_start[cy * g.nx + cx + 1]);
+    for (int r = 1;; ++r) {
+      const int xlo = max(cx - r, 0), xhi = min(cx + r, g.nx - 1);
+      for (int yy = max(cy - r, 0); yy <= min(cy + r, g.ny - 1); ++yy) {
+        const int rowbase = yy * g.nx;
+        if (yy == cy - r || yy == cy + r) {
+          scan(cell_start[rowbase + xlo], cell_start[rowbase + xhi + 1]);
+        } else {
+          if (cx - r >= 0) scan(cell_start[rowbase + cx - r], cell_start[rowbase + cx - r + 1]);
+          if (cx + r <= g.nx - 1) scan(cell_start[rowbase + cx + r], cell_start[rowbase + cx + r + 1]);
+        }
+      }
+      double gap = INFINITY;
+      if (cx - r > 0) gap = fmin(gap, ux - (double)(cx - r));
+      if (cx + r < g.nx - 1) gap = fmin(gap, (double)(cx + r + 1) - ux);
+      if (cy - r > 0) gap = fmin(gap, uy - (double)(cy - r));
+      if (cy + r < g.ny - 1) gap = fmin(gap, (double)(cy + r + 1) - uy);
+      if (isinf(gap)) break;  // the block covers the whole grid
+      const double safe = gap * g.h * (1.0 - 1e-6) - g.margin;
+      if (safe > 0 && bd <= safe * safe) break;
+    }
+    idx_out[q] = bi;
+    if (dist_out) dist_out[q] = sqrt(bd);
+  }
+}
+
+// out partial[b] = {min over pairs of d, sum over pairs of d} for the A rows of block b against all
+// of B (staged through shared memory in tiles).  FP64, fixed reduction order.
+constexpr int kPairTile = 1024;
+__global__ void __launch_bounds__(256)
+pairwise_reduce_kernel(const double* __restrict__ A, int64_t na, const double* __restrict__ B,
+                       int64_t nb, double* __restrict__ partial) {
+  __shared__ double2 sb[kPairTile];
+  __shared__ double sred[2][8];
+  double vmin = INFINITY, vsum = 0.0;
+  for (int64_t a0 = (int64_t)blockIdx.x * blockDim.x; a0 < na; a0 += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t a = a0 + threadIdx.x;
+    const bool live = a < na;
+    const double2 pa = live ? reinterpret_cast<const double2*>(A)[a] : make_double2(0, 0);
+    for (int64_t b0 = 0; b0 < nb; b0 += kPairTile) {
+      const int cnt = (int)min((int64_t)kPairTile, nb - b0);
+      __syncthreads();
+      for (int t = threadIdx.x; t < cnt; t += blockDim.x) sb[t] = reinterpret_cast<const double2*>(B)[b0 + t];
+      __syncthreads();
+      if (live) {
+        double lmin = INFINITY, lsum = 0.0;
+        for (int t = 0; t < cnt; ++t) {
+          const double d2 = sq_dist(pa.x, pa.y, sb[t].x, sb[t].y);
+          lmin = fmin(lmin, d2);
+          lsum += sqrt(d2);
+        }
+        vmin = fmin(vmin, lmin);
+        vsum += lsum;
+      }
+    }
+  }
+  // block reduction
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    vmin = fmin(vmin, shfl_f64(vmin, lane ^ o));
+  }
+  vsum = warp_sum(vsum);
+  if (lane == 0) { sred[0][w] = vmin; sred[1][w] = vsum; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double m = INFINITY, sm = 0.0;
+    for (int j = 0; j < 8; ++j) { m = fmin(m, sred[0][j]); sm += sred[1][j]; }
+    partial[2 * blockIdx.x] = m;
+    partial[2 * blockIdx.x + 1] = sm;
+  }
+}
+
+__global__ void pairwise_final_kernel(const double* __restrict__ partial, int blocks, double* __restrict__ out) {
+  double m = INFINITY, sm = 0.0;
+  for (int b = 0; b < blocks; ++b) { m = fmin(m, partial[2 * b]); sm += partial[2 * b + 1]; }
+  out[0] = sqrt(m);
+  out[1] = sm;
+}
+
 constexpr int kMomentBlocks = 592;
 
 }  // namespace sc
@@ -1271,6 +1379,48 @@ extern "C" int sc_grid_radius_fill(const double* coords, int64_t n, double r,
   radius_query_kernel<true><<<blocks, threads, 0, st>>>(b.gp, b.cell_start, b.xs, b.ys, b.order, n,
                                                        r * r, nullptr, indptr, tmp_idx, tmp_dist,
                                                        indices, dist, nullptr, 0, nullptr, nullptr, nullptr);
+  SC_LAUNCH_OK();
+  return SC_OK;
+}
+
+extern "C" size_t sc_cross_nn_workspace_bytes(int64_t n_targets) {
+  if (n_targets <= 0) return 256;
+  return binning_bytes(n_targets) + 1024;
+}
+
+extern "C" int sc_cross_nn(const double* targets, int64_t n_targets, const double* queries,
+                           int64_t n_queries, int32_t* idx_out, double* dist_out, void* ws,
+                           size_t ws_bytes, sc_stream_t stream) {
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  SC_CHECK_ARG(targets && queries && idx_out && ws, "sc_cross_nn: null argument");
+  SC_CHECK_ARG(n_targets >= 1 && n_targets < (1ll << 31) - 2048 && n_queries >= 1, "sc_cross_nn: sizes out of range");
+  if (ws_bytes < sc_cross_nn_workspace_bytes(n_targets)) { set_error("sc_cross_nn: workspace too small"); return SC_ERR_WORKSPACE; }
+  Arena arena(ws, ws_bytes);
+  Binning b;
+  if (!carve_binning(arena, n_targets, &b)) { set_error("sc_cross_nn: workspace carve failed"); return SC_ERR_WORKSPACE; }
+  int rc = run_binning(targets, n_targets, 2.0, 0.0, b, st);
+  if (rc) return rc;
+  int64_t want = (n_queries + 255) / 256;
+  int blocks = (int)(want > sm_count() * 16 ? sm_count() * 16 : want);
+  cross_nn_kernel<<<blocks, 256, 0, st>>>(b.gp, b.cell_start, b.xs, b.ys, b.order, queries, n_queries, idx_out, dist_out);
+  SC_LAUNCH_OK();
+  return SC_OK;
+}
+
+extern "C" size_t sc_pairwise_reduce_workspace_bytes(void) { return sizeof(double) * 2 * 148 * 8 + 256; }
+
+extern "C" int sc_pairwise_reduce(const double* a, int64_t na, const double* b, int64_t nb, double* out,
+                                  void* ws, size_t ws_bytes, sc_stream_t stream) {
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  SC_CHECK_ARG(a && b && out && ws, "sc_pairwise_reduce: null argument");
+  SC_CHECK_ARG(na >= 1 && nb >= 1, "sc_pairwise_reduce: empty point set");
+  if (ws_bytes < sc_pairwise_reduce_workspace_bytes()) { set_error("sc_pairwise_reduce: workspace too small"); return SC_ERR_WORKSPACE; }
+  int64_t want = (na + 255) / 256;
+  int blocks = (int)(want > 148 * 8 ? 148 * 8 : want);
+  double* partial = static_cast<double*>(ws);
+  pairwise_reduce_kernel<<<blocks, 256, 0, st>>>(a, na, b, nb, partial);
+  SC_LAUNCH_OK();
+  pairwise_final_kernel<<<1, 1, 0, st>>>(partial, blocks, out);
   SC_LAUNCH_OK();
   return SC_OK;
 }

@@ -628,3 +628,37 @@ class KMeansDevice:
 
     def rows(self, idx) -> np.ndarray:
         return self.X[torch.as_tensor(np.asarray(idx, dtype=np.int64), device=self.X.device)].cpu().numpy()
+
+
+# --------------------------------------------------------------------------------------------------
+# domain distances
+# --------------------------------------------------------------------------------------------------
+
+
+def cross_nn(targets, queries, device="cuda") -> Tuple[np.ndarray, np.ndarray]:
+    """``sc_cross_nn``: index (into ``targets``) and FP64 distance of the nearest target of every query
+    point -- ``cKDTree(targets).query(queries, k=1)``.  Returns host arrays ``(dist, idx)``."""
+    t = _coords_tensor(targets, device)
+    q = _coords_tensor(queries, device)
+    L = _lib.lib()
+    idx = torch.empty(q.shape[0], dtype=torch.int32, device=t.device)
+    dist = torch.empty(q.shape[0], dtype=torch.float64, device=t.device)
+    ws = _workspace(L.sc_cross_nn_workspace_bytes(t.shape[0]), t.device)
+    check(L.sc_cross_nn(_ptr(t), t.shape[0], _ptr(q), q.shape[0], _ptr(idx), _ptr(dist), _ptr(ws), ws.numel(), _stream()),
+          "sc_cross_nn")
+    _count(8)
+    return dist.cpu().numpy(), idx.cpu().numpy().astype(np.int64)
+
+
+def pairwise_reduce(a, b, device="cuda") -> Tuple[float, float]:
+    """``sc_pairwise_reduce``: ``(cdist(a, b).min(), cdist(a, b).sum())`` in FP64 on the device."""
+    A = a if isinstance(a, torch.Tensor) else _coords_tensor(a, device)
+    B = b if isinstance(b, torch.Tensor) else _coords_tensor(b, device)
+    L = _lib.lib()
+    out = torch.empty(2, dtype=torch.float64, device=A.device)
+    ws = _workspace(L.sc_pairwise_reduce_workspace_bytes(), A.device)
+    check(L.sc_pairwise_reduce(_ptr(A), A.shape[0], _ptr(B), B.shape[0], _ptr(out), _ptr(ws), ws.numel(), _stream()),
+          "sc_pairwise_reduce")
+    _count(2)
+    o = out.cpu().numpy()
+    return float(o[0]), float(o[1])

@@ -1,9 +1,10 @@
 """B200 drop-in for the hot path of ``spatialcore.spatial`` [R src/spatialcore/spatial/__init__.py:11-52].
 
 In scope: neighbour graphs, global/local Moran's I, global/local Lee's L,
-neighbourhood composition and -- the first "next" row of §8f -- ``identify_niches`` (k-means on the
-profile matrix).  ``make_spatial_domains``, ``get_domain_summary``, ``calculate_domain_distances``
-and ``get_distance_matrix`` are out of scope for this build.
+neighbourhood composition and the "next" rows of §8f: ``identify_niches`` (k-means on the profile
+matrix) and ``calculate_domain_distances`` / ``get_distance_matrix`` (cross-set nearest neighbour and
+pairwise distance reductions).  ``make_spatial_domains`` and ``get_domain_summary`` (R-side
+computational geometry) are out of scope for this build.
 """
 
 from spatialcore_b200.spatial.autocorrelation import (
@@ -15,6 +16,7 @@ from spatialcore_b200.spatial.autocorrelation import (
     morans_i,
     spatial_neighbors,
 )
+from spatialcore_b200.spatial.distance import calculate_domain_distances, get_distance_matrix
 from spatialcore_b200.spatial.neighborhoods import compute_neighborhood_profile
 from spatialcore_b200.spatial.niches import identify_niches
 
@@ -28,4 +30,6 @@ __all__ = [
     "spatial_neighbors",
     "compute_neighborhood_profile",
     "identify_niches",
+    "calculate_domain_distances",
+    "get_distance_matrix",
 ]

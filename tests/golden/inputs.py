@@ -71,3 +71,19 @@ def niche_profiles(n: int = 20000, n_types: int = 12, n_niches: int = 6, seed: i
     which = rng.integers(0, n_niches, n)
     counts = np.stack([rng.multinomial(15, arche[w]) for w in which]).astype(np.float32)
     return counts / counts.sum(1, keepdims=True)
+
+
+def domains(n: int = 6000, seed: int = 31):
+    """Clustered cells with two partial labelings: ``src`` (3 "Bcell" domains around blob centres,
+    most cells unlabelled) and ``tgt`` (4 "Tumor" domains by quadrant, 30 % unlabelled)."""
+    coords = clustered(n, seed=seed)
+    rng = np.random.default_rng(seed + 1)
+    centres = rng.uniform(150, 850, (3, 2))
+    d = np.sqrt(((coords[:, None, :] - centres[None]) ** 2).sum(-1))
+    src = np.full(n, None, dtype=object)
+    for j in range(3):
+        src[d[:, j] < 70.0] = f"Bcell_{j + 1}"
+    quad = (coords[:, 0] > 500).astype(int) + 2 * (coords[:, 1] > 500).astype(int)
+    tgt = np.array([f"Tumor_{q + 1}" for q in quad], dtype=object)
+    tgt[rng.random(n) < 0.3] = None
+    return coords, src, tgt

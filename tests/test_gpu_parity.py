@@ -729,3 +729,72 @@ def test_identify_niches_matches_reference(api, golden_dir):
     a.obsm["neighborhood_profile"][7] = 0
     with pytest.raises(ValueError, match="1 cells have empty neighborhood profiles"):
         api.identify_niches(a, n_niches=3)
+
+
+# ---------------------------------------------------------------------------------------------
+# domain distances
+# ---------------------------------------------------------------------------------------------
+
+
+def test_cross_nn_and_pairwise_kernels(eng):
+    from scipy.spatial import cKDTree
+    from scipy.spatial.distance import cdist
+
+    rng = np.random.default_rng(12)
+    for nt, nq in ((1, 50), (7, 300), (5000, 20000)):
+        T = rng.uniform(0, 100, (nt, 2))
+        Q = np.concatenate([rng.uniform(-400, 500, (nq // 2, 2)), rng.uniform(0, 100, (nq - nq // 2, 2))])  # inside and far outside the target box
+        d, j = eng.cross_nn(T, Q)
+        wd, wj = cKDTree(T).query(Q, k=1)
+        assert np.array_equal(j, wj)
+        assert np.array_equal(d, wd)  # sqrt(dx*dx + dy*dy) in FP64 on both sides
+    T = inputs.lattice(12, 9)  # exact ties: lowest target index wins
+    d, j = eng.cross_nn(T, np.array([[0.5, 0.5], [3.5, 2.0]]))
+    assert list(j) == [0, 27] and np.allclose(d, [np.sqrt(0.5), 0.5])
+    A, B = rng.normal(size=(1300, 2)) * 50, rng.normal(size=(2700, 2)) * 50 + 20
+    dmin, dsum = eng.pairwise_reduce(A, B)
+    D = cdist(A, B)
+    assert dmin == D.min()
+    np.testing.assert_allclose(dsum, D.sum(), rtol=1e-13)
+
+
+def test_calculate_domain_distances_matches_reference(api, golden_dir):
+    g = np.load(os.path.join(golden_dir, "ref_distances.npz"))
+    coords, src, tgt = inputs.domains()
+    cases = [("min_both", "src", "tgt", "minimum", "both"), ("min_matrix", "src", "tgt", "minimum", "matrix"),
+             ("centroid_both", "src", "tgt", "centroid", "both"), ("mean_both", "src", "tgt", "mean", "both"),
+             ("same_min_both", "tgt", "tgt", "minimum", "both"), ("same_centroid_both", "tgt", "tgt", "centroid", "both")]
+    for tag, sc, tc, metric, mode in cases:
+        obs = pd.DataFrame({"src": pd.Series(src, dtype=object), "tgt": pd.Series(tgt, dtype=object)})
+        a = _adata(np.zeros((coords.shape[0], 1), np.float32), coords, obs=obs)
+        api.calculate_domain_distances(a, sc, tc, distance_metric=metric, output_mode=mode)
+        M = api.get_distance_matrix(a)
+        assert list(M.index) == list(g[f"{tag}_rows"]) and list(M.columns) == list(g[f"{tag}_cols"])
+        np.testing.assert_allclose(M.to_numpy(dtype=np.float64), g[f"{tag}_matrix"], rtol=1e-12, equal_nan=True)
+        if mode != "matrix":
+            np.testing.assert_allclose(a.obs["distance_to_target"].to_numpy(dtype=np.float64), g[f"{tag}_dist"], rtol=1e-13, equal_nan=True)
+            near = np.array(["" if v is None or v != v else str(v) for v in a.obs["nearest_target_domain"]])
+            assert np.array_equal(near, g[f"{tag}_nearest"]), tag
+        else:
+            assert "distance_to_target" not in a.obs.columns
+        meta = a.uns["domain_distances"]
+        assert meta["distance_metric"] == metric and set(meta["summary_statistics"]) == {"min_distance", "max_distance", "mean_distance", "median_distance"}
+        assert a.uns["spatialcore_metadata"]["operations"][-1]["function"] == "calculate_domain_distances"
+    # subsets and error behaviour [R distance.py:142-196]
+    obs = pd.DataFrame({"src": pd.Series(src, dtype=object), "tgt": pd.Series(tgt, dtype=object)})
+    a = _adata(np.zeros((coords.shape[0], 1), np.float32), coords, obs=obs)
+    api.calculate_domain_distances(a, "src", "tgt", source_domain_subset=["Bcell_2"], target_domain_subset=["Tumor_1", "Tumor_4"], output_mode="matrix")
+    M = api.get_distance_matrix(a)
+    assert list(M.index) == ["Bcell_2"] and sorted(M.columns) == ["Tumor_1", "Tumor_4"]
+    d, _, Mref = R.domain_distances(coords, src, tgt, ["Bcell_2"], list(M.columns), "minimum", "matrix")
+    np.testing.assert_allclose(M.to_numpy(dtype=np.float64), Mref, rtol=1e-12)
+    with pytest.raises(ValueError, match="Source column 'nope' not found"):
+        api.calculate_domain_distances(a, "nope", "tgt")
+    with pytest.raises(ValueError, match="Invalid distance_metric"):
+        api.calculate_domain_distances(a, "src", "tgt", distance_metric="manhattan")
+    with pytest.raises(ValueError, match="Invalid output_mode"):
+        api.calculate_domain_distances(a, "src", "tgt", output_mode="table")
+    with pytest.raises(ValueError, match="No valid source domains"):
+        api.calculate_domain_distances(a, "src", "tgt", source_domain_subset=["Bcell_9"])
+    with pytest.raises(KeyError, match="not found in adata.uns"):
+        api.get_distance_matrix(_adata(np.zeros((5, 1), np.float32), np.zeros((5, 2))))
