@@ -221,6 +221,22 @@ SC_API int sc_gather_rows(const float* src, int64_t lds, int64_t n, int64_t cols
 SC_API int sc_perm_conjugate(const int32_t* perm_idx, int64_t n, int n_perms, const int32_t* order,
                              const int32_t* rank, int32_t* out, sc_stream_t stream);
 
+/* Local Moran epilogue (autocorrelation.py:888-928 with 132-183 and 219-265): from the per-cell
+ * exceedance counts cnt i32[n, ldc] of n_perms permutations, the standardised values Z, their lag and
+ * local I (all f32[n, ldz], stored in the order given by `order`, or NULL = user order) produce, at each
+ * cell's ORIGINAL row and tightly packed [n, g]: z, lag, local I, p = (cnt+1)/(n_perms+1),
+ * the adjusted p (method 0 none, 1 bonferroni, 2 Benjamini-Hochberg per gene over the n cells, computed
+ * from a (n_perms+1)-bin histogram, no sort) and the LISA quadrant i8 (0 NS, 1 HH, 2 LL, 3 HL, 4 LH;
+ * set to 0 where adjusted p >= alpha when n_perms > 0).  zero_var u8[g] or NULL: those genes get
+ * z = lag = I = 0, p = 1. */
+SC_API size_t sc_local_moran_finish_workspace_bytes(int g, int n_perms);
+SC_API int sc_local_moran_finish(const int32_t* cnt, int64_t ldc, const float* Z, const float* lag,
+                                 const float* local, int64_t ldz, const int32_t* order, int64_t n, int g,
+                                 int n_perms, const uint8_t* zero_var, int method, float alpha,
+                                 float* z_out, float* lag_out, float* local_out, float* p_out,
+                                 float* padj_out, int8_t* quad_out, void* ws, size_t ws_bytes,
+                                 sc_stream_t stream);
+
 /* Materialise Philox permutation `perm_index` of [0,n) into out i32[n] (tests, replay export). */
 SC_API int sc_philox_permutation(uint64_t seed, int64_t perm_index, int64_t n, int32_t* out,
                           sc_stream_t stream);

@@ -53,6 +53,9 @@ SIGNATURES = {
     "sc_spatial_order": (_i32, [_vp, _i64, _vp, _vp, _vp, _sz, _vp]),
     "sc_graph_relabel_workspace_bytes": (_sz, [_i64]),
     "sc_graph_relabel": (_i32, [_vp, _vp, _vp, _i64, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
+    "sc_local_moran_finish_workspace_bytes": (_sz, [_i32, _i32]),
+    "sc_local_moran_finish": (_i32, [_vp, _i64, _vp, _vp, _vp, _i64, _vp, _i64, _i32, _i32, _vp, _i32, C.c_float,
+                                     _vp, _vp, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
     "sc_philox_permutation": (_i32, [_u64, _i64, _i64, _vp, _vp]),
     "sc_philox_permutation_host": (_i32, [_u64, _i64, _i64, _vp]),
     "sc_null_accumulate": (_i32, [_vp, _i32, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),

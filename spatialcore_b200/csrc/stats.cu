@@ -937,6 +937,112 @@ __global__ void perm_conjugate_kernel(const int32_t* __restrict__ perm, int64_t 
   }
 }
 
+// ------------------------------------------------------------------------------------------------
+// local Moran epilogue: per-cell p-values, multiple-testing adjustment and LISA quadrants on the device
+// (replaces the reference's N x G Python loop and the per-gene numpy sorts of
+// [R autocorrelation.py:132-183, 219-265, 888-928]).
+//
+// A per-cell permutation p-value takes only P+1 values, (c+1)/(P+1), so the Benjamini-Hochberg
+// step-up over the N cells of a gene needs no sort: with h[v] = number of cells at level v and
+// cum[v] = sum_{u<=v} h[u], every cell at level v gets  min_{u>=v, h[u]>0} p_u*N/cum[u]  -- exactly what
+// sorting, dividing by the rank and taking the running minimum from the end produces (tied cells share
+// the value of the last of them).  The arithmetic follows numpy's: p*N in FP32, the division in FP64.
+// ------------------------------------------------------------------------------------------------
+
+__global__ void __launch_bounds__(256)
+local_hist_kernel(const int32_t* __restrict__ cnt, int64_t ldc, int64_t n, int g, int n_perms,
+                  const uint8_t* __restrict__ zero_var, int genes_per_block,
+                  unsigned int* __restrict__ hist /*[g][P+1]*/) {
+  extern __shared__ unsigned int sh_hist[];  // [genes_per_block][P+1]
+  const int levels = n_perms + 1;
+  const int g0 = blockIdx.x * genes_per_block;
+  const int gb = min(genes_per_block, g - g0);
+  for (int t = threadIdx.x; t < gb * levels; t += blockDim.x) sh_hist[t] = 0;
+  __syncthreads();
+  const int64_t total = n * gb;
+  for (int64_t t = (int64_t)blockIdx.y * blockDim.x + threadIdx.x; t < total; t += (int64_t)gridDim.y * blockDim.x) {
+    const int64_t row = t / gb;
+    const int j = (int)(t - row * gb);
+    int c = zero_var && zero_var[g0 + j] ? n_perms : cnt[row * ldc + g0 + j];
+    c = min(max(c, 0), n_perms);
+    atomicAdd(&sh_hist[j * levels + c], 1u);
+  }
+  __syncthreads();
+  for (int t = threadIdx.x; t < gb * levels; t += blockDim.x)
+    if (sh_hist[t]) atomicAdd(&hist[(int64_t)g0 * levels + t], sh_hist[t]);
+}
+
+// One thread per gene: adjusted p-value of every level.  method 0 none, 1 bonferroni, 2 fdr_bh.
+__global__ void local_adjust_table_kernel(const unsigned int* __restrict__ hist, int g, int n_perms,
+                                          int64_t n, int method, float* __restrict__ table /*[g][P+1]*/) {
+  const int gene = blockIdx.x * blockDim.x + threadIdx.x;
+  if (gene >= g) return;
+  const int levels = n_perms + 1;
+  const unsigned int* h = hist + (int64_t)gene * levels;
+  float* tb = table + (int64_t)gene * levels;
+  const float nf = (float)n;
+  if (method != 2) {
+    for (int v = 0; v < levels; ++v) {
+      const float p = (float)((double)(v + 1) / (double)levels);
+      tb[v] = method == 0 ? p : fminf(fmaxf(__fmul_rn(p, nf), 0.f), 1.f);
+    }
+    return;
+  }
+  int64_t cum = n;  // walk the levels from the top: cum = number of cells at levels <= v
+  double running = INFINITY;
+  for (int v = levels - 1; v >= 0; --v) {
+    if (h[v]) {
+      const float p = (float)((double)(v + 1) / (double)levels);
+      const double t = (double)__fmul_rn(p, nf) / (double)cum;
+      running = fmin(running, t);
+    }
+    tb[v] = (float)fmin(fmax(running, 0.0), 1.0);
+    cum -= h[v];
+  }
+}
+
+// Per cell and gene: p, adjusted p, quadrant; every per-cell output is written at the cell's ORIGINAL
+// row (order[a] = original id of stored row a), tightly packed [n][g].
+__global__ void __launch_bounds__(256)
+local_finish_kernel(const int32_t* __restrict__ cnt, int64_t ldc, const float* __restrict__ Z,
+                    const float* __restrict__ lag, const float* __restrict__ loc, int64_t ldz,
+                    const int32_t* __restrict__ order, int64_t n, int g, int n_perms,
+                    const uint8_t* __restrict__ zero_var, const float* __restrict__ table, float alpha,
+                    float* __restrict__ z_out, float* __restrict__ lag_out, float* __restrict__ loc_out,
+                    float* __restrict__ p_out, float* __restrict__ padj_out, int8_t* __restrict__ quad_out) {
+  const int levels = n_perms + 1;
+  const int64_t total = n * g;
+  for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < total; t += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t a = t / g;
+    const int j = (int)(t - a * g);
+    const int64_t dst = (order ? (int64_t)order[a] : a) * g + j;
+    const bool dead = zero_var && zero_var[j];
+    const float z = dead ? 0.f : Z[a * ldz + j];
+    const float lg = dead ? 0.f : lag[a * ldz + j];
+    z_out[dst] = z;
+    lag_out[dst] = lg;
+    loc_out[dst] = dead ? 0.f : loc[a * ldz + j];
+    int q = 0;
+    if (z > 0.f && lg > 0.f) q = 1;
+    else if (z < 0.f && lg < 0.f) q = 2;
+    else if (z > 0.f && lg < 0.f) q = 3;
+    else if (z < 0.f && lg > 0.f) q = 4;
+    if (n_perms > 0) {
+      int c = dead ? n_perms : cnt[a * ldc + j];
+      c = min(max(c, 0), n_perms);
+      const float p = (float)((double)(c + 1) / (double)levels);
+      const float pa = table[(int64_t)j * levels + c];
+      p_out[dst] = p;
+      padj_out[dst] = pa;
+      if (pa >= alpha) q = 0;
+    } else {
+      p_out[dst] = 1.f;
+      padj_out[dst] = 1.f;
+    }
+    quad_out[dst] = (int8_t)q;
+  }
+}
+
 __global__ void philox_permutation_kernel(PermDomain dom, const __grid_constant__ PermBatch pb,
                                           int32_t* __restrict__ out) {
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < dom.n;
@@ -1473,6 +1579,53 @@ extern "C" int sc_perm_conjugate(const int32_t* perm_idx, int64_t n, int n_perms
   int64_t want = (n * n_perms + 255) / 256;
   int blocks = (int)(want > sm_count() * 16 ? sm_count() * 16 : want);
   perm_conjugate_kernel<<<blocks, 256, 0, st>>>(perm_idx, n, n_perms, order, rank, out);
+  SC_LAUNCH_OK();
+  return SC_OK;
+}
+
+extern "C" size_t sc_local_moran_finish_workspace_bytes(int g, int n_perms) {
+  const size_t levels = (size_t)(n_perms > 0 ? n_perms : 0) + 1;
+  return align_up(sizeof(unsigned int) * (size_t)(g > 0 ? g : 1) * levels, 256) +
+         align_up(sizeof(float) * (size_t)(g > 0 ? g : 1) * levels, 256) + 512;
+}
+
+extern "C" int sc_local_moran_finish(const int32_t* cnt, int64_t ldc, const float* Z, const float* lag,
+                                     const float* local, int64_t ldz, const int32_t* order, int64_t n,
+                                     int g, int n_perms, const uint8_t* zero_var, int method, float alpha,
+                                     float* z_out, float* lag_out, float* local_out, float* p_out,
+                                     float* padj_out, int8_t* quad_out, void* ws, size_t ws_bytes,
+                                     sc_stream_t stream) {
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  SC_CHECK_ARG(Z && lag && local && z_out && lag_out && local_out && p_out && padj_out && quad_out && ws,
+               "sc_local_moran_finish: null argument");
+  SC_CHECK_ARG(n >= 1 && g >= 1 && ldz >= g && n_perms >= 0, "sc_local_moran_finish: bad sizes");
+  SC_CHECK_ARG(n_perms == 0 || (cnt && ldc >= g), "sc_local_moran_finish: permutation counts missing");
+  SC_CHECK_ARG(method >= 0 && method <= 2, "sc_local_moran_finish: method must be 0 (none), 1 (bonferroni) or 2 (fdr_bh)");
+  if (ws_bytes < sc_local_moran_finish_workspace_bytes(g, n_perms)) { set_error("sc_local_moran_finish: workspace too small"); return SC_ERR_WORKSPACE; }
+  const int levels = n_perms + 1;
+  unsigned int* hist = static_cast<unsigned int*>(ws);
+  float* table = reinterpret_cast<float*>(static_cast<char*>(ws) + align_up(sizeof(unsigned int) * (size_t)g * levels, 256));
+  if (n_perms > 0) {
+    if (method == 2) {
+      SC_CUDA_OK(cudaMemsetAsync(hist, 0, sizeof(unsigned int) * (size_t)g * levels, st));
+      int gpb = (int)(48 * 1024 / (sizeof(unsigned int) * levels));
+      if (gpb < 1) { set_error("sc_local_moran_finish: more than 12287 permutations are not supported"); return SC_ERR_UNSUPPORTED; }
+      if (gpb > g) gpb = g;
+      const int bx = (g + gpb - 1) / gpb;
+      int by = (sm_count() * 8 + bx - 1) / bx;
+      const int64_t max_by = (n * gpb + 255) / 256;
+      if (by > max_by) by = (int)max_by;
+      if (by < 1) by = 1;
+      local_hist_kernel<<<dim3(bx, by), 256, sizeof(unsigned int) * (size_t)gpb * levels, st>>>(cnt, ldc, n, g, n_perms, zero_var, gpb, hist);
+      SC_LAUNCH_OK();
+    }
+    local_adjust_table_kernel<<<(g + 63) / 64, 64, 0, st>>>(hist, g, n_perms, n, method, table);
+    SC_LAUNCH_OK();
+  }
+  int64_t want = (n * g + 255) / 256;
+  int blocks = (int)(want > sm_count() * 16 ? sm_count() * 16 : want);
+  local_finish_kernel<<<blocks, 256, 0, st>>>(cnt, ldc, Z, lag, local, ldz, order, n, g, n_perms, zero_var, table, alpha,
+                                              z_out, lag_out, local_out, p_out, padj_out, quad_out);
   SC_LAUNCH_OK();
   return SC_OK;
 }

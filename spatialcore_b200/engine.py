@@ -662,3 +662,29 @@ def pairwise_reduce(a, b, device="cuda") -> Tuple[float, float]:
     _count(2)
     o = out.cpu().numpy()
     return float(o[0]), float(o[1])
+
+
+_FDR_METHODS = {"none": 0, "bonferroni": 1, "fdr_bh": 2}
+
+
+def local_moran_finish(cnt: Optional[torch.Tensor], Z: torch.Tensor, lag: torch.Tensor, loc: torch.Tensor, g: int,
+                       n_perms: int, zero_var: Optional[torch.Tensor], method: str, alpha: float,
+                       order: Optional[torch.Tensor] = None):
+    """``sc_local_moran_finish``: per-cell p, adjusted p and LISA quadrant on the device, every output
+    un-sorted to the user's cell order.  Returns device tensors ``(z, lag, I, p, p_adj, quadrant)`` of
+    shape [n, g] (float32 x5, int8)."""
+    L = _lib.lib()
+    n, ld = Z.shape
+    dev = Z.device
+    outs = [torch.empty((n, g), dtype=torch.float32, device=dev) for _ in range(5)]
+    quad = torch.empty((n, g), dtype=torch.int8, device=dev)
+    ws = _workspace(L.sc_local_moran_finish_workspace_bytes(g, n_perms), dev)
+    check(
+        L.sc_local_moran_finish(_ptr(cnt), cnt.shape[1] if cnt is not None else 0, _ptr(Z), _ptr(lag), _ptr(loc), ld,
+                                _ptr(order), n, g, int(n_perms), _ptr(zero_var), _FDR_METHODS[method], float(alpha),
+                                _ptr(outs[0]), _ptr(outs[1]), _ptr(outs[2]), _ptr(outs[3]), _ptr(outs[4]), _ptr(quad),
+                                _ptr(ws), ws.numel(), _stream()),
+        "sc_local_moran_finish",
+    )
+    _count(4)
+    return outs[0], outs[1], outs[2], outs[3], outs[4], quad

@@ -486,6 +486,8 @@ def local_morans_i(
     z_values = np.zeros((n, g), dtype=np.float32)
     lag_values = np.zeros((n, g), dtype=np.float32)
     p_values = np.ones((n, g), dtype=np.float32)
+    p_adj = np.ones((n, g), dtype=np.float32)
+    quadrants = np.zeros((n, g), dtype=np.int8)
     zero_mask = np.zeros(g, dtype=bool)
 
     source = _pick_perm_source(perm_source, n, n_permutations) if n_permutations > 0 else "none"
@@ -499,9 +501,7 @@ def local_morans_i(
         std = engine.zscore_dense(Xd, cols=cols, rows=co.order)
         _, _, lag, loc = engine.lag_moran(graph, std.Z, gb, want_lag=True, want_local=True)
         zero_mask[s:e] = std.zero_var.cpu().numpy().astype(bool)
-        z_values[:, s:e] = engine.gather_rows(std.Z, co.rank)[:, :gb].cpu().numpy()
-        lag_values[:, s:e] = engine.gather_rows(lag, co.rank)[:, :gb].cpu().numpy()
-        local_I[:, s:e] = engine.gather_rows(loc, co.rank)[:, :gb].cpu().numpy()
+        cnt = None
         if n_permutations > 0:
             cnt = torch.zeros(std.Z.shape, dtype=torch.int32, device=std.Z.device)
             if source == "philox":
@@ -511,29 +511,26 @@ def local_morans_i(
                 for _, idx in _replay_chunks(rng, n, n_permutations, std.Z.device):
                     idx = engine.conjugate_perms(idx, co)
                     engine.perm_null_values(graph, std.Z, gb, idx.shape[0], perm_idx=idx, cell_obs=loc, cell_cnt=cnt)
-            cnt = engine.gather_rows(cnt.view(torch.float32), co.rank).view(torch.int32)  # bit-preserving row move
-            p_values[:, s:e] = ((cnt[:, :gb].cpu().numpy() + 1) / (n_permutations + 1)).astype(np.float32)
+        # p-values, per-gene multiple-testing adjustment, quadrants and the un-sort to the user's cell
+        # order in one device epilogue (the reference: an N x G Python loop, per-gene sorts, numpy masks)
+        z_d, lag_d, loc_d, p_d, pa_d, q_d = engine.local_moran_finish(
+            cnt, std.Z, lag, loc, gb, n_permutations, std.zero_var, fdr_correction, alpha, order=co.order)
+        z_values[:, s:e] = z_d.cpu().numpy()
+        lag_values[:, s:e] = lag_d.cpu().numpy()
+        local_I[:, s:e] = loc_d.cpu().numpy()
+        p_values[:, s:e] = p_d.cpu().numpy()
+        p_adj[:, s:e] = pa_d.cpu().numpy()
+        quadrants[:, s:e] = q_d.cpu().numpy()
 
     zero_genes = [names[i] for i in np.where(zero_mask)[0]]
     if zero_mask.any():
         logger.warning(f"{int(zero_mask.sum())} genes have zero variance and will be skipped: {zero_genes[:5]}")
-        local_I[:, zero_mask] = 0.0
-        z_values[:, zero_mask] = 0.0
-        lag_values[:, zero_mask] = 0.0
-        p_values[:, zero_mask] = 1.0
-
-    if n_permutations > 0:
-        p_adj = np.ones_like(p_values)
-        for j in range(g):
-            p_adj[:, j] = _fdr(p_values[:, j], fdr_correction)
-        quadrants = _classify_quadrants(z_values, lag_values, p_adj, alpha)
-    else:
+    if n_permutations == 0:
         logger.warning(
             "n_permutations=0: Quadrants classified by z/lag signs only, "
             "without significance filtering. Consider n_permutations>=99 for p-values."
         )
         p_adj = p_values
-        quadrants = _classify_quadrants(z_values, lag_values, p_values=None, alpha=alpha)
 
     adata.obsm[f"{key_added}_I"] = local_I
     adata.obsm[f"{key_added}_z"] = z_values

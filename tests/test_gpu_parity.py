@@ -798,3 +798,45 @@ def test_calculate_domain_distances_matches_reference(api, golden_dir):
         api.calculate_domain_distances(a, "src", "tgt", source_domain_subset=["Bcell_9"])
     with pytest.raises(KeyError, match="not found in adata.uns"):
         api.get_distance_matrix(_adata(np.zeros((5, 1), np.float32), np.zeros((5, 2))))
+
+
+@pytest.mark.parametrize("method", ["fdr_bh", "bonferroni", "none"])
+@pytest.mark.parametrize("n_perms", [19, 999])
+def test_local_moran_epilogue_matches_numpy(eng, method, n_perms):
+    """p = (c+1)/(P+1), per-gene BH / Bonferroni over the cells, quadrants and the un-sort, against the
+    reference's numpy recipe [R autocorrelation.py:132-183, 219-265] evaluated on the host."""
+    from spatialcore_b200.spatial import autocorrelation as ac
+
+    rng = np.random.default_rng(n_perms)
+    n, g = 5003, 7
+    ld = eng.padded_ld(g)
+    cnt = rng.integers(0, n_perms + 1, (n, ld)).astype(np.int32)
+    cnt[:, 1] = np.minimum(cnt[:, 1], 2)          # heavy ties at small p
+    cnt[: n // 50, 2] = 0                          # a block of minimal p-values
+    Z = rng.normal(size=(n, ld)).astype(np.float32)
+    lag = rng.normal(size=(n, ld)).astype(np.float32)
+    Z[rng.random((n, ld)) < 0.01] = 0.0
+    zero = np.zeros(g, np.uint8); zero[4] = 1
+    order = rng.permutation(n).astype(np.int32)
+    alpha = 0.05
+    outs = eng.local_moran_finish(torch.from_numpy(cnt).cuda(), torch.from_numpy(Z).cuda(), torch.from_numpy(lag).cuda(),
+                                  torch.from_numpy(Z * lag).cuda(), g, n_perms, torch.from_numpy(zero).cuda(), method, alpha,
+                                  order=torch.from_numpy(order).cuda())
+    z_d, lag_d, loc_d, p_d, pa_d, q_d = [o.cpu().numpy() for o in outs]
+    inv = np.empty(n, np.int64); inv[order] = np.arange(n)     # original row i is stored at inv[i]
+    zr, lr = Z[inv][:, :g].copy(), lag[inv][:, :g].copy()
+    p = ((cnt[inv][:, :g] + 1) / (n_perms + 1)).astype(np.float32)
+    zr[:, 4] = 0; lr[:, 4] = 0; p[:, 4] = 1.0
+    assert np.array_equal(z_d, zr) and np.array_equal(lag_d, lr) and np.array_equal(p_d, p)
+    loc_want = (Z * lag)[inv][:, :g].copy(); loc_want[:, 4] = 0
+    assert np.array_equal(loc_d, loc_want)
+    pa = np.ones_like(p)
+    for j in range(g):
+        pa[:, j] = ac._fdr(p[:, j], method)
+    assert np.array_equal(pa_d, pa)
+    assert np.array_equal(q_d, ac._classify_quadrants(zr, lr, pa, alpha))
+    # no permutations: sign-only quadrants, p = p_adj = 1
+    outs0 = eng.local_moran_finish(None, torch.from_numpy(Z).cuda(), torch.from_numpy(lag).cuda(), torch.from_numpy(Z * lag).cuda(),
+                                   g, 0, torch.from_numpy(zero).cuda(), method, alpha, order=torch.from_numpy(order).cuda())
+    assert np.array_equal(outs0[5].cpu().numpy(), ac._classify_quadrants(zr, lr, None, alpha))
+    assert bool((outs0[3] == 1).all()) and bool((outs0[4] == 1).all())
