@@ -255,9 +255,11 @@ SC_API int sc_null_accumulate(const double* sims, int n_perms, int g, const doub
 /* ---------------------------------------------------------------------------------------------
  * Lee's L for all ordered gene pairs: L[x, y] = Σ_i A[i, x] · B[i, y]  (A = Z, B = W Z), i.e. the
  * matrix of autocorrelation.py:307-315 over every pair.
- * impl 1 (and 0 = default): CUDA-core kernel, FP64 accumulation (exact up to input rounding).
- * impl 2: tensor cores — tcgen05.mma kind::tf32 with 3xTF32 operand splitting, FP32 accumulation in
- *         TMEM per 1024-cell chunk, chunks summed in FP64 (~1e-6 of the matrix scale sqrt(n)).
+ * impl 1: CUDA-core kernel, FP64 accumulation (exact up to input rounding).
+ * impl 2: tensor cores -- tcgen05.mma kind::tf32 with 3xTF32 operand splitting (fused in-kernel), FP32
+ *         accumulation in TMEM per 256-cell chunk, chunks folded in FP32 registers, CTA partials summed
+ *         in FP64 (~2e-6 relative).
+ * impl 0 (default): impl 2 when n >= 8192 and g >= 64, else impl 1.
  * L f32[g, ldl].
  * ------------------------------------------------------------------------------------------- */
 SC_API size_t sc_lee_gemm_workspace_bytes(int64_t n, int g);

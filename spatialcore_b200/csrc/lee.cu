@@ -159,7 +159,9 @@ extern "C" int sc_lee_gemm(const float* A, int64_t lda, const float* B, int64_t 
   if (ws_bytes < sc_lee_gemm_workspace_bytes(n, g)) { set_error("sc_lee_gemm: workspace too small"); return SC_ERR_WORKSPACE; }
   LeePlan p = lee_plan(n, g);
   double* partial = static_cast<double*>(ws);
-  if (impl == 0) impl = 1;  // exact FP64 accumulation by default; tensor cores (3xTF32) on request
+  // impl 0 = auto: tensor cores (3xTF32, ~2e-6 relative) for contractions big enough to fill them,
+  // the exact FP64 CUDA-core kernel otherwise
+  if (impl == 0) impl = (n >= 8192 && g >= 64 && lee_tc_supported(n, g, lda, ldb) && !((reinterpret_cast<uintptr_t>(A) | reinterpret_cast<uintptr_t>(B)) & 15)) ? 2 : 1;
   if (impl == 2) {
     if (!lee_tc_supported(n, g, lda, ldb)) { set_error("sc_lee_gemm: tcgen05 path unsupported for this shape"); return SC_ERR_UNSUPPORTED; }
     char* extra = static_cast<char*>(ws) + align_up(sizeof(double) * (size_t)p.splits * p.ldt * p.ldt, 256);
