@@ -83,12 +83,12 @@ if want("lag"):
 
 if want("lagsweep"):
     sweep = {}
-    for unr in (4, 8, 16):
-        for chunk in (256, 512, 1024):
-            os.environ["SC_LAG_UNR"], os.environ["SC_LAG_CHUNK"] = str(unr), str(chunk)
-            sweep[f"unr{unr}_chunk{chunk}"] = [round(timed(lambda: eng.lag_moran(gs, std.Z, g)), 3),
-                                               round(timed(lambda: eng.lag_moran(gs, std.Z, g, want_lag=False)), 3)]
-    del os.environ["SC_LAG_UNR"], os.environ["SC_LAG_CHUNK"]
+    for q in (8, 16, 32):
+        for chunk in (64, 128, 256, 512):
+            os.environ["SC_LAG_Q"], os.environ["SC_LAG_CHUNK"] = str(q), str(chunk)
+            sweep[f"q{q}_chunk{chunk}"] = [round(timed(lambda: eng.lag_moran(gs, std.Z, g)), 3),
+                                           round(timed(lambda: eng.lag_moran(gs, std.Z, g, want_lag=False)), 3)]
+    del os.environ["SC_LAG_Q"], os.environ["SC_LAG_CHUNK"]
     out["lag_sweep_ms_[with_lag,stat_only]"] = sweep
 
 if want("lagocc"):

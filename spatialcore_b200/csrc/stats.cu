@@ -303,7 +303,10 @@ __device__ __forceinline__ void fma4(float4& a, float w, const float4& v) {
 // bytes in flight: UNR = 4 -> 56 registers, 32 warps/SM; 8 -> 24 warps; 16 -> 16 warps.  Measured on
 // B200 (C4 / C2, ms): UNR 4: 32.8 / 1.44, 8: 45 / 1.57, 16: 45-55 / 2.2-2.6 -- occupancy wins, so 4 is
 // the default.  (One 16-byte load for four column indices was also tried: 38 / 1.72, slower.)
-template <bool HAS_W, int UNR>
+// Q = lanes (column quads) per row: a warp-wide load touches 32/Q different rows, and it completes only
+// when the slowest of them has arrived (P(all hit L1) = hit^(32/Q)); wider Q means fewer rows per load
+// but a larger per-row footprint in L1.
+template <bool HAS_W, int UNR, int Q>
 __global__ void __launch_bounds__(kStatThreads, UNR >= 16 ? 2 : (UNR >= 8 ? 3 : 4))
 lag_stat_kernel(const int32_t* __restrict__ indptr, const int32_t* __restrict__ indices,
                 const float* __restrict__ weights, int64_t n, int k_fixed,
@@ -311,11 +314,12 @@ lag_stat_kernel(const int32_t* __restrict__ indptr, const int32_t* __restrict__ 
                 float* __restrict__ lag, float* __restrict__ local, int64_t ldl,
                 double* __restrict__ partial, const float* __restrict__ cell_obs,
                 int32_t* __restrict__ cell_cnt, int64_t ldc, int64_t n_chunks, int chunk_rows) {
-  __shared__ double sh[2][kLagRowsPerPass][kLagColQuads][4];
+  constexpr int kRows = kStatThreads / Q;  // rows per pass
+  __shared__ double sh[2][kRows][Q][4];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int q = lane & (kLagColQuads - 1);
-  const int rslot = warp * (32 / kLagColQuads) + (lane >> 3);
-  const int64_t col = ((int64_t)blockIdx.x * kLagColQuads + q) * 4;
+  const int q = lane & (Q - 1);
+  const int rslot = warp * (32 / Q) + lane / Q;
+  const int64_t col = ((int64_t)blockIdx.x * Q + q) * 4;
   const bool active = col < ldz;
   const float* Zs = Zself ? Zself : Zlag;
   const char* zbase = reinterpret_cast<const char*>(Zlag + col);
@@ -325,7 +329,7 @@ lag_stat_kernel(const int32_t* __restrict__ indptr, const int32_t* __restrict__ 
   for (int64_t chunk = blockIdx.y; chunk < n_chunks; chunk += gridDim.y) {
     const int64_t r0 = chunk * chunk_rows;
 #pragma unroll 1
-    for (int pass = 0; pass < chunk_rows; pass += kLagRowsPerPass) {
+    for (int pass = 0; pass < chunk_rows; pass += kRows) {
       const int64_t row = r0 + pass + rslot;
       if (row >= n || !active) continue;
       int64_t b;
@@ -400,7 +404,7 @@ lag_stat_kernel(const int32_t* __restrict__ indptr, const int32_t* __restrict__ 
     for (int c = 0; c < 4; ++c) {
       double a = 0, d = 0;
 #pragma unroll 4
-      for (int r = 0; r < kLagRowsPerPass; ++r) { a += sh[0][r][q][c]; d += sh[1][r][q][c]; }
+      for (int r = 0; r < kRows; ++r) { a += sh[0][r][q][c]; d += sh[1][r][q][c]; }
       p[c] = a; p[ldz + c] = d;
     }
   }
@@ -1097,15 +1101,15 @@ static void fill_batch(PermBatch* pb, int source, const int32_t* perm_idx, uint6
 constexpr int kMaxStatBlocks = 148 * 8;
 
 // Launch lag_stat_kernel; *by_out = number of partial rows written ([by][2][ldz] doubles).
-// SC_LAG_UNR (4|8|16), SC_LAG_CHUNK (multiple of 32) and SC_LAG_VARIANT=tile override the geometry for
-// experiments.
-template <bool HAS_W, int UNR>
+// SC_LAG_UNR (4|8|16), SC_LAG_Q (8|16|32), SC_LAG_CHUNK (multiple of 32) and SC_LAG_VARIANT=tile override
+// the geometry for experiments.
+template <bool HAS_W, int UNR, int Q>
 static void launch_lag_stat_t(dim3 grid, cudaStream_t st, const int32_t* indptr, const int32_t* indices,
                               const float* weights, int64_t n, int k_fixed, const float* Zself,
                               const float* Zlag, int64_t ldz, float* lag, float* local, int64_t ldl,
                               double* partial, const float* cell_obs, int32_t* cell_cnt, int64_t ldc,
                               int64_t n_chunks, int chunk_rows) {
-  lag_stat_kernel<HAS_W, UNR><<<grid, kStatThreads, 0, st>>>(indptr, indices, weights, n, k_fixed, Zself, Zlag, ldz, lag,
+  lag_stat_kernel<HAS_W, UNR, Q><<<grid, kStatThreads, 0, st>>>(indptr, indices, weights, n, k_fixed, Zself, Zlag, ldz, lag,
                                                              local, ldl, partial, cell_obs, cell_cnt, ldc, n_chunks,
                                                              chunk_rows);
 }
@@ -1119,13 +1123,16 @@ static int launch_lag_stat(const int32_t* indptr, const int32_t* indices, const 
   int chunk_rows = 512;
   while (chunk_rows > 64 && ((n + chunk_rows - 1) / chunk_rows) * ((ldz + 31) / 32) < 4 * (int64_t)sm_count()) chunk_rows /= 2;
   if (const char* e = getenv("SC_LAG_UNR")) { int v = atoi(e); if (v == 4 || v == 8 || v == 16) unr = v; }
+  int quads = kLagColQuads;
+  if (const char* e = getenv("SC_LAG_Q")) { int v = atoi(e); if (v == 8 || v == 16 || v == 32) quads = v; }
+  if (ldz < 4 * quads) quads = kLagColQuads;
   if (const char* e = getenv("SC_LAG_CHUNK")) { int v = atoi(e); if (v >= 32 && v % 32 == 0 && v <= 4096) chunk_rows = v; }
   // SC_LAG_VARIANT=tile selects the shared-memory variant.  Measured on B200: it wins on C2 (kNN k=15,
   // 500 k x 400: 1.22 vs 1.44 ms) and loses on C4 (radius, 5 M x 1000: 42 vs 33 ms) -- the tile's 64 KB
   // per CTA costs resident warps, and this kernel's time is inversely proportional to them.
   const char* variant = getenv("SC_LAG_VARIANT");
   const bool tile = ldz >= 32 && variant && !strcmp(variant, "tile");
-  const int bx = (int)((ldz + 31) / 32);
+  const int bx = tile ? (int)((ldz + 31) / 32) : (int)((ldz + 4 * quads - 1) / (4 * quads));
   const int64_t n_chunks = (n + chunk_rows - 1) / chunk_rows;
   int64_t by = ((int64_t)sm_count() * 8 + bx - 1) / bx;
   if (by > n_chunks) by = n_chunks;
@@ -1147,11 +1154,18 @@ static int launch_lag_stat(const int32_t* indptr, const int32_t* indices, const 
     return SC_OK;
   }
 #define SC_LAG_ARGS grid, st, indptr, indices, weights, n, k_fixed, Zself, Zlag, ldz, lag, local, ldl, partial, cell_obs, cell_cnt, ldc, n_chunks, chunk_rows
+#define SC_LAG_Q(W, U)                                                                      \
+  do {                                                                                      \
+    if (quads == 32) launch_lag_stat_t<W, U, 32>(SC_LAG_ARGS);                              \
+    else if (quads == 16) launch_lag_stat_t<W, U, 16>(SC_LAG_ARGS);                         \
+    else launch_lag_stat_t<W, U, 8>(SC_LAG_ARGS);                                           \
+  } while (0)
   if (weights) {
-    if (unr == 16) launch_lag_stat_t<true, 16>(SC_LAG_ARGS); else if (unr == 8) launch_lag_stat_t<true, 8>(SC_LAG_ARGS); else launch_lag_stat_t<true, 4>(SC_LAG_ARGS);
+    if (unr == 16) SC_LAG_Q(true, 16); else if (unr == 8) SC_LAG_Q(true, 8); else SC_LAG_Q(true, 4);
   } else {
-    if (unr == 16) launch_lag_stat_t<false, 16>(SC_LAG_ARGS); else if (unr == 8) launch_lag_stat_t<false, 8>(SC_LAG_ARGS); else launch_lag_stat_t<false, 4>(SC_LAG_ARGS);
+    if (unr == 16) SC_LAG_Q(false, 16); else if (unr == 8) SC_LAG_Q(false, 8); else SC_LAG_Q(false, 4);
   }
+#undef SC_LAG_Q
 #undef SC_LAG_ARGS
   SC_LAUNCH_OK();
   *by_out = (int)by;
