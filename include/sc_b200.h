@@ -263,6 +263,11 @@ SC_API int sc_null_accumulate(const double* sims, int n_perms, int g, const doub
  * L f32[g, ldl].
  * ------------------------------------------------------------------------------------------- */
 SC_API size_t sc_lee_gemm_workspace_bytes(int64_t n, int g);
+
+/* Two-tailed exceedance counts for an all-pairs permutation null: cnt[x,y] += |Lp[x,y]| >= |L[x,y]|
+ * (autocorrelation.py:331-332 for every pair at once).  Lp, L f32[g, ld*]; cnt i32[g, ldc]. */
+SC_API int sc_lee_abs_ge_accumulate(const float* Lp, int64_t ldp, const float* L, int64_t ldl, int g,
+                                    int32_t* cnt, int64_t ldc, sc_stream_t stream);
 SC_API int sc_lee_gemm(const float* A, int64_t lda, const float* B, int64_t ldb, int64_t n, int g,
                 float* L, int64_t ldl, int impl, void* ws, size_t ws_bytes, sc_stream_t stream);
 

@@ -85,6 +85,13 @@ if want("lee"):
             out[f"C3_lee_gemm_impl{impl}_useful_tflops"] = 2.0 * n * g * g / (ms / 1e3) / 1e12
         except Exception as e:
             out[f"C3_lee_gemm_impl{impl}"] = "unavailable: " + str(e)[:80]
+    # all-pairs permutation null at C3: per permutation one row gather + lag pass + contraction
+    co = eng.spatial_order(cd); gs = eng.relabel_graph(graph, co); std_s = eng.zscore_dense(X, rows=co.order)
+    def one_perm():
+        Zp = eng.gather_rows(std_s.Z, eng.philox_permutation(1, 0, n))
+        _, _, lp, _ = eng.lag_moran(gs, Zp, g)
+        eng.lee_gemm(std_s.Z, lp, g, impl=2)
+    out["C3_lee_all_pairs_ms_per_permutation"] = timed(one_perm)
     L = eng.lee_gemm(std.Z, lag, g, impl=1)
     ref = (std.Z[:, :g].double().T @ lag[:, :g].double())
     out["C3_lee_impl1_max_abs_err_vs_fp64_torch"] = float((L.double() - ref).abs().max())

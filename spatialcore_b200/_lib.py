@@ -64,6 +64,7 @@ SIGNATURES = {
     "sc_kmeans_pp_potential": (_i32, [_vp, _i64, _i64, _i32, _vp, _i32, _vp, _vp, _i32, _vp, _vp, _sz, _vp]),
     "sc_kmeans_pp_sample_workspace_bytes": (_sz, [_i64]),
     "sc_kmeans_pp_sample": (_i32, [_vp, _i64, _vp, _i32, _vp, _vp, _sz, _vp]),
+    "sc_lee_abs_ge_accumulate": (_i32, [_vp, _i64, _vp, _i64, _i32, _vp, _i64, _vp]),
     "sc_lee_gemm_workspace_bytes": (_sz, [_i64, _i32]),
     "sc_lee_gemm": (_i32, [_vp, _i64, _vp, _i64, _i64, _i32, _vp, _i64, _i32, _vp, _sz, _vp]),
 }

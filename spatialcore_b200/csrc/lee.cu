@@ -143,6 +143,24 @@ int lee_reduce(const double* partial, const LeePlan& p, int g, float* L, int64_t
 
 using namespace sc;
 
+// cnt[x,y] += (|Lp[x,y]| >= |L[x,y]|): two-tailed exceedance counts of one permuted all-pairs matrix
+// (autocorrelation.py:331-332 applied to every pair at once).
+__global__ void lee_abs_ge_kernel(const float* __restrict__ Lp, int64_t ldp, const float* __restrict__ L,
+                                  int64_t ldl, int g, int32_t* __restrict__ cnt, int64_t ldc) {
+  const int y = blockIdx.x * blockDim.x + threadIdx.x, x = blockIdx.y;
+  if (y >= g) return;
+  cnt[(int64_t)x * ldc + y] += fabsf(Lp[(int64_t)x * ldp + y]) >= fabsf(L[(int64_t)x * ldl + y]);
+}
+
+extern "C" int sc_lee_abs_ge_accumulate(const float* Lp, int64_t ldp, const float* L, int64_t ldl, int g,
+                                        int32_t* cnt, int64_t ldc, sc_stream_t stream) {
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  SC_CHECK_ARG(Lp && L && cnt && g >= 1 && ldp >= g && ldl >= g && ldc >= g, "sc_lee_abs_ge_accumulate: bad argument");
+  lee_abs_ge_kernel<<<dim3((g + 127) / 128, g), 128, 0, st>>>(Lp, ldp, L, ldl, g, cnt, ldc);
+  SC_LAUNCH_OK();
+  return SC_OK;
+}
+
 extern "C" size_t sc_lee_gemm_workspace_bytes(int64_t n, int g) {
   LeePlan p = lee_plan(n > 0 ? n : 1, g > 0 ? g : 1);
   return align_up(sizeof(double) * (size_t)p.splits * p.ldt * p.ldt, 256) + lee_tc_extra_workspace_bytes(n, g) + 512;

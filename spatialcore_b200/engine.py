@@ -553,6 +553,15 @@ def lee_gemm(A: torch.Tensor, B: torch.Tensor, g: int, impl: int = 0) -> torch.T
     return out
 
 
+def lee_abs_ge_accumulate(Lp: torch.Tensor, L_obs: torch.Tensor, cnt: torch.Tensor) -> None:
+    """``sc_lee_abs_ge_accumulate``: ``cnt += (|Lp| >= |L_obs|)`` for a permuted all-pairs matrix."""
+    Lb = _lib.lib()
+    g = L_obs.shape[0]
+    check(Lb.sc_lee_abs_ge_accumulate(_ptr(Lp), Lp.stride(0), _ptr(L_obs), L_obs.stride(0), g, _ptr(cnt), cnt.stride(0), _stream()),
+          "sc_lee_abs_ge_accumulate")
+    _count()
+
+
 # --------------------------------------------------------------------------------------------------
 # k-means on neighbourhood profiles (identify_niches)
 # --------------------------------------------------------------------------------------------------

@@ -676,21 +676,37 @@ def lees_l_matrix(
     layer: Optional[str] = None,
     spatial_key: str = "spatial",
     n_neighbors: int = 6,
+    n_permutations: int = 0,
+    seed: int = 0,
     *,
     variant: Literal["reference", "lee2001"] = "reference",
     key_added: Optional[str] = None,
     impl: int = 0,
+    perm_source: str = "auto",
     device="cuda",
-) -> pd.DataFrame:
+):
     """Lee's L for ALL ordered gene pairs in one dense contraction (replaces the reference's
     G(G-1)/2-iteration Python loop over :func:`lees_l` / ``lees_l_local(genes=...)``).
 
     ``variant="reference"``: ``L = Zᵀ(WZ)`` — entry (x, y) equals ``lees_l(adata, (x, y))["L"]``.
-    ``variant="lee2001"``:  ``L = (WZ)ᵀ(WZ)/N`` — the textbook statistic (symmetric)."""
+    ``variant="lee2001"``:  ``L = (WZ)ᵀ(WZ)/N`` — the textbook statistic (symmetric).
+
+    ``n_permutations > 0`` (reference variant) adds the two-tailed permutation p-value of every pair,
+    ``p[x, y] = (#{|L_p[x,y]| >= |L[x,y]|} + 1)/(P + 1)`` with ``L_p = Zᵀ(W Z[π_p])`` — the null of
+    [R autocorrelation.py:322-332] (only the y side is permuted), evaluated for all pairs per
+    permutation: one row gather, one lag pass and one contraction each.  All pairs share the P
+    permutations (the reference draws fresh ones per pair).  Returns ``L`` or ``(L, p)`` DataFrames."""
     _check_spatial(adata, spatial_key)
     if n_neighbors < 1:
         raise ValueError(f"n_neighbors must be >= 1, got {n_neighbors}")
+    if n_permutations < 0:
+        raise ValueError(f"n_permutations must be >= 0, got {n_permutations}")
+    if variant not in ("reference", "lee2001"):
+        raise ValueError(f"variant must be 'reference' or 'lee2001', got '{variant}'")
+    if n_permutations > 0 and variant != "reference":
+        raise ValueError("permutation p-values are defined for variant='reference' (only the y side is permuted)")
     names = _resolve_genes(adata, genes, "") if genes is not None else list(adata.var_names)
+    n = adata.n_obs
     graph = _build_knn(adata, spatial_key, n_neighbors, device)
     co = engine.spatial_order(adata.obsm[spatial_key], device=device)
     graph = engine.relabel_graph(graph, co)
@@ -699,14 +715,39 @@ def lees_l_matrix(
     _, _, lag, _ = engine.lag_moran(graph, std.Z, g, want_lag=True)
     if variant == "reference":
         Lm = engine.lee_gemm(std.Z, lag, g, impl=impl)
-    elif variant == "lee2001":
-        Lm = engine.lee_gemm(lag, lag, g, impl=impl) / float(adata.n_obs)
     else:
-        raise ValueError(f"variant must be 'reference' or 'lee2001', got '{variant}'")
+        Lm = engine.lee_gemm(lag, lag, g, impl=impl) / float(n)
     df = pd.DataFrame(Lm.cpu().numpy(), index=names, columns=names)
     if key_added is not None:
         adata.uns[key_added] = df
-    return df
+    if n_permutations == 0:
+        return df
+
+    source = _pick_perm_source(perm_source, n, n_permutations)
+    cnt = torch.zeros((g, g), dtype=torch.int32, device=Lm.device)
+
+    def one(idx_sorted: torch.Tensor) -> None:
+        Zp = engine.gather_rows(std.Z, idx_sorted)
+        _, _, lag_p, _ = engine.lag_moran(graph, Zp, g, want_lag=True)
+        engine.lee_abs_ge_accumulate(engine.lee_gemm(std.Z, lag_p, g, impl=impl), Lm, cnt)
+
+    if source == "philox":
+        for p in range(n_permutations):
+            one(engine.philox_permutation(seed, p, n, device=Lm.device))
+    else:
+        rng = np.random.default_rng(seed)
+        for _, idx in _replay_chunks(rng, n, n_permutations, Lm.device):
+            idx = engine.conjugate_perms(idx, co)
+            for j in range(idx.shape[0]):
+                one(idx[j])
+    pv = (cnt.cpu().numpy() + 1) / (n_permutations + 1)
+    zero = std.zero_var.cpu().numpy().astype(bool)
+    pv[zero, :] = 1.0  # zero-variance genes: L = 0, p = 1 [R autocorrelation.py:1129-1140]
+    pv[:, zero] = 1.0
+    pdf = pd.DataFrame(pv, index=names, columns=names)
+    if key_added is not None:
+        adata.uns[f"{key_added}_pvalues"] = pdf
+    return df, pdf
 
 
 def lees_l_local(

@@ -840,3 +840,45 @@ def test_local_moran_epilogue_matches_numpy(eng, method, n_perms):
                                    g, 0, torch.from_numpy(zero).cuda(), method, alpha, order=torch.from_numpy(order).cuda())
     assert np.array_equal(outs0[5].cpu().numpy(), ac._classify_quadrants(zr, lr, None, alpha))
     assert bool((outs0[3] == 1).all()) and bool((outs0[4] == 1).all())
+
+
+def test_lee_matrix_permutation_pvalues(api):
+    """All-pairs Lee's L with the reference's null (only y permuted) for every pair per permutation:
+    p-values identical to a numpy FP64 evaluation driven by the same replayed permutations."""
+    rng = np.random.default_rng(17)
+    n, g, P, k = 3001, 12, 29, 6
+    coords = rng.uniform(0, 300, (n, 2))
+    X = (np.log1p(rng.poisson(1.0, (n, g))) + 0.3 * rng.normal(size=(n, g))).astype(np.float32)
+    X[:, 3] += np.sin(coords[:, 0] / 25.0).astype(np.float32)
+    X[:, 7] += np.sin(coords[:, 0] / 25.0 + 0.4).astype(np.float32)
+    X[:, 9] = 2.0  # zero variance
+    a = _adata(X, coords)
+    L, pv = api.lees_l_matrix(a, n_neighbors=k, n_permutations=P, seed=5, perm_source="replay", impl=1, key_added="lee")
+    W = R.build_spatial_weights(coords, k).astype(np.float64)
+    Z, _, _, zero = R.zscore(X)
+    want_L = R.lees_l_all_pairs(Z, W)
+    prng = np.random.default_rng(5)
+    cnt = np.zeros((g, g), dtype=np.int64)
+    margin = np.full((g, g), np.inf)
+    for _ in range(P):
+        perm = prng.permutation(n)
+        Lp = Z.T @ (W @ Z[perm])
+        cnt += np.abs(Lp) >= np.abs(want_L)
+        margin = np.minimum(margin, np.abs(np.abs(Lp) - np.abs(want_L)))
+    want_p = (cnt + 1) / (P + 1)
+    want_p[zero, :] = 1.0
+    want_p[:, zero] = 1.0
+    live = ~zero
+    np.testing.assert_allclose(L.to_numpy()[np.ix_(live, live)], want_L[np.ix_(live, live)], rtol=1e-5, atol=4e-6 * np.sqrt(n))
+    safe = margin > 1e-3  # a permuted value within FP32 noise of the observed one may fall either side
+    safe[zero, :] = True; safe[:, zero] = True
+    assert safe.mean() > 0.98
+    assert np.array_equal(pv.to_numpy()[safe], want_p[safe])
+    assert pv.loc["g3", "g7"] <= 2 / (P + 1) and pv.loc["g9", "g1"] == 1.0
+    assert a.uns["lee_pvalues"] is not None and list(pv.index) == list(L.index)
+    # Philox source: deterministic, and the tensor-core path gives the same decisions away from ties
+    _, p1 = api.lees_l_matrix(a, n_neighbors=k, n_permutations=P, seed=5, perm_source="philox", impl=1)
+    _, p2 = api.lees_l_matrix(a, n_neighbors=k, n_permutations=P, seed=5, perm_source="philox", impl=2)
+    assert (p1.to_numpy() != p2.to_numpy()).mean() < 0.03
+    with pytest.raises(ValueError, match="variant='reference'"):
+        api.lees_l_matrix(a, n_permutations=3, variant="lee2001")
