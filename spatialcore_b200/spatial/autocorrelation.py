@@ -113,9 +113,9 @@ def _standardize_row_sharded(adata, layer, names: List[str], device, rows: Optio
         Xd, cols = engine.expression_to_device(X[lo:hi], pos, dev)
         part = engine.zscore_dense(Xd, cols=cols, want_z=False)
         stats[0].fill_(float(have)); stats[1].copy_(part.mean); stats[2].copy_(part.std)
-    allst = torch.empty((world, 3, g), dtype=torch.float64, device=dev)
+    allst = torch.empty((world * 3, g), dtype=torch.float64, device=dev)  # concatenation form (gloo and NCCL)
     dist.all_gather_into_tensor(allst, stats, group=group)
-    h = allst.cpu().numpy()
+    h = allst.view(world, 3, g).cpu().numpy()
     live = h[:, 0, 0] > 0
     mean, std, zero = dist_util.combine_moments(h[live, 0, 0], h[live, 1], h[live, 2])
     mean_d = torch.from_numpy(mean).to(dev)

@@ -157,8 +157,25 @@ def _worker(rank, world, port_no, out_dir):
     glo, ghi = du.block_slice(G, rank, world)
     local = np.stack([obs[glo:ghi], obs[glo:ghi] * 2])
     gathered = du.all_gather_columns(local, G, "cpu")
+    # --- row-sharded ingest: per-block moments all-gathered and pooled, blocks all-gathered into Z
+    n, g = 1001, 5
+    X = np.random.default_rng(3).normal(2.0, 3.0, (n, g))
+    X[:, 2] = 0.75  # constant gene: must pool to exactly zero variance
+    per, rlo, rhi = du.row_block(n, rank, world)
+    stats = torch.zeros((3, g), dtype=torch.float64)
+    stats[0] = float(rhi - rlo)
+    stats[1] = torch.from_numpy(X[rlo:rhi].mean(0))
+    stats[2] = torch.from_numpy(X[rlo:rhi].std(0))
+    allst = torch.empty((world * 3, g), dtype=torch.float64)  # concatenation form: accepted by gloo and NCCL
+    dist.all_gather_into_tensor(allst, stats)
+    h = allst.view(world, 3, g).numpy()
+    mean, std, zero = du.combine_moments(h[:, 0, 0], h[:, 1], h[:, 2])
+    Zu = torch.zeros((world * per, g), dtype=torch.float64)
+    Zu[rlo:rhi] = torch.from_numpy(np.where(zero, 0.0, (X[rlo:rhi] - mean) / np.where(zero, 1.0, std)))
+    dist.all_gather_into_tensor(Zu, Zu[rank * per:(rank + 1) * per].clone())
     np.savez(os.path.join(out_dir, f"r{rank}.npz"), cnt=null.cnt_ge.numpy(), cabs=null.cnt_abs_ge.numpy(),
-             s=null.sum.numpy(), ss=null.sumsq.numpy(), gathered=gathered, slice=np.array([lo, hi]))
+             s=null.sum.numpy(), ss=null.sumsq.numpy(), gathered=gathered, slice=np.array([lo, hi]),
+             mean=mean, std=std, zero=zero, Z=Zu[:n].numpy())
     dist.destroy_process_group()
 
 
@@ -176,3 +193,12 @@ def test_two_rank_sharding_and_reduction_gloo(tmp_path):
         np.testing.assert_allclose(r["s"], sims.sum(0), rtol=1e-12)
         np.testing.assert_allclose(r["ss"], (sims**2).sum(0), rtol=1e-12)
         np.testing.assert_array_equal(r["gathered"], np.stack([obs, obs * 2]))
+    X = np.random.default_rng(3).normal(2.0, 3.0, (1001, 5))
+    X[:, 2] = 0.75
+    for r in (r0, r1):
+        np.testing.assert_allclose(r["mean"], X.mean(0), rtol=1e-13)
+        np.testing.assert_allclose(r["std"], X.std(0), rtol=1e-12, atol=0)
+        assert r["zero"].tolist() == [False, False, True, False, False] and r["std"][2] == 0.0
+        want = (X - X.mean(0)) / np.where(X.std(0) == 0, 1.0, X.std(0))
+        want[:, 2] = 0.0
+        np.testing.assert_allclose(r["Z"], want, rtol=1e-9, atol=1e-12)
