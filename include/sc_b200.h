@@ -154,6 +154,15 @@ SC_API int sc_zscore_apply(const void* X, int dtype, int64_t n, int64_t ldx, int
                            const int32_t* rows, const double* mean, const double* std,
                            const uint8_t* zero_var, float* Z, int64_t ldz, sc_stream_t stream);
 
+/* Fused standardise + all-gather + re-order over NVLink peer memory (row-sharded ingest, multi-GPU):
+ * z-score the n rows of this GPU's block of X (f32, float4-readable rows) with the pooled moments and
+ * store output row a at row dst_rows[a] of the Z matrix of EVERY peer.  peer_ptrs_host: HOST array of
+ * n_peers (<= 16) device addresses, the peer-mapped bases of the symmetric Z buffers [*, ldz] (the local
+ * buffer included).  The caller synchronises the peers afterwards (a barrier over the same group). */
+SC_API int sc_zscore_scatter(const float* X, int64_t n, int64_t ldx, int g, const int32_t* dst_rows,
+                             const double* mean, const double* std, const uint8_t* zero_var,
+                             const uint64_t* peer_ptrs_host, int n_peers, int64_t ldz, sc_stream_t stream);
+
 /* Scatter CSR expression (indptr i64[n+1], indices i32, data of `dtype`) into dense f32 [n, ldo]
  * (zero-filled first).  colmap i32[n_cols_x] or NULL: source column -> output column, -1 = drop. */
 SC_API int sc_csr_densify(const int64_t* indptr, const int32_t* indices, const void* data, int dtype,

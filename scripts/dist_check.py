@@ -33,7 +33,15 @@ Xc = X.copy(); Xc[:, 5] = 0.75  # zero-variance gene must pool to exactly zero v
 shc = spatial.morans_i(AnnDataLite(Xc, obsm={"spatial": coords}), n_permutations=9, seed=4, perm_source="philox",
                        shard="perms", ingest="sharded", device=dev).uns["morans_i"]
 assert np.isnan(shc["I"].to_numpy()[5]) and np.isfinite(np.delete(shc["I"].to_numpy(), 5)).all()
-if rank == 0: print("ingest=sharded ok", flush=True)
+os.environ["SC_INGEST_NCCL"] = "1"  # the NCCL all-gather variant must give the same Z bit for bit
+sh2 = spatial.morans_i(AnnDataLite(X, obsm={"spatial": coords}), n_permutations=101, seed=4, perm_source="philox",
+                       shard="perms", ingest="sharded", device=dev).uns["morans_i"]
+del os.environ["SC_INGEST_NCCL"]
+assert np.array_equal(sh2["I"].to_numpy(), sh["I"].to_numpy()) and np.array_equal(sh2["p_value"].to_numpy(), sh["p_value"].to_numpy())
+sh3 = spatial.morans_i(AnnDataLite(X, obsm={"spatial": coords}), n_permutations=101, seed=4, perm_source="philox",
+                       shard="perms", ingest="sharded", device=dev).uns["morans_i"]  # cached symmetric buffer re-used
+assert np.array_equal(sh3["I"].to_numpy(), sh["I"].to_numpy())
+if rank == 0: print("ingest=sharded ok (fused peer-memory scatter == NCCL all-gather)", flush=True)
 rep = spatial.morans_i(AnnDataLite(X, obsm={"spatial": coords}), n_permutations=33, seed=4, perm_source="replay",
                        shard="perms", device=dev).uns["morans_i"]
 one = spatial.morans_i(AnnDataLite(X, obsm={"spatial": coords}), n_permutations=33, seed=4, perm_source="replay",

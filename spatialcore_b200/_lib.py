@@ -40,6 +40,7 @@ SIGNATURES = {
     "sc_zscore_workspace_bytes": (_sz, [_i64, _i32]),
     "sc_zscore": (_i32, [_vp, _i32, _i64, _i64, _i32, _vp, _vp, _vp, _i64, _vp, _vp, _vp, _vp, _sz, _vp]),
     "sc_zscore_apply": (_i32, [_vp, _i32, _i64, _i64, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _vp]),
+    "sc_zscore_scatter": (_i32, [_vp, _i64, _i64, _i32, _vp, _vp, _vp, _vp, _vp, _i32, _i64, _vp]),
     "sc_csr_densify": (_i32, [_vp, _vp, _vp, _i32, _i64, _vp, _i32, _vp, _i64, _vp]),
     "sc_csr_lag_moran_workspace_bytes": (_sz, [_i64, _i32]),
     "sc_csr_lag_moran": (_i32, [_vp, _vp, _vp, _i64, _i32, _vp, _i64, _i32, _vp, _vp, _i64, _vp, _vp, _vp, _sz, _vp]),

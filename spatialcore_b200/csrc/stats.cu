@@ -205,6 +205,48 @@ zscore_write4_kernel(const float* __restrict__ X, int64_t n, int64_t ldx, int g,
   }
 }
 
+// Fused standardise + all-gather + spatial re-order over NVLink peer memory (row-sharded ingest): this
+// GPU z-scores ITS block of cells once and stores every output row into the Z matrix of EVERY GPU
+// (peers[] are the peer-mapped base addresses of the symmetric Z buffers, peers[self] the local one) at
+// the row's position in the spatial order, dst_rows[a].  No staging copy, no separate collective, no
+// re-order pass: the NVLink stores overlap the streaming read of X.
+constexpr int kMaxPeers = 16;
+struct PeerPtrs { float* p[kMaxPeers]; };
+
+__global__ void __launch_bounds__(256)
+zscore_scatter4_kernel(const float* __restrict__ X, int64_t n, int64_t ldx, int g,
+                       const int32_t* __restrict__ dst_rows, const double* __restrict__ mean,
+                       const double* __restrict__ std, const uint8_t* __restrict__ zero_var,
+                       const __grid_constant__ PeerPtrs peers, int n_peers, int64_t ldz, int qw_log2) {
+  const int qw = 1 << qw_log2;
+  const int qx = threadIdx.x & (qw - 1), ry = threadIdx.x >> qw_log2, rpc = 256 >> qw_log2;
+  const int col = (blockIdx.x * qw + qx) * 4;
+  if (col >= ldz) return;
+  double m[4], inv[4];
+  bool live[4];
+#pragma unroll
+  for (int c = 0; c < 4; ++c) {
+    live[c] = col + c < g && !zero_var[col + c];
+    m[c] = live[c] ? mean[col + c] : 0.0;
+    inv[c] = live[c] ? 1.0 / std[col + c] : 0.0;
+  }
+  const bool in_x = col < g;
+  const int64_t step = (int64_t)gridDim.y * rpc;
+  for (int64_t a = (int64_t)blockIdx.y * rpc + ry; a < n; a += step) {
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (in_x) v = ld_stream4(X + a * ldx + col);
+    float4 o;
+    o.x = live[0] ? (float)(((double)v.x - m[0]) * inv[0]) : 0.f;
+    o.y = live[1] ? (float)(((double)v.y - m[1]) * inv[1]) : 0.f;
+    o.z = live[2] ? (float)(((double)v.z - m[2]) * inv[2]) : 0.f;
+    o.w = live[3] ? (float)(((double)v.w - m[3]) * inv[3]) : 0.f;
+    const int64_t off = (int64_t)dst_rows[a] * ldz + col;
+#pragma unroll
+    for (int p = 0; p < kMaxPeers; ++p)
+      if (p < n_peers) *reinterpret_cast<float4*>(peers.p[p] + off) = o;
+  }
+}
+
 template <typename T>
 __global__ void __launch_bounds__(256)
 csr_densify_kernel(const int64_t* __restrict__ indptr, const int32_t* __restrict__ indices,
@@ -1293,6 +1335,33 @@ extern "C" int sc_zscore_apply(const void* X, int dtype, int64_t n, int64_t ldx,
     else
       zscore_write_kernel<double><<<blocks, 256, 0, st>>>(static_cast<const double*>(X), n, ldx, g, cols, rows, mean, std, zero_var, Z, ldz);
   }
+  SC_LAUNCH_OK();
+  return SC_OK;
+}
+
+extern "C" int sc_zscore_scatter(const float* X, int64_t n, int64_t ldx, int g, const int32_t* dst_rows,
+                                 const double* mean, const double* std, const uint8_t* zero_var,
+                                 const uint64_t* peer_ptrs_host, int n_peers, int64_t ldz,
+                                 sc_stream_t stream) {
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  SC_CHECK_ARG(X && dst_rows && mean && std && zero_var && peer_ptrs_host, "sc_zscore_scatter: null argument");
+  SC_CHECK_ARG(n >= 1 && g >= 1 && ldz % 4 == 0 && ldz >= g, "sc_zscore_scatter: bad shape");
+  SC_CHECK_ARG(n_peers >= 1 && n_peers <= kMaxPeers, "sc_zscore_scatter: need 1 <= n_peers <= %d", kMaxPeers);
+  SC_CHECK_ARG(ldx % 4 == 0 && ldx >= (g + 3) / 4 * 4 && (reinterpret_cast<uintptr_t>(X) & 15) == 0,
+               "sc_zscore_scatter: X rows must be float4-readable (ldx %% 4 == 0, 16-byte aligned)");
+  PeerPtrs pp;
+  for (int p = 0; p < kMaxPeers; ++p) pp.p[p] = p < n_peers ? reinterpret_cast<float*>(peer_ptrs_host[p]) : nullptr;
+  for (int p = 0; p < n_peers; ++p) SC_CHECK_ARG(pp.p[p] && (peer_ptrs_host[p] & 15) == 0, "sc_zscore_scatter: peer pointer %d null or misaligned", p);
+  const int zquads = (int)(ldz / 4);
+  int zq_log2 = 0;
+  while ((1 << zq_log2) < zquads && zq_log2 < 8) ++zq_log2;
+  const int zqw = 1 << zq_log2, zrpc = 256 >> zq_log2;
+  const int zbx = (zquads + zqw - 1) / zqw;
+  int64_t zby = ((int64_t)sm_count() * 16 + zbx - 1) / zbx;
+  const int64_t zmax = (n + zrpc - 1) / zrpc;
+  if (zby > zmax) zby = zmax;
+  if (zby > 65535) zby = 65535;
+  zscore_scatter4_kernel<<<dim3(zbx, (unsigned)zby), 256, 0, st>>>(X, n, ldx, g, dst_rows, mean, std, zero_var, pp, n_peers, ldz, zq_log2);
   SC_LAUNCH_OK();
   return SC_OK;
 }

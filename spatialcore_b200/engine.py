@@ -382,6 +382,25 @@ def zscore_apply(X: torch.Tensor, mean: torch.Tensor, std: torch.Tensor, zero_va
     return out
 
 
+def zscore_scatter(X: torch.Tensor, mean: torch.Tensor, std: torch.Tensor, zero_var: torch.Tensor,
+                   dst_rows: torch.Tensor, peer_ptrs, ld: int) -> None:
+    """``sc_zscore_scatter``: z-score this rank's row block and store each output row at
+    ``dst_rows[a]`` of the Z matrix of every peer (``peer_ptrs``: peer-mapped base addresses of the
+    symmetric Z buffers).  One kernel: standardise + all-gather + spatial re-order over NVLink."""
+    import ctypes as C
+
+    _require_cuda(X, "X")
+    L = _lib.lib()
+    n, g = X.shape
+    arr = (C.c_uint64 * len(peer_ptrs))(*[int(q) for q in peer_ptrs])
+    check(
+        L.sc_zscore_scatter(_ptr(X), n, X.stride(0), g, _ptr(dst_rows), _ptr(mean), _ptr(std), _ptr(zero_var),
+                            C.cast(arr, C.c_void_p), len(peer_ptrs), int(ld), _stream()),
+        "sc_zscore_scatter",
+    )
+    _count()
+
+
 def densify_csr(indptr: torch.Tensor, indices: torch.Tensor, data: torch.Tensor, n: int, n_cols: int,
                 colmap: Optional[torch.Tensor], g_out: int) -> torch.Tensor:
     """``sc_csr_densify``: CSR expression -> dense float32 [n, padded_ld(g_out)] on the device."""

@@ -89,11 +89,38 @@ def _standardize(adata, layer, names: List[str], device, rows: Optional[torch.Te
     return engine.zscore_dense(Xd, cols=cols, rows=rows)
 
 
-def _standardize_row_sharded(adata, layer, names: List[str], device, rows: Optional[torch.Tensor], group) -> engine.Standardized:
+_symm_cache = {}
+
+
+def _symmetric_z(n: int, ld: int, dev: torch.device, group):
+    """A [n, ld] float32 buffer in symmetric memory plus the peer-mapped base address of every rank's
+    copy (``torch.distributed._symmetric_memory``: plumbing for NVLink peer access).  Cached per shape:
+    the buffer is consumed inside the calling function and re-used by the next call."""
+    import torch.distributed as dist
+    import torch.distributed._symmetric_memory as symm
+
+    grp = group if group is not None else dist.group.WORLD
+    key = (n, ld, dev.index, id(grp))
+    if key not in _symm_cache:
+        _symm_cache.clear()  # one live buffer: these are tens of GB
+        buf = symm.empty((n, ld), dtype=torch.float32, device=dev)
+        hdl = symm.rendezvous(buf, grp)
+        _symm_cache[key] = (buf, hdl)
+    return _symm_cache[key]
+
+
+def _standardize_row_sharded(adata, layer, names: List[str], device, co: engine.CellOrder, group) -> engine.Standardized:
     """Row-sharded ingest (multi-GPU, ``shard="perms"``): every rank uploads and standardises only
     its block of N/W cells, the per-gene moments are pooled over the ranks (one all-gather of
-    [2, G] FP64) and the standardised blocks are exchanged with ONE all-gather over NVLink, so the
-    host->device copy per GPU shrinks W-fold while every rank still ends up with all of Z."""
+    [3, G] FP64), and every rank ends up with all of Z in spatial order.
+
+    Fused path (dense FP32 ``X``, all columns): ONE kernel standardises the block and stores each row
+    straight into the Z buffer of every GPU at its spatial position, through NVLink peer mappings
+    (``sc_zscore_scatter``) -- no staging copy, no NCCL collective on the data path, no re-order pass.
+    Otherwise (sparse input, gene subsets, ``SC_INGEST_NCCL=1``): ``sc_zscore_apply`` on the block, one
+    ``all_gather_into_tensor`` and a row gather into spatial order."""
+    import os
+
     import torch.distributed as dist
 
     rank, world = dist_util.world(group)
@@ -121,12 +148,26 @@ def _standardize_row_sharded(adata, layer, names: List[str], device, rows: Optio
     mean_d = torch.from_numpy(mean).to(dev)
     std_d = torch.from_numpy(std).to(dev)
     zero_d = torch.from_numpy(zero.astype(np.uint8)).to(dev)
+
+    fused = (cols is None and (Xd is None or (Xd.dtype == torch.float32 and Xd.stride(1) == 1 and Xd.stride(0) % 4 == 0
+                                               and Xd.stride(0) >= (g + 3) // 4 * 4 and Xd.data_ptr() % 16 == 0))
+             and world <= 16 and not os.environ.get("SC_INGEST_NCCL"))
+    flag = torch.tensor([1 if fused else 0], dtype=torch.int32, device=dev)
+    dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=group)  # every rank must take the same path
+    if int(flag.item()) == 1:
+        Z, hdl = _symmetric_z(n, ld, dev, group)
+        hdl.barrier()  # peers are done reading the previous contents of the cached buffer
+        if have > 0:
+            engine.zscore_scatter(Xd, mean_d, std_d, zero_d, co.rank[lo:hi], hdl.buffer_ptrs, ld)
+        hdl.barrier()  # every peer's rows have landed
+        return engine.Standardized(Z=Z, g=g, mean=mean_d, std=std_d, zero_var=zero_d)
+
     Zu = torch.empty((world * per, ld), dtype=torch.float32, device=dev)  # user order, padded to W equal blocks
     if have > 0:
         engine.zscore_apply(Xd, mean_d, std_d, zero_d, cols=cols, out=Zu[lo:hi])
     del Xd
     dist.all_gather_into_tensor(Zu, Zu[rank * per:(rank + 1) * per], group=group)
-    Z = engine.gather_rows(Zu[:n], rows) if rows is not None else Zu[:n]
+    Z = engine.gather_rows(Zu[:n], co.order)
     return engine.Standardized(Z=Z, g=g, mean=mean_d, std=std_d, zero_var=zero_d)
 
 
@@ -373,7 +414,7 @@ def morans_i(
     co = engine.spatial_order(adata.obsm[spatial_key], device=device)
     graph_s = engine.relabel_graph(graph, co)
     if mode == "perms" and ingest == "sharded":
-        std = _standardize_row_sharded(adata, layer, names, device, co.order, group)
+        std = _standardize_row_sharded(adata, layer, names, device, co, group)
     else:
         std = _standardize(adata, layer, names, device, rows=co.order)
     num, den, lag, _ = engine.lag_moran(graph_s, std.Z, g, want_lag=n_permutations > 0)
