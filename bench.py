@@ -336,7 +336,7 @@ def run_b200(args):
         e2e_s = float(dt.item()) / args.steps
         e2e = {"value": round(g_total * P / e2e_s, 1), "unit": UNIT, "ms_per_step": round(e2e_s * 1e3, 2),
                "h2d_bytes_per_step": int(Xn.nbytes * (n_gene_groups if group is not None else world) + cn.nbytes * world), "d2h_bytes_per_step": int(2 * 8 * g + 3 * 8),
-               "h2d_note": "bytes per step over all ranks" + ("; row-sharded ingest: each rank uploads N/W cells, Z blocks all-gathered over NVLink" if group is not None else ""),
+               "h2d_note": "bytes per step over all ranks" + ("; row-sharded ingest: each rank uploads N/W cells; fused standardise + all-gather + re-order kernel over NVLink peer memory" if group is not None else ""),
                "api": "spatialcore_b200.spatial.morans_i(adata[numpy, pinned host], shard='perms', ingest='sharded') per rank"}
         X_dev = None
 
