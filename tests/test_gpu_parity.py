@@ -882,3 +882,36 @@ def test_lee_matrix_permutation_pvalues(api):
     assert (p1.to_numpy() != p2.to_numpy()).mean() < 0.03
     with pytest.raises(ValueError, match="variant='reference'"):
         api.lees_l_matrix(a, n_permutations=3, variant="lee2001")
+
+
+def test_philox_null_pvalues_are_calibrated(eng):
+    """on pure-noise genes the two-tailed permutation p-values of the on-device Philox
+    null are uniform (Kolmogorov-Smirnov), for both nulls; disjoint permutation ranges (what different
+    ranks run) give independent nulls with the same distribution."""
+    from scipy import stats
+
+    rng = np.random.default_rng(2)
+    n, g, P, k = 4000, 600, 199, 6
+    coords = rng.uniform(0, 400, (n, 2))
+    X = rng.normal(size=(n, g)).astype(np.float32)
+    cd = torch.from_numpy(coords).cuda()
+    graph, _, _ = eng.knn_graph(cd, k)
+    co = eng.spatial_order(cd)
+    gs = eng.relabel_graph(graph, co)
+    std = eng.zscore_dense(torch.from_numpy(X).cuda(), rows=co.order)
+    num, den, lag, _ = eng.lag_moran(gs, std.Z, g)
+    for name, sims in (("graph_rows", eng.perm_null_graph_rows(std.Z, lag, g, P, seed=9)),
+                       ("values", eng.perm_null_values(gs, std.Z, g, P, seed=9))):
+        # centre on the null mean so the two-tailed statistic is symmetric (E[I] = -1/(n-1), tiny)
+        c = (sims.abs() >= num.abs()[None, :]).sum(0).cpu().numpy()
+        p = (c + 1) / (P + 1)
+        ks = stats.kstest(p, "uniform")
+        assert ks.pvalue > 1e-3, (name, ks)
+        assert abs(p.mean() - 0.5) < 0.04 and abs((p <= 0.05).mean() - 0.05) < 0.03, name
+    a = eng.perm_null_graph_rows(std.Z, lag, g, 50, seed=9, perm_offset=0)
+    b = eng.perm_null_graph_rows(std.Z, lag, g, 50, seed=9, perm_offset=50)
+    assert not torch.equal(a, b)
+    corr = np.corrcoef(a.cpu().numpy().ravel(), b.cpu().numpy().ravel())[0, 1]
+    assert abs(corr) < 0.03  # different global permutation indices: independent draws
+    again = eng.perm_null_graph_rows(std.Z, lag, g, 100, seed=9, perm_offset=0)
+    assert torch.equal(again[:50], a) and torch.equal(again[50:], b)  # addressed by global index, not by batch
