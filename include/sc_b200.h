@@ -49,6 +49,9 @@ enum sc_perm_source { SC_PERM_REPLAY = 0, SC_PERM_PHILOX = 1 };
 
 SC_API int sc_version(void);
 SC_API const char* sc_last_error(void);
+/* Number of kernels this library has launched in this process (bench.py reports the delta over the
+ * timed region as gpu_launches; CUB sorts / scans called inside are not counted). */
+SC_API long long sc_launch_count(void);
 
 /* ---------------------------------------------------------------------------------------------
  * Neighbour graphs.  Replace sklearn BallTree kneighbors (autocorrelation.py:393-395), squidpy's

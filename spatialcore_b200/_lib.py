@@ -24,6 +24,7 @@ _i32, _i64, _u64, _f64, _sz, _vp = C.c_int, C.c_int64, C.c_uint64, C.c_double, C
 SIGNATURES = {
     "sc_version": (_i32, []),
     "sc_last_error": (C.c_char_p, []),
+    "sc_launch_count": (C.c_longlong, []),
     "sc_grid_knn_workspace_bytes": (_sz, [_i64, _i32]),
     "sc_grid_knn": (_i32, [_vp, _i64, _i32, _i32, _vp, _vp, _vp, _vp, _i32, _vp, _vp, _sz, _vp]),
     "sc_grid_radius_workspace_bytes": (_sz, [_i64]),

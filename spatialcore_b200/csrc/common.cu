@@ -1,4 +1,5 @@
 // Error channel and device queries shared by all translation units of libsc_b200.
+#include <atomic>
 #include <stdarg.h>
 #include <string.h>
 
@@ -14,6 +15,10 @@ void set_error(const char* fmt, ...) {
   vsnprintf(g_error, sizeof(g_error), fmt, ap);
   va_end(ap);
 }
+
+static std::atomic<long long> g_launches{0};
+void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
+long long launches() { return g_launches.load(std::memory_order_relaxed); }
 
 int sm_count() {
   static thread_local int cached_dev = -1;
@@ -33,6 +38,8 @@ int sm_count() {
 
 extern "C" int sc_version(void) { return 100; }
 extern "C" const char* sc_last_error(void) { return sc::g_error; }
+namespace sc { long long launches(); }
+extern "C" long long sc_launch_count(void) { return sc::launches(); }
 
 extern "C" int sc_philox_permutation_host(uint64_t seed, int64_t perm_index, int64_t n,
                                           int32_t* out_host) {

@@ -29,7 +29,14 @@ void set_error(const char* fmt, ...);
     }                                                                                 \
   } while (0)
 
-#define SC_LAUNCH_OK() SC_CUDA_OK(cudaGetLastError())
+void count_launch();
+
+// after every kernel launch: count it (sc_launch_count) and surface launch errors
+#define SC_LAUNCH_OK()     \
+  do {                     \
+    sc::count_launch();    \
+    SC_CUDA_OK(cudaGetLastError()); \
+  } while (0)
 
 constexpr int kWarp = 32;
 constexpr unsigned kFull = 0xffffffffu;

@@ -16,11 +16,13 @@ import torch
 from spatialcore_b200 import _lib
 from spatialcore_b200._lib import SC_F32, SC_F64, SC_PERM_PHILOX, SC_PERM_REPLAY, check
 
-_launches = 0  # kernels-API calls issued (bench.py reports it as gpu_launches)
+_launches = 0  # per-call estimates kept for reference; bench.py reports the library's own counter
 
 
 def launches() -> int:
-    return _launches
+    """Kernels launched by ``libsc_b200.so`` in this process so far (``sc_launch_count``: incremented at
+    every launch site of the library; CUB sorts / scans it calls are not counted)."""
+    return int(_lib.lib().sc_launch_count())
 
 
 def _count(n: int = 1) -> None:
