@@ -2,15 +2,24 @@
 [R src/spatialcore/spatial/distance.py:46-500].
 
 Same arguments, outputs (``adata.obs`` distance / nearest-domain columns, ``adata.uns
-['domain_distances']``), control flow and error messages as the reference; the compiled routines it
-calls are replaced: ``cKDTree(target).query(source, k=1)`` by ``sc_cross_nn`` (grid-hashed exact 1-NN)
-and ``scipy.spatial.distance.cdist(a, b).min() / .mean()`` by ``sc_pairwise_reduce`` (FP64 brute force
-on the device).  The per-domain bookkeeping stays pandas on the host, like the reference.
+['domain_distances']``), results and error messages as the reference.  The compiled routines it
+calls are replaced: ``cKDTree(target).query(source, k=1)`` by ``sc_cross_nn`` (grid-hashed exact 1-NN,
+distances bit-identical) and ``scipy.spatial.distance.cdist(a, b).min() / .mean()`` by
+``sc_pairwise_reduce`` (FP64 brute force on the device).  The bookkeeping is organised around integer
+domain codes instead of the reference's per-domain boolean masks; the behaviour pinned by
+``tests/golden/ref_distances.npz`` is the same, including the reference's quirks:
+
+* ``minimum`` with per-cell output fills the matrix from the per-cell nearest-target results (the
+  minimum over the cells of ``src`` whose nearest target cell lies in ``tgt``) and only falls back to
+  the true pairwise minimum when no cell of ``src`` has its nearest target in ``tgt``;
+* with identical source and target columns the diagonal is 0 and a cell's nearest target cell is
+  itself (distance 0) for ``minimum`` / ``mean``, while ``centroid`` skips the cell's own domain;
+* ``mean`` annotates cells with the minimum distance.
 """
 
 from __future__ import annotations
 
-from typing import List, Optional
+from typing import Dict, List, Optional, Sequence, Tuple
 
 import numpy as np
 import pandas as pd
@@ -22,9 +31,50 @@ from spatialcore_b200.core.metadata import update_metadata
 
 logger = get_logger(__name__)
 
+_METRICS = ("minimum", "centroid", "mean")
+_MODES = ("cell", "matrix", "both")
 
-def _dev(coords: np.ndarray, device) -> torch.Tensor:
-    return torch.from_numpy(np.ascontiguousarray(coords[:, :2], dtype=np.float64)).to(device)
+
+def _codes(values: np.ndarray, domains: Sequence) -> np.ndarray:
+    """Integer code of every cell: position of its label in ``domains``, -1 for unlabelled / unlisted."""
+    lookup = {d: i for i, d in enumerate(domains)}
+    return np.fromiter((lookup.get(v, -1) if v == v and v is not None else -1 for v in values), dtype=np.int64,
+                       count=len(values))
+
+
+class _PointSets:
+    """Device copies (FP64 [m, 2]) of the coordinates of each domain, made on first use."""
+
+    def __init__(self, xy: np.ndarray, codes: np.ndarray, device) -> None:
+        self.xy, self.codes, self.device, self._cache = xy, codes, device, {}
+
+    def host(self, code: int) -> np.ndarray:
+        return self.xy[self.codes == code]
+
+    def dev(self, code: int) -> Optional[torch.Tensor]:
+        if code not in self._cache:
+            pts = self.host(code)
+            self._cache[code] = torch.from_numpy(np.ascontiguousarray(pts)).to(self.device) if len(pts) else None
+        return self._cache[code]
+
+
+def _nearest_target_cells(xy, s_codes, t_codes, device) -> Optional[Tuple[np.ndarray, np.ndarray, np.ndarray]]:
+    """For every source cell (code >= 0) the distance to, and the domain code of, its nearest target
+    cell.  Returns ``(source_rows, distances, nearest_target_codes)`` or None when either set is empty."""
+    s_rows = np.flatnonzero(s_codes >= 0)
+    t_rows = np.flatnonzero(t_codes >= 0)
+    if len(s_rows) == 0 or len(t_rows) == 0:
+        return None
+    dist, j = engine.cross_nn(xy[t_rows], xy[s_rows], device=device)
+    return s_rows, dist, t_codes[t_rows][j]
+
+
+def _pairwise(sets_s: _PointSets, sets_t: _PointSets, a: int, b: int) -> Optional[Tuple[float, float, int]]:
+    A, B = sets_s.dev(a), sets_t.dev(b)
+    if A is None or B is None:
+        return None
+    dmin, dsum = engine.pairwise_reduce(A, B)
+    return dmin, dsum, A.shape[0] * B.shape[0]
 
 
 def calculate_domain_distances(
@@ -43,195 +93,134 @@ def calculate_domain_distances(
 ):
     if "spatial" not in adata.obsm:
         raise ValueError(f"adata.obsm['spatial'] not found. Available keys: {list(adata.obsm.keys())}")
-    if source_domain_column not in adata.obs.columns:
-        raise ValueError(
-            f"Source column '{source_domain_column}' not found in adata.obs. Available columns: {list(adata.obs.columns)}"
-        )
-    if target_domain_column not in adata.obs.columns:
-        raise ValueError(
-            f"Target column '{target_domain_column}' not found in adata.obs. Available columns: {list(adata.obs.columns)}"
-        )
-    if distance_metric not in ["minimum", "centroid", "mean"]:
+    for role, column in (("Source", source_domain_column), ("Target", target_domain_column)):
+        if column not in adata.obs.columns:
+            raise ValueError(f"{role} column '{column}' not found in adata.obs. Available columns: {list(adata.obs.columns)}")
+    if distance_metric not in _METRICS:
         raise ValueError(f"Invalid distance_metric: '{distance_metric}'. Must be 'minimum', 'centroid', or 'mean'.")
-    if output_mode not in ["cell", "matrix", "both"]:
+    if output_mode not in _MODES:
         raise ValueError(f"Invalid output_mode: '{output_mode}'. Must be 'cell', 'matrix', or 'both'.")
     adata = adata.copy() if copy else adata
     logger.info(
         f"Calculating domain distances: {source_domain_column} → {target_domain_column} "
         f"(metric={distance_metric}, mode={output_mode})"
     )
-    source_domains = adata.obs[source_domain_column].dropna().unique().tolist()
-    target_domains = adata.obs[target_domain_column].dropna().unique().tolist()
-    if source_domain_subset:
-        source_domains = [d for d in source_domains if d in source_domain_subset]
-    if target_domain_subset:
-        target_domains = [d for d in target_domains if d in target_domain_subset]
-    if not source_domains:
+
+    def listed(column, subset):
+        found = adata.obs[column].dropna().unique().tolist()
+        return [d for d in found if d in subset] if subset else found
+
+    S = listed(source_domain_column, source_domain_subset)
+    T = listed(target_domain_column, target_domain_subset)
+    if not S:
         raise ValueError(f"No valid source domains found in '{source_domain_column}'")
-    if not target_domains:
+    if not T:
         raise ValueError(f"No valid target domains found in '{target_domain_column}'")
 
-    distance_matrix = pd.DataFrame(index=source_domains, columns=target_domains, dtype=float)
-    spatial = np.asarray(adata.obsm["spatial"])
+    xy = np.ascontiguousarray(np.asarray(adata.obsm["spatial"])[:, :2], dtype=np.float64)
+    s_codes = _codes(adata.obs[source_domain_column].values, S)
+    t_codes = _codes(adata.obs[target_domain_column].values, T)
     same_column = source_domain_column == target_domain_column
-    src_vals = adata.obs[source_domain_column].values
-    tgt_vals = adata.obs[target_domain_column].values
+    want_cells = output_mode in ("cell", "both")
+    M = np.full((len(S), len(T)), np.nan)
+    diag = [(a, T.index(s)) for a, s in enumerate(S) if same_column and s in T]  # pairs fixed at 0
 
-    # device copies of each domain's coordinates, made on first use
-    cache = {}
+    n = adata.n_obs
+    cell_dist = np.full(n, np.nan)
+    cell_near = np.full(n, None, dtype=object)
+    sets_s = _PointSets(xy, s_codes, device)
+    sets_t = _PointSets(xy, t_codes, device)
+    T_arr = np.asarray(T, dtype=object)
 
-    def dom_coords(column_vals, name, tag):
-        key = (tag, name)
-        if key not in cache:
-            mask = np.asarray(column_vals == name)
-            cache[key] = (_dev(spatial[mask], device) if mask.any() else None)
-        return cache[key]
-
-    def per_cell_nearest():
-        """Nearest target cell of every source cell (the cKDTree branch of the reference)."""
-        target_mask = adata.obs[target_domain_column].isin(target_domains)
-        target_indices = np.where(target_mask.values)[0]
-        target_coords = spatial[target_indices]
-        target_domains_arr = adata.obs[target_domain_column].iloc[target_indices].values
-        source_mask = adata.obs[source_domain_column].isin(source_domains)
-        source_indices = np.where(source_mask.values)[0]
-        source_coords = spatial[source_indices]
-        if len(source_coords) == 0 or len(target_coords) == 0:
-            return None
-        distances, nearest_idx = engine.cross_nn(target_coords, source_coords, device=device)
-        nearest_domains = target_domains_arr[nearest_idx]
-        dist_col_idx = adata.obs.columns.get_loc(output_distance_column)
-        nearest_col_idx = adata.obs.columns.get_loc(output_nearest_column)
-        adata.obs.iloc[source_indices, dist_col_idx] = distances
-        adata.obs.iloc[source_indices, nearest_col_idx] = nearest_domains
-        return source_indices, source_coords, target_coords, target_domains_arr, distances, nearest_domains
-
-    if output_mode in ["cell", "both"]:
-        adata.obs[output_distance_column] = np.nan
-        adata.obs[output_nearest_column] = None
-
-    if distance_metric == "minimum" and output_mode in ["cell", "both"]:
-        res = per_cell_nearest()
+    def annotate_with_nearest_cells():
+        res = _nearest_target_cells(xy, s_codes, t_codes, device)
         if res is not None:
-            source_indices, source_coords, target_coords, target_domains_arr, distances, nearest_domains = res
-            source_domains_arr = adata.obs[source_domain_column].iloc[source_indices].values
-            for src in source_domains:
-                src_mask = np.asarray(source_domains_arr == src)
-                if not src_mask.any():
-                    continue
-                src_distances = distances[src_mask]
-                src_nearest = nearest_domains[src_mask]
-                for tgt in target_domains:
-                    if src == tgt and same_column:
-                        distance_matrix.loc[src, tgt] = 0.0
-                        continue
-                    tgt_mask_local = np.asarray(src_nearest == tgt)
-                    if tgt_mask_local.any():
-                        distance_matrix.loc[src, tgt] = src_distances[tgt_mask_local].min()
-                    else:
-                        tgt_cell_mask = np.asarray(target_domains_arr == tgt)
-                        if tgt_cell_mask.any():
-                            dmin, _ = engine.pairwise_reduce(_dev(source_coords[src_mask], device),
-                                                             _dev(target_coords[tgt_cell_mask], device))
-                            distance_matrix.loc[src, tgt] = dmin
+            rows, dist, near = res
+            cell_dist[rows] = dist
+            cell_near[rows] = T_arr[near]
+        return res
 
+    if distance_metric == "minimum" and want_cells:
+        res = annotate_with_nearest_cells()
+        if res is not None:
+            rows, dist, near = res
+            src_of_row = s_codes[rows]
+            # minimum over the cells of each source domain, grouped by the domain of their nearest target
+            best = np.full((len(S), len(T)), np.inf)
+            np.minimum.at(best, (src_of_row, near), dist)
+            present_s = np.bincount(src_of_row, minlength=len(S)) > 0
+            present_t = np.bincount(t_codes[t_codes >= 0], minlength=len(T)) > 0
+            for a in np.flatnonzero(present_s):
+                for b in range(len(T)):
+                    if np.isfinite(best[a, b]):
+                        M[a, b] = best[a, b]
+                    elif present_t[b] and (a, b) not in diag:
+                        M[a, b] = _pairwise(sets_s, sets_t, a, b)[0]
+            for a, b in diag:
+                if present_s[a]:
+                    M[a, b] = 0.0
     elif distance_metric == "centroid":
-        source_centroids, target_centroids = {}, {}
-        for src in source_domains:
-            coords = spatial[np.asarray(src_vals == src)]
-            if len(coords) > 0:
-                source_centroids[src] = coords.mean(axis=0)
-        for tgt in target_domains:
-            coords = spatial[np.asarray(tgt_vals == tgt)]
-            if len(coords) > 0:
-                target_centroids[tgt] = coords.mean(axis=0)
-        for src in source_domains:
-            if src not in source_centroids:
-                continue
-            for tgt in target_domains:
-                if src == tgt and same_column:
-                    distance_matrix.loc[src, tgt] = 0.0
+        cs = {a: sets_s.host(a).mean(axis=0) for a in range(len(S)) if (s_codes == a).any()}
+        ct = {b: sets_t.host(b).mean(axis=0) for b in range(len(T)) if (t_codes == b).any()}
+        for a, ca in cs.items():
+            for b, cb in ct.items():
+                M[a, b] = np.linalg.norm(ca - cb)
+        for a, b in diag:
+            if a in cs:
+                M[a, b] = 0.0
+        if want_cells and ct:
+            rows = np.flatnonzero(s_codes >= 0)
+            order_t = sorted(ct)  # the reference scans target centroids in domain order, first minimum wins
+            d = np.linalg.norm(xy[rows][:, None, :] - np.stack([ct[b] for b in order_t])[None, :, :], axis=2)
+            if same_column:  # a cell never measures to the centroid of its own domain
+                own = np.asarray(S, dtype=object)[s_codes[rows]][:, None] == T_arr[order_t][None, :]
+                d[own] = np.inf
+            pick = d.argmin(axis=1)
+            dmin = d[np.arange(len(rows)), pick]
+            cell_dist[rows] = dmin
+            found = np.isfinite(dmin)
+            cell_near[rows[found]] = T_arr[np.asarray(order_t)[pick[found]]]
+    else:  # "mean", or "minimum" with matrix-only output: one device reduction per domain pair
+        for a in range(len(S)):
+            for b in range(len(T)):
+                if (a, b) in diag:
+                    if sets_s.dev(a) is not None:
+                        M[a, b] = 0.0
                     continue
-                if tgt not in target_centroids:
-                    continue
-                distance_matrix.loc[src, tgt] = np.linalg.norm(source_centroids[src] - target_centroids[tgt])
-        if output_mode in ["cell", "both"]:
-            # nearest target CENTROID of every source cell (the reference loops over rows in Python)
-            source_mask = adata.obs[source_domain_column].isin(source_domains).values
-            src_idx = np.where(source_mask)[0]
-            names = list(target_centroids.keys())
-            if len(src_idx) and names:
-                cent = np.stack([target_centroids[t] for t in names])
-                d = np.linalg.norm(spatial[src_idx][:, None, :] - cent[None, :, :], axis=2)
-                if same_column:  # a cell never measures to its own domain's centroid
-                    d[np.asarray(src_vals[src_idx])[:, None] == np.asarray(names, dtype=object)[None, :]] = np.inf
-                best = d.argmin(1)  # first minimum, like the reference's strict `<` scan in dict order
-                bestd = d[np.arange(len(src_idx)), best]
-                found = np.isfinite(bestd)
-                dist_col_idx = adata.obs.columns.get_loc(output_distance_column)
-                nearest_col_idx = adata.obs.columns.get_loc(output_nearest_column)
-                adata.obs.iloc[src_idx, dist_col_idx] = bestd
-                adata.obs.iloc[src_idx[found], nearest_col_idx] = np.asarray(names, dtype=object)[best[found]]
+                r = _pairwise(sets_s, sets_t, a, b)
+                if r is not None:
+                    M[a, b] = r[1] / r[2] if distance_metric == "mean" else r[0]
+        if distance_metric == "mean" and want_cells:
+            annotate_with_nearest_cells()  # per-cell output uses the minimum distance for this metric too
 
-    elif distance_metric == "mean":
-        for src in source_domains:
-            a = dom_coords(src_vals, src, "s")
-            if a is None:
-                continue
-            for tgt in target_domains:
-                if src == tgt and same_column:
-                    distance_matrix.loc[src, tgt] = 0.0
-                    continue
-                b = dom_coords(tgt_vals, tgt, "t")
-                if b is None:
-                    continue
-                _, dsum = engine.pairwise_reduce(a, b)
-                distance_matrix.loc[src, tgt] = dsum / (a.shape[0] * b.shape[0])
-        if output_mode in ["cell", "both"]:
-            per_cell_nearest()  # the reference falls back to the minimum distance per cell
+    if want_cells:
+        adata.obs[output_distance_column] = cell_dist
+        adata.obs[output_nearest_column] = cell_near
 
-    else:  # minimum, matrix only
-        for src in source_domains:
-            a = dom_coords(src_vals, src, "s")
-            if a is None:
-                continue
-            for tgt in target_domains:
-                if src == tgt and same_column:
-                    distance_matrix.loc[src, tgt] = 0.0
-                    continue
-                b = dom_coords(tgt_vals, tgt, "t")
-                if b is None:
-                    continue
-                dmin, _ = engine.pairwise_reduce(a, b)
-                distance_matrix.loc[src, tgt] = dmin
-
-    valid = distance_matrix.values[~np.isnan(distance_matrix.values.astype(float))].astype(float)
-    summary = {
-        "min_distance": float(valid.min()) if len(valid) > 0 else None,
-        "max_distance": float(valid.max()) if len(valid) > 0 else None,
-        "mean_distance": float(valid.mean()) if len(valid) > 0 else None,
-        "median_distance": float(np.median(valid)) if len(valid) > 0 else None,
-    }
-    if len(valid) > 0:
+    valid = M[~np.isnan(M)]
+    stat = (lambda f: float(f(valid)) if valid.size else None)
+    summary = {"min_distance": stat(np.min), "max_distance": stat(np.max), "mean_distance": stat(np.mean),
+               "median_distance": stat(np.median)}
+    if valid.size:
         logger.info(
             f"Distance statistics: min={summary['min_distance']:.1f}, "
             f"max={summary['max_distance']:.1f}, mean={summary['mean_distance']:.1f}"
         )
-    if output_mode in ["matrix", "both"]:
+    outputs: Dict[str, object] = {"summary_statistics": summary}
+    if want_cells:
+        outputs["obs_distance"] = output_distance_column
+        outputs["obs_nearest"] = output_nearest_column
+    if output_mode in ("matrix", "both"):
+        frame = pd.DataFrame(M, index=S, columns=T, dtype=float)
         adata.uns["domain_distances"] = {
             "source_domain_column": source_domain_column,
             "target_domain_column": target_domain_column,
             "distance_metric": distance_metric,
-            "source_domains": source_domains,
-            "target_domains": target_domains,
+            "source_domains": S,
+            "target_domains": T,
             "summary_statistics": summary,
-            "distance_matrix": distance_matrix.to_dict(orient="index"),
+            "distance_matrix": frame.to_dict(orient="index"),
         }
-    outputs = {"summary_statistics": summary}
-    if output_mode in ["cell", "both"]:
-        outputs["obs_distance"] = output_distance_column
-        outputs["obs_nearest"] = output_nearest_column
-    if output_mode in ["matrix", "both"]:
         outputs["uns"] = "domain_distances"
     update_metadata(
         adata,
@@ -256,7 +245,7 @@ def get_distance_matrix(adata, key: str = "domain_distances") -> pd.DataFrame:
             f"'{key}' not found in adata.uns. "
             "Run calculate_domain_distances() with output_mode='matrix' or 'both' first."
         )
-    data = adata.uns[key]
-    if "distance_matrix" not in data:
+    stored = adata.uns[key]
+    if "distance_matrix" not in stored:
         raise KeyError(f"'distance_matrix' not found in adata.uns['{key}']")
-    return pd.DataFrame(data["distance_matrix"]).T
+    return pd.DataFrame(stored["distance_matrix"]).T
