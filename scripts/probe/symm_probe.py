@@ -1,5 +1,5 @@
 """Probe: does torch symmetric memory give usable peer pointers on this box?  (torchrun, 2+ GPUs)"""
-import os, sys, torch, torch.distributed as dist
+import os, torch, torch.distributed as dist
 import torch.distributed._symmetric_memory as symm
 rank = int(os.environ["RANK"]); local = int(os.environ["LOCAL_RANK"]); world = int(os.environ["WORLD_SIZE"])
 torch.cuda.set_device(local)

@@ -18,7 +18,7 @@ takes ~0.1 ms on a B200, so the mini-batch approximation buys nothing); its iner
 
 from __future__ import annotations
 
-from typing import Literal, Optional, Tuple
+from typing import Literal, Tuple
 
 import numpy as np
 import pandas as pd

@@ -5,7 +5,7 @@ minutes with numpy) and is deterministic for a given seed and GPU model."""
 from __future__ import annotations
 
 import math
-from typing import Tuple
+
 
 import numpy as np
 import torch

@@ -9,7 +9,7 @@ import os
 import sys
 
 import numpy as np
-import pandas as pd
+
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, os.path.dirname(os.path.dirname(HERE)))
