@@ -91,14 +91,6 @@ if want("lagsweep"):
     del os.environ["SC_LAG_Q"], os.environ["SC_LAG_CHUNK"]
     out["lag_sweep_ms_[with_lag,stat_only]"] = sweep
 
-if want("lagocc"):
-    occ = {}
-    for pad in (0, 40, 60, 100):
-        os.environ["SC_LAG_PAD_KB"] = str(pad)
-        occ[f"pad{pad}KB"] = round(timed(lambda: eng.lag_moran(gs, std.Z, g)), 3)
-    del os.environ["SC_LAG_PAD_KB"]
-    out["lag_ms_vs_smem_pad(occupancy)"] = occ
-
 if want("values"):
     k1 = nnz / n + 1.0
     P = 4
