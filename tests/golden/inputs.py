@@ -87,3 +87,18 @@ def domains(n: int = 6000, seed: int = 31):
     tgt = np.array([f"Tumor_{q + 1}" for q in quad], dtype=object)
     tgt[rng.random(n) < 0.3] = None
     return coords, src, tgt
+
+
+def torus_rook(nx: int, ny: int):
+    """Rook (4-neighbour) adjacency of an nx x ny torus, binary CSR, plus lattice coordinates: a graph on
+    which Moran's I has closed forms (Cliff & Ord): checkerboard -> -1, cos(2 pi i / nx) -> (1 + cos(2 pi / nx)) / 2,
+    and for the row-standardised graph s0 = N, s1 = N/2, s2 = 4N."""
+    from scipy import sparse
+
+    idx = np.arange(nx * ny).reshape(ny, nx)
+    rows = np.repeat(idx.ravel(), 4)
+    cols = np.stack([np.roll(idx, 1, 0), np.roll(idx, -1, 0), np.roll(idx, 1, 1), np.roll(idx, -1, 1)], axis=-1).ravel()
+    A = sparse.csr_matrix((np.ones(rows.size), (rows, cols)), shape=(nx * ny, nx * ny))
+    A.sort_indices()
+    xs, ys = np.meshgrid(np.arange(nx, dtype=np.float64), np.arange(ny, dtype=np.float64))
+    return A, np.stack([xs.ravel(), ys.ravel()], axis=1)

@@ -925,3 +925,27 @@ def test_philox_null_pvalues_are_calibrated(eng):
     assert abs(corr) < 0.03  # different global permutation indices: independent draws
     again = eng.perm_null_graph_rows(std.Z, lag, g, 100, seed=9, perm_offset=0)
     assert torch.equal(again[:50], a) and torch.equal(again[50:], b)  # addressed by global index, not by batch
+
+
+def test_moran_known_answers_on_a_torus(api):
+    """Closed-form Moran's I, analytic moments and z-scores on a 4-regular torus through the public API
+    (``use_existing_graph=True``): checkerboard -> -1, cosine waves -> (1 + cos(2 pi / n)) / 2."""
+    nx, ny = 24, 18
+    A, coords = inputs.torus_rook(nx, ny)
+    n = nx * ny
+    i, j = coords[:, 0], coords[:, 1]
+    X = np.stack([(-1.0) ** (i + j), np.cos(2 * np.pi * i / nx), np.cos(2 * np.pi * j / ny) + 0.5 * np.cos(2 * np.pi * i / nx)], axis=1)
+    a = _adata(X.astype(np.float32), coords)
+    a.obsp["spatial_connectivities"] = A
+    api.morans_i(a, n_permutations=0, use_existing_graph=True)
+    df = a.uns["morans_i"]
+    l1, l2 = (1 + np.cos(2 * np.pi / ny)) / 2, (1 + np.cos(2 * np.pi / nx)) / 2
+    want = np.array([-1.0, l2, (0.5 * l1 + 0.125 * l2) / 0.625])
+    np.testing.assert_allclose(df["I"].to_numpy(), want, rtol=1e-5, atol=1e-7)
+    vn = (n * n * (n / 2) - n * 4 * n + 3 * n * n) / ((n - 1) * (n + 1) * n * n) - 1 / (n - 1) ** 2
+    np.testing.assert_allclose(df["z_score"].to_numpy(), (want + 1 / (n - 1)) / np.sqrt(vn), rtol=1e-5)
+    assert np.all(df["expected_I"].to_numpy() == -1 / (n - 1))
+    # the checkerboard is the most extreme negative pattern: every permuted statistic is larger
+    api.morans_i(a, n_permutations=99, use_existing_graph=True, perm_source="philox", key_added="perm")
+    p = a.uns["perm"]["p_value"].to_numpy()
+    assert p[0] == 0.01 and p[1] == 0.01
