@@ -169,17 +169,26 @@ def calculate_domain_distances(
             if a in cs:
                 M[a, b] = 0.0
         if want_cells and ct:
-            rows = np.flatnonzero(s_codes >= 0)
-            order_t = sorted(ct)  # the reference scans target centroids in domain order, first minimum wins
-            d = np.linalg.norm(xy[rows][:, None, :] - np.stack([ct[b] for b in order_t])[None, :, :], axis=2)
-            if same_column:  # a cell never measures to the centroid of its own domain
-                own = np.asarray(S, dtype=object)[s_codes[rows]][:, None] == T_arr[order_t][None, :]
-                d[own] = np.inf
-            pick = d.argmin(axis=1)
-            dmin = d[np.arange(len(rows)), pick]
-            cell_dist[rows] = dmin
-            found = np.isfinite(dmin)
-            cell_near[rows[found]] = T_arr[np.asarray(order_t)[pick[found]]]
+            # nearest target CENTROID of every source cell: the same device 1-NN kernel, with the centroids
+            # as the target set (first minimum in domain order, like the reference's strict `<` scan).
+            # With identical columns a cell never measures to the centroid of its own domain.
+            order_t = sorted(ct)
+            cent = np.stack([ct[b] for b in order_t])
+            groups = [(np.flatnonzero(s_codes >= 0), np.arange(len(order_t)))]
+            if same_column:
+                groups = []
+                for a, name in enumerate(S):
+                    keep = np.asarray([k for k, b in enumerate(order_t) if T[b] != name], dtype=np.int64)
+                    groups.append((np.flatnonzero(s_codes == a), keep))
+            for rows, keep in groups:
+                if len(rows) == 0:
+                    continue
+                if len(keep) == 0:
+                    cell_dist[rows] = np.inf  # no other domain to measure to
+                    continue
+                dist, j = engine.cross_nn(cent[keep], xy[rows], device=device)
+                cell_dist[rows] = dist
+                cell_near[rows] = T_arr[np.asarray(order_t)[keep[j]]]
     else:  # "mean", or "minimum" with matrix-only output: one device reduction per domain pair
         for a in range(len(S)):
             for b in range(len(T)):
