@@ -155,7 +155,14 @@ def _standardize_row_sharded(adata, layer, names: List[str], device, co: engine.
     flag = torch.tensor([1 if fused else 0], dtype=torch.int32, device=dev)
     dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=group)  # every rank must take the same path
     if int(flag.item()) == 1:
-        Z, hdl = _symmetric_z(n, ld, dev, group)
+        try:
+            Z, hdl = _symmetric_z(n, ld, dev, group)
+        except Exception as exc:  # no peer access / symmetric memory on this system: every rank falls back
+            logger.warning(f"symmetric memory unavailable ({exc}); using the NCCL all-gather ingest")
+            Z = hdl = None
+        flag.fill_(0 if hdl is None else 1)
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=group)
+    if int(flag.item()) == 1:
         hdl.barrier()  # peers are done reading the previous contents of the cached buffer
         if have > 0:
             engine.zscore_scatter(Xd, mean_d, std_d, zero_d, co.rank[lo:hi], hdl.buffer_ptrs, ld)
