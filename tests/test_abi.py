@@ -125,3 +125,34 @@ def test_no_cpu_fallback_when_cuda_is_missing():
     # argument errors still surface first, exactly like the reference
     with pytest.raises(ValueError, match="n_neighbors must be >= 1"):
         spatial.morans_i(a, n_neighbors=0)
+
+
+def test_argument_validation_of_the_wider_abi_without_gpu():
+    """Every export rejects malformed calls before touching CUDA, with a message in sc_last_error()."""
+    from spatialcore_b200 import _lib
+
+    L = _lib.lib()
+    one = C.c_void_p(16)  # a non-null, 16-byte aligned dummy address: validation must fail before any dereference
+    cases = [
+        (L.sc_kmeans_assign(one, 10, 4, 4, one, 0, one, None, one, one, 1 << 20, None), b"k"),
+        (L.sc_kmeans_assign(one, 10, 4, 200, one, 3, one, None, one, one, 1 << 20, None), b"d"),
+        (L.sc_kmeans_pp_potential(one, 10, 4, 4, one, 99, None, None, -1, one, one, 1 << 20, None), b"n_cand"),
+        (L.sc_kmeans_pp_sample(one, 10, one, 0, one, one, 1 << 20, None), b"bad sizes"),
+        (L.sc_cross_nn(None, 5, one, 5, one, None, one, 1 << 20, None), b"null"),
+        (L.sc_pairwise_reduce(one, 0, one, 5, one, one, 1 << 20, None), b"empty"),
+        (L.sc_local_moran_finish(None, 0, one, one, one, 8, None, 10, 4, 0, None, 7, 0.05, one, one, one, one, one, one, one, 1 << 20, None), b"method"),
+        (L.sc_zscore_scatter(one, 10, 8, 8, one, one, one, one, one, 0, 8, None), b"n_peers"),
+        (L.sc_zscore_apply(one, 5, 10, 8, 8, None, None, one, one, one, one, 8, None), b"dtype"),
+        (L.sc_gather_rows(one, 8, 10, 6, one, one, 8, None), b"multiples of 4"),
+        (L.sc_perm_conjugate(one, 10, 1, one, one, one, None), b"aliased"),
+        (L.sc_graph_relabel(None, one, None, 10, 0, one, one, None, one, None, None, 0, None), b"indptr or k_fixed"),
+        (L.sc_lee_abs_ge_accumulate(one, 4, one, 4, 8, one, 8, None), b"bad argument"),
+    ]
+    for rc, needle in cases:
+        assert rc == -1, (rc, needle)
+    # the last message belongs to the last failing call
+    assert b"sc_lee_abs_ge_accumulate" in L.sc_last_error()
+    assert L.sc_kmeans_workspace_bytes(2_000_000, 30, 8) > 0 and L.sc_kmeans_pp_sample_workspace_bytes(2_000_000) > 16_000_000
+    assert L.sc_local_moran_finish_workspace_bytes(100, 999) >= 100 * 1000 * 8
+    assert L.sc_cross_nn_workspace_bytes(1_000_000) > 1_000_000 * 16
+    assert L.sc_launch_count() >= 0
