@@ -202,3 +202,79 @@ def test_two_rank_sharding_and_reduction_gloo(tmp_path):
         want = (X - X.mean(0)) / np.where(X.std(0) == 0, 1.0, X.std(0))
         want[:, 2] = 0.0
         np.testing.assert_allclose(r["Z"], want, rtol=1e-9, atol=1e-12)
+
+
+# ---------------------------------------------------------------------------------------------
+# identify_niches host control flow (k-means++ stream, Lloyd convergence, restarts) on a numpy stand-in
+# for the device object: the same Python code the GPU path runs, without a GPU
+# ---------------------------------------------------------------------------------------------
+
+
+class _NumpyKM:
+    """Duck type of ``engine.KMeansDevice`` evaluated with numpy (FP64 distances)."""
+
+    def __init__(self, X, k):
+        self.X64 = np.asarray(X, dtype=np.float64)
+        self.n, self.d = self.X64.shape
+        self.k = k
+        self.labels = torch.full((self.n,), -1, dtype=torch.int32)
+        self.mind = torch.zeros(self.n, dtype=torch.float32)
+
+    def _d2(self, C):
+        return ((self.X64[:, None, :] - np.asarray(C, dtype=np.float64)[None, :, :]) ** 2).sum(-1)
+
+    def assign(self, centers, want_mind=False):
+        d2 = self._d2(centers)
+        lab = d2.argmin(1).astype(np.int32)
+        changed = int((self.labels.numpy() != lab).sum())
+        self.labels = torch.from_numpy(lab)
+        best = d2[np.arange(self.n), lab]
+        if want_mind:
+            self.mind = torch.from_numpy(best.astype(np.float32))
+        sums = np.zeros((self.k, self.d))
+        np.add.at(sums, lab, self.X64)
+        return sums, np.bincount(lab, minlength=self.k).astype(np.float64), float(best.sum()), changed
+
+    def pp_potential(self, cand, first, commit=-1):
+        d2 = self._d2(self.X64[np.asarray(cand)])
+        m = d2 if first else np.minimum(self.mind.numpy().astype(np.float64)[:, None], d2)
+        if commit >= 0:
+            self.mind = torch.from_numpy(m[:, commit].astype(np.float32))
+        return m.sum(0)
+
+    def pp_sample(self, vals):
+        cum = np.cumsum(self.mind.numpy().astype(np.float64))
+        return np.minimum(np.searchsorted(cum, vals), self.n - 1).astype(np.int64)
+
+    def rows(self, idx):
+        return self.X64[np.asarray(idx, dtype=np.int64)].astype(np.float32)
+
+
+def test_kmeans_host_control_flow_matches_sklearn():
+    from oracle import restate as R
+    from spatialcore_b200.spatial import niches
+    from tests.golden import inputs
+
+    P = inputs.niche_profiles(n=4000, n_types=9, n_niches=5, seed=4)
+    k = 5
+    # Lloyd from sklearn's own starting point lands on sklearn's fixed point
+    c0 = P[np.random.default_rng(1).choice(len(P), k, replace=False)]
+    want_l, want_c, want_i, _ = R.kmeans_lloyd_from(P, c0)
+    km = _NumpyKM(P, k)
+    cent, inertia, n_iter = niches.lloyd(km, c0, 300, float(P.astype(np.float64).var(0).mean() * 1e-4))
+    assert R.adjusted_rand_index(km.labels.numpy(), want_l) > 0.995
+    np.testing.assert_allclose(inertia, want_i, rtol=1e-4)
+    np.testing.assert_allclose(cent, want_c, atol=2e-3)
+    assert 1 <= n_iter <= 300
+    # seeding: k distinct rows of X, first index drawn like RandomState.choice(n) with uniform p
+    rs = np.random.RandomState(7)
+    first_expected = min(int(np.random.RandomState(7).random_sample() * km.n), km.n - 1)
+    init = niches._kmeans_plusplus(km, rs)
+    assert init.shape == (k, P.shape[1]) and len({tuple(r) for r in init.round(6)}) == k
+    np.testing.assert_array_equal(init[0], P[first_expected])
+    # an empty cluster takes the farthest point (sklearn's relocation) and the loop still converges
+    far = np.vstack([c0[:4], np.full((1, P.shape[1]), 50.0)]).astype(np.float32)
+    km2 = _NumpyKM(P, k)
+    cent2, inertia2, _ = niches.lloyd(km2, far, 300, 0.0)
+    assert np.bincount(km2.labels.numpy(), minlength=k).min() >= 1 and np.isfinite(inertia2)
+    assert inertia2 < 2.0 * want_i
