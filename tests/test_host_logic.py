@@ -278,3 +278,43 @@ def test_kmeans_host_control_flow_matches_sklearn():
     cent2, inertia2, _ = niches.lloyd(km2, far, 300, 0.0)
     assert np.bincount(km2.labels.numpy(), minlength=k).min() >= 1 and np.isfinite(inertia2)
     assert inertia2 < 2.0 * want_i
+
+
+def test_domain_distance_host_logic_matches_reference_golden(monkeypatch):
+    """The pandas / numpy bookkeeping of ``calculate_domain_distances`` (domain lists, matrix assembly from
+    per-cell results, diagonal and fallback rules, output slots) against the frozen reference output,
+    with the two device kernels replaced by the scipy calls they stand for."""
+    import pandas as pd
+    from scipy.spatial import cKDTree
+    from scipy.spatial.distance import cdist
+
+    from spatialcore_b200 import AnnDataLite, engine
+    from spatialcore_b200.spatial import distance
+    from tests.golden import inputs
+
+    def fake_cross_nn(targets, queries, device="cpu"):
+        d, j = cKDTree(np.asarray(targets)).query(np.asarray(queries), k=1)
+        return d, j.astype(np.int64)
+
+    def fake_pairwise(a, b, device="cpu"):
+        D = cdist(a.numpy() if hasattr(a, "numpy") else a, b.numpy() if hasattr(b, "numpy") else b)
+        return float(D.min()), float(D.sum())
+
+    monkeypatch.setattr(engine, "cross_nn", fake_cross_nn)
+    monkeypatch.setattr(engine, "pairwise_reduce", fake_pairwise)
+    g = np.load(os.path.join(ROOT, "tests", "golden", "ref_distances.npz"))
+    coords, src, tgt = inputs.domains()
+    cases = [("min_both", "src", "tgt", "minimum", "both"), ("min_matrix", "src", "tgt", "minimum", "matrix"),
+             ("centroid_both", "src", "tgt", "centroid", "both"), ("mean_both", "src", "tgt", "mean", "both"),
+             ("same_min_both", "tgt", "tgt", "minimum", "both"), ("same_centroid_both", "tgt", "tgt", "centroid", "both")]
+    for tag, sc, tc, metric, mode in cases:
+        obs = pd.DataFrame({"src": pd.Series(src, dtype=object), "tgt": pd.Series(tgt, dtype=object)})
+        a = AnnDataLite(np.zeros((coords.shape[0], 1), np.float32), obs=obs, obsm={"spatial": coords})
+        distance.calculate_domain_distances(a, sc, tc, distance_metric=metric, output_mode=mode, device="cpu")
+        M = distance.get_distance_matrix(a)
+        assert list(M.index) == list(g[f"{tag}_rows"]) and list(M.columns) == list(g[f"{tag}_cols"])
+        np.testing.assert_allclose(M.to_numpy(dtype=np.float64), g[f"{tag}_matrix"], rtol=1e-12, equal_nan=True)
+        if mode != "matrix":
+            np.testing.assert_allclose(a.obs["distance_to_target"].to_numpy(dtype=np.float64), g[f"{tag}_dist"], rtol=1e-12, equal_nan=True)
+            near = np.array(["" if v is None or v != v else str(v) for v in a.obs["nearest_target_domain"]])
+            assert np.array_equal(near, g[f"{tag}_nearest"]), tag
