@@ -305,7 +305,10 @@ def run_b200(args):
     # ---------------- end-to-end leg through the public API, host buffers ------------------------
     e2e = None
     if not args.no_e2e:
-        X_host = torch.empty((n, g), dtype=torch.float32, pin_memory=True)
+        try:
+            X_host = torch.empty((n, g), dtype=torch.float32, pin_memory=True)
+        except RuntimeError:  # not enough lockable host memory for one pinned copy per rank
+            X_host = torch.empty((n, g), dtype=torch.float32)
         X_host.copy_(X_dev)
         del X_dev
         torch.cuda.empty_cache()
