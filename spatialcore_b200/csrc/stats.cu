@@ -1529,6 +1529,9 @@ extern "C" int sc_perm_null_graph_rows(const float* A, int64_t lda, const float*
   if (ws_bytes < sc_perm_null_workspace_bytes(n, g)) { set_error("sc_perm_null_graph_rows: workspace too small"); return SC_ERR_WORKSPACE; }
   double* partial = static_cast<double*>(ws);
   int variant = perm_rows_variant();
+  // narrow rows (<= 1 KB per gathered row): 8 permutations per pass keep more, smaller stages in flight and
+  // measured 5-12 % faster than 16 (profiles/r01c_perm_rows_width_sweep.txt); an explicit choice wins
+  if (!getenv("SC_PERM_ROWS_VARIANT") && lda <= 256) variant = 10;
   if (variant >= 10) {
     rc = variant == 11
              ? launch_perm_rows_bulk<16>(A, lda, B, ldb, n, g, source, perm_idx, seed, perm_offset, n_perms, sims, partial, st)
