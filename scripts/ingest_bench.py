@@ -9,6 +9,8 @@ import logging; logging.getLogger("spatialcore").setLevel(logging.ERROR)
 
 rank = int(os.environ["RANK"]); local = int(os.environ["LOCAL_RANK"]); world = int(os.environ["WORLD_SIZE"])
 torch.cuda.set_device(local); dev = torch.device("cuda", local)
+from spatialcore_b200 import distributed as du
+bound = du.bind_host_to_gpu(local) if os.environ.get("SC_BIND_NUMA", "1") == "1" else False
 dist.init_process_group("nccl", device_id=dev)
 n, g = 5_000_000, 1000
 coords = synthetic.coords_uniform(n, 1.2e5, 3)
@@ -31,5 +33,5 @@ for name, env in (("fused_peer_memory", None), ("nccl_allgather_reorder", "1")):
         del std
     res[name] = {"ms": round(1e3 * float(np.median(ts)), 2), "checksum": chk}
 if rank == 0:
-    print({"world": world, "n": n, "g": g, **res}, flush=True)
+    print({"world": world, "n": n, "g": g, "numa_bound": bound, "cpus": len(os.sched_getaffinity(0)), **res}, flush=True)
 dist.destroy_process_group()

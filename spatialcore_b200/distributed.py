@@ -75,6 +75,34 @@ def row_block(n: int, rank: int, world_size: int) -> Tuple[int, int, int]:
     return per, lo, min(n, lo + per)
 
 
+def bind_host_to_gpu(device_index: int) -> bool:
+    """Restrict this process to the CPUs local to the GPU's PCIe root complex (its NUMA node), so that
+    host buffers pinned afterwards are NUMA-local and eight ranks uploading at once do not funnel through
+    one socket's memory and the inter-socket link.  Returns False (and changes nothing) when the
+    topology cannot be read."""
+    import os
+
+    try:
+        props = torch.cuda.get_device_properties(device_index)
+        pci = f"{props.pci_domain_id:04x}:{props.pci_bus_id:02x}:{props.pci_device_id:02x}.0"
+        with open(f"/sys/bus/pci/devices/{pci}/local_cpulist") as fh:
+            text = fh.read().strip()
+        cpus = set()
+        for part in text.split(","):
+            if not part:
+                continue
+            lo, _, hi = part.partition("-")
+            cpus.update(range(int(lo), int(hi or lo) + 1))
+        allowed = os.sched_getaffinity(0)
+        cpus &= allowed
+        if not cpus or cpus == allowed:
+            return False
+        os.sched_setaffinity(0, cpus)
+        return True
+    except (OSError, ValueError, AttributeError, RuntimeError):
+        return False
+
+
 def all_reduce_null(null, group=None) -> None:
     """Sum a ``MoranNull`` over the ranks of ``group`` (counts travel as exact FP64 integers)."""
     _, ws = world(group)
