@@ -1,0 +1,140 @@
+"""numpy / torch-CPU stand-in for ``spatialcore_b200.engine`` (TEST INFRASTRUCTURE ONLY).
+
+Implements, with the oracle's arithmetic, the subset of the engine that ``spatial.morans_i`` drives, so
+that the drop-in's HOST logic (validation, gene resolution, sharding arithmetic, spatial re-ordering and
+permutation conjugation, p-value folding, z-scores, table / metadata / obsp assembly) can be exercised
+without a GPU.  The CUDA path is compared with the oracle in tests/test_gpu_parity.py; nothing here is
+imported by the product."""
+
+from __future__ import annotations
+
+import numpy as np
+import torch
+from scipy import sparse
+
+from oracle import restate as R
+from spatialcore_b200 import engine as real
+from spatialcore_b200 import philox
+
+DeviceGraph = real.DeviceGraph
+CellOrder = real.CellOrder
+Standardized = real.Standardized
+padded_ld = real.padded_ld
+
+
+def _csr(indptr, indices, n):
+    return DeviceGraph(n=n, indices=torch.from_numpy(indices.astype(np.int32)), indptr=torch.from_numpy(indptr.astype(np.int32)))
+
+
+def knn_graph(coords, k, include_self=False, want_dist=False, want_order=False, labels=None, n_types=0, want_idx=True,
+              device="cpu"):
+    c = np.asarray(coords, dtype=np.float64)[:, :2]
+    if k < 1:
+        raise ValueError(f"n_neighbors must be >= 1, got {k}")
+    if k >= c.shape[0]:
+        raise ValueError(f"k must be < number of cells ({c.shape[0]}), got {k}")
+    idx, dist = R.knn_canonical(c, k)
+    g = DeviceGraph(n=c.shape[0], indices=torch.from_numpy(idx.astype(np.int32)), k_fixed=k,
+                    dist=torch.from_numpy(dist) if want_dist else None)
+    return g, None, None
+
+
+def radius_graph(coords, radius, want_dist=False, labels=None, n_types=0, want_graph=True, device="cpu"):
+    c = np.asarray(coords, dtype=np.float64)[:, :2]
+    indptr, indices, dist = R.radius_graph(c, radius)
+    g = _csr(indptr, indices, c.shape[0])
+    g.dist = torch.from_numpy(dist) if want_dist else None
+    return g, None
+
+
+def graph_from_scipy(adj, device="cpu", use_weights=False):
+    a = sparse.csr_matrix(adj)
+    a.sort_indices()
+    g = _csr(a.indptr, a.indices, a.shape[0])
+    if use_weights:
+        g.weights = torch.from_numpy(a.data.astype(np.float32))
+    return g
+
+
+def spatial_order(coords, device="cpu"):
+    c = np.asarray(coords, dtype=np.float64)[:, :2]
+    order = np.lexsort((c[:, 0], c[:, 1])).astype(np.int32)  # any bijection exercises the conjugation logic
+    rank = np.empty_like(order)
+    rank[order] = np.arange(len(order), dtype=np.int32)
+    return CellOrder(order=torch.from_numpy(order), rank=torch.from_numpy(rank))
+
+
+def _to_scipy(graph):
+    indptr = graph.indptr_tensor().numpy()
+    idx = graph.indices.reshape(-1).numpy()
+    if graph.weights is not None:
+        vals = graph.weights.numpy().astype(np.float64)
+    else:
+        deg = np.diff(indptr)
+        vals = np.repeat(1.0 / np.maximum(deg, 1), deg)
+    return sparse.csr_matrix((vals, idx, indptr), shape=(graph.n, graph.n))
+
+
+def relabel_graph(graph, co):
+    o = co.order.numpy()
+    A = _to_scipy(graph)[o][:, o].tocsr()
+    A.sort_indices()
+    out = _csr(A.indptr, A.indices, graph.n)
+    if graph.weights is not None:
+        out.weights = torch.from_numpy(A.data.astype(np.float32))
+    return out
+
+
+def expression_to_device(X, gene_idx, device="cpu"):
+    Xd = np.asarray(X.todense()) if sparse.issparse(X) else np.asarray(X)
+    if gene_idx is not None:
+        Xd = Xd[:, np.asarray(gene_idx)]
+    return torch.from_numpy(np.ascontiguousarray(Xd)), None
+
+
+def zscore_dense(X, cols=None, rows=None, want_z=True):
+    Z, mean, std, zero = R.zscore(X.numpy())
+    if rows is not None:
+        Z = Z[rows.numpy()]
+    n, g = Z.shape
+    out = np.zeros((n, padded_ld(g)), dtype=np.float32)
+    out[:, :g] = Z
+    return Standardized(Z=torch.from_numpy(out) if want_z else None, g=g, mean=torch.from_numpy(mean),
+                        std=torch.from_numpy(std), zero_var=torch.from_numpy(zero.astype(np.uint8)))
+
+
+def lag_moran(graph, Z, g, want_lag=True, want_local=False):
+    W = _to_scipy(graph)
+    z = Z.numpy().astype(np.float64)
+    lag = (W @ z).astype(np.float32)
+    num = (z[:, :g] * lag[:, :g].astype(np.float64)).sum(0)
+    den = (z[:, :g] ** 2).sum(0)
+    return torch.from_numpy(num), torch.from_numpy(den), torch.from_numpy(lag) if want_lag else None, None
+
+
+def graph_moments(graph):
+    return R.graph_moments(_to_scipy(graph))
+
+
+def conjugate_perms(perm_idx, co):
+    o, r = co.order.numpy(), co.rank.numpy()
+    return torch.from_numpy(r[perm_idx.numpy()[:, o]].astype(np.int32))
+
+
+def perm_null_graph_rows(A, B, g, n_perms, perm_idx=None, seed=0, perm_offset=0, out=None, ws=None):
+    a = A.numpy().astype(np.float64)[:, :g]
+    b = B.numpy().astype(np.float64)[:, :g]
+    n = a.shape[0]
+    sims = np.empty((n_perms, g))
+    for p in range(n_perms):
+        pi = perm_idx[p].numpy() if perm_idx is not None else philox.permutation(seed, perm_offset + p, n)
+        sims[p] = (a * b[pi]).sum(0)
+    return torch.from_numpy(sims)
+
+
+def null_accumulate(sims, scale, obs, cnt_ge, cnt_abs_ge, ssum, ssq):
+    s = sims * scale if scale is not None else sims
+    cnt_ge += (s >= obs).sum(0)
+    cnt_abs_ge += (s.abs() >= obs.abs()).sum(0)
+    ssum += s.sum(0)
+    ssq += (s * s).sum(0)

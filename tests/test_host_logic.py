@@ -318,3 +318,75 @@ def test_domain_distance_host_logic_matches_reference_golden(monkeypatch):
             np.testing.assert_allclose(a.obs["distance_to_target"].to_numpy(dtype=np.float64), g[f"{tag}_dist"], rtol=1e-12, equal_nan=True)
             near = np.array(["" if v is None or v != v else str(v) for v in a.obs["nearest_target_domain"]])
             assert np.array_equal(near, g[f"{tag}_nearest"]), tag
+
+
+# ---------------------------------------------------------------------------------------------
+# morans_i host logic on the numpy stand-in engine (tests/cpu_engine.py)
+# ---------------------------------------------------------------------------------------------
+
+
+def test_morans_i_host_logic_on_cpu_stand_in(monkeypatch):
+    """Validation, gene resolution, spatial re-ordering + permutation conjugation, null folding,
+    p-value / z-score / table / metadata / obsp assembly of ``spatial.morans_i`` against the oracle,
+    with every device call replaced by its numpy equivalent."""
+    from oracle import restate as R
+    from spatialcore_b200 import AnnDataLite
+    from spatialcore_b200.spatial import autocorrelation as ac
+    from tests import cpu_engine
+    from tests.golden import inputs
+
+    monkeypatch.setattr(ac, "engine", cpu_engine)
+    coords, X = inputs.g0()
+    coords, X = coords[:2500], X[:2500, :12]
+    names = [f"g{i}" for i in range(12)]
+    sel = ["g7", "g0", "g1", "g11"]
+    idx = [names.index(s) for s in sel]
+    a = AnnDataLite(X, obsm={"spatial": coords}, var_names=names)
+    out = ac.morans_i(a, genes=sel, n_neighbors=6, n_permutations=49, seed=3, perm_source="replay", device="cpu")
+    assert out is a
+    df = a.uns["morans_i"]
+    t = R.morans_i_table(coords, X[:, idx], k=6, n_perms=49, seed=3)
+    assert list(df.columns) == ["gene", "I", "expected_I", "z_score", "p_value"] and df["gene"].tolist() == sel
+    np.testing.assert_allclose(df["I"].to_numpy(), t["I"], rtol=1e-5, atol=1e-7)
+    tie = np.abs(t["sims"] - t["I"][None, :]).min(0) < 1e-9     # Poisson counts: exact lattice ties are order dependent
+    assert np.array_equal(df["p_value"].to_numpy()[~tie], t["p_value"][~tie])
+    np.testing.assert_allclose(df["z_score"].to_numpy(), t["z_score"], rtol=1e-6)
+    adj, dst = R.spatial_neighbors(coords, k=6)
+    assert (a.obsp["spatial_connectivities"] != adj).nnz == 0 and (a.obsp["spatial_distances"] != dst).nnz == 0
+    assert a.uns["spatial_neighbors"]["params"] == {"n_neighbors": 6, "coord_type": "generic", "radius": None, "transform": None}
+    op = a.uns["spatialcore_metadata"]["operations"][-1]
+    assert op["function"] == "morans_i" and op["parameters"]["n_permutations"] == 49
+    # Philox source goes through the host mirror of the device bijection: deterministic
+    p1 = ac.morans_i(AnnDataLite(X, obsm={"spatial": coords}, var_names=names), genes=sel, n_permutations=29, seed=5,
+                     perm_source="philox", device="cpu").uns["morans_i"]["p_value"].to_numpy()
+    p2 = ac.morans_i(AnnDataLite(X, obsm={"spatial": coords}, var_names=names), genes=sel, n_permutations=29, seed=5,
+                     perm_source="philox", device="cpu").uns["morans_i"]["p_value"].to_numpy()
+    assert np.array_equal(p1, p2) and np.all((p1 > 0) & (p1 <= 0.5))
+    # analytic p-value without permutations; copy semantics; existing weighted graph; radius keyword
+    b = AnnDataLite(X, obsm={"spatial": coords}, var_names=names)
+    c = ac.morans_i(b, genes=sel, n_permutations=0, copy=True, device="cpu")
+    assert "morans_i" not in b.uns and c is not b
+    np.testing.assert_allclose(c.uns["morans_i"]["p_value"].to_numpy(), t["pval_norm"], rtol=1e-6)
+    adj_r, _ = R.spatial_neighbors(coords, radius=40.0)
+    d = AnnDataLite(X, obsm={"spatial": coords}, var_names=names)
+    d.obsp["spatial_connectivities"] = adj_r
+    ac.morans_i(d, genes=sel, n_permutations=0, use_existing_graph=True, device="cpu")
+    tr = R.morans_i_table(coords, X[:, idx], n_perms=0, adj=adj_r)
+    np.testing.assert_allclose(d.uns["morans_i"]["I"].to_numpy(), tr["I"], rtol=1e-5, atol=1e-7)
+    np.testing.assert_allclose(d.uns["morans_i"]["z_score"].to_numpy(), tr["z_score"], rtol=1e-6)
+    e = AnnDataLite(X, obsm={"spatial": coords}, var_names=names)
+    ac.morans_i(e, genes=sel, n_permutations=0, radius=40.0, device="cpu")
+    np.testing.assert_allclose(e.uns["morans_i"]["I"].to_numpy(), tr["I"], rtol=1e-5, atol=1e-7)
+    assert (e.obsp["spatial_connectivities"] != adj_r).nnz == 0
+    # errors are raised before any compute [R autocorrelation.py:517-547]
+    import pytest as _pytest
+    with _pytest.raises(ValueError, match="not found"):
+        ac.morans_i(AnnDataLite(X, obsm={}, var_names=names), device="cpu")
+    with _pytest.raises(ValueError, match="n_neighbors must be >= 1"):
+        ac.morans_i(a, n_neighbors=0, device="cpu")
+    with _pytest.raises(ValueError, match="n_permutations must be >= 0"):
+        ac.morans_i(a, n_permutations=-1, device="cpu")
+    with _pytest.raises(ValueError, match="Genes not found"):
+        ac.morans_i(a, genes=["nope"], device="cpu")
+    with _pytest.raises(ValueError, match="perm_source"):
+        ac.morans_i(a, genes=sel, perm_source="sobol", device="cpu")
