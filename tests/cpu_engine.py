@@ -138,3 +138,55 @@ def null_accumulate(sims, scale, obs, cnt_ge, cnt_abs_ge, ssum, ssq):
     cnt_abs_ge += (s.abs() >= obs.abs()).sum(0)
     ssum += s.sum(0)
     ssq += (s * s).sum(0)
+
+
+def perm_null_values(graph, Zy, g, n_perms, Zx=None, perm_idx=None, seed=0, perm_offset=0, cell_obs=None, cell_cnt=None):
+    """Value-permuting null [R autocorrelation.py:322-328, 877-896] in FP32 like the kernel: lag of the
+    permuted matrix, local statistic, optional per-cell exceedance counts."""
+    W = _to_scipy(graph).astype(np.float32)
+    zy = Zy.numpy()
+    n = zy.shape[0]
+    sims = np.empty((n_perms, g))
+    for p in range(n_perms):
+        pi = perm_idx[p].numpy() if perm_idx is not None else philox.permutation(seed, perm_offset + p, n)
+        zp = zy[pi]
+        lag = (W @ zp).astype(np.float32)
+        s = Zx.numpy() if Zx is not None else zp
+        loc = s * lag
+        sims[p] = loc[:, :g].astype(np.float64).sum(0)
+        if cell_cnt is not None:
+            cell_cnt += torch.from_numpy((np.abs(loc) >= np.abs(cell_obs.numpy())).astype(np.int32))
+    return torch.from_numpy(sims)
+
+
+def lag_moran(graph, Z, g, want_lag=True, want_local=False):  # noqa: F811  (adds the local statistic)
+    W = _to_scipy(graph).astype(np.float32)
+    z32 = Z.numpy()
+    lag = (W @ z32).astype(np.float32)
+    z = z32.astype(np.float64)
+    num = (z[:, :g] * lag[:, :g].astype(np.float64)).sum(0)
+    den = (z[:, :g] ** 2).sum(0)
+    return (torch.from_numpy(num), torch.from_numpy(den), torch.from_numpy(lag) if want_lag else None,
+            torch.from_numpy(z32 * lag) if want_local else None)
+
+
+def local_moran_finish(cnt, Z, lag, loc, g, n_perms, zero_var, method, alpha, order=None):
+    """Per-cell p, adjusted p and quadrants with the reference's numpy recipe, un-sorted to user order."""
+    from spatialcore_b200.spatial import autocorrelation as ac
+
+    n = Z.shape[0]
+    inv = np.arange(n) if order is None else np.argsort(order.numpy())  # original row i is stored at inv[i]
+    zr, lr, ir = (t.numpy()[inv][:, :g].copy() for t in (Z, lag, loc))
+    dead = zero_var.numpy().astype(bool) if zero_var is not None else np.zeros(g, bool)
+    zr[:, dead] = 0; lr[:, dead] = 0; ir[:, dead] = 0
+    p = np.ones((n, g), dtype=np.float32)
+    pa = np.ones((n, g), dtype=np.float32)
+    if n_perms > 0:
+        p = ((cnt.numpy()[inv][:, :g] + 1) / (n_perms + 1)).astype(np.float32)
+        p[:, dead] = 1.0
+        for j in range(g):
+            pa[:, j] = ac._fdr(p[:, j], method)
+        q = ac._classify_quadrants(zr, lr, pa, alpha)
+    else:
+        q = ac._classify_quadrants(zr, lr, None, alpha)
+    return tuple(torch.from_numpy(np.ascontiguousarray(x)) for x in (zr, lr, ir, p, pa, q))

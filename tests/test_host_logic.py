@@ -390,3 +390,32 @@ def test_morans_i_host_logic_on_cpu_stand_in(monkeypatch):
         ac.morans_i(a, genes=["nope"], device="cpu")
     with _pytest.raises(ValueError, match="perm_source"):
         ac.morans_i(a, genes=sel, perm_source="sobol", device="cpu")
+
+
+def test_local_morans_i_host_logic_on_cpu_stand_in(monkeypatch):
+    """``local_morans_i`` end to end on the numpy stand-in engine against the frozen output of the
+    unmodified reference: batching over one shared permutation stream, spatial re-ordering and un-sorting,
+    output slots and parameters."""
+    from spatialcore_b200 import AnnDataLite
+    from spatialcore_b200.spatial import autocorrelation as ac
+    from tests import cpu_engine
+    from tests.golden import inputs
+
+    monkeypatch.setattr(ac, "engine", cpu_engine)
+    ref = np.load(os.path.join(ROOT, "tests", "golden", "ref_g0.npz"))
+    coords, X = inputs.g0_continuous()
+    a = AnnDataLite(X, obsm={"spatial": coords})
+    ac.local_morans_i(a, genes=["g0", "g1", "g2"], n_neighbors=6, n_permutations=99, seed=0, perm_source="replay", device="cpu")
+    I, z, lag, p = (a.obsm[f"local_morans_{s}"] for s in ("I", "z", "lag", "p"))
+    assert I.dtype == np.float32 and a.obsm["local_morans_quadrant"].dtype == np.int8
+    np.testing.assert_allclose(I, ref["lmc_I"], rtol=5e-5, atol=2e-6)
+    np.testing.assert_allclose(z, ref["lmc_z"], rtol=5e-6, atol=1e-6)
+    np.testing.assert_allclose(lag, ref["lmc_lag"], rtol=5e-5, atol=2e-6)
+    assert (p != ref["lmc_p"]).mean() < 2e-4
+    assert (a.obsm["local_morans_quadrant"] != ref["lmc_quadrant"]).mean() < 2e-4
+    prm = a.uns["local_morans_params"]
+    assert prm["genes"] == ["g0", "g1", "g2"] and prm["n_cells"] == 10000 and prm["zero_variance_genes"] == []
+    b = AnnDataLite(X, obsm={"spatial": coords})
+    ac.local_morans_i(b, genes=["g0", "g1", "g2"], n_permutations=99, seed=0, batch_size=2, perm_source="replay", device="cpu")
+    assert np.array_equal(b.obsm["local_morans_p"][:, :2], p[:, :2])       # first batch: same draws
+    assert (b.obsm["local_morans_p"][:, 2] != p[:, 2]).mean() > 0.3         # second batch continues the stream
