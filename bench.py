@@ -41,8 +41,16 @@ WORKLOADS = {
     "C1": dict(n=10_000, g=50, graph="knn", degree=None, k=6, perms=99, extent=1_000.0, coords="uniform",
                desc="10k cells x 50 genes, kNN k=6, Moran's I, 99 permutations"),
 }
-METRIC = "gene-perms/sec Moran's I (graph build + statistic + permutation null)"
+METRIC = "gene-perms/sec Moran's I @5M cells x 1k genes (graph build + statistic + 999-permutation null)"  # BASELINE.json's metric, quoted on C4
 UNIT = "gene-perms/s"
+
+
+def metric_name(workload: str) -> str:
+    """BASELINE.json's metric; the other workloads name their own size."""
+    if workload == "C4":
+        return METRIC
+    w = WORKLOADS[workload]
+    return f"gene-perms/sec Moran's I @{w['n']} cells x {w['g']} genes (graph build + statistic + {w['perms']}-permutation null)"
 
 
 def parse_args():
@@ -350,7 +358,7 @@ def run_b200(args):
 
     if rank == 0:
         line = {
-            "metric": METRIC, "value": round(value, 1), "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "metric": metric_name(args.workload), "value": round(value, 1), "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": round(ms_per_step, 3), "higher_is_better": True, "scaling": "strong",
             "vs_baseline": None, "dtype": "f32 storage, f64 accumulation", "data": "synthetic",
             "config": {"workload": f"{args.workload}: {w['desc']}", "n_cells": n, "n_genes": g_total, "n_permutations": P,
@@ -450,7 +458,7 @@ def run_reference(args):
     secs = float(np.mean([s["seconds"] for s in samples]))
     cpu = dict(samples[-1], value=round(value, 2), graph_build_s=round(graph_s, 2), kind="port")
     line = {
-        "impl": "reference", "metric": METRIC, "value": round(value, 2), "unit": UNIT, "n_gpus": args.gpus,
+        "impl": "reference", "metric": metric_name(args.workload), "value": round(value, 2), "unit": UNIT, "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(secs * 1e3, 2), "higher_is_better": True,
         "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": {"workload": f"{args.workload}: {w['desc']}", "n_cells": w["n"], "n_genes": w["g"],
