@@ -1,7 +1,8 @@
 """numpy / torch-CPU stand-in for ``spatialcore_b200.engine`` (TEST INFRASTRUCTURE ONLY).
 
-Implements, with the oracle's arithmetic, the subset of the engine that ``spatial.morans_i`` drives, so
-that the drop-in's HOST logic (validation, gene resolution, sharding arithmetic, spatial re-ordering and
+Implements, with the oracle's arithmetic, the subset of the engine that the ``spatial`` entry points
+(``morans_i``, ``local_morans_i``, ``lees_l*``, ``build_spatial_weights``, ``compute_neighborhood_profile``)
+drive, so that the drop-in's HOST logic (validation, gene resolution, sharding arithmetic, spatial re-ordering and
 permutation conjugation, p-value folding, z-scores, table / metadata / obsp assembly) can be exercised
 without a GPU.  The CUDA path is compared with the oracle in tests/test_gpu_parity.py; nothing here is
 imported by the product."""
@@ -26,6 +27,16 @@ def _csr(indptr, indices, n):
     return DeviceGraph(n=n, indices=torch.from_numpy(indices.astype(np.int32)), indptr=torch.from_numpy(indptr.astype(np.int32)))
 
 
+def _composition(indptr, indices, labels, n_types):
+    """Per-row label histogram of a CSR graph, FP32 [R neighborhoods.py:226-233, 246-250]."""
+    n = len(indptr) - 1
+    lab = np.asarray(labels.numpy() if hasattr(labels, "numpy") else labels, dtype=np.int64)
+    rows = np.repeat(np.arange(n), np.diff(indptr))
+    prof = np.zeros((n, n_types), dtype=np.float32)
+    np.add.at(prof, (rows, lab[indices]), 1.0)
+    return torch.from_numpy(prof)
+
+
 def knn_graph(coords, k, include_self=False, want_dist=False, want_order=False, labels=None, n_types=0, want_idx=True,
               device="cpu"):
     c = np.asarray(coords, dtype=np.float64)[:, :2]
@@ -33,10 +44,19 @@ def knn_graph(coords, k, include_self=False, want_dist=False, want_order=False, 
         raise ValueError(f"n_neighbors must be >= 1, got {k}")
     if k >= c.shape[0]:
         raise ValueError(f"k must be < number of cells ({c.shape[0]}), got {k}")
+    n = c.shape[0]
+    if include_self:  # [R autocorrelation.py:398-401]: the k+1 nearest, the cell itself among them
+        idx, dist = R.knn_canonical(c, k)
+        idx = np.sort(np.concatenate([np.arange(n)[:, None], idx], axis=1), axis=1)
+        g = DeviceGraph(n=n, indices=torch.from_numpy(idx.astype(np.int32)), k_fixed=k + 1)
+        return g, None, None
     idx, dist = R.knn_canonical(c, k)
-    g = DeviceGraph(n=c.shape[0], indices=torch.from_numpy(idx.astype(np.int32)), k_fixed=k,
+    g = DeviceGraph(n=n, indices=torch.from_numpy(idx.astype(np.int32)) if want_idx else None, k_fixed=k,
                     dist=torch.from_numpy(dist) if want_dist else None)
-    return g, None, None
+    prof = None
+    if labels is not None:
+        prof = _composition(np.arange(0, n * k + 1, k), idx.reshape(-1), labels, n_types)
+    return g, None, prof
 
 
 def radius_graph(coords, radius, want_dist=False, labels=None, n_types=0, want_graph=True, device="cpu"):
@@ -44,7 +64,21 @@ def radius_graph(coords, radius, want_dist=False, labels=None, n_types=0, want_g
     indptr, indices, dist = R.radius_graph(c, radius)
     g = _csr(indptr, indices, c.shape[0])
     g.dist = torch.from_numpy(dist) if want_dist else None
-    return g, None
+    prof = _composition(indptr, indices, labels, n_types) if labels is not None else None
+    return (g if want_graph else None), prof
+
+
+def nbhd_counts(graph, labels, n_types):
+    return _composition(graph.indptr_tensor().numpy(), graph.indices.reshape(-1).numpy(), labels, n_types)
+
+
+def profile_normalize(profile, normalize):
+    """In place; number of all-zero rows [R neighborhoods.py:253-264]."""
+    sums = profile.sum(1, keepdim=True)
+    n_empty = int((sums == 0).sum())
+    if normalize and n_empty == 0:
+        profile /= sums
+    return n_empty
 
 
 def graph_from_scipy(adj, device="cpu", use_weights=False):
@@ -93,7 +127,8 @@ def expression_to_device(X, gene_idx, device="cpu"):
 
 
 def zscore_dense(X, cols=None, rows=None, want_z=True):
-    Z, mean, std, zero = R.zscore(X.numpy())
+    x = X.numpy()
+    Z, mean, std, zero = R.zscore(x if cols is None else x[:, cols.numpy()])
     if rows is not None:
         Z = Z[rows.numpy()]
     n, g = Z.shape
@@ -119,6 +154,23 @@ def graph_moments(graph):
 def conjugate_perms(perm_idx, co):
     o, r = co.order.numpy(), co.rank.numpy()
     return torch.from_numpy(r[perm_idx.numpy()[:, o]].astype(np.int32))
+
+
+def gather_rows(src, rows):
+    return src[rows.long()]
+
+
+def philox_permutation(seed, perm_index, n, device="cpu"):
+    return torch.from_numpy(philox.permutation(seed, perm_index, n).astype(np.int32))
+
+
+def lee_gemm(A, B, g, impl=0):
+    """``L[x, y] = sum_i A[i, x] B[i, y]`` in FP64, stored FP32 like the device kernels."""
+    return torch.from_numpy((A.numpy()[:, :g].astype(np.float64).T @ B.numpy()[:, :g].astype(np.float64)).astype(np.float32))
+
+
+def lee_abs_ge_accumulate(Lp, L_obs, cnt):
+    cnt += (Lp.abs() >= L_obs.abs()).to(cnt.dtype)
 
 
 def perm_null_graph_rows(A, B, g, n_perms, perm_idx=None, seed=0, perm_offset=0, out=None, ws=None):

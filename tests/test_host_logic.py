@@ -419,3 +419,248 @@ def test_local_morans_i_host_logic_on_cpu_stand_in(monkeypatch):
     ac.local_morans_i(b, genes=["g0", "g1", "g2"], n_permutations=99, seed=0, batch_size=2, perm_source="replay", device="cpu")
     assert np.array_equal(b.obsm["local_morans_p"][:, :2], p[:, :2])       # first batch: same draws
     assert (b.obsm["local_morans_p"][:, 2] != p[:, 2]).mean() > 0.3         # second batch continues the stream
+
+
+# ---------------------------------------------------------------------------------------------
+# Lee's L, spatial weights and neighbourhood composition host logic on the stand-in engine
+# ---------------------------------------------------------------------------------------------
+
+
+def test_lees_l_host_logic_matches_reference_golden(monkeypatch):
+    """``lees_l`` [R autocorrelation.py:991-1163] on the stand-in engine against the frozen output of the
+    unmodified reference: pair normalisation, one permutation stream shared by the pairs in order,
+    zero-variance short-cut, purity (no adata mutation), errors."""
+    import pytest as _pytest
+
+    from spatialcore_b200 import AnnDataLite
+    from spatialcore_b200.spatial import autocorrelation as ac
+    from tests import cpu_engine
+    from tests.golden import inputs
+
+    monkeypatch.setattr(ac, "engine", cpu_engine)
+    ref = np.load(os.path.join(ROOT, "tests", "golden", "ref_g0.npz"))
+    coords, X = inputs.g0_continuous()
+    a = AnnDataLite(X, obsm={"spatial": coords})
+    res = ac.lees_l(a, [("g0", "g1"), ("g1", "g0"), ("g5", "g5")], n_permutations=99, seed=0, perm_source="replay", device="cpu")
+    L = np.array([r["L"] for r in res])
+    assert np.all(np.abs(L - ref["leec_L"]) <= 1e-5 * np.abs(ref["leec_L"]) + 1e-4)
+    assert np.array_equal([r["p_value"] for r in res], ref["leec_p"])
+    assert [(r["gene_x"], r["gene_y"]) for r in res] == [("g0", "g1"), ("g1", "g0"), ("g5", "g5")]
+    assert "spatialcore_metadata" not in a.uns and not a.obsp           # pure
+    single = ac.lees_l(a, ("g0", "g1"), n_permutations=0, device="cpu")
+    assert isinstance(single, dict) and single["p_value"] == 1.0 and abs(single["L"] - ref["leec_L"][0]) < 1e-3
+    # the second pair of a list continues the stream of the first: evaluating it alone gives other draws,
+    # evaluating the first alone gives the same p-value
+    assert ac.lees_l(a, ("g0", "g1"), n_permutations=99, seed=0, perm_source="replay", device="cpu")["p_value"] == ref["leec_p"][0]
+    Xz = X.copy()
+    Xz[:, 2] = 1.0
+    r = ac.lees_l(AnnDataLite(Xz, obsm={"spatial": coords}), [("g2", "g1"), ("g0", "g1")], n_permutations=9, seed=0,
+                  perm_source="replay", device="cpu")
+    assert r[0] == {"gene_x": "g2", "gene_y": "g1", "L": 0.0, "p_value": 1.0}
+    # Philox source: deterministic, addressed by (pair index, permutation index)
+    p1 = [r["p_value"] for r in ac.lees_l(a, [("g0", "g1"), ("g2", "g3")], n_permutations=19, seed=4, perm_source="philox", device="cpu")]
+    p2 = [r["p_value"] for r in ac.lees_l(a, [("g0", "g1"), ("g2", "g3")], n_permutations=19, seed=4, perm_source="philox", device="cpu")]
+    assert p1 == p2 and all(0 < p <= 1 for p in p1)
+    with _pytest.raises(ValueError, match="Genes not found"):
+        ac.lees_l(a, ("g0", "nope"), device="cpu")
+    with _pytest.raises(ValueError, match="not found"):
+        ac.lees_l(AnnDataLite(X, obsm={}), ("g0", "g1"), device="cpu")
+    with _pytest.raises(ValueError, match="n_permutations must be >= 0"):
+        ac.lees_l(a, ("g0", "g1"), n_permutations=-2, device="cpu")
+
+
+def test_lees_l_local_host_logic_matches_reference_golden(monkeypatch):
+    """``lees_l_local`` [R autocorrelation.py:1171-1479]: two draws of P permutations per pair from one
+    stream (global test, then per-cell test), categorical quadrants, parameter dicts, all-pairs
+    expansion, zero-variance pairs, copy semantics, errors."""
+    import pytest as _pytest
+
+    from spatialcore_b200 import AnnDataLite
+    from spatialcore_b200.spatial import autocorrelation as ac
+    from tests import cpu_engine
+    from tests.golden import inputs
+
+    monkeypatch.setattr(ac, "engine", cpu_engine)
+    ref = np.load(os.path.join(ROOT, "tests", "golden", "ref_g0.npz"))
+    coords, X = inputs.g0_continuous()
+    a = AnnDataLite(X, obsm={"spatial": coords})
+    out = ac.lees_l_local(a, gene_pairs=[("g0", "g1"), ("g2", "g3")], n_neighbors=6, n_permutations=19, compute_cell_pvalues=True,
+                          significance_filter=True, alpha=0.2, seed=0, perm_source="replay", device="cpu")
+    assert out is a
+    for key in ("g0_g1", "g2_g3"):
+        np.testing.assert_allclose(a.obs[f"{key}_lees_l"].to_numpy(), ref[f"llc_{key}_L"], rtol=5e-5, atol=2e-6)
+        assert (a.obs[f"{key}_pvalue"].to_numpy() != ref[f"llc_{key}_p"]).mean() < 2e-4
+        assert (a.obs[f"{key}_quadrant"].cat.codes.to_numpy() != ref[f"llc_{key}_q"]).mean() < 2e-4
+        prm = a.uns[f"{key}_lees_l_params"]
+        assert abs(prm["global_L"] - ref[f"llc_{key}_global"][0]) <= 1e-5 * abs(ref[f"llc_{key}_global"][0]) + 1e-4
+        assert prm["global_pvalue"] == ref[f"llc_{key}_global"][1]
+        assert sum(prm["quadrant_counts"].values()) == 10000 and prm["compute_cell_pvalues"] is True
+    assert a.obs["g0_g1_quadrant"].cat.categories.tolist() == ["NS", "HH", "LL", "HL", "LH"]
+    op = a.uns["spatialcore_metadata"]["operations"][-1]
+    assert op["function"] == "lees_l_local" and op["parameters"]["n_pairs"] == 2
+    # all-pairs expansion in combinations() order; copy=True leaves the input untouched; without per-cell
+    # p-values every p is 1 and the quadrants are sign-only
+    small = AnnDataLite(X[:1500], obsm={"spatial": coords[:1500]})
+    c = ac.lees_l_local(small, genes=["g0", "g1", "g2"], n_permutations=5, seed=1, copy=True, perm_source="replay", device="cpu")
+    assert c is not small and not [k for k in small.obs.columns if k.endswith("_lees_l")]
+    assert [k for k in c.obs.columns if k.endswith("_lees_l")] == ["g0_g1_lees_l", "g0_g2_lees_l", "g1_g2_lees_l"]
+    assert np.all(c.obs["g0_g2_pvalue"].to_numpy() == 1.0) and (c.obs["g0_g2_quadrant"] != "NS").mean() > 0.9
+    Xz = X[:1500].copy()
+    Xz[:, 1] = 3.0
+    z = ac.lees_l_local(AnnDataLite(Xz, obsm={"spatial": coords[:1500]}), gene_pairs=("g0", "g1"), n_permutations=3, device="cpu",
+                        perm_source="replay")
+    assert z.uns["g0_g1_lees_l_params"]["zero_variance"] is True and np.all(z.obs["g0_g1_lees_l"].to_numpy() == 0)
+    assert set(z.obs["g0_g1_quadrant"]) == {"NS"}
+    with _pytest.raises(ValueError, match="Must provide either"):
+        ac.lees_l_local(a, device="cpu")
+    with _pytest.raises(ValueError, match="significance_filter=True requires"):
+        ac.lees_l_local(a, gene_pairs=("g0", "g1"), significance_filter=True, device="cpu")
+    with _pytest.raises(ValueError, match="Genes not found"):
+        ac.lees_l_local(a, gene_pairs=("g0", "zz"), device="cpu")
+
+
+def test_lees_l_matrix_host_logic_on_cpu_stand_in(monkeypatch):
+    """All-pairs matrix: spatial re-ordering of Z / graph / replayed permutations leaves L and the
+    permutation p-values equal to a direct FP64 evaluation in the user's labelling."""
+    import pytest as _pytest
+
+    from oracle import restate as R
+    from spatialcore_b200 import AnnDataLite
+    from spatialcore_b200.spatial import autocorrelation as ac
+    from tests import cpu_engine
+
+    monkeypatch.setattr(ac, "engine", cpu_engine)
+    rng = np.random.default_rng(17)
+    n, g, P, k = 1201, 7, 19, 6
+    coords = rng.uniform(0, 200, (n, 2))
+    X = (np.log1p(rng.poisson(1.0, (n, g))) + 0.3 * rng.normal(size=(n, g))).astype(np.float32)
+    X[:, 2] += np.sin(coords[:, 0] / 20.0).astype(np.float32)
+    X[:, 4] += np.sin(coords[:, 0] / 20.0 + 0.4).astype(np.float32)
+    X[:, 5] = 2.0
+    a = AnnDataLite(X, obsm={"spatial": coords})
+    L, pv = ac.lees_l_matrix(a, n_neighbors=k, n_permutations=P, seed=5, perm_source="replay", key_added="lee", device="cpu")
+    W = R.build_spatial_weights(coords, k).astype(np.float64)
+    Z, _, _, zero = R.zscore(X)
+    want_L = R.lees_l_all_pairs(Z, W)
+    prng = np.random.default_rng(5)
+    cnt = np.zeros((g, g), dtype=np.int64)
+    margin = np.full((g, g), np.inf)
+    for _ in range(P):
+        perm = prng.permutation(n)
+        Lp = Z.T @ (W @ Z[perm])
+        cnt += np.abs(Lp) >= np.abs(want_L)
+        margin = np.minimum(margin, np.abs(np.abs(Lp) - np.abs(want_L)))
+    want_p = (cnt + 1) / (P + 1)
+    want_p[zero, :] = 1.0
+    want_p[:, zero] = 1.0
+    live = ~zero
+    np.testing.assert_allclose(L.to_numpy()[np.ix_(live, live)], want_L[np.ix_(live, live)], rtol=1e-5, atol=4e-6 * np.sqrt(n))
+    safe = margin > 1e-3
+    safe[zero, :] = True
+    safe[:, zero] = True
+    assert safe.mean() > 0.95 and np.array_equal(pv.to_numpy()[safe], want_p[safe])
+    assert pv.loc["g2", "g4"] <= 2 / (P + 1) and pv.loc["g5", "g1"] == 1.0
+    assert list(a.uns["lee"].index) == [f"g{i}" for i in range(g)] and a.uns["lee_pvalues"] is pv
+    sym = ac.lees_l_matrix(a, genes=["g0", "g2", "g4"], n_neighbors=k, variant="lee2001", device="cpu")
+    lagZ = (W @ Z)[:, [0, 2, 4]]
+    np.testing.assert_allclose(sym.to_numpy(), lagZ.T @ lagZ / n, rtol=1e-5, atol=1e-6)
+    with _pytest.raises(ValueError, match="variant='reference'"):
+        ac.lees_l_matrix(a, n_permutations=3, variant="lee2001", device="cpu")
+    with _pytest.raises(ValueError, match="variant must be"):
+        ac.lees_l_matrix(a, variant="moran", device="cpu")
+
+
+def test_spatial_weights_and_neighbors_host_logic(monkeypatch):
+    """``build_spatial_weights`` [R autocorrelation.py:342-413] (scipy CSR assembly, FP32 data, int32
+    indices) against the reference golden; squidpy-style graph slots for kNN and radius graphs."""
+    import pytest as _pytest
+
+    from oracle import restate as R
+    from spatialcore_b200 import AnnDataLite
+    from spatialcore_b200.spatial import autocorrelation as ac
+    from tests import cpu_engine
+    from tests.golden import inputs
+
+    monkeypatch.setattr(ac, "engine", cpu_engine)
+    ref = np.load(os.path.join(ROOT, "tests", "golden", "ref_g0.npz"))
+    coords, X = inputs.g0()
+    a = AnnDataLite(X, obsm={"spatial": coords})
+    for k in (6, 15):
+        W = ac.build_spatial_weights(a, n_neighbors=k, device="cpu")
+        assert W.dtype == np.float32 and W.indices.dtype == np.int32 and W.shape == (10000, 10000)
+        assert np.array_equal(W.indices, ref[f"W_k{k}_indices"]) and np.array_equal(W.indptr, ref[f"W_k{k}_indptr"])
+        assert np.array_equal(W.data[:8], ref[f"W_k{k}_data0"]) and np.all(W.data == W.data[0])
+    Ws = ac.build_spatial_weights(a, n_neighbors=6, include_self=True, device="cpu")
+    assert np.array_equal(Ws.indices, ref["W_k6_self_indices"]) and np.array_equal(Ws.data[:8], ref["W_k6_self_data0"])
+    assert not a.obsp and "spatialcore_metadata" not in a.uns             # returns W, writes nothing
+    b = AnnDataLite(X, obsm={"xy": coords})
+    ac.spatial_neighbors(b, radius=25.0, spatial_key="xy", device="cpu")
+    adj, dst = R.spatial_neighbors(coords, radius=25.0)
+    assert b.obsp["spatial_connectivities"].dtype == np.float64 and (b.obsp["spatial_connectivities"] != adj).nnz == 0
+    assert (b.obsp["spatial_distances"] != dst).nnz == 0
+    assert b.uns["spatial_neighbors"]["params"]["radius"] == 25.0
+    c = AnnDataLite(X, obsm={"spatial": coords})
+    ac.spatial_neighbors(c, n_neighs=4, write=False, device="cpu")
+    assert not c.obsp and "spatial_neighbors" not in c.uns
+    with _pytest.raises(ValueError, match="not found"):
+        ac.build_spatial_weights(b, device="cpu")
+    with _pytest.raises(ValueError, match="n_neighbors must be >= 1"):
+        ac.build_spatial_weights(a, n_neighbors=0, device="cpu")
+
+
+def test_neighborhood_profile_host_logic_matches_reference_golden(monkeypatch):
+    """``compute_neighborhood_profile`` [R neighborhoods.py:48-296]: label coding in sorted order, kNN and
+    radius composition, normalisation, output slots, metadata and every argument error, bit-identical to
+    the frozen reference output."""
+    import pytest as _pytest
+
+    from spatialcore_b200 import AnnDataLite
+    from spatialcore_b200.spatial import neighborhoods as nb
+    from tests import cpu_engine
+    from tests.golden import inputs
+
+    monkeypatch.setattr(nb, "engine", cpu_engine)
+    ref = np.load(os.path.join(ROOT, "tests", "golden", "ref_nbhd.npz"))
+    coords, labels = inputs.nbhd()
+    n = coords.shape[0]
+
+    def run(obs=None, **kw):
+        obs = pd.DataFrame({"ct": pd.Categorical([f"t{c:02d}" for c in labels])}) if obs is None else obs
+        a = AnnDataLite(np.zeros((n, 1), np.float32), obs=obs, obsm={"spatial": coords})
+        return a, nb.compute_neighborhood_profile(a, "ct", device="cpu", **kw)
+
+    a, out = run(method="knn", k=5)
+    assert out is a and a.obsm["neighborhood_profile"].dtype == np.float32
+    assert np.array_equal(a.obsm["neighborhood_profile"], ref["knn5_norm"])
+    assert a.uns["neighborhood_profile_celltypes"] == ref["celltypes"].tolist()
+    op = a.uns["spatialcore_metadata"]["operations"][-1]
+    assert op["function"] == "compute_neighborhood_profile" and op["parameters"]["k"] == 5 and op["parameters"]["radius"] is None
+    assert np.array_equal(run(method="knn", k=30)[0].obsm["neighborhood_profile"], ref["knn30_norm"])
+    assert np.array_equal(run(method="knn", k=30, normalize=False)[0].obsm["neighborhood_profile"], ref["knn30_raw"])
+    assert np.array_equal(run(method="radius", radius=inputs.NBHD_RADIUS, normalize=False)[0].obsm["neighborhood_profile"], ref["radius_raw"])
+    assert np.array_equal(run(method="radius", radius=inputs.NBHD_RADIUS)[0].obsm["neighborhood_profile"], ref["radius_norm"])
+    # string labels in arbitrary order are coded by sorted unique value; copy / key_added
+    a2, out2 = run(obs=pd.DataFrame({"ct": pd.Series([f"t{c:02d}" for c in labels], dtype=object)}), method="knn", k=5,
+                   key_added="nbhd", copy=True)
+    assert out2 is not a2 and "nbhd" not in a2.obsm and np.array_equal(out2.obsm["nbhd"], ref["knn5_norm"])
+    assert out2.uns["nbhd_celltypes"] == ref["celltypes"].tolist()
+    with _pytest.raises(ValueError, match="cells have empty neighborhood profiles"):
+        run(method="radius", radius=0.5)
+    with _pytest.raises(ValueError, match="'radius' must be provided"):
+        run(method="radius")
+    with _pytest.raises(ValueError, match="radius must be > 0"):
+        run(method="radius", radius=-1.0)
+    with _pytest.raises(ValueError, match="k must be < number of cells"):
+        run(method="knn", k=n)
+    with _pytest.raises(ValueError, match="k must be >= 1"):
+        run(method="knn", k=0)
+    with _pytest.raises(ValueError, match="Invalid method"):
+        run(method="ball")
+    with _pytest.raises(ValueError, match="not found in adata.obs"):
+        nb.compute_neighborhood_profile(AnnDataLite(np.zeros((n, 1), np.float32), obsm={"spatial": coords}), "ct", device="cpu")
+    with _pytest.raises(ValueError, match="At least 2 unique cell types"):
+        run(obs=pd.DataFrame({"ct": ["a"] * n}))
+    holes = pd.Series([f"t{c:02d}" for c in labels], dtype=object)
+    holes[:7] = None
+    with _pytest.raises(ValueError, match="7 cells have missing labels"):
+        run(obs=pd.DataFrame({"ct": holes}))
