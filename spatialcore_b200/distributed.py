@@ -127,3 +127,31 @@ def all_gather_columns(local, total_cols: int, device, group=None):
     out = [torch.empty_like(buf) for _ in range(ws)]
     dist.all_gather(out, buf, group=group)
     return torch.cat([o[:, : hi - lo] for o, (lo, hi) in zip(out, sizes)], dim=1).cpu().numpy()
+
+
+def all_gather_column_blocks(local, sizes, device, group=None, max_rows: int = 1 << 20):
+    """Every rank contributes the columns it owns of a per-cell matrix (numpy ``[n, sizes[rank]]``, any
+    dtype); returns the full ``[n, sum(sizes)]`` matrix in rank order on every rank.  The exchange goes
+    through ``device`` in row chunks (NCCL all-gather on GPUs, gloo on CPU), so the staging buffers stay
+    small next to the matrices themselves.  Ranks may own zero columns."""
+    import numpy as np
+
+    rank, ws = world(group)
+    if ws == 1:
+        return local
+    n = local.shape[0]
+    pad = max(max(sizes), 1)
+    tdtype = torch.from_numpy(np.empty(0, dtype=local.dtype)).dtype
+    out = np.empty((n, int(sum(sizes))), dtype=local.dtype)
+    starts = np.concatenate([[0], np.cumsum(sizes)]).astype(np.int64)
+    for r0 in range(0, n, max_rows):
+        r1 = min(n, r0 + max_rows)
+        buf = torch.zeros((r1 - r0, pad), dtype=tdtype, device=device)
+        if sizes[rank] > 0:
+            buf[:, : sizes[rank]] = torch.from_numpy(np.ascontiguousarray(local[r0:r1])).to(device)
+        parts = [torch.empty_like(buf) for _ in range(ws)]
+        dist.all_gather(parts, buf, group=group)
+        for r in range(ws):
+            if sizes[r] > 0:
+                out[r0:r1, starts[r]:starts[r + 1]] = parts[r][:, : sizes[r]].cpu().numpy()
+    return out

@@ -131,7 +131,7 @@ def _standardize_row_sharded(adata, layer, names: List[str], device, co: engine.
     g = len(names)
     ld = engine.padded_ld(g)
     dev = torch.device(device) if not isinstance(device, torch.device) else device
-    if dev.index is None:
+    if dev.type == "cuda" and dev.index is None:
         dev = torch.device("cuda", torch.cuda.current_device())
     have = hi - lo
     stats = torch.zeros((3, g), dtype=torch.float64, device=dev)  # rows: count, mean, std of this block
@@ -509,16 +509,26 @@ def local_morans_i(
     copy: bool = False,
     *,
     perm_source: str = "auto",
+    shard: str = "auto",
+    group=None,
     device="cuda",
 ):
     """Local Moran's I (LISA), API and outputs of [R autocorrelation.py:656-983].  The null permutes
     VALUES and re-applies W (gather-SpMM kernel); one permutation stream is shared across gene
-    batches exactly like the reference, so results depend on ``batch_size`` the same way."""
+    batches exactly like the reference, so results depend on ``batch_size`` the same way.
+
+    With ``torch.distributed`` initialised (``shard="auto"`` / ``"genes"``) the gene batches are split
+    into contiguous blocks over the ranks of ``group``: batch ``b`` keeps the permutations it has in a
+    single-process run (draws ``[b·P, (b+1)·P)`` of the replayed stream, Philox offsets ``b·P``), so the
+    outputs do not depend on the world size, and the six per-cell matrices are all-gathered so that
+    every rank holds the full result.  ``shard="none"``: ranks work independently."""
     t0 = time.time()
     _check_spatial(adata, spatial_key)
     _check_counts(n_neighbors, n_permutations)
     if fdr_correction not in ["bonferroni", "fdr_bh", "none"]:
         raise ValueError(f"Invalid fdr_correction: '{fdr_correction}'. Must be 'bonferroni', 'fdr_bh', or 'none'.")
+    if shard not in ("auto", "genes", "none"):
+        raise ValueError(f"shard must be 'auto', 'genes' or 'none', got '{shard}'")
     adata = adata.copy() if copy else adata
     names = _resolve_genes(adata, genes, "This may be slow and memory-intensive.")
     n, g = adata.n_obs, len(names)
@@ -542,7 +552,12 @@ def local_morans_i(
     rng = np.random.default_rng(seed)
     n_batches = (g + batch_size - 1) // batch_size
     logger.info(f"Processing {g} genes in {n_batches} batches")
-    for b in range(n_batches):
+    rank, world = dist_util.world(group) if shard != "none" else (0, 1)
+    b_lo, b_hi = dist_util.block_slice(n_batches, rank, world)
+    if source == "replay":
+        for _ in range(b_lo * n_permutations):  # the draws of the batches other ranks own
+            rng.permutation(n)
+    for b in range(b_lo, b_hi):
         s, e = b * batch_size, min((b + 1) * batch_size, g)
         gb = e - s
         Xd, cols = engine.expression_to_device(X, pos_all[s:e], device)
@@ -569,6 +584,19 @@ def local_morans_i(
         p_values[:, s:e] = p_d.cpu().numpy()
         p_adj[:, s:e] = pa_d.cpu().numpy()
         quadrants[:, s:e] = q_d.cpu().numpy()
+
+    if world > 1:  # every rank ends up with every gene's columns
+        spans = [dist_util.block_slice(n_batches, r, world) for r in range(world)]
+        sizes = [min(hi * batch_size, g) - min(lo * batch_size, g) for lo, hi in spans]
+        c_lo, c_hi = min(b_lo * batch_size, g), min(b_hi * batch_size, g)
+        gdev = co.order.device
+
+        def gathered(a: np.ndarray) -> np.ndarray:
+            return dist_util.all_gather_column_blocks(a[:, c_lo:c_hi], sizes, gdev, group)
+
+        local_I, z_values, lag_values, p_values, p_adj, quadrants = (
+            gathered(a) for a in (local_I, z_values, lag_values, p_values, p_adj, quadrants))
+        zero_mask = gathered(zero_mask.astype(np.uint8)[None, :])[0].astype(bool)
 
     zero_genes = [names[i] for i in np.where(zero_mask)[0]]
     if zero_mask.any():
@@ -731,6 +759,8 @@ def lees_l_matrix(
     key_added: Optional[str] = None,
     impl: int = 0,
     perm_source: str = "auto",
+    shard: str = "auto",
+    group=None,
     device="cuda",
 ):
     """Lee's L for ALL ordered gene pairs in one dense contraction (replaces the reference's
@@ -743,8 +773,14 @@ def lees_l_matrix(
     ``p[x, y] = (#{|L_p[x,y]| >= |L[x,y]|} + 1)/(P + 1)`` with ``L_p = Zᵀ(W Z[π_p])`` — the null of
     [R autocorrelation.py:322-332] (only the y side is permuted), evaluated for all pairs per
     permutation: one row gather, one lag pass and one contraction each.  All pairs share the P
-    permutations (the reference draws fresh ones per pair).  Returns ``L`` or ``(L, p)`` DataFrames."""
+    permutations (the reference draws fresh ones per pair).  Returns ``L`` or ``(L, p)`` DataFrames.
+
+    With ``torch.distributed`` initialised (``shard="auto"`` / ``"perms"``) every rank evaluates a
+    contiguous block of the P permutations (addressed by global index, so the counts do not depend on
+    the world size) and the G x G exceedance counts are summed with one all-reduce."""
     _check_spatial(adata, spatial_key)
+    if shard not in ("auto", "perms", "none"):
+        raise ValueError(f"shard must be 'auto', 'perms' or 'none', got '{shard}'")
     if n_neighbors < 1:
         raise ValueError(f"n_neighbors must be >= 1, got {n_neighbors}")
     if n_permutations < 0:
@@ -779,15 +815,23 @@ def lees_l_matrix(
         _, _, lag_p, _ = engine.lag_moran(graph, Zp, g, want_lag=True)
         engine.lee_abs_ge_accumulate(engine.lee_gemm(std.Z, lag_p, g, impl=impl), Lm, cnt)
 
+    _, world = dist_util.world(group) if shard != "none" else (0, 1)
+    p_lo, p_hi = dist_util.my_slice(n_permutations, group) if world > 1 else (0, n_permutations)
     if source == "philox":
-        for p in range(n_permutations):
+        for p in range(p_lo, p_hi):
             one(engine.philox_permutation(seed, p, n, device=Lm.device))
     else:
         rng = np.random.default_rng(seed)
-        for _, idx in _replay_chunks(rng, n, n_permutations, Lm.device):
+        for _ in range(p_lo):  # permutation p is the p-th draw of the stream on every rank
+            rng.permutation(n)
+        for _, idx in _replay_chunks(rng, n, p_hi - p_lo, Lm.device):
             idx = engine.conjugate_perms(idx, co)
             for j in range(idx.shape[0]):
                 one(idx[j])
+    if world > 1:
+        import torch.distributed as dist
+
+        dist.all_reduce(cnt, op=dist.ReduceOp.SUM, group=group)
     pv = (cnt.cpu().numpy() + 1) / (n_permutations + 1)
     zero = std.zero_var.cpu().numpy().astype(bool)
     pv[zero, :] = 1.0  # zero-variance genes: L = 0, p = 1 [R autocorrelation.py:1129-1140]

@@ -138,6 +138,21 @@ def zscore_dense(X, cols=None, rows=None, want_z=True):
                         std=torch.from_numpy(std), zero_var=torch.from_numpy(zero.astype(np.uint8)))
 
 
+def zscore_apply(X, mean, std, zero_var, cols=None, rows=None, out=None):
+    """z-score with GIVEN moments (row-sharded ingest) in the kernel's arithmetic: FP64, stored FP32."""
+    x = X.numpy().astype(np.float64)
+    x = x if cols is None else x[:, cols.numpy()]
+    x = x if rows is None else x[rows.numpy()]
+    zero = zero_var.numpy().astype(bool)
+    z = np.where(zero, 0.0, (x - mean.numpy()) / np.where(zero, 1.0, std.numpy())).astype(np.float32)
+    n, g = z.shape
+    if out is None:
+        out = torch.zeros((n, padded_ld(g)), dtype=torch.float32)
+    out.zero_()
+    out[:, :g] = torch.from_numpy(z)
+    return out
+
+
 def lag_moran(graph, Z, g, want_lag=True, want_local=False):
     W = _to_scipy(graph)
     z = Z.numpy().astype(np.float64)

@@ -664,3 +664,86 @@ def test_neighborhood_profile_host_logic_matches_reference_golden(monkeypatch):
     holes[:7] = None
     with _pytest.raises(ValueError, match="7 cells have missing labels"):
         run(obs=pd.DataFrame({"ct": holes}))
+
+
+# ---------------------------------------------------------------------------------------------
+# the public entry points on 2 gloo ranks (stand-in engine): results do not depend on the world size
+# ---------------------------------------------------------------------------------------------
+
+
+def _sharded_inputs():
+    rng = np.random.default_rng(23)
+    n, g = 1501, 9
+    coords = rng.uniform(0, 220, (n, 2))
+    X = (np.log1p(rng.poisson(1.0, (n, g))) + 0.3 * rng.normal(size=(n, g))).astype(np.float32)
+    X[:, 1] += np.sin(coords[:, 0] / 18.0).astype(np.float32)
+    X[:, 6] = 4.0  # zero variance
+    return coords, X
+
+
+def _run_entry_points(ac, AnnDataLite, **kw):
+    """The calls whose outputs must not depend on how many ranks share the work."""
+    coords, X = _sharded_inputs()
+    out = {}
+    for tag, extra in (("perms_replay", dict(shard="perms", perm_source="replay")),
+                       ("perms_philox", dict(shard="perms", perm_source="philox")),
+                       ("genes_replay", dict(shard="genes", perm_source="replay")),
+                       ("rows_philox", dict(shard="perms", ingest="sharded", perm_source="philox"))):
+        a = AnnDataLite(X, obsm={"spatial": coords})
+        if not kw.get("distributed", True):
+            extra = dict(extra, shard="none", ingest="replicated")
+        ac.morans_i(a, n_neighbors=6, n_permutations=23, seed=2, device="cpu", **extra)
+        df = a.uns["morans_i"]
+        out[f"mi_{tag}"] = np.stack([df["I"].to_numpy(), df["z_score"].to_numpy(), df["p_value"].to_numpy()])
+    for src in ("replay", "philox"):
+        a = AnnDataLite(X, obsm={"spatial": coords})
+        ac.local_morans_i(a, n_neighbors=6, n_permutations=19, seed=4, batch_size=2, perm_source=src, device="cpu",
+                          shard="auto" if kw.get("distributed", True) else "none")
+        for s in ("I", "z", "lag", "p", "p_adj", "quadrant"):
+            out[f"lm_{src}_{s}"] = a.obsm[f"local_morans_{s}"]
+        out[f"lm_{src}_zero"] = np.array(a.uns["local_morans_params"]["zero_variance_genes"])
+        L, pv = ac.lees_l_matrix(AnnDataLite(X, obsm={"spatial": coords}), n_neighbors=6, n_permutations=13, seed=6,
+                                 perm_source=src, device="cpu", shard="auto" if kw.get("distributed", True) else "none")
+        out[f"lee_{src}_L"], out[f"lee_{src}_p"] = L.to_numpy(), pv.to_numpy()
+    return out
+
+
+def _entry_point_worker(rank, world, port_no, out_dir):
+    sys.path.insert(0, ROOT)
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port_no)
+    os.environ["SC_INGEST_NCCL"] = "1"  # no peer-mapped memory on CPU: all-gather form of the row-sharded ingest
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from spatialcore_b200 import AnnDataLite
+    from spatialcore_b200.spatial import autocorrelation as ac
+    from tests import cpu_engine
+
+    ac.engine = cpu_engine
+    np.savez(os.path.join(out_dir, f"e{rank}.npz"), **_run_entry_points(ac, AnnDataLite))
+    dist.destroy_process_group()
+
+
+def test_entry_points_on_two_gloo_ranks_match_single_process(tmp_path, monkeypatch):
+    """SURVEY E13 on CPU: ``morans_i`` (permutation / gene / row sharding), ``local_morans_i`` (gene-batch
+    sharding + all-gather of the per-cell matrices) and ``lees_l_matrix`` (permutation sharding) give,
+    on every rank of a 2-rank job, the single-process result: identical counts and p-values in both
+    replay and Philox mode."""
+    from spatialcore_b200 import AnnDataLite
+    from spatialcore_b200.spatial import autocorrelation as ac
+    from tests import cpu_engine
+
+    world = 2
+    mp.spawn(_entry_point_worker, args=(world, _free_port(), str(tmp_path)), nprocs=world, join=True)
+    monkeypatch.setattr(ac, "engine", cpu_engine)
+    want = _run_entry_points(ac, AnnDataLite, distributed=False)
+    for r in range(world):
+        got = np.load(tmp_path / f"e{r}.npz")
+        assert sorted(got.files) == sorted(want)
+        for key, ref in want.items():
+            if key == "mi_rows_philox":  # pooled moments differ in the last FP64 bit: Z agrees to FP32 rounding
+                np.testing.assert_allclose(got[key][:2], ref[:2], rtol=2e-5, atol=1e-7, equal_nan=True, err_msg=key)
+                assert (got[key][2] != ref[2]).sum() <= 1, key
+            elif ref.dtype.kind == "f":
+                np.testing.assert_allclose(got[key], ref, rtol=1e-12, atol=0, equal_nan=True, err_msg=key)
+            else:
+                assert np.array_equal(got[key], ref), key
