@@ -1,5 +1,6 @@
 """torchrun check (NCCL): morans_i with shard='genes' and shard='perms' on W ranks returns, on every
-rank, the same table as a single-rank run (Philox permutations are addressed by global index)."""
+rank, the same table as a single-rank run (Philox permutations are addressed by global index); the same
+for the row-sharded ingest, local_morans_i (gene batches) and lees_l_matrix (permutations)."""
 import os, sys
 import numpy as np, torch, torch.distributed as dist
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
@@ -48,4 +49,19 @@ one = spatial.morans_i(AnnDataLite(X, obsm={"spatial": coords}), n_permutations=
                        shard="none", device=dev).uns["morans_i"]
 assert np.array_equal(rep["p_value"].to_numpy(), one["p_value"].to_numpy())
 if rank == 0: print("replay shard=perms ok", flush=True)
+# local_morans_i (gene batches over ranks, per-cell matrices all-gathered) and lees_l_matrix (permutations
+# over ranks): every rank returns the single-process result, replay and Philox mode
+Xs, cs = X[:6000, :9], coords[:6000]
+for src in ("philox", "replay"):
+    one = AnnDataLite(Xs, obsm={"spatial": cs}); many = AnnDataLite(Xs, obsm={"spatial": cs})
+    spatial.local_morans_i(one, n_permutations=19, seed=4, batch_size=2, perm_source=src, shard="none", device=dev)
+    spatial.local_morans_i(many, n_permutations=19, seed=4, batch_size=2, perm_source=src, shard="genes", device=dev)
+    for key in ("I", "z", "lag", "p", "p_adj", "quadrant"):
+        assert np.array_equal(one.obsm[f"local_morans_{key}"], many.obsm[f"local_morans_{key}"]), (src, key)
+    L1, p1 = spatial.lees_l_matrix(AnnDataLite(Xs, obsm={"spatial": cs}), n_permutations=13, seed=6, perm_source=src,
+                                   shard="none", impl=1, device=dev)
+    L2, p2 = spatial.lees_l_matrix(AnnDataLite(Xs, obsm={"spatial": cs}), n_permutations=13, seed=6, perm_source=src,
+                                   shard="perms", impl=1, device=dev)
+    assert np.array_equal(L1.to_numpy(), L2.to_numpy()) and np.array_equal(p1.to_numpy(), p2.to_numpy()), src
+if rank == 0: print("local_morans_i shard=genes and lees_l_matrix shard=perms ok", flush=True)
 dist.destroy_process_group()
