@@ -62,6 +62,7 @@ def parse_args():
     ap.add_argument("--workload", default=os.environ.get("SC_BENCH_WORKLOAD", "C4"), choices=list(WORKLOADS))
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-values", action="store_true", help="skip the value-permuting-null leg")
     ap.add_argument("--seed", type=int, default=3)
     return ap.parse_args()
 
@@ -180,6 +181,36 @@ def device_step(engine, ac, coords_dev, X_dev, w, radius, seed, events=None, per
     c = torch.minimum(null.cnt_ge, P - null.cnt_ge)
     p_value = (c + 1).double() / (P + 1)
     return I, p_value
+
+
+def values_null_leg(engine, coords_dev, X_dev, w, radius, seed, n_perms=4):
+    """Secondary figure (the headline is reported for both nulls): gene-perms/s of the
+    VALUE-permuting null (the reference's own ``local_morans_i`` / Lee's L scheme, ``sc_perm_null_values``)
+    on the same workload, ``n_perms`` permutations after one warm-up pass, CUDA events."""
+    import torch
+
+    n, g = X_dev.shape
+    if radius is not None:
+        graph, _ = engine.radius_graph(coords_dev, radius, device=coords_dev.device)
+    else:
+        graph, _, _ = engine.knn_graph(coords_dev, w["k"], device=coords_dev.device)
+    co = engine.spatial_order(coords_dev, device=coords_dev.device)
+    graph_s = engine.relabel_graph(graph, co)
+    std = engine.zscore_dense(X_dev, rows=co.order)
+    engine.perm_null_values(graph_s, std.Z, g, 1, seed=seed)  # warm-up
+    t0 = torch.cuda.Event(enable_timing=True)
+    t1 = torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    t0.record()
+    engine.perm_null_values(graph_s, std.Z, g, n_perms, seed=seed, perm_offset=1)
+    t1.record()
+    torch.cuda.synchronize()
+    ms = t0.elapsed_time(t1)
+    k1 = graph_s.nnz / n + 1.0
+    return {"value": round(g * n_perms / (ms / 1e3), 1), "unit": UNIT, "ms_per_permutation": round(ms / n_perms, 3),
+            "perms_timed": n_perms, "null": "values (reference's own scheme: permute z, re-apply W)",
+            "bound": "L1/L2 gather (SURVEY.md §8d), not HBM",
+            "hbm_compulsory_gbs": round(4.0 * n * (1.0 + k1 / g) * g * n_perms / (ms / 1e3) / 1e9, 1)}
 
 
 def run_b200(args):
@@ -310,6 +341,15 @@ def run_b200(args):
                 "launch_ms": round(perm_ms / n_launch, 4), "perms_per_launch": PB,
                 "bytes_per_launch": bytes_per_launch}
 
+    # ---------------- the other null, same workload (single-GPU runs) ---------------------------
+    values_null = None
+    if world == 1 and not args.no_values:
+        try:
+            values_null = values_null_leg(engine, coords_dev, X_dev, w, radius, args.seed)
+        except Exception as exc:  # a secondary figure must never cost the headline line
+            values_null = {"error": f"{type(exc).__name__}: {exc}"}
+        torch.cuda.empty_cache()
+
     # ---------------- end-to-end leg through the public API, host buffers ------------------------
     e2e = None
     if not args.no_e2e:
@@ -368,6 +408,7 @@ def run_b200(args):
             "phases_ms": {k: round(v, 3) for k, v in phase_ms.items()},
             "knn_build_ms": round(phase_ms.get("graph", float("nan")), 3),
             "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "e2e": e2e, "cpu_baseline": cpu,
+            "values_null": values_null,
             "check": {"I_mean": float(np.nanmean(I_h)), "p_min": float(np.nanmin(p_h)), "n_sig_0.01": int((p_h <= 0.01).sum())},
         }
         print(json.dumps(line))
