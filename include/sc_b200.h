@@ -185,6 +185,23 @@ SC_API int sc_csr_lag_moran(const int32_t* indptr, const int32_t* indices, const
                      float* local, int64_t ldl, double* num, double* den, void* ws,
                      size_t ws_bytes, sc_stream_t stream);
 
+/* EXPERIMENTAL (opt-in, SC_LAG_GROUP=2|4|8 in the Python layer): the same lag + Moran sums for a
+ * row-standardised binary graph, with the L1 gathers shared between `group_rows` consecutive rows.  In
+ * spatial order consecutive rows share most neighbours; sc_graph_group_build merges the column-sorted
+ * neighbour lists of each group of rows into one list of words (membership mask << (32 - group_rows)) |
+ * column, written at the CSR offset of the group's first row (uwords u32[nnz], ucnt i32[ceil(n /
+ * group_rows)] = union length per group); sc_csr_lag_moran_grouped walks each union once and adds every
+ * gathered value to the rows that own it.  n <= 2^(32 - group_rows).  Agrees with sc_csr_lag_moran to FP32
+ * rounding (different summation order).  cell_obs / cell_cnt as in sc_perm_null_values (or NULL).
+ * Workspace: sc_csr_lag_moran_workspace_bytes. */
+SC_API int sc_graph_group_build(const int32_t* indptr, const int32_t* indices, int64_t n, int k_fixed,
+                                int group_rows, uint32_t* uwords, int32_t* ucnt, sc_stream_t stream);
+SC_API int sc_csr_lag_moran_grouped(const int32_t* indptr, int64_t n, int k_fixed, int group_rows,
+                                    const uint32_t* uwords, const int32_t* ucnt, const float* Z,
+                                    int64_t ldz, int g, float* lag, float* local, int64_t ldl,
+                                    double* num, double* den, const float* cell_obs, int32_t* cell_cnt,
+                                    int64_t ldc, void* ws, size_t ws_bytes, sc_stream_t stream);
+
 /* ---------------------------------------------------------------------------------------------
  * Permutation nulls.
  *

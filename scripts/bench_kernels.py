@@ -91,6 +91,25 @@ if want("lagsweep"):
     del os.environ["SC_LAG_Q"], os.environ["SC_LAG_CHUNK"]
     out["lag_sweep_ms_[with_lag,stat_only]"] = sweep
 
+if want("laggroup"):
+    # experimental row-group lag (SC_LAG_GROUP): gathers shared between 2 / 4 / 8 consecutive rows
+    res = {}
+    for rows in (0, 2, 4, 8):
+        gs.groups = None
+        if rows:
+            res[f"group{rows}_build_ms"] = round(timed(lambda: eng.group_graph(gs, rows)), 3)
+            res[f"group{rows}_union_fraction"] = round(float(gs.groups[2].sum().item()) / nnz, 4)
+        res[f"group{rows}_lag_ms_[with_lag,stat_only]"] = [round(timed(lambda: eng.lag_moran(gs, std.Z, g)), 3),
+                                                          round(timed(lambda: eng.lag_moran(gs, std.Z, g, want_lag=False)), 3)]
+        if rows:
+            num_g, _, _, _ = eng.lag_moran(gs, std.Z, g, want_lag=False)
+            res[f"group{rows}_num_rel_diff_vs_default"] = float(((num_g - num_ref).abs() / num_ref.abs().clamp_min(1e-30)).max())
+            res[f"group{rows}_values_null_ms_per_perm"] = round(timed(lambda: eng.perm_null_values(gs, std.Z, g, 2, seed=1), reps=2) / 2, 3)
+        else:
+            num_ref, _, _, _ = eng.lag_moran(gs, std.Z, g, want_lag=False)
+    gs.groups = None
+    out["lag_row_groups"] = res
+
 if want("values"):
     k1 = nnz / n + 1.0
     P = 4

@@ -76,6 +76,9 @@ class DeviceGraph:
     k_fixed: int = 0
     weights: Optional[torch.Tensor] = None
     dist: Optional[torch.Tensor] = None
+    # experimental row-group form for the lag kernel: (group_rows, union words int32[nnz], union length
+    # per group int32[ceil(n / group_rows)]); see group_graph()
+    groups: Optional[Tuple[int, torch.Tensor, torch.Tensor]] = None
 
     @property
     def nnz(self) -> int:
@@ -250,7 +253,42 @@ def relabel_graph(graph: DeviceGraph, co: CellOrder) -> DeviceGraph:
         "sc_graph_relabel",
     )
     _count(3 if graph.indptr is not None else 1)
-    return DeviceGraph(n=graph.n, indices=out_idx, indptr=out_ptr, k_fixed=graph.k_fixed, weights=out_w)
+    out = DeviceGraph(n=graph.n, indices=out_idx, indptr=out_ptr, k_fixed=graph.k_fixed, weights=out_w)
+    rows = _lag_group_rows()
+    if rows and out_w is None and graph.n <= 2 ** (32 - rows):
+        group_graph(out, rows)
+    return out
+
+
+def _lag_group_rows() -> int:
+    """``SC_LAG_GROUP=2|4|8`` (experiment switch, default off): graphs put into spatial order also get the
+    row-group form, and ``lag_moran`` then runs ``sc_csr_lag_moran_grouped`` on them."""
+    v = os.environ.get("SC_LAG_GROUP", "")
+    if v in ("", "0"):
+        return 0
+    if v not in ("2", "4", "8"):
+        raise ValueError(f"SC_LAG_GROUP must be 2, 4 or 8, got '{v}'")
+    return int(v)
+
+
+def group_graph(graph: DeviceGraph, group_rows: int) -> DeviceGraph:
+    """``sc_graph_group_build``: merge the neighbour lists of every ``group_rows`` consecutive rows into one
+    union list with membership masks (rows must be column-sorted; binary graphs only).  Pays off when
+    consecutive rows are spatial neighbours, i.e. after ``relabel_graph``."""
+    if graph.weights is not None:
+        raise ValueError("group_graph: explicitly weighted graphs are not supported")
+    L = _lib.lib()
+    dev = graph.indices.device
+    uwords = torch.empty(graph.nnz, dtype=torch.int32, device=dev)
+    ucnt = torch.empty((graph.n + group_rows - 1) // group_rows, dtype=torch.int32, device=dev)
+    check(
+        L.sc_graph_group_build(_ptr(graph.indptr), _ptr(graph.indices), graph.n, int(graph.k_fixed), int(group_rows),
+                               _ptr(uwords), _ptr(ucnt), _stream()),
+        "sc_graph_group_build",
+    )
+    _count()
+    graph.groups = (int(group_rows), uwords, ucnt)
+    return graph
 
 
 def gather_rows(src: torch.Tensor, rows: torch.Tensor) -> torch.Tensor:
@@ -495,6 +533,16 @@ def lag_moran(graph: DeviceGraph, Z: torch.Tensor, g: int, want_lag: bool = True
     num = torch.empty(g, dtype=torch.float64, device=dev)
     den = torch.empty(g, dtype=torch.float64, device=dev)
     ws = _workspace(L.sc_csr_lag_moran_workspace_bytes(n, g), dev)
+    if graph.groups is not None and graph.weights is None:
+        rows, uwords, ucnt = graph.groups
+        check(
+            L.sc_csr_lag_moran_grouped(_ptr(graph.indptr), n, int(graph.k_fixed), rows, _ptr(uwords), _ptr(ucnt), _ptr(Z), ld, g,
+                                       _ptr(lag), _ptr(local), ld, _ptr(num), _ptr(den), None, None, 0, _ptr(ws), ws.numel(),
+                                       _stream()),
+            "sc_csr_lag_moran_grouped",
+        )
+        _count(2)
+        return num, den, lag, local
     check(
         L.sc_csr_lag_moran(_ptr(graph.indptr), _ptr(graph.indices), _ptr(graph.weights), n, int(graph.k_fixed), _ptr(Z),
                            ld, g, _ptr(lag), _ptr(local), ld, _ptr(num), _ptr(den), _ptr(ws), ws.numel(), _stream()),
@@ -540,6 +588,24 @@ def perm_null_values(graph: DeviceGraph, Zy: torch.Tensor, g: int, n_perms: int,
     n, ld = Zy.shape
     source, pidx = _perm_source(perm_idx, n, n_perms)
     sims = torch.empty((n_perms, g), dtype=torch.float64, device=Zy.device)
+    if graph.groups is not None and graph.weights is None and Zx is None and ld >= 32:
+        # experimental (SC_LAG_GROUP): the same materialised scheme -- permuted copy of Z, then lag and
+        # local statistic of the copy -- composed from sc_gather_rows and the row-group lag kernel
+        rows, uwords, ucnt = graph.groups
+        ws = _workspace(L.sc_csr_lag_moran_workspace_bytes(n, g), Zy.device)
+        den = torch.empty(g, dtype=torch.float64, device=Zy.device)
+        ldc = cell_cnt.shape[1] if cell_cnt is not None else 0
+        for p in range(n_perms):
+            perm = pidx[p] if pidx is not None else philox_permutation(seed, perm_offset + p, n, device=Zy.device)
+            Zp = gather_rows(Zy, perm)
+            check(
+                L.sc_csr_lag_moran_grouped(_ptr(graph.indptr), n, int(graph.k_fixed), rows, _ptr(uwords), _ptr(ucnt), _ptr(Zp), ld,
+                                           g, None, None, ld, _ptr(sims[p]), _ptr(den), _ptr(cell_obs), _ptr(cell_cnt), ldc,
+                                           _ptr(ws), ws.numel(), _stream()),
+                "sc_csr_lag_moran_grouped",
+            )
+            _count(2)
+        return sims
     ws = _workspace(L.sc_perm_null_values_workspace_bytes(n, g), Zy.device)
     ldc = cell_cnt.shape[1] if cell_cnt is not None else 0
     check(

@@ -156,3 +156,20 @@ def test_argument_validation_of_the_wider_abi_without_gpu():
     assert L.sc_local_moran_finish_workspace_bytes(100, 999) >= 100 * 1000 * 8
     assert L.sc_cross_nn_workspace_bytes(1_000_000) > 1_000_000 * 16
     assert L.sc_launch_count() >= 0
+
+
+def test_row_group_lag_core_on_the_host(tmp_path):
+    """The __host__ __device__ core of the experimental row-group lag kernel (union build with membership
+    masks + masked accumulation, ``csrc/lag_group_core.cuh``) compiled for the CPU and checked against plain
+    per-row sums -- the part of that kernel that can be verified without a GPU."""
+    import shutil
+    import subprocess
+
+    nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
+    if not os.path.exists(nvcc):
+        pytest.skip("nvcc not available")
+    exe = str(tmp_path / "lag_group_host_test")
+    src = os.path.join(ROOT, "tests", "native", "lag_group_host_test.cu")
+    subprocess.run([nvcc, "-O2", "-std=c++17", "-Wno-deprecated-gpu-targets", "-o", exe, src], check=True, capture_output=True)
+    out = subprocess.run([exe], check=True, capture_output=True, text=True).stdout
+    assert out.count(" ok") == 21 and "R=8 n=1001 k_fixed=6" in out
