@@ -394,7 +394,9 @@ def run_b200(args):
     # ---------------- CPU baseline on a bounded sample (rank 0, single-GPU runs only) --------------
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:
-        cpu = cpu_baseline_sample(w, coords, radius, args.seed)
+        cpu = cpu_baseline_sample(w, coords, radius, args.seed, values=isinstance(values_null, dict) and "error" not in values_null)
+        if "values_null" in cpu:  # the CPU arm of the second null sits with its GPU figure
+            values_null["cpu_baseline"] = cpu.pop("values_null")
 
     if rank == 0:
         line = {
@@ -457,7 +459,32 @@ def cpu_sample_plan(w):
     return g, p
 
 
-def cpu_baseline_sample(w, coords, radius, seed, graph=None):
+def cpu_values_null_sample(w, graph, seed):
+    """CPU arm of the ``values_null`` leg: the permutation loop of the reference's own ``local_morans_i``
+    [R spatial/autocorrelation.py:877-884] -- ``Zs = Z[perm]; lag = W @ Zs; I = Zs * lag`` with scipy's
+    CSR x dense product in FP32 -- as restated in oracle/restate.py, on a bounded sample (full N, a few
+    genes, one or two permutations).  scipy's product is single-threaded, as in the reference."""
+    from oracle import restate
+
+    n = w["n"]
+    nnz = graph.nnz
+    g_cpu = int(max(2, min(w["g"], 8, 4e9 / max(nnz, 1))))
+    p_cpu = 2 if nnz * g_cpu <= 2e9 else 1
+    rng = np.random.default_rng(seed + 17)
+    Z = rng.standard_normal((n, g_cpu), dtype=np.float32)
+    W = graph.astype(np.float32)
+    perms = restate.squidpy_perm_indices(n, p_cpu, seed + 17)  # default_rng(seed).permutation(n) per permutation
+    restate.morans_values_null(Z[:, :1], W, perms[:1])  # touch pages
+    t0 = time.perf_counter()
+    restate.morans_values_null(Z, W, perms)
+    dt = time.perf_counter() - t0
+    return {"value": round(g_cpu * p_cpu / dt, 2), "unit": UNIT, "cores": 1, "kind": "port",
+            "sample": f"full N={n} cells, {g_cpu} genes x {p_cpu} permutation(s), oracle/restate.py morans_values_null "
+                      f"(the reference's own scipy CSR x dense loop, FP32)",
+            "seconds": round(dt, 2)}
+
+
+def cpu_baseline_sample(w, coords, radius, seed, graph=None, values=False):
     from oracle import port, restate
 
     port.use_all_cores()
@@ -473,11 +500,17 @@ def cpu_baseline_sample(w, coords, radius, seed, graph=None):
     port.morans_i(graph, vals, perms)
     dt = time.perf_counter() - t0
     value = g_cpu * p_cpu / dt
-    return {"value": round(value, 2), "unit": UNIT, "cores": port.threads(), "kind": "port",
-            "sample": f"full N={n} cells, {g_cpu} genes x {p_cpu} permutations (+1 observed pass), "
-                      f"oracle/moran_port.c (OpenMP over genes, CSR row gather per permutation)",
-            "seconds": round(dt, 2), "graph_build_s": None if graph_s is None else round(graph_s, 2),
-            "graph_build": "sklearn NearestNeighbors (squidpy's call), n_jobs=-1"}
+    out = {"value": round(value, 2), "unit": UNIT, "cores": port.threads(), "kind": "port",
+           "sample": f"full N={n} cells, {g_cpu} genes x {p_cpu} permutations (+1 observed pass), "
+                     f"oracle/moran_port.c (OpenMP over genes, CSR row gather per permutation)",
+           "seconds": round(dt, 2), "graph_build_s": None if graph_s is None else round(graph_s, 2),
+           "graph_build": "sklearn NearestNeighbors (squidpy's call), n_jobs=-1"}
+    if values:
+        try:
+            out["values_null"] = cpu_values_null_sample(w, graph, seed)
+        except Exception as exc:  # secondary figure
+            out["values_null"] = {"error": f"{type(exc).__name__}: {exc}"}
+    return out
 
 
 def run_reference(args):
