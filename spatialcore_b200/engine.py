@@ -17,18 +17,11 @@ import torch
 from spatialcore_b200 import _lib
 from spatialcore_b200._lib import SC_F32, SC_F64, SC_PERM_PHILOX, SC_PERM_REPLAY, check
 
-_launches = 0  # per-call estimates kept for reference; bench.py reports the library's own counter
-
 
 def launches() -> int:
     """Kernels launched by ``libsc_b200.so`` in this process so far (``sc_launch_count``: incremented at
     every launch site of the library; CUB sorts / scans it calls are not counted)."""
     return int(_lib.lib().sc_launch_count())
-
-
-def _count(n: int = 1) -> None:
-    global _launches
-    _launches += n
 
 
 def _ptr(t: Optional[torch.Tensor]) -> Optional[int]:
@@ -161,7 +154,6 @@ def knn_graph(
                       int(n_types), _ptr(profile), _ptr(ws), ws.numel(), _stream()),
         "sc_grid_knn",
     )
-    _count(7)
     graph = DeviceGraph(n=n, indices=idx, k_fixed=kk, dist=dist) if want_idx else None
     return graph, order, profile
 
@@ -194,7 +186,6 @@ def radius_graph(
                                _ptr(profile), _ptr(ws), ws.numel(), _stream()),
         "sc_grid_radius_count",
     )
-    _count(9)
     if not want_graph:
         return None, profile
     nnz = int(nnz_t.item())  # host sync: the caller-owned index buffer must be sized
@@ -209,7 +200,6 @@ def radius_graph(
                                   nnz * (12 if want_dist else 4), _ptr(ws), ws.numel(), _stream()),
             "sc_grid_radius_fill",
         )
-        _count(1)
     return DeviceGraph(n=n, indices=indices, indptr=indptr, dist=dist), profile
 
 
@@ -233,7 +223,6 @@ def spatial_order(coords, device="cuda") -> CellOrder:
     rank = torch.empty(n, dtype=torch.int32, device=c.device)
     ws = _workspace(L.sc_spatial_order_workspace_bytes(n), c.device)
     check(L.sc_spatial_order(_ptr(c), n, _ptr(order), _ptr(rank), _ptr(ws), ws.numel(), _stream()), "sc_spatial_order")
-    _count(6)
     return CellOrder(order=order, rank=rank)
 
 
@@ -252,7 +241,6 @@ def relabel_graph(graph: DeviceGraph, co: CellOrder) -> DeviceGraph:
                            _stream()),
         "sc_graph_relabel",
     )
-    _count(3 if graph.indptr is not None else 1)
     out = DeviceGraph(n=graph.n, indices=out_idx, indptr=out_ptr, k_fixed=graph.k_fixed, weights=out_w)
     rows = _lag_group_rows()
     if rows and out_w is None and graph.n <= 2 ** (32 - rows):
@@ -286,7 +274,6 @@ def group_graph(graph: DeviceGraph, group_rows: int) -> DeviceGraph:
                                _ptr(uwords), _ptr(ucnt), _stream()),
         "sc_graph_group_build",
     )
-    _count()
     graph.groups = (int(group_rows), uwords, ucnt)
     return graph
 
@@ -298,7 +285,6 @@ def gather_rows(src: torch.Tensor, rows: torch.Tensor) -> torch.Tensor:
     n, ld = src.shape
     dst = torch.empty_like(src)
     check(L.sc_gather_rows(_ptr(src), src.stride(0), n, ld, _ptr(rows), _ptr(dst), ld, _stream()), "sc_gather_rows")
-    _count()
     return dst
 
 
@@ -308,7 +294,6 @@ def conjugate_perms(perm_idx: torch.Tensor, co: CellOrder) -> torch.Tensor:
     P, n = perm_idx.shape
     out = torch.empty_like(perm_idx)
     check(L.sc_perm_conjugate(_ptr(perm_idx), n, P, _ptr(co.order), _ptr(co.rank), _ptr(out), _stream()), "sc_perm_conjugate")
-    _count()
     return out
 
 
@@ -334,7 +319,6 @@ def nbhd_counts(graph: DeviceGraph, labels: torch.Tensor, n_types: int) -> torch
                          int(n_types), _ptr(prof), _stream()),
         "sc_nbhd_counts",
     )
-    _count()
     return prof
 
 
@@ -346,7 +330,6 @@ def profile_normalize(profile: torch.Tensor, normalize: bool) -> int:
         L.sc_profile_normalize(_ptr(profile), profile.shape[0], profile.shape[1], int(normalize), _ptr(n_empty), _stream()),
         "sc_profile_normalize",
     )
-    _count()
     return int(n_empty.item())
 
 
@@ -360,7 +343,6 @@ def graph_moments(graph: DeviceGraph) -> Tuple[float, float, float]:
                            _ptr(out), _ptr(ws), ws.numel(), _stream()),
         "sc_graph_moments",
     )
-    _count(3)
     s = out.cpu().numpy()
     return float(s[0]), float(s[1]), float(s[2])
 
@@ -404,7 +386,6 @@ def zscore_dense(X: torch.Tensor, cols: Optional[torch.Tensor] = None, rows: Opt
                     _ptr(Z), ld, _ptr(mean), _ptr(std), _ptr(zero), _ptr(ws), ws.numel(), _stream()),
         "sc_zscore",
     )
-    _count(3)
     return Standardized(Z=Z, g=g, mean=mean, std=std, zero_var=zero)
 
 
@@ -431,7 +412,6 @@ def zscore_apply(X: torch.Tensor, mean: torch.Tensor, std: torch.Tensor, zero_va
                           _ptr(rows), _ptr(mean), _ptr(std), _ptr(zero_var), _ptr(out), ld, _stream()),
         "sc_zscore_apply",
     )
-    _count()
     return out
 
 
@@ -451,7 +431,6 @@ def zscore_scatter(X: torch.Tensor, mean: torch.Tensor, std: torch.Tensor, zero_
                             C.cast(arr, C.c_void_p), len(peer_ptrs), int(ld), _stream()),
         "sc_zscore_scatter",
     )
-    _count()
 
 
 def densify_csr(indptr: torch.Tensor, indices: torch.Tensor, data: torch.Tensor, n: int, n_cols: int,
@@ -467,7 +446,6 @@ def densify_csr(indptr: torch.Tensor, indices: torch.Tensor, data: torch.Tensor,
                          _ptr(colmap), g_out, _ptr(out), ld, _stream()),
         "sc_csr_densify",
     )
-    _count(2)
     return out
 
 
@@ -541,14 +519,12 @@ def lag_moran(graph: DeviceGraph, Z: torch.Tensor, g: int, want_lag: bool = True
                                        _stream()),
             "sc_csr_lag_moran_grouped",
         )
-        _count(2)
         return num, den, lag, local
     check(
         L.sc_csr_lag_moran(_ptr(graph.indptr), _ptr(graph.indices), _ptr(graph.weights), n, int(graph.k_fixed), _ptr(Z),
                            ld, g, _ptr(lag), _ptr(local), ld, _ptr(num), _ptr(den), _ptr(ws), ws.numel(), _stream()),
         "sc_csr_lag_moran",
     )
-    _count(3)
     return num, den, lag, local
 
 
@@ -576,7 +552,6 @@ def perm_null_graph_rows(A: torch.Tensor, B: torch.Tensor, g: int, n_perms: int,
                                   int(perm_offset), int(n_perms), _ptr(sims), _ptr(ws), ws.numel(), _stream()),
         "sc_perm_null_graph_rows",
     )
-    _count(2 * ((n_perms + 15) // 16))
     return sims
 
 
@@ -604,7 +579,6 @@ def perm_null_values(graph: DeviceGraph, Zy: torch.Tensor, g: int, n_perms: int,
                                            _ptr(ws), ws.numel(), _stream()),
                 "sc_csr_lag_moran_grouped",
             )
-            _count(2)
         return sims
     ws = _workspace(L.sc_perm_null_values_workspace_bytes(n, g), Zy.device)
     ldc = cell_cnt.shape[1] if cell_cnt is not None else 0
@@ -615,7 +589,6 @@ def perm_null_values(graph: DeviceGraph, Zy: torch.Tensor, g: int, n_perms: int,
                               _stream()),
         "sc_perm_null_values",
     )
-    _count(3 * n_perms if ld >= 32 else 2 * ((n_perms + 3) // 4))
     return sims
 
 
@@ -623,7 +596,6 @@ def philox_permutation(seed: int, perm_index: int, n: int, device="cuda") -> tor
     L = _lib.lib()
     out = torch.empty(n, dtype=torch.int32, device=device)
     check(L.sc_philox_permutation(int(seed) & (2**64 - 1), int(perm_index), n, _ptr(out), _stream()), "sc_philox_permutation")
-    _count()
     return out
 
 
@@ -636,7 +608,6 @@ def null_accumulate(sims: torch.Tensor, scale: Optional[torch.Tensor], obs: torc
                              _ptr(ssq), _stream()),
         "sc_null_accumulate",
     )
-    _count()
 
 
 def lee_gemm(A: torch.Tensor, B: torch.Tensor, g: int, impl: int = 0) -> torch.Tensor:
@@ -649,7 +620,6 @@ def lee_gemm(A: torch.Tensor, B: torch.Tensor, g: int, impl: int = 0) -> torch.T
         L.sc_lee_gemm(_ptr(A), A.shape[1], _ptr(B), B.shape[1], n, g, _ptr(out), g, int(impl), _ptr(ws), ws.numel(), _stream()),
         "sc_lee_gemm",
     )
-    _count(2)
     return out
 
 
@@ -659,7 +629,6 @@ def lee_abs_ge_accumulate(Lp: torch.Tensor, L_obs: torch.Tensor, cnt: torch.Tens
     g = L_obs.shape[0]
     check(Lb.sc_lee_abs_ge_accumulate(_ptr(Lp), Lp.stride(0), _ptr(L_obs), L_obs.stride(0), g, _ptr(cnt), cnt.stride(0), _stream()),
           "sc_lee_abs_ge_accumulate")
-    _count()
 
 
 # --------------------------------------------------------------------------------------------------
@@ -701,7 +670,6 @@ class KMeansDevice:
                                _ptr(self.mind) if want_mind else None, _ptr(self.out), _ptr(self.ws), self.ws.numel(), _stream()),
             "sc_kmeans_assign",
         )
-        _count(2)
         o = self.out.cpu().numpy()
         kd = self.k * self.d
         return o[:kd].reshape(self.k, self.d).copy(), o[kd:kd + self.k].copy(), float(o[kd + self.k]), int(round(o[kd + self.k + 1]))
@@ -717,7 +685,6 @@ class KMeansDevice:
                                      _ptr(self.ws), self.ws.numel(), _stream()),
             "sc_kmeans_pp_potential",
         )
-        _count(2)
         if commit >= 0:
             self.mind, self.mind_tmp = self.mind_tmp, self.mind
         return pot.cpu().numpy()
@@ -732,7 +699,6 @@ class KMeansDevice:
                                   self.ws_sample.numel(), _stream()),
             "sc_kmeans_pp_sample",
         )
-        _count(3)
         return idx.cpu().numpy().astype(np.int64)
 
     def rows(self, idx) -> np.ndarray:
@@ -755,7 +721,6 @@ def cross_nn(targets, queries, device="cuda") -> Tuple[np.ndarray, np.ndarray]:
     ws = _workspace(L.sc_cross_nn_workspace_bytes(t.shape[0]), t.device)
     check(L.sc_cross_nn(_ptr(t), t.shape[0], _ptr(q), q.shape[0], _ptr(idx), _ptr(dist), _ptr(ws), ws.numel(), _stream()),
           "sc_cross_nn")
-    _count(8)
     return dist.cpu().numpy(), idx.cpu().numpy().astype(np.int64)
 
 
@@ -768,7 +733,6 @@ def pairwise_reduce(a, b, device="cuda") -> Tuple[float, float]:
     ws = _workspace(L.sc_pairwise_reduce_workspace_bytes(), A.device)
     check(L.sc_pairwise_reduce(_ptr(A), A.shape[0], _ptr(B), B.shape[0], _ptr(out), _ptr(ws), ws.numel(), _stream()),
           "sc_pairwise_reduce")
-    _count(2)
     o = out.cpu().numpy()
     return float(o[0]), float(o[1])
 
@@ -795,5 +759,4 @@ def local_moran_finish(cnt: Optional[torch.Tensor], Z: torch.Tensor, lag: torch.
                                 _ptr(ws), ws.numel(), _stream()),
         "sc_local_moran_finish",
     )
-    _count(4)
     return outs[0], outs[1], outs[2], outs[3], outs[4], quad
