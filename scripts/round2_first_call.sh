@@ -20,6 +20,7 @@ SC_TEST_EXPERIMENTAL=1 python -m pytest tests/test_zz_gpu_experimental.py -m gpu
 for cfg in C4 C2; do
   python scripts/bench_kernels.py $cfg laggroup > gpurun_out/r02_laggroup_${cfg}_align8.json 2> gpurun_out/r02_laggroup_${cfg}_align8.err
   SC_ROW_ALIGN=32 python scripts/bench_kernels.py $cfg laggroup > gpurun_out/r02_laggroup_${cfg}_align32.json 2> gpurun_out/r02_laggroup_${cfg}_align32.err
+  SC_ORDER_POINTS_PER_CELL=2 python scripts/bench_kernels.py $cfg laggroup > gpurun_out/r02_laggroup_${cfg}_ppc2.json 2> gpurun_out/r02_laggroup_${cfg}_ppc2.err
 done
 SC_ROW_ALIGN=32 python -m pytest tests/test_gpu_parity.py -m gpu -q > gpurun_out/r02_pytest_gpu_align32.log 2>&1; echo "pytest align32 rc=$?"
 tail -3 gpurun_out/r02_pytest_gpu.log gpurun_out/r02_pytest_experimental.log gpurun_out/r02_pytest_gpu_align32.log
