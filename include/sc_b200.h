@@ -4,8 +4,8 @@
  *
  * The reference has no FFI: its boundary is the Python function API
  * (src/spatialcore/spatial/__init__.py:11-52).  Each export below replaces the third-party
- * compiled routine the reference calls at the cited line; the Python layer
- * (spatialcore_b200/spatial/*.py) keeps the reference's signatures and calls these through ctypes.
+ * compiled routine the reference calls at the cited line; the Python layer (the modules under
+ * spatialcore_b200/spatial/) keeps the reference's signatures and calls these through ctypes.
  *
  * Conventions
  *   - every pointer is a DEVICE pointer on the current CUDA device unless marked host;

@@ -173,3 +173,30 @@ def test_row_group_lag_core_on_the_host(tmp_path):
     subprocess.run([nvcc, "-O2", "-std=c++17", "-Wno-deprecated-gpu-targets", "-o", exe, src], check=True, capture_output=True)
     out = subprocess.run([exe], check=True, capture_output=True, text=True).stdout
     assert out.count(" ok") == 21 and "R=8 n=1001 k_fixed=6" in out
+
+
+def test_header_is_plain_c_and_links_from_c(tmp_path):
+    """The boundary is a C ABI: ``include/sc_b200.h`` must compile as C99 (no C++ in the signatures) and a
+    C program must link against the shared library and call it."""
+    import shutil
+    import subprocess
+
+    from spatialcore_b200 import _lib
+
+    gcc = shutil.which("gcc")
+    if gcc is None:
+        pytest.skip("gcc not available")
+    src = tmp_path / "use_abi.c"
+    src.write_text(
+        '#include "sc_b200.h"\n#include <stdio.h>\n'
+        "int main(void) {\n"
+        "  size_t ws = sc_grid_knn_workspace_bytes(1000, 6);\n"
+        "  int rc = sc_philox_permutation_host(1u, 0, 0, (int32_t*)0);\n"
+        '  printf("%d %d %d %s\\n", sc_version(), ws > 0, rc, sc_last_error());\n'
+        "  return 0;\n}\n")
+    exe = str(tmp_path / "use_abi")
+    libdir = os.path.dirname(_lib.LIB_PATH)
+    subprocess.run([gcc, "-std=c99", "-pedantic", "-Wall", "-Werror", "-I", os.path.join(ROOT, "include"), str(src), "-o", exe,
+                    "-L", libdir, "-l:libsc_b200.so", f"-Wl,-rpath,{libdir}"], check=True, capture_output=True)
+    out = subprocess.run([exe], check=True, capture_output=True, text=True).stdout.split(None, 3)
+    assert int(out[0]) >= 100 and out[1] == "1" and out[2] == "-1" and "bad argument" in out[3]
