@@ -11,8 +11,8 @@ mkdir -p gpurun_out
 NCU="ncu --set full --clock-control none --import-source on -c 1"
 SC_ROW_ALIGN=32 $NCU -k regex:lag_stat_kernel -s 4 -o gpurun_out/r02_lag_stat_align32_c4 \
     python scripts/bench_kernels.py C4 lag > gpurun_out/r02_ncu_lag_align32.log 2>&1
-$NCU -k regex:lag_group_kernel -s 2 -o gpurun_out/r02_lag_group4_c4 \
+$NCU -k "regex:lag_group_kernel.*4.*8" -s 2 -o gpurun_out/r02_lag_group4_c4 \
     python scripts/bench_kernels.py C4 laggroup > gpurun_out/r02_ncu_lag_group.log 2>&1
-SC_ROW_ALIGN=32 $NCU -k regex:lag_group_kernel -s 2 -o gpurun_out/r02_lag_group4_align32_c4 \
+SC_ROW_ALIGN=32 $NCU -k "regex:lag_group_kernel.*4.*8" -s 2 -o gpurun_out/r02_lag_group4_align32_c4 \
     python scripts/bench_kernels.py C4 laggroup > gpurun_out/r02_ncu_lag_group_align32.log 2>&1
 ls -la gpurun_out/*.ncu-rep
