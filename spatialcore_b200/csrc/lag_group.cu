@@ -33,104 +33,30 @@ group_build_kernel(const int32_t* __restrict__ indptr, const int32_t* __restrict
     ucnt[a] = group_union<R>(indptr, indices, n, k_fixed, a, uwords);
 }
 
-__device__ __forceinline__ float4 gather4(const char* base, uint32_t j, uint32_t ld_bytes) {
-  return __ldg(reinterpret_cast<const float4*>(base + (uint64_t)j * ld_bytes));
-}
-
-// Geometry as lag_stat_kernel: blockIdx.x = column block of Q float4 quads, blockIdx.y strides over chunks
-// of `chunk_groups` groups; a thread owns one (group, float4 column quad) and R float4 accumulators.
+// Per-thread work in lag_group_core.cuh (shared with the host-side test); here: launch geometry and the
+// fixed-order reduction of the per-thread Moran sums over the CTA.
 template <int R, int Q>
 __global__ void __launch_bounds__(kThreads, R >= 8 ? 2 : 3)
-lag_group_kernel(const int32_t* __restrict__ indptr, int k_fixed, const uint32_t* __restrict__ uwords,
-                 const int32_t* __restrict__ ucnt, int64_t n, int64_t n_groups,
-                 const float* __restrict__ Z, int64_t ldz, float* __restrict__ lag,
-                 float* __restrict__ local, int64_t ldl, double* __restrict__ partial,
-                 const float* __restrict__ cell_obs, int32_t* __restrict__ cell_cnt, int64_t ldc,
-                 int64_t n_chunks, int chunk_groups) {
-  constexpr int kSlots = kThreads / Q;  // groups per pass
+lag_group_kernel(const __grid_constant__ LagGroupArgs args, double* __restrict__ partial) {
+  constexpr int kSlots = kThreads / Q;
   __shared__ double sh[2][kSlots][Q][4];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int q = lane & (Q - 1);
   const int slot = warp * (32 / Q) + lane / Q;
   const int64_t col = ((int64_t)blockIdx.x * Q + q) * 4;
-  const bool active = col < ldz;
-  const char* zbase = reinterpret_cast<const char*>(Z + col);
-  const uint32_t ldzb = (uint32_t)ldz * 4u;
   double num[4] = {0, 0, 0, 0}, den[4] = {0, 0, 0, 0};
-
-  for (int64_t chunk = blockIdx.y; chunk < n_chunks; chunk += gridDim.y) {
-    const int64_t g0 = chunk * chunk_groups;
-#pragma unroll 1
-    for (int pass = 0; pass < chunk_groups; pass += kSlots) {
-      const int64_t a = g0 + pass + slot;
-      if (a >= n_groups || !active) continue;
-      const int64_t row0 = a * R;
-      int64_t b0;
-      int deg0;
-      row_span(indptr, k_fixed, row0, &b0, &deg0);
-      const uint32_t* __restrict__ up = uwords + b0;
-      const int cnt = ucnt[a];
-      float4 acc[R];
-#pragma unroll
-      for (int r = 0; r < R; ++r) acc[r] = make_float4(0.f, 0.f, 0.f, 0.f);
-      int t = 0;
-#pragma unroll 1
-      for (; t + 4 <= cnt; t += 4) {
-        uint32_t w[4];
-        float4 v[4];
-#pragma unroll
-        for (int u = 0; u < 4; ++u) w[u] = up[t + u];
-#pragma unroll
-        for (int u = 0; u < 4; ++u) v[u] = gather4(zbase, word_column<R>(w[u]), ldzb);
-#pragma unroll
-        for (int u = 0; u < 4; ++u) scatter_add<R>(acc, w[u], v[u]);
-      }
-#pragma unroll 1
-      for (; t < cnt; ++t) {
-        const uint32_t w = up[t];
-        scatter_add<R>(acc, w, gather4(zbase, word_column<R>(w), ldzb));
-      }
-#pragma unroll
-      for (int r = 0; r < R; ++r) {
-        const int64_t row = row0 + r;
-        if (row >= n) break;
-        int64_t b;
-        int deg;
-        row_span(indptr, k_fixed, row, &b, &deg);
-        const float inv = (deg > 0) ? 1.f / (float)deg : 0.f;
-        float4 s = acc[r];
-        s.x *= inv; s.y *= inv; s.z *= inv; s.w *= inv;
-        const float4 z = ldg4(Z + row * ldz + col);
-        const float4 loc = make_float4(z.x * s.x, z.y * s.y, z.z * s.z, z.w * s.w);
-        if (lag) *reinterpret_cast<float4*>(lag + row * ldl + col) = s;
-        if (local) *reinterpret_cast<float4*>(local + row * ldl + col) = loc;
-        if (cell_cnt) {
-          const float4 o = ldg4(cell_obs + row * ldc + col);
-          int4* cp = reinterpret_cast<int4*>(cell_cnt + row * ldc + col);
-          int4 cc = *cp;
-          cc.x += fabsf(loc.x) >= fabsf(o.x); cc.y += fabsf(loc.y) >= fabsf(o.y);
-          cc.z += fabsf(loc.z) >= fabsf(o.z); cc.w += fabsf(loc.w) >= fabsf(o.w);
-          *cp = cc;
-        }
-        const double zx = z.x, zy = z.y, zz = z.z, zw = z.w;
-        num[0] = fma(zx, (double)s.x, num[0]); den[0] = fma(zx, zx, den[0]);
-        num[1] = fma(zy, (double)s.y, num[1]); den[1] = fma(zy, zy, den[1]);
-        num[2] = fma(zz, (double)s.z, num[2]); den[2] = fma(zz, zz, den[2]);
-        num[3] = fma(zw, (double)s.w, num[3]); den[3] = fma(zw, zw, den[3]);
-      }
-    }
-  }
+  lag_group_thread<R, Q, kThreads>(args, threadIdx.x, blockIdx.x, blockIdx.y, gridDim.y, num, den);
 #pragma unroll
   for (int c = 0; c < 4; ++c) { sh[0][slot][q][c] = num[c]; sh[1][slot][q][c] = den[c]; }
   __syncthreads();
-  if (slot == 0 && active) {
-    double* p = partial + ((int64_t)blockIdx.y * 2) * ldz + col;
+  if (slot == 0 && col < args.ldz) {
+    double* p = partial + ((int64_t)blockIdx.y * 2) * args.ldz + col;
 #pragma unroll
     for (int c = 0; c < 4; ++c) {
       double s0 = 0, s1 = 0;
 #pragma unroll 4
       for (int r = 0; r < kSlots; ++r) { s0 += sh[0][r][q][c]; s1 += sh[1][r][q][c]; }
-      p[c] = s0; p[ldz + c] = s1;
+      p[c] = s0; p[args.ldz + c] = s1;
     }
   }
 }
@@ -167,9 +93,11 @@ int launch_group(const int32_t* indptr, int k_fixed, const uint32_t* uwords, con
   if (by > n_chunks) by = n_chunks;
   if (by > kMaxBlocks) by = kMaxBlocks;
   if (by < 1) by = 1;
-  lag_group_kernel<R, Q><<<dim3(bx, (unsigned)by), kThreads, 0, st>>>(
-      indptr, k_fixed, uwords, ucnt, n, n_groups, Z, ldz, lag, local, ldl, partial, cell_obs, cell_cnt, ldc,
-      n_chunks, chunk_groups);
+  LagGroupArgs args;
+  args.indptr = indptr; args.k_fixed = k_fixed; args.uwords = uwords; args.ucnt = ucnt;
+  args.n = n; args.n_groups = n_groups; args.Z = Z; args.ldz = ldz; args.lag = lag; args.local = local; args.ldl = ldl;
+  args.cell_obs = cell_obs; args.cell_cnt = cell_cnt; args.ldc = ldc; args.n_chunks = n_chunks; args.chunk_groups = chunk_groups;
+  lag_group_kernel<R, Q><<<dim3(bx, (unsigned)by), kThreads, 0, st>>>(args, partial);
   SC_LAUNCH_OK();
   group_reduce_kernel<<<(g + 127) / 128, 128, 0, st>>>(partial, (int)by, ldz, g, num, den);
   SC_LAUNCH_OK();

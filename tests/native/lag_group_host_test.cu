@@ -67,8 +67,88 @@ static int check(int n, int max_deg, int k_fixed) {
   return 0;
 }
 
+// The whole per-thread body of lag_group_kernel over an emulated launch grid: every (block_x, block_y, thread)
+// is executed in turn on the host; lag / local / per-cell counters and the Moran sums must equal a direct
+// evaluation, which also proves that the (chunk, pass, slot) geometry visits every (row, column) exactly once.
+template <int R>
+static int check_kernel_body(int n, int g, int ld, int k_fixed, int grid_y) {
+  constexpr int Q = 8, THREADS = 256;
+  std::vector<int32_t> indptr(1, 0), indices;
+  for (int i = 0; i < n; ++i) {
+    int deg = k_fixed > 0 ? k_fixed : (int)(rnd() % 8);  // CSR case: some empty rows
+    int lo = i - 9 < 0 ? 0 : i - 9, hi = i + 9 >= n ? n - 1 : i + 9;
+    if (deg > hi - lo + 1) deg = hi - lo + 1;
+    std::vector<char> seen(n, 0);
+    for (int t = 0; t < deg;) { int j = lo + (int)(rnd() % (hi - lo + 1)); if (!seen[j]) { seen[j] = 1; ++t; } }
+    for (int j = lo; j <= hi; ++j) if (seen[j]) indices.push_back(j);
+    indptr.push_back((int32_t)indices.size());
+  }
+  const int32_t* ip = k_fixed > 0 ? nullptr : indptr.data();
+  const int n_groups = (n + R - 1) / R;
+  std::vector<uint32_t> words(indices.size() + 1, 0u);
+  std::vector<int32_t> ucnt(n_groups);
+  for (int a = 0; a < n_groups; ++a) ucnt[a] = sc::group_union<R>(ip, indices.data(), n, k_fixed, a, words.data());
+  const size_t quads = (size_t)n * ld / 4;
+  std::vector<float4> Zs(quads), lag(quads), loc(quads), obs(quads);
+  std::vector<int4> cnt(quads);
+  float* Z = reinterpret_cast<float*>(Zs.data());
+  float* O = reinterpret_cast<float*>(obs.data());
+  for (int i = 0; i < n; ++i)
+    for (int c = 0; c < ld; ++c) {
+      Z[(size_t)i * ld + c] = c < g ? ((float)(rnd() % 2001) - 1000.f) / 512.f : 0.f;
+      O[(size_t)i * ld + c] = (float)(rnd() % 1000) / 4096.f;
+    }
+  for (size_t e = 0; e < quads; ++e) { lag[e] = make_float4(-7, -7, -7, -7); loc[e] = lag[e]; cnt[e] = make_int4(5, 5, 5, 5); }
+  sc::LagGroupArgs A;
+  A.indptr = ip; A.k_fixed = k_fixed; A.uwords = words.data(); A.ucnt = ucnt.data(); A.n = n; A.n_groups = n_groups;
+  A.Z = Z; A.ldz = ld; A.lag = reinterpret_cast<float*>(lag.data()); A.local = reinterpret_cast<float*>(loc.data()); A.ldl = ld;
+  A.cell_obs = O; A.cell_cnt = reinterpret_cast<int32_t*>(cnt.data()); A.ldc = ld;
+  A.chunk_groups = 64; A.n_chunks = (n_groups + A.chunk_groups - 1) / A.chunk_groups;
+  const int grid_x = (ld + 4 * Q - 1) / (4 * Q);
+  std::vector<double> num(ld, 0.0), den(ld, 0.0);
+  for (int bx = 0; bx < grid_x; ++bx)
+    for (int by = 0; by < grid_y; ++by)
+      for (int tid = 0; tid < THREADS; ++tid) {
+        double a[4] = {0, 0, 0, 0}, d[4] = {0, 0, 0, 0};
+        sc::lag_group_thread<R, Q, THREADS>(A, tid, bx, by, grid_y, a, d);
+        const int col = (bx * Q + (tid & (Q - 1))) * 4;
+        for (int c = 0; c < 4; ++c) if (col + c < ld) { num[col + c] += a[c]; den[col + c] += d[c]; }
+      }
+  const float* L = reinterpret_cast<const float*>(lag.data());
+  const float* I = reinterpret_cast<const float*>(loc.data());
+  const int32_t* C = reinterpret_cast<const int32_t*>(cnt.data());
+  for (int c = 0; c < ld; ++c) {
+    double want_num = 0, want_den = 0;
+    for (int i = 0; i < n; ++i) {
+      float s = 0.f;
+      for (int e = indptr[i]; e < indptr[i + 1]; ++e) s += Z[(size_t)indices[e] * ld + c];  // ascending columns
+      const int deg = indptr[i + 1] - indptr[i];
+      s *= deg > 0 ? 1.f / (float)deg : 0.f;
+      const float z = Z[(size_t)i * ld + c], l = z * s;
+      const size_t at = (size_t)i * ld + c;
+      if (L[at] != s || I[at] != l || C[at] != 5 + (fabsf(l) >= fabsf(O[at]) ? 1 : 0)) {
+        printf("R=%d n=%d ld=%d row %d col %d: lag %g/%g local %g/%g cnt %d\n", R, n, ld, i, c, L[at], s, I[at], l, C[at]);
+        return 1;
+      }
+      want_num += (double)z * (double)s;
+      want_den += (double)z * (double)z;
+    }
+    if (fabs(num[c] - want_num) > 1e-9 * (fabs(want_num) + 1.0) || fabs(den[c] - want_den) > 1e-9 * (want_den + 1.0)) {
+      printf("R=%d col %d: num %.12g/%.12g den %.12g/%.12g\n", R, c, num[c], want_num, den[c], want_den);
+      return 1;
+    }
+  }
+  printf("R=%d n=%d g=%d ld=%d k_fixed=%d grid_y=%d: kernel body ok\n", R, n, g, ld, k_fixed, grid_y);
+  return 0;
+}
+
 int main() {
   int rc = 0;
+  rc |= check_kernel_body<2>(1003, 40, 40, 0, 3);
+  rc |= check_kernel_body<4>(1003, 37, 40, 0, 5);   // padded columns, ragged rows, n % R != 0
+  rc |= check_kernel_body<4>(515, 5, 8, 6, 1);      // narrow matrix, fixed degree, one CTA row
+  rc |= check_kernel_body<8>(1003, 70, 96, 0, 2);   // three column blocks, ld = round_up(g, 32)
+  rc |= check_kernel_body<8>(64, 33, 40, 6, 7);     // more CTA rows than chunks
   for (int n : {1, 7, 64, 1001}) {
     rc |= check<2>(n, 9, 0); rc |= check<4>(n, 9, 0); rc |= check<8>(n, 9, 0);
     if (n > 6) { rc |= check<2>(n, 0, 6); rc |= check<4>(n, 0, 6); rc |= check<8>(n, 0, 6); }
