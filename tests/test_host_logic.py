@@ -747,3 +747,68 @@ def test_entry_points_on_two_gloo_ranks_match_single_process(tmp_path, monkeypat
                 np.testing.assert_allclose(got[key], ref, rtol=1e-12, atol=0, equal_nan=True, err_msg=key)
             else:
                 assert np.array_equal(got[key], ref), key
+
+
+# ---------------------------------------------------------------------------------------------
+# property tests of the small host-side building blocks
+# ---------------------------------------------------------------------------------------------
+
+
+def test_host_building_blocks_properties():
+    from hypothesis import given, settings
+    from hypothesis import strategies as st
+
+    from oracle import restate as R
+    from spatialcore_b200 import distributed as du
+    from spatialcore_b200 import philox
+    from spatialcore_b200.spatial import autocorrelation as ac
+
+    @settings(max_examples=60, deadline=None)
+    @given(st.integers(1, 4000), st.integers(0, 2**40), st.integers(0, 10**6))
+    def philox_is_a_bijection(n, seed, p):
+        perm = philox.permutation(seed, p, n)
+        assert perm.shape == (n,) and np.array_equal(np.sort(perm), np.arange(n))
+        if n > 50:
+            assert not np.array_equal(perm, philox.permutation(seed, p + 1, n))
+
+    @settings(max_examples=60, deadline=None)
+    @given(st.integers(0, 10**6), st.integers(1, 64))
+    def block_slices_tile_the_range(total, world):
+        spans = [du.block_slice(total, r, world) for r in range(world)]
+        assert spans[0][0] == 0 and spans[-1][1] == total
+        assert all(a[1] == b[0] for a, b in zip(spans, spans[1:]))
+        sizes = [hi - lo for lo, hi in spans]
+        assert max(sizes) - min(sizes) <= 1
+        per, lo, hi = du.row_block(total, world - 1, world)
+        assert per * world >= total and 0 <= lo <= hi <= total
+
+    @settings(max_examples=40, deadline=None)
+    @given(st.integers(2, 400), st.integers(1, 6), st.integers(0, 2**31 - 1))
+    def pooled_moments_equal_global_moments(n, blocks, seed):
+        rng = np.random.default_rng(seed)
+        X = rng.normal(3.0, 2.0, (n, 4))
+        X[:, 1] = -1.25                      # constant everywhere: exactly zero pooled variance
+        cuts = np.sort(rng.integers(1, n, size=min(blocks, n) - 1)) if min(blocks, n) > 1 else np.array([], int)
+        parts = [p for p in np.split(X, cuts) if len(p)]
+        mean, std, zero = du.combine_moments([len(p) for p in parts], np.stack([p.mean(0) for p in parts]),
+                                             np.stack([p.std(0) for p in parts]))
+        np.testing.assert_allclose(mean, X.mean(0), rtol=1e-12, atol=1e-12)
+        np.testing.assert_allclose(std, X.std(0), rtol=1e-9, atol=1e-12)
+        assert zero.tolist() == [False, True, False, False] and std[1] == 0.0
+
+    @settings(max_examples=60, deadline=None)
+    @given(st.lists(st.floats(0.0, 1.0), min_size=1, max_size=200))
+    def bh_matches_the_oracle_and_is_monotone(ps):
+        p = np.asarray(ps)
+        adj = ac._fdr(p, "fdr_bh")
+        np.testing.assert_allclose(adj, R.bh_adjust(p), rtol=1e-12, atol=0)
+        assert np.all(adj >= p - 1e-15) and np.all(adj <= 1.0)
+        order = np.argsort(p, kind="stable")
+        assert np.all(np.diff(adj[order]) >= -1e-15)       # adjusted p-values keep the order of the raw ones
+        np.testing.assert_allclose(ac._fdr(p, "bonferroni"), np.minimum(p * len(p), 1.0))
+        assert np.array_equal(ac._fdr(p, "none"), p)
+
+    philox_is_a_bijection()
+    block_slices_tile_the_range()
+    pooled_moments_equal_global_moments()
+    bh_matches_the_oracle_and_is_monotone()
