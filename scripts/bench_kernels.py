@@ -102,6 +102,11 @@ if want("laggroup"):
         res[f"group{rows}_lag_ms_[with_lag,stat_only]"] = [round(timed(lambda: eng.lag_moran(gs, std.Z, g)), 3),
                                                           round(timed(lambda: eng.lag_moran(gs, std.Z, g, want_lag=False)), 3)]
         if rows:
+            for q in (16, 32):  # wider column blocks per group (SC_LAG_GROUP_Q)
+                os.environ["SC_LAG_GROUP_Q"] = str(q)
+                res[f"group{rows}_q{q}_lag_ms"] = round(timed(lambda: eng.lag_moran(gs, std.Z, g)), 3)
+            del os.environ["SC_LAG_GROUP_Q"]
+        if rows:
             num_g, _, _, _ = eng.lag_moran(gs, std.Z, g, want_lag=False)
             res[f"group{rows}_num_rel_diff_vs_default"] = float(((num_g - num_ref).abs() / num_ref.abs().clamp_min(1e-30)).max())
             res[f"group{rows}_values_null_ms_per_perm"] = round(timed(lambda: eng.perm_null_values(gs, std.Z, g, 2, seed=1), reps=2) / 2, 3)

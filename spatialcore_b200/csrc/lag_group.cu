@@ -12,6 +12,7 @@
 // Arithmetic: each row's neighbours are summed in ascending column order in FP32 and scaled by 1/deg
 // (the default kernel sums them four at a time), so the two kernels agree to FP32 rounding, not bit for bit.
 #include <limits.h>
+#include <stdlib.h>
 
 #include "common.cuh"
 #include "lag_group_core.cuh"
@@ -75,12 +76,11 @@ __global__ void group_reduce_kernel(const double* __restrict__ partial, int nblo
   den[col] = d;
 }
 
-template <int R>
-int launch_group(const int32_t* indptr, int k_fixed, const uint32_t* uwords, const int32_t* ucnt, int64_t n,
+template <int R, int Q>
+int launch_group_q(const int32_t* indptr, int k_fixed, const uint32_t* uwords, const int32_t* ucnt, int64_t n,
                  const float* Z, int64_t ldz, int g, float* lag, float* local, int64_t ldl, double* num,
                  double* den, const float* cell_obs, int32_t* cell_cnt, int64_t ldc, double* partial,
                  cudaStream_t st) {
-  constexpr int Q = 8;
   const int64_t n_groups = (n + R - 1) / R;
   constexpr int kSlots = kThreads / Q;  // groups per pass of the kernel: chunks must be multiples of it
   int chunk_groups = 512 / R;           // the default kernel's 512-row chunks
@@ -102,6 +102,23 @@ int launch_group(const int32_t* indptr, int k_fixed, const uint32_t* uwords, con
   group_reduce_kernel<<<(g + 127) / 128, 128, 0, st>>>(partial, (int)by, ldz, g, num, den);
   SC_LAUNCH_OK();
   return SC_OK;
+}
+
+// Q = lanes (float4 column quads) per group: 8 = the default kernel's 128-byte column blocks; SC_LAG_GROUP_Q=16|32
+// (experiment switch) widens them to 256 / 512 bytes per gathered row piece.
+template <int R>
+int launch_group(const int32_t* indptr, int k_fixed, const uint32_t* uwords, const int32_t* ucnt, int64_t n,
+                 const float* Z, int64_t ldz, int g, float* lag, float* local, int64_t ldl, double* num,
+                 double* den, const float* cell_obs, int32_t* cell_cnt, int64_t ldc, double* partial,
+                 cudaStream_t st) {
+  int q = 8;
+  if (const char* e = getenv("SC_LAG_GROUP_Q")) { int v = atoi(e); if (v == 16 || v == 32) q = v; }
+  if (ldz < 4 * q) q = 8;
+  if (q == 32)
+    return launch_group_q<R, 32>(indptr, k_fixed, uwords, ucnt, n, Z, ldz, g, lag, local, ldl, num, den, cell_obs, cell_cnt, ldc, partial, st);
+  if (q == 16)
+    return launch_group_q<R, 16>(indptr, k_fixed, uwords, ucnt, n, Z, ldz, g, lag, local, ldl, num, den, cell_obs, cell_cnt, ldc, partial, st);
+  return launch_group_q<R, 8>(indptr, k_fixed, uwords, ucnt, n, Z, ldz, g, lag, local, ldl, num, den, cell_obs, cell_cnt, ldc, partial, st);
 }
 
 }  // namespace

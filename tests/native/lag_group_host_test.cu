@@ -70,9 +70,9 @@ static int check(int n, int max_deg, int k_fixed) {
 // The whole per-thread body of lag_group_kernel over an emulated launch grid: every (block_x, block_y, thread)
 // is executed in turn on the host; lag / local / per-cell counters and the Moran sums must equal a direct
 // evaluation, which also proves that the (chunk, pass, slot) geometry visits every (row, column) exactly once.
-template <int R>
+template <int R, int Q = 8>
 static int check_kernel_body(int n, int g, int ld, int k_fixed, int grid_y) {
-  constexpr int Q = 8, THREADS = 256;
+  constexpr int THREADS = 256;
   std::vector<int32_t> indptr(1, 0), indices;
   for (int i = 0; i < n; ++i) {
     int deg = k_fixed > 0 ? k_fixed : (int)(rnd() % 8);  // CSR case: some empty rows
@@ -138,7 +138,7 @@ static int check_kernel_body(int n, int g, int ld, int k_fixed, int grid_y) {
       return 1;
     }
   }
-  printf("R=%d n=%d g=%d ld=%d k_fixed=%d grid_y=%d: kernel body ok\n", R, n, g, ld, k_fixed, grid_y);
+  printf("R=%d Q=%d n=%d g=%d ld=%d k_fixed=%d grid_y=%d: kernel body ok\n", R, Q, n, g, ld, k_fixed, grid_y);
   return 0;
 }
 
@@ -149,6 +149,8 @@ int main() {
   rc |= check_kernel_body<4>(515, 5, 8, 6, 1);      // narrow matrix, fixed degree, one CTA row
   rc |= check_kernel_body<8>(1003, 70, 96, 0, 2);   // three column blocks, ld = round_up(g, 32)
   rc |= check_kernel_body<8>(64, 33, 40, 6, 7);     // more CTA rows than chunks
+  rc |= check_kernel_body<4, 16>(1003, 100, 128, 0, 3);  // wider column blocks
+  rc |= check_kernel_body<8, 32>(777, 130, 160, 6, 2);
   for (int n : {1, 7, 64, 1001}) {
     rc |= check<2>(n, 9, 0); rc |= check<4>(n, 9, 0); rc |= check<8>(n, 9, 0);
     if (n > 6) { rc |= check<2>(n, 0, 6); rc |= check<4>(n, 0, 6); rc |= check<8>(n, 0, 6); }
