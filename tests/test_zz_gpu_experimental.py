@@ -84,11 +84,11 @@ def test_grouped_lag_matches_default_kernel(eng, rows):
             g.groups = None
             torch.testing.assert_close(lag1[:, :g_cols], lag0[:, :g_cols], rtol=1e-5, atol=1e-6)
             torch.testing.assert_close(loc1[:, :g_cols], loc0[:, :g_cols], rtol=1e-5, atol=1e-6)
-            torch.testing.assert_close(num1, num0, rtol=1e-6, atol=1e-6)
+            torch.testing.assert_close(num1, num0, rtol=1e-5, atol=5e-5)  # sums of 3001 products of FP32-rounded lags
             assert torch.equal(den1, den0) or torch.allclose(den1, den0, rtol=1e-14)
             W = g.to_scipy("weights", np.float64)
             z = std.Z[:, :g_cols].double().cpu().numpy()
-            np.testing.assert_allclose(num1.cpu().numpy(), (z * (W @ z)).sum(0), rtol=1e-5, atol=1e-5)
+            np.testing.assert_allclose(num1.cpu().numpy(), (z * (W @ z)).sum(0), rtol=1e-5, atol=5e-5)
 
 
 def test_grouped_values_null_matches_default(eng):
@@ -106,7 +106,7 @@ def test_grouped_values_null_matches_default(eng):
         cnt1 = torch.zeros_like(cnt0)
         sims1 = eng.perm_null_values(g, std.Z, g_cols, P, seed=9, perm_offset=3, cell_obs=loc, cell_cnt=cnt1)
         g.groups = None
-        torch.testing.assert_close(sims1, sims0, rtol=1e-6, atol=1e-5)
+        torch.testing.assert_close(sims1, sims0, rtol=1e-5, atol=5e-5)
         assert (cnt1[:, :g_cols] != cnt0[:, :g_cols]).float().mean() < 1e-4, kind
 
 
