@@ -82,8 +82,8 @@ def test_grouped_lag_matches_default_kernel(eng, rows):
             eng.group_graph(g, rows)
             num1, den1, lag1, loc1 = eng.lag_moran(g, std.Z, g_cols, want_lag=True, want_local=True)
             g.groups = None
-            torch.testing.assert_close(lag1[:, :g_cols], lag0[:, :g_cols], rtol=1e-5, atol=1e-6)
-            torch.testing.assert_close(loc1[:, :g_cols], loc0[:, :g_cols], rtol=1e-5, atol=1e-6)
+            torch.testing.assert_close(lag1[:, :g_cols], lag0[:, :g_cols], rtol=1e-5, atol=5e-6)
+            torch.testing.assert_close(loc1[:, :g_cols], loc0[:, :g_cols], rtol=1e-5, atol=2e-5)
             torch.testing.assert_close(num1, num0, rtol=1e-5, atol=5e-5)  # sums of 3001 products of FP32-rounded lags
             assert torch.equal(den1, den0) or torch.allclose(den1, den0, rtol=1e-12)
             W = g.to_scipy("weights", np.float64)
