@@ -540,19 +540,22 @@ def local_morans_i(
     X = _expression(adata, layer)
     pos_all = np.asarray([adata.var_names.get_loc(x) for x in names], dtype=np.int64)
 
-    local_I = np.zeros((n, g), dtype=np.float32)
-    z_values = np.zeros((n, g), dtype=np.float32)
-    lag_values = np.zeros((n, g), dtype=np.float32)
-    p_values = np.ones((n, g), dtype=np.float32)
-    p_adj = np.ones((n, g), dtype=np.float32)
-    quadrants = np.zeros((n, g), dtype=np.int8)
-    zero_mask = np.zeros(g, dtype=bool)
-
     source = _pick_perm_source(perm_source, n, n_permutations) if n_permutations > 0 else "none"
     rng = np.random.default_rng(seed)
     n_batches = (g + batch_size - 1) // batch_size
     logger.info(f"Processing {g} genes in {n_batches} batches")
     rank, world = dist_util.world(group) if shard != "none" else (0, 1)
+    # one batch on one rank (the common case): the device results become the outputs as they are; otherwise
+    # the batches are assembled in host matrices
+    single = n_batches == 1 and world == 1
+    zero_mask = np.zeros(g, dtype=bool)
+    if not single:
+        local_I = np.zeros((n, g), dtype=np.float32)
+        z_values = np.zeros((n, g), dtype=np.float32)
+        lag_values = np.zeros((n, g), dtype=np.float32)
+        p_values = np.ones((n, g), dtype=np.float32)
+        p_adj = np.ones((n, g), dtype=np.float32)
+        quadrants = np.zeros((n, g), dtype=np.int8)
     b_lo, b_hi = dist_util.block_slice(n_batches, rank, world)
     if source == "replay":
         for _ in range(b_lo * n_permutations):  # the draws of the batches other ranks own
@@ -578,6 +581,10 @@ def local_morans_i(
         # order in one device epilogue (the reference: an N x G Python loop, per-gene sorts, numpy masks)
         z_d, lag_d, loc_d, p_d, pa_d, q_d = engine.local_moran_finish(
             cnt, std.Z, lag, loc, gb, n_permutations, std.zero_var, fdr_correction, alpha, order=co.order)
+        if single:
+            z_values, lag_values, local_I, p_values, p_adj, quadrants = (
+                np.ascontiguousarray(t.cpu().numpy()) for t in (z_d, lag_d, loc_d, p_d, pa_d, q_d))
+            continue
         z_values[:, s:e] = z_d.cpu().numpy()
         lag_values[:, s:e] = lag_d.cpu().numpy()
         local_I[:, s:e] = loc_d.cpu().numpy()
