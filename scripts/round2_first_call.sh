@@ -1,6 +1,6 @@
 #!/usr/bin/env bash
 # First GPU call of the next round (everything below was written after round 1's GPU budget was spent):
-#   gpurun --timeout 1500 -- 'bash scripts/round2_first_call.sh'
+#   gpurun --timeout 2700 -- 'bash scripts/round2_first_call.sh'      (about 25-35 box minutes)
 # 1. the GPU suite and the default bench (now with the values_null leg);
 # 2. the row-alignment experiment (SC_ROW_ALIGN=32: 128-byte aligned rows) on the lag kernel, the
 #    value-permuting null and the graph-row null, C4 and C2, plus the parity tests under that alignment;
