@@ -188,9 +188,11 @@ SC_API int sc_csr_lag_moran(const int32_t* indptr, const int32_t* indices, const
 /* EXPERIMENTAL (opt-in, SC_LAG_GROUP=2|4|8 in the Python layer): the same lag + Moran sums for a
  * row-standardised binary graph, with the L1 gathers shared between `group_rows` consecutive rows.  In
  * spatial order consecutive rows share most neighbours; sc_graph_group_build merges the column-sorted
- * neighbour lists of each group of rows into one list of words (membership mask << (32 - group_rows)) |
- * column, written at the CSR offset of the group's first row (uwords u32[nnz], ucnt i32[ceil(n /
- * group_rows)] = union length per group); sc_csr_lag_moran_grouped walks each union once and adds every
+ * neighbour lists of each group of rows into one ascending list of words (membership mask << (32 -
+ * group_rows)) | column.  Group a's list starts at word round_up(b, 4) + 8 * a (b = CSR offset of its first
+ * row: 16-byte aligned, no scan needed) and is padded to a multiple of four with owner-less words, so
+ * uwords holds nnz + 8 * n_groups + 8 words, n_groups = ceil(n / group_rows); ucnt i32[n_groups] = union
+ * length per group.  sc_csr_lag_moran_grouped walks each union once (16-byte word loads) and adds every
  * gathered value to the rows that own it.  n <= 2^(32 - group_rows).  Agrees with sc_csr_lag_moran to FP32
  * rounding (different summation order).  cell_obs / cell_cnt as in sc_perm_null_values (or NULL).
  * Workspace: sc_csr_lag_moran_workspace_bytes. */

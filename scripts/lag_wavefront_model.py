@@ -33,18 +33,23 @@ def default_kernel(n, ld, deg, aligned):
     rows_per_load = 32 // Q                                   # 4 rows per warp-level gather
     per_item = deg * (rows_per_load * al + span_lines(rows_per_load, 4 * deg))   # gathers + index loads
     per_item += 2 * rows_per_load * al + 2                    # own z row, lag store, indptr
+    issue = (deg * (4 + 6) + 40) / 4.0                        # 4 FFMA + ~6 other per neighbour per warp
     items = (n / rows_per_load) * math.ceil(ld / (4 * Q)) / SMS
-    return per_item * items
+    return max(per_item, issue) * items
 
 
 def grouped_kernel(n, ld, deg, aligned, R, union_fraction):
     al = lines_per_piece(ld, aligned)
     groups_per_load = 32 // Q
     U = union_fraction * R * deg                              # union length per group
-    per_item = U * (groups_per_load * al + span_lines(groups_per_load, 4 * R * deg))  # gathers + word loads
+    # gathers + word loads (one 16-byte load per four union words, one line per group)
+    per_item = U * (groups_per_load * al + span_lines(groups_per_load, 4 * R * deg) / 4.0)
     per_item += 2 * groups_per_load * R * al + groups_per_load + 2
+    # issue-slot floor: per union word 4R predicated FADDs + ~8 address / mask instructions per warp, ~40 per
+    # row in the epilogue; four schedulers per SM issue one warp instruction per cycle each
+    issue = (U * (4 * R + 8) + 40 * R) / 4.0
     items = (n / (groups_per_load * R)) * math.ceil(ld / (4 * Q)) / SMS
-    return per_item * items
+    return max(per_item, issue) * items
 
 
 def ms(wavefronts):
@@ -67,4 +72,5 @@ if __name__ == "__main__":
             row = [f"default {ms(default_kernel(n, ld, deg, aligned)):6.2f} ms"]
             for R, f in uf.items():
                 row.append(f"R={R} {ms(grouped_kernel(n, ld, deg, aligned, R, f)):6.2f} ms")
-            print(f"  {tag:26s} ld={ld:5d}  " + "   ".join(row))
+            hbm_ms = (8.0 * n * ld + 4.0 * n * deg + 4.0 * n) / 6532.2e9 * 1e3   # Z in, lag out, CSR: the HBM floor
+            print(f"  {tag:26s} ld={ld:5d}  " + "   ".join(row) + f"   (HBM floor {hbm_ms:.2f} ms)")

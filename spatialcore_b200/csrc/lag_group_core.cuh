@@ -21,10 +21,17 @@ __host__ __device__ __forceinline__ void row_span(const int32_t* __restrict__ in
   }
 }
 
-// R-way merge of the (column-sorted) neighbour lists of rows [R*a, R*a + R) of an n-row CSR graph.
-// The union is written at the CSR offset of the group's first row -- the R rows are contiguous in the CSR
-// and the union is never longer than their summed lengths, so `uwords` has the size of `indices` and no
-// scan is needed.  word = (membership mask << (32 - R)) | column.  Returns the union length.
+// Word offset of group a's union list: 16-byte aligned (the kernel reads four words per load) with room for
+// the union (never longer than the group's summed row lengths) plus padding to a multiple of four.
+// b0 = CSR offset of the group's first row.  The buffer holds nnz + 8 * n_groups + 8 words.
+__host__ __device__ __forceinline__ int64_t group_offset(int64_t b0, int64_t a) {
+  return ((b0 + 3) & ~(int64_t)3) + 8 * a;
+}
+
+// R-way merge of the (column-sorted) neighbour lists of rows [R*a, R*a + R) of an n-row CSR graph into one
+// ascending list of words (membership mask << (32 - R)) | column at group_offset(); the list is padded to a
+// multiple of four with null words (mask 0, a valid column) so that it can be walked with 16-byte loads.
+// Returns the union length (without padding).
 template <int R>
 __host__ __device__ __forceinline__ int group_union(const int32_t* __restrict__ indptr,
                                                     const int32_t* __restrict__ indices, int64_t n,
@@ -37,8 +44,9 @@ __host__ __device__ __forceinline__ int group_union(const int32_t* __restrict__ 
     beg[r] = 0; len[r] = 0; pos[r] = 0;
     if (row < n) row_span(indptr, k_fixed, row, &beg[r], &len[r]);
   }
-  uint32_t* out = uwords + beg[0];
+  uint32_t* out = uwords + group_offset(beg[0], a);
   int cnt = 0;
+  uint32_t last = 0;
   for (;;) {
     int best = INT_MAX;
 #pragma unroll
@@ -49,8 +57,10 @@ __host__ __device__ __forceinline__ int group_union(const int32_t* __restrict__ 
 #pragma unroll
     for (int r = 0; r < R; ++r)
       if (pos[r] < len[r] && indices[beg[r] + pos[r]] == best) { mask |= 1u << r; ++pos[r]; }
-    out[cnt++] = (mask << (32 - R)) | (uint32_t)best;
+    last = (uint32_t)best;
+    out[cnt++] = (mask << (32 - R)) | last;
   }
+  for (int t = cnt; t & 3; ++t) out[t] = last;  // null words: no owner, a column that is in cache anyway
   return cnt;
 }
 
@@ -72,7 +82,7 @@ __host__ __device__ __forceinline__ uint32_t word_column(uint32_t word) {
 struct LagGroupArgs {
   const int32_t* indptr;   // CSR row pointers or NULL (k_fixed entries per row)
   int k_fixed;
-  const uint32_t* uwords;  // union words, group a at the CSR offset of row R*a
+  const uint32_t* uwords;  // union words, group a at group_offset(CSR offset of row R*a, a)
   const int32_t* ucnt;     // union length per group
   int64_t n, n_groups;
   const float* Z;
@@ -92,6 +102,14 @@ __host__ __device__ __forceinline__ float4 load4(const float* p) {
   return __ldg(reinterpret_cast<const float4*>(p));
 #else
   return *reinterpret_cast<const float4*>(p);
+#endif
+}
+
+__host__ __device__ __forceinline__ uint4 load_words4(const uint4* p) {
+#ifdef __CUDA_ARCH__
+  return __ldg(p);
+#else
+  return *p;
 #endif
 }
 
@@ -121,27 +139,20 @@ __host__ __device__ __forceinline__ void lag_group_thread(const LagGroupArgs& A,
       int64_t b0;
       int deg0;
       row_span(A.indptr, A.k_fixed, row0, &b0, &deg0);
-      const uint32_t* __restrict__ up = A.uwords + b0;
+      const uint4* __restrict__ up = reinterpret_cast<const uint4*>(A.uwords + group_offset(b0, a));
       const int cnt = A.ucnt[a];
       float4 acc[R];
 #pragma unroll
       for (int r = 0; r < R; ++r) acc[r] = make_float4(0.f, 0.f, 0.f, 0.f);
-      int t = 0;
 #pragma unroll 1
-      for (; t + 4 <= cnt; t += 4) {
-        uint32_t w[4];
+      for (int t = 0; t < cnt; t += 4) {  // the list is padded to a multiple of four with null words
+        const uint4 w4 = load_words4(up + (t >> 2));
+        const uint32_t w[4] = {w4.x, w4.y, w4.z, w4.w};
         float4 v[4];
-#pragma unroll
-        for (int u = 0; u < 4; ++u) w[u] = up[t + u];
 #pragma unroll
         for (int u = 0; u < 4; ++u) v[u] = load4(reinterpret_cast<const float*>(zbytes + (uint64_t)word_column<R>(w[u]) * ldzb));
 #pragma unroll
         for (int u = 0; u < 4; ++u) scatter_add<R>(acc, w[u], v[u]);
-      }
-#pragma unroll 1
-      for (; t < cnt; ++t) {
-        const uint32_t w = up[t];
-        scatter_add<R>(acc, w, load4(reinterpret_cast<const float*>(zbytes + (uint64_t)word_column<R>(w) * ldzb)));
       }
 #pragma unroll
       for (int r = 0; r < R; ++r) {

@@ -69,8 +69,8 @@ class DeviceGraph:
     k_fixed: int = 0
     weights: Optional[torch.Tensor] = None
     dist: Optional[torch.Tensor] = None
-    # experimental row-group form for the lag kernel: (group_rows, union words int32[nnz], union length
-    # per group int32[ceil(n / group_rows)]); see group_graph()
+    # experimental row-group form for the lag kernel: (group_rows, union words int32[nnz + 8 * n_groups + 8],
+    # union length per group int32[n_groups]), n_groups = ceil(n / group_rows); see group_graph()
     groups: Optional[Tuple[int, torch.Tensor, torch.Tensor]] = None
 
     @property
@@ -267,8 +267,9 @@ def group_graph(graph: DeviceGraph, group_rows: int) -> DeviceGraph:
         raise ValueError("group_graph: explicitly weighted graphs are not supported")
     L = _lib.lib()
     dev = graph.indices.device
-    uwords = torch.empty(graph.nnz, dtype=torch.int32, device=dev)
-    ucnt = torch.empty((graph.n + group_rows - 1) // group_rows, dtype=torch.int32, device=dev)
+    n_groups = (graph.n + group_rows - 1) // group_rows
+    uwords = torch.empty(graph.nnz + 8 * n_groups + 8, dtype=torch.int32, device=dev)  # 16-byte aligned, padded lists
+    ucnt = torch.empty(n_groups, dtype=torch.int32, device=dev)
     check(
         L.sc_graph_group_build(_ptr(graph.indptr), _ptr(graph.indices), graph.n, int(graph.k_fixed), int(group_rows),
                                _ptr(uwords), _ptr(ucnt), _stream()),

@@ -26,22 +26,28 @@ static int check(int n, int max_deg, int k_fixed) {
   }
   std::vector<float4> z(n);
   for (int i = 0; i < n; ++i) z[i] = make_float4((float)(rnd() % 1000) / 37.f, (float)(rnd() % 1000) / 91.f, 1.f, (float)i);
-  std::vector<uint32_t> words(indices.size() + 1, 0xdeadbeefu);
   const int32_t* ip = k_fixed > 0 ? nullptr : indptr.data();
   const int n_groups = (n + R - 1) / R;
+  const size_t cap = indices.size() + 8 * (size_t)n_groups + 8;  // the documented buffer size
+  std::vector<uint32_t> words(cap + 1, 0xdeadbeefu);
   long total = 0;
   for (int a = 0; a < n_groups; ++a) {
     const int cnt = sc::group_union<R>(ip, indices.data(), n, k_fixed, a, words.data());
     total += cnt;
     int64_t b0; int d0;
     sc::row_span(ip, k_fixed, (int64_t)a * R, &b0, &d0);
-    int64_t span_end = indptr[(a + 1) * R < n ? (a + 1) * R : n];
-    if (b0 + cnt > span_end) { printf("R=%d group %d overflows its CSR span\n", R, a); return 1; }
+    const int64_t off = sc::group_offset(b0, a);
+    int64_t next_b0 = indptr[(a + 1) * R < n ? (a + 1) * R : n];
+    const int64_t limit = a + 1 < n_groups ? sc::group_offset(next_b0, a + 1) : (int64_t)cap;
+    const int padded = (cnt + 3) & ~3;
+    if ((off & 3) || off + padded > limit) { printf("R=%d group %d: list [%lld, +%d) misaligned or past %lld\n", R, a, (long long)off, padded, (long long)limit); return 1; }
+    for (int t = cnt; t < padded; ++t)
+      if ((words[off + t] >> (32 - R)) != 0 || sc::word_column<R>(words[off + t]) >= (uint32_t)n) { printf("R=%d group %d bad padding\n", R, a); return 1; }
     float4 acc[R];
     for (int r = 0; r < R; ++r) acc[r] = make_float4(0, 0, 0, 0);
     uint32_t prev = 0;
     for (int t = 0; t < cnt; ++t) {
-      const uint32_t w = words[b0 + t], c = sc::word_column<R>(w);
+      const uint32_t w = words[off + t], c = sc::word_column<R>(w);
       if (t > 0 && c < prev) { printf("R=%d group %d union not ascending\n", R, a); return 1; }
       if ((w >> (32 - R)) == 0) { printf("R=%d group %d empty mask\n", R, a); return 1; }
       prev = c;
@@ -62,7 +68,7 @@ static int check(int n, int max_deg, int k_fixed) {
       }
     }
   }
-  if (words[indices.size()] != 0xdeadbeefu) { printf("R=%d wrote past the end\n", R); return 1; }
+  if (words[cap] != 0xdeadbeefu) { printf("R=%d wrote past the end\n", R); return 1; }
   printf("R=%d n=%d k_fixed=%d: union/nnz = %.3f ok\n", R, n, k_fixed, (double)total / (double)indices.size());
   return 0;
 }
@@ -85,7 +91,9 @@ static int check_kernel_body(int n, int g, int ld, int k_fixed, int grid_y) {
   }
   const int32_t* ip = k_fixed > 0 ? nullptr : indptr.data();
   const int n_groups = (n + R - 1) / R;
-  std::vector<uint32_t> words(indices.size() + 1, 0u);
+  std::vector<uint4> word_store((indices.size() + 8 * (size_t)n_groups + 8) / 4 + 1);  // 16-byte aligned
+  uint32_t* words_p = reinterpret_cast<uint32_t*>(word_store.data());
+  struct { uint32_t* p; uint32_t* data() { return p; } } words{words_p};
   std::vector<int32_t> ucnt(n_groups);
   for (int a = 0; a < n_groups; ++a) ucnt[a] = sc::group_union<R>(ip, indices.data(), n, k_fixed, a, words.data());
   const size_t quads = (size_t)n * ld / 4;

@@ -27,19 +27,21 @@ def eng():
 
 def _union_model(indptr, indices, n, rows):
     """numpy model of sc_graph_group_build: per group of ``rows`` consecutive rows the sorted union of the
-    neighbour lists with membership masks, placed at the CSR offset of the group's first row."""
-    words = np.zeros(len(indices), dtype=np.uint32)
-    cnt = np.zeros((n + rows - 1) // rows, dtype=np.int32)
-    for a in range(len(cnt)):
+    neighbour lists with membership masks, at word round_up(CSR offset of the group's first row, 4) + 8 * group."""
+    n_groups = (n + rows - 1) // rows
+    words = np.zeros(len(indices) + 8 * n_groups + 8, dtype=np.uint32)
+    cnt = np.zeros(n_groups, dtype=np.int32)
+    offs = np.zeros(n_groups, dtype=np.int64)
+    for a in range(n_groups):
         member = {}
         for r, row in enumerate(range(a * rows, min(n, (a + 1) * rows))):
             for j in indices[indptr[row]:indptr[row + 1]]:
                 member[int(j)] = member.get(int(j), 0) | (1 << r)
-        base = indptr[a * rows]
+        offs[a] = (int(indptr[a * rows]) + 3) // 4 * 4 + 8 * a
         for t, j in enumerate(sorted(member)):
-            words[base + t] = (member[j] << (32 - rows)) | j
+            words[offs[a] + t] = (member[j] << (32 - rows)) | j
         cnt[a] = len(member)
-    return words, cnt
+    return words, cnt, offs
 
 
 def _graphs(eng):
@@ -60,12 +62,15 @@ def test_group_build_matches_numpy_model(eng, rows):
         indices = g.indices.reshape(-1).cpu().numpy()
         eng.group_graph(g, rows)
         r, uwords, ucnt = g.groups
-        want_w, want_c = _union_model(indptr, indices, g.n, rows)
+        want_w, want_c, offs = _union_model(indptr, indices, g.n, rows)
         got_w = uwords.cpu().numpy().view(np.uint32)
         assert r == rows and np.array_equal(ucnt.cpu().numpy(), want_c), kind
+        assert got_w.size == want_w.size
         for a in range(len(want_c)):
-            b = indptr[a * rows]
+            b = offs[a]
             assert np.array_equal(got_w[b:b + want_c[a]], want_w[b:b + want_c[a]]), (kind, a)
+            pad = got_w[b + want_c[a]:b + (want_c[a] + 3) // 4 * 4]
+            assert np.all(pad >> (32 - rows) == 0) and np.all((pad & ((1 << (32 - rows)) - 1)) < g.n)  # owner-less
         assert want_c.sum() < 0.95 * len(indices)  # spatial order: consecutive rows do share neighbours
 
 
