@@ -7,6 +7,7 @@ has a CPU path: inputs must live on a CUDA device.
 
 from __future__ import annotations
 
+import functools
 import os
 from dataclasses import dataclass
 from typing import Optional, Tuple
@@ -26,6 +27,43 @@ def launches() -> int:
 
 def _ptr(t: Optional[torch.Tensor]) -> Optional[int]:
     return None if t is None else t.data_ptr()
+
+
+def _target_device(args, kwargs) -> Optional[torch.device]:
+    """The CUDA device a call works on: its first CUDA tensor / device graph / cell order, else an
+    explicitly indexed ``device=`` argument."""
+    for a in list(args) + list(kwargs.values()):
+        if isinstance(a, torch.Tensor):
+            if a.is_cuda:
+                return a.device
+        elif isinstance(a, (DeviceGraph, CellOrder, Standardized)):
+            t = a.indices if isinstance(a, DeviceGraph) else (a.order if isinstance(a, CellOrder) else a.Z)
+            if t is not None and t.is_cuda:
+                return t.device
+        elif isinstance(a, KMeansDevice):
+            return a.X.device
+    dev = kwargs.get("device")
+    if dev is not None:
+        dev = torch.device(dev)
+        if dev.type == "cuda" and dev.index is not None:
+            return dev
+    return None
+
+
+def _on_device(fn):
+    """Run ``fn`` with the CUDA device of its operands current.  The library launches on the CURRENT
+    device (``cudaGetDevice`` for the SM count and function attributes, the stream handed over is the
+    current stream), so a call on tensors of ``cuda:1`` while ``cuda:0`` is current must switch first."""
+
+    @functools.wraps(fn)
+    def wrapper(*args, **kwargs):
+        dev = _target_device(args, kwargs)
+        if dev is None or dev.index == torch.cuda.current_device():
+            return fn(*args, **kwargs)
+        with torch.cuda.device(dev):
+            return fn(*args, **kwargs)
+
+    return wrapper
 
 
 def _stream() -> int:
@@ -106,8 +144,23 @@ class DeviceGraph:
 # --------------------------------------------------------------------------------------------------
 
 
+def check_planar(extra_is_constant: bool, shape) -> None:
+    """The kernels are 2-D.  The reference hands the whole ``obsm['spatial']`` array to its tree
+    libraries [R autocorrelation.py:393-395, neighborhoods.py:213-223], so coordinates with a third
+    column that VARIES would give different neighbours there: refuse them instead of silently dropping
+    the column.  Constant extra columns (e.g. z = 0) do not change any distance and are accepted."""
+    if not extra_is_constant:
+        raise ValueError(
+            f"spatial coordinates have shape {tuple(shape)}: only 2-D coordinates are supported "
+            "(columns beyond the first two must be constant); project or slice obsm['spatial'] to (n_cells, 2)")
+
+
 def _coords_tensor(coords, device) -> torch.Tensor:
     if isinstance(coords, torch.Tensor):
+        if coords.dim() != 2 or coords.shape[1] < 2:
+            raise ValueError(f"spatial coordinates must have shape (n_cells, >=2), got {tuple(coords.shape)}")
+        if coords.shape[1] > 2 and coords.shape[0] > 0:
+            check_planar(bool((coords[:, 2:] == coords[:1, 2:]).all().item()), coords.shape)
         c = coords.to(device=device, dtype=torch.float64)
     else:
         a = np.asarray(coords)
@@ -115,10 +168,13 @@ def _coords_tensor(coords, device) -> torch.Tensor:
             raise ValueError(f"spatial coordinates must have shape (n_cells, >=2), got {a.shape}")
         if not np.isfinite(a[:, :2]).all():
             raise ValueError("spatial coordinates contain NaN or infinite values")
+        if a.shape[1] > 2 and a.shape[0] > 0:
+            check_planar(bool((a[:, 2:] == a[:1, 2:]).all()), a.shape)
         c = torch.from_numpy(np.ascontiguousarray(a[:, :2], dtype=np.float64)).to(device)
     return c[:, :2].contiguous()
 
 
+@_on_device
 def knn_graph(
     coords,
     k: int,
@@ -158,6 +214,7 @@ def knn_graph(
     return graph, order, profile
 
 
+@_on_device
 def radius_graph(
     coords,
     radius: float,
@@ -214,6 +271,7 @@ class CellOrder:
     rank: torch.Tensor  # int32 [n]
 
 
+@_on_device
 def spatial_order(coords, device="cuda") -> CellOrder:
     """``sc_spatial_order``: Z-order curve over a uniform grid of the coordinates."""
     c = _coords_tensor(coords, device)
@@ -226,6 +284,7 @@ def spatial_order(coords, device="cuda") -> CellOrder:
     return CellOrder(order=order, rank=rank)
 
 
+@_on_device
 def relabel_graph(graph: DeviceGraph, co: CellOrder) -> DeviceGraph:
     """``sc_graph_relabel``: the same graph on sorted positions (rows permuted, columns mapped and
     re-sorted; weights follow their edges)."""
@@ -259,6 +318,7 @@ def _lag_group_rows() -> int:
     return int(v)
 
 
+@_on_device
 def group_graph(graph: DeviceGraph, group_rows: int) -> DeviceGraph:
     """``sc_graph_group_build``: merge the neighbour lists of every ``group_rows`` consecutive rows into one
     union list with membership masks (rows must be column-sorted; binary graphs only).  Pays off when
@@ -279,6 +339,7 @@ def group_graph(graph: DeviceGraph, group_rows: int) -> DeviceGraph:
     return graph
 
 
+@_on_device
 def gather_rows(src: torch.Tensor, rows: torch.Tensor) -> torch.Tensor:
     """``sc_gather_rows``: ``dst[a] = src[rows[a]]`` for a float32 [n, ld] matrix (ld % 4 == 0)."""
     _require_cuda(src, "src")
@@ -289,6 +350,7 @@ def gather_rows(src: torch.Tensor, rows: torch.Tensor) -> torch.Tensor:
     return dst
 
 
+@_on_device
 def conjugate_perms(perm_idx: torch.Tensor, co: CellOrder) -> torch.Tensor:
     """``sc_perm_conjugate``: replayed permutations of cell ids -> permutations of sorted positions."""
     L = _lib.lib()
@@ -298,6 +360,7 @@ def conjugate_perms(perm_idx: torch.Tensor, co: CellOrder) -> torch.Tensor:
     return out
 
 
+@_on_device
 def graph_from_scipy(adj, device="cuda", use_weights: bool = False) -> DeviceGraph:
     """Upload an existing scipy CSR connectivity matrix (``use_existing_graph`` path)."""
     from scipy import sparse
@@ -312,6 +375,7 @@ def graph_from_scipy(adj, device="cuda", use_weights: bool = False) -> DeviceGra
     return DeviceGraph(n=n, indices=indices, indptr=indptr, weights=weights)
 
 
+@_on_device
 def nbhd_counts(graph: DeviceGraph, labels: torch.Tensor, n_types: int) -> torch.Tensor:
     L = _lib.lib()
     prof = torch.empty((graph.n, n_types), dtype=torch.float32, device=labels.device)
@@ -323,6 +387,7 @@ def nbhd_counts(graph: DeviceGraph, labels: torch.Tensor, n_types: int) -> torch
     return prof
 
 
+@_on_device
 def profile_normalize(profile: torch.Tensor, normalize: bool) -> int:
     """Normalises in place; returns the number of empty rows (host sync)."""
     L = _lib.lib()
@@ -334,6 +399,7 @@ def profile_normalize(profile: torch.Tensor, normalize: bool) -> int:
     return int(n_empty.item())
 
 
+@_on_device
 def graph_moments(graph: DeviceGraph) -> Tuple[float, float, float]:
     L = _lib.lib()
     dev = graph.indices.device
@@ -362,6 +428,7 @@ class Standardized:
     zero_var: torch.Tensor  # [g] uint8
 
 
+@_on_device
 def zscore_dense(X: torch.Tensor, cols: Optional[torch.Tensor] = None, rows: Optional[torch.Tensor] = None,
                  want_z: bool = True) -> Standardized:
     """``sc_zscore`` on a dense device matrix (float32 or float64, row-major, any row stride)."""
@@ -390,6 +457,7 @@ def zscore_dense(X: torch.Tensor, cols: Optional[torch.Tensor] = None, rows: Opt
     return Standardized(Z=Z, g=g, mean=mean, std=std, zero_var=zero)
 
 
+@_on_device
 def zscore_apply(X: torch.Tensor, mean: torch.Tensor, std: torch.Tensor, zero_var: torch.Tensor,
                  cols: Optional[torch.Tensor] = None, rows: Optional[torch.Tensor] = None,
                  out: Optional[torch.Tensor] = None) -> torch.Tensor:
@@ -416,6 +484,7 @@ def zscore_apply(X: torch.Tensor, mean: torch.Tensor, std: torch.Tensor, zero_va
     return out
 
 
+@_on_device
 def zscore_scatter(X: torch.Tensor, mean: torch.Tensor, std: torch.Tensor, zero_var: torch.Tensor,
                    dst_rows: torch.Tensor, peer_ptrs, ld: int) -> None:
     """``sc_zscore_scatter``: z-score this rank's row block and store each output row at
@@ -434,6 +503,7 @@ def zscore_scatter(X: torch.Tensor, mean: torch.Tensor, std: torch.Tensor, zero_
     )
 
 
+@_on_device
 def densify_csr(indptr: torch.Tensor, indices: torch.Tensor, data: torch.Tensor, n: int, n_cols: int,
                 colmap: Optional[torch.Tensor], g_out: int) -> torch.Tensor:
     """``sc_csr_densify``: CSR expression -> dense float32 [n, padded_ld(g_out)] on the device."""
@@ -450,6 +520,7 @@ def densify_csr(indptr: torch.Tensor, indices: torch.Tensor, data: torch.Tensor,
     return out
 
 
+@_on_device
 def expression_to_device(X, gene_idx: Optional[np.ndarray], device="cuda") -> Tuple[torch.Tensor, Optional[torch.Tensor]]:
     """Bring an AnnData expression matrix to the device as a dense matrix plus an optional column
     selector.  Accepts numpy, scipy sparse (CSR/CSC/…), or torch tensors (host or device)."""
@@ -501,6 +572,7 @@ def expression_to_device(X, gene_idx: Optional[np.ndarray], device="cuda") -> Tu
 # --------------------------------------------------------------------------------------------------
 
 
+@_on_device
 def lag_moran(graph: DeviceGraph, Z: torch.Tensor, g: int, want_lag: bool = True, want_local: bool = False):
     """``sc_csr_lag_moran``: returns ``(num[g], den[g], lag|None, local|None)``."""
     _require_cuda(Z, "Z")
@@ -538,6 +610,7 @@ def _perm_source(perm_idx: Optional[torch.Tensor], n: int, n_perms: int):
     return SC_PERM_REPLAY, perm_idx
 
 
+@_on_device
 def perm_null_graph_rows(A: torch.Tensor, B: torch.Tensor, g: int, n_perms: int,
                          perm_idx: Optional[torch.Tensor] = None, seed: int = 0, perm_offset: int = 0,
                          out: Optional[torch.Tensor] = None, ws: Optional[torch.Tensor] = None) -> torch.Tensor:
@@ -556,6 +629,7 @@ def perm_null_graph_rows(A: torch.Tensor, B: torch.Tensor, g: int, n_perms: int,
     return sims
 
 
+@_on_device
 def perm_null_values(graph: DeviceGraph, Zy: torch.Tensor, g: int, n_perms: int, Zx: Optional[torch.Tensor] = None,
                      perm_idx: Optional[torch.Tensor] = None, seed: int = 0, perm_offset: int = 0,
                      cell_obs: Optional[torch.Tensor] = None, cell_cnt: Optional[torch.Tensor] = None) -> torch.Tensor:
@@ -593,6 +667,7 @@ def perm_null_values(graph: DeviceGraph, Zy: torch.Tensor, g: int, n_perms: int,
     return sims
 
 
+@_on_device
 def philox_permutation(seed: int, perm_index: int, n: int, device="cuda") -> torch.Tensor:
     L = _lib.lib()
     out = torch.empty(n, dtype=torch.int32, device=device)
@@ -600,6 +675,7 @@ def philox_permutation(seed: int, perm_index: int, n: int, device="cuda") -> tor
     return out
 
 
+@_on_device
 def null_accumulate(sims: torch.Tensor, scale: Optional[torch.Tensor], obs: torch.Tensor, cnt_ge: torch.Tensor,
                     cnt_abs_ge: torch.Tensor, ssum: torch.Tensor, ssq: torch.Tensor) -> None:
     L = _lib.lib()
@@ -611,6 +687,7 @@ def null_accumulate(sims: torch.Tensor, scale: Optional[torch.Tensor], obs: torc
     )
 
 
+@_on_device
 def lee_gemm(A: torch.Tensor, B: torch.Tensor, g: int, impl: int = 0) -> torch.Tensor:
     """``sc_lee_gemm``: ``L[x,y] = Σ_i A[i,x]·B[i,y]`` (float32 [g,g])."""
     L = _lib.lib()
@@ -624,6 +701,7 @@ def lee_gemm(A: torch.Tensor, B: torch.Tensor, g: int, impl: int = 0) -> torch.T
     return out
 
 
+@_on_device
 def lee_abs_ge_accumulate(Lp: torch.Tensor, L_obs: torch.Tensor, cnt: torch.Tensor) -> None:
     """``sc_lee_abs_ge_accumulate``: ``cnt += (|Lp| >= |L_obs|)`` for a permuted all-pairs matrix."""
     Lb = _lib.lib()
@@ -642,6 +720,7 @@ class KMeansDevice:
     Every numeric step is a kernel of ``csrc/niches.cu``; the host only draws random numbers, divides
     K x d sums by counts and tests convergence."""
 
+    @_on_device
     def __init__(self, X: torch.Tensor, k: int) -> None:
         _require_cuda(X, "X")
         if X.dim() != 2:
@@ -661,6 +740,7 @@ class KMeansDevice:
         self.ws = _workspace(L.sc_kmeans_workspace_bytes(self.n, self.d, self.k), dev)
         self.ws_sample = _workspace(L.sc_kmeans_pp_sample_workspace_bytes(self.n), dev)
 
+    @_on_device
     def assign(self, centers: np.ndarray, want_mind: bool = False):
         """One Lloyd pass with ``centers`` (float32 [k, d]).  Returns (sums[k,d], counts[k], inertia,
         n_changed) as host float64 / ints; ``self.labels`` holds the new labels."""
@@ -675,6 +755,7 @@ class KMeansDevice:
         kd = self.k * self.d
         return o[:kd].reshape(self.k, self.d).copy(), o[kd:kd + self.k].copy(), float(o[kd + self.k]), int(round(o[kd + self.k + 1]))
 
+    @_on_device
     def pp_potential(self, cand: np.ndarray, first: bool, commit: int = -1) -> np.ndarray:
         """Potentials of candidate centres (row indices); ``commit`` folds that candidate into mind."""
         L = _lib.lib()
@@ -690,6 +771,7 @@ class KMeansDevice:
             self.mind, self.mind_tmp = self.mind_tmp, self.mind
         return pot.cpu().numpy()
 
+    @_on_device
     def pp_sample(self, vals: np.ndarray) -> np.ndarray:
         """``searchsorted(cumsum(mind), vals)``: D^2 sampling of candidate rows."""
         L = _lib.lib()
@@ -711,6 +793,7 @@ class KMeansDevice:
 # --------------------------------------------------------------------------------------------------
 
 
+@_on_device
 def cross_nn(targets, queries, device="cuda") -> Tuple[np.ndarray, np.ndarray]:
     """``sc_cross_nn``: index (into ``targets``) and FP64 distance of the nearest target of every query
     point -- ``cKDTree(targets).query(queries, k=1)``.  Returns host arrays ``(dist, idx)``."""
@@ -725,6 +808,7 @@ def cross_nn(targets, queries, device="cuda") -> Tuple[np.ndarray, np.ndarray]:
     return dist.cpu().numpy(), idx.cpu().numpy().astype(np.int64)
 
 
+@_on_device
 def pairwise_reduce(a, b, device="cuda") -> Tuple[float, float]:
     """``sc_pairwise_reduce``: ``(cdist(a, b).min(), cdist(a, b).sum())`` in FP64 on the device."""
     A = a if isinstance(a, torch.Tensor) else _coords_tensor(a, device)
@@ -741,6 +825,7 @@ def pairwise_reduce(a, b, device="cuda") -> Tuple[float, float]:
 _FDR_METHODS = {"none": 0, "bonferroni": 1, "fdr_bh": 2}
 
 
+@_on_device
 def local_moran_finish(cnt: Optional[torch.Tensor], Z: torch.Tensor, lag: torch.Tensor, loc: torch.Tensor, g: int,
                        n_perms: int, zero_var: Optional[torch.Tensor], method: str, alpha: float,
                        order: Optional[torch.Tensor] = None):

@@ -117,7 +117,12 @@ def calculate_domain_distances(
     if not T:
         raise ValueError(f"No valid target domains found in '{target_domain_column}'")
 
-    xy = np.ascontiguousarray(np.asarray(adata.obsm["spatial"])[:, :2], dtype=np.float64)
+    xy_all = np.asarray(adata.obsm["spatial"])
+    if xy_all.ndim == 2 and xy_all.shape[1] > 2 and xy_all.shape[0] > 0:
+        # the reference takes centroids and tree queries over ALL columns [R distance.py:222-233]; the
+        # kernels are 2-D, so a varying third coordinate is refused instead of silently dropped
+        engine.check_planar(bool((xy_all[:, 2:] == xy_all[:1, 2:]).all()), xy_all.shape)
+    xy = np.ascontiguousarray(xy_all[:, :2], dtype=np.float64)
     s_codes = _codes(adata.obs[source_domain_column].values, S)
     t_codes = _codes(adata.obs[target_domain_column].values, T)
     same_column = source_domain_column == target_domain_column
