@@ -185,24 +185,33 @@ SC_API int sc_csr_lag_moran(const int32_t* indptr, const int32_t* indices, const
                      float* local, int64_t ldl, double* num, double* den, void* ws,
                      size_t ws_bytes, sc_stream_t stream);
 
-/* EXPERIMENTAL (opt-in, SC_LAG_GROUP=2|4|8 in the Python layer): the same lag + Moran sums for a
- * row-standardised binary graph, with the L1 gathers shared between `group_rows` consecutive rows.  In
- * spatial order consecutive rows share most neighbours; sc_graph_group_build merges the column-sorted
- * neighbour lists of each group of rows into one ascending list of words (membership mask << (32 -
- * group_rows)) | column.  Group a's list starts at word round_up(b, 4) + 8 * a (b = CSR offset of its first
- * row: 16-byte aligned, no scan needed) and is padded to a multiple of four with owner-less words, so
- * uwords holds nnz + 8 * n_groups + 8 words, n_groups = ceil(n / group_rows); ucnt i32[n_groups] = union
- * length per group.  sc_csr_lag_moran_grouped walks each union once (16-byte word loads) and adds every
- * gathered value to the rows that own it.  n <= 2^(32 - group_rows).  Agrees with sc_csr_lag_moran to FP32
- * rounding (different summation order).  cell_obs / cell_cnt as in sc_perm_null_values (or NULL).
+/* The fast path of the same step for row-standardised binary graphs held in spatial order
+ * (sc_spatial_order + sc_graph_relabel): the lag through SHARED-MEMORY TILES.  The L1 load path delivers
+ * ~46 B/clk/SM for 128-byte row pieces (measured), the shared-memory crossbar 128 B/clk/SM, so:
+ * sc_graph_tile_build (once per graph) finds, for every chunk of 256 consecutive rows, the sorted union of
+ * its neighbour columns and own rows (`urows`, at most `cap` = 576 / 864 / 1728 rows, chosen from the mean
+ * degree) and, for every group of `group_rows` (1, 2 or 4) consecutive rows, the merged neighbour list as
+ * 16-bit words (membership mask << (16 - group_rows)) | index into urows, padded to a multiple of four;
+ * sc_csr_lag_moran_tiled stages the urows' 128-byte pieces per column block with cp.async and walks the
+ * word lists out of shared memory.  Chunks whose union exceeds `cap` are computed by direct gathers.
+ * A row's neighbours are added in ascending column order, as in sc_csr_lag_moran: the two agree bit for bit.
+ *
+ * `tiles` is one caller-owned device buffer of sc_graph_tile_bytes(n, nnz, group_rows) bytes (0 = invalid
+ * arguments); pass the same n / nnz / group_rows to all three calls.  nnz = n * k_fixed when indptr is NULL.
+ * Zself f32[n, ldz] or NULL (NULL: the row's own value is the operand's); perm i32[n] or NULL: the operand
+ * is Z[perm[j]] for row j -- the value-permuting null (autocorrelation.py:877-884) without materialising
+ * the permuted matrix.  cell_obs / cell_cnt as in sc_perm_null_values (or NULL).
  * Workspace: sc_csr_lag_moran_workspace_bytes. */
-SC_API int sc_graph_group_build(const int32_t* indptr, const int32_t* indices, int64_t n, int k_fixed,
-                                int group_rows, uint32_t* uwords, int32_t* ucnt, sc_stream_t stream);
-SC_API int sc_csr_lag_moran_grouped(const int32_t* indptr, int64_t n, int k_fixed, int group_rows,
-                                    const uint32_t* uwords, const int32_t* ucnt, const float* Z,
-                                    int64_t ldz, int g, float* lag, float* local, int64_t ldl,
-                                    double* num, double* den, const float* cell_obs, int32_t* cell_cnt,
-                                    int64_t ldc, void* ws, size_t ws_bytes, sc_stream_t stream);
+SC_API size_t sc_graph_tile_bytes(int64_t n, int64_t nnz, int group_rows);
+SC_API int sc_graph_tile_build(const int32_t* indptr, const int32_t* indices, int64_t n, int k_fixed,
+                               int64_t nnz, int group_rows, void* tiles, size_t tile_bytes,
+                               sc_stream_t stream);
+SC_API int sc_csr_lag_moran_tiled(const int32_t* indptr, const int32_t* indices, int64_t n, int k_fixed,
+                                  int64_t nnz, int group_rows, const void* tiles, size_t tile_bytes,
+                                  const float* Zself, const float* Z, const int32_t* perm, int64_t ldz,
+                                  int g, float* lag, float* local, int64_t ldl, double* num, double* den,
+                                  const float* cell_obs, int32_t* cell_cnt, int64_t ldc, void* ws,
+                                  size_t ws_bytes, sc_stream_t stream);
 
 /* ---------------------------------------------------------------------------------------------
  * Permutation nulls.

@@ -243,25 +243,55 @@ def pval_norm(I: np.ndarray, n: int, vnorm: float) -> np.ndarray:
     return np.where(z > 0, 1.0 - ndtr(z), ndtr(z))
 
 
-def morans_i_table(coords, X, k=6, n_perms=10, seed=0, adj: Optional[sparse.csr_matrix] = None):
+def pval_sim_two_tailed(score: np.ndarray, sims: np.ndarray) -> np.ndarray:
+    """Two-tailed permutation p-value, the reference's own convention [R spatial/autocorrelation.py:330,
+    :888-896]: ``(#{|sims| >= |score|} + 1)/(P + 1)`` (the ``two_tailed=True`` switch of the drop-in)."""
+    P = sims.shape[0]
+    return ((np.abs(sims) >= np.abs(score)[None, :]).sum(axis=0) + 1) / (P + 1)
+
+
+def morans_i_perms_values(g: sparse.csr_matrix, X: np.ndarray, perms: np.ndarray) -> np.ndarray:
+    """Global Moran's I under the VALUE-permuting null (the ``null_mode="values"`` switch of the drop-in):
+    ``z_p = z[idx_p]; sims[p] = N/S0 · Σ_i z_p,i (g z_p)_i / Σ z²`` -- the permutation scheme of the reference's
+    own ``local_morans_i`` [R spatial/autocorrelation.py:877-884] applied to the global statistic."""
+    X = np.asarray(X, dtype=np.float64)
+    n = X.shape[0]
+    z = X - X.mean(axis=0)
+    den = (z * z).sum(axis=0)
+    s0 = g.data.sum()
+    sims = np.empty((perms.shape[0], X.shape[1]), dtype=np.float64)
+    for p in range(perms.shape[0]):
+        zp = z[perms[p]]
+        sims[p] = n / s0 * (zp * (g @ zp)).sum(axis=0) / den
+    return sims
+
+
+def morans_i_table(coords, X, k=6, n_perms=10, seed=0, adj: Optional[sparse.csr_matrix] = None,
+                   null_mode: str = "graph_rows", two_tailed: bool = False, transformation: bool = True):
     """End-to-end restatement of ``morans_i`` [R spatial/autocorrelation.py:421-648]:
     the squidpy segment [unpinned] + the reference's own result assembly (:589-616).
-    Returns a dict of per-gene arrays in input gene order."""
+    Returns a dict of per-gene arrays in input gene order.
+
+    The keyword defaults are the recalled squidpy behaviour (Appendix A); the alternatives restate the other
+    reading of each convention so that the drop-in's switches have an oracle: ``null_mode="values"`` (values
+    permuted instead of graph rows), ``two_tailed=True`` (|sims| >= |I| counts, normal p doubled),
+    ``transformation=False`` (binary / stored weights instead of L1-row-normalised)."""
     n = X.shape[0]
     if adj is None:
         adj, _ = spatial_neighbors(coords, k=k)
-    g = row_normalize(adj)
+    g = row_normalize(adj) if transformation else adj.astype(np.float64).tocsr()
     I = morans_i_stat(g, X)
     s0, s1, s2 = graph_moments(g)
     vn = var_norm(n, s0, s1, s2)
     expected = -1.0 / (n - 1)
-    out = {"I": I, "expected_I": expected, "var_norm": vn, "pval_norm": pval_norm(I, n, vn), "s": (s0, s1, s2)}
+    pn = pval_norm(I, n, vn)
+    out = {"I": I, "expected_I": expected, "var_norm": vn, "pval_norm": pn * 2.0 if two_tailed else pn, "s": (s0, s1, s2)}
     out["z_score"] = (I - expected) / np.sqrt(vn) if vn > 0 else np.zeros_like(I)
     if n_perms and n_perms > 0:
         perms = squidpy_perm_indices(n, n_perms, seed)
-        sims = morans_i_perms_graph_rows(g, X, perms)
+        sims = morans_i_perms_graph_rows(g, X, perms) if null_mode == "graph_rows" else morans_i_perms_values(g, X, perms)
         out["sims"] = sims
-        out["pval_sim"] = pval_sim_folded(I, sims)
+        out["pval_sim"] = pval_sim_two_tailed(I, sims) if two_tailed else pval_sim_folded(I, sims)
         out["p_value"] = out["pval_sim"]
         out["count_ge"] = (sims >= I[None, :]).sum(axis=0)
     else:

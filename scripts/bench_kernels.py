@@ -91,29 +91,31 @@ if want("lagsweep"):
     del os.environ["SC_LAG_Q"], os.environ["SC_LAG_CHUNK"]
     out["lag_sweep_ms_[with_lag,stat_only]"] = sweep
 
-if want("laggroup"):
-    # experimental row-group lag (SC_LAG_GROUP): gathers shared between 2 / 4 / 8 consecutive rows
+if want("lagtile"):
+    # shared-memory tile lag (csrc/lag_tile.cu) per group size; rows = 0 is the L1-gather kernel
     res = {}
-    for rows in (0, 2, 4, 8):
-        gs.groups = None
+    gs.tiles = None
+    num_ref, _, lag_ref, _ = eng.lag_moran(gs, std.Z, g)
+    lag_bytes = 8.0 * n * g + 4.0 * nnz + 4.0 * n
+    for rows in [int(x) for x in os.environ.get("SC_BENCH_TILE_ROWS", "0,1,2,4").split(",")]:
+        gs.tiles = None
         if rows:
-            res[f"group{rows}_build_ms"] = round(timed(lambda: eng.group_graph(gs, rows)), 3)
-            res[f"group{rows}_union_fraction"] = round(float(gs.groups[2].sum().item()) / nnz, 4)
-        res[f"group{rows}_lag_ms_[with_lag,stat_only]"] = [round(timed(lambda: eng.lag_moran(gs, std.Z, g)), 3),
-                                                          round(timed(lambda: eng.lag_moran(gs, std.Z, g, want_lag=False)), 3)]
+            res[f"rows{rows}_build_ms"] = round(timed(lambda: eng.tile_graph(gs, rows)), 3)
+        t_lag = timed(lambda: eng.lag_moran(gs, std.Z, g))
+        t_stat = timed(lambda: eng.lag_moran(gs, std.Z, g, want_lag=False))
+        res[f"rows{rows}_lag"] = roof(lag_bytes, t_lag)
+        res[f"rows{rows}_stat_only_ms"] = round(t_stat, 3)
+        num_g, _, lag_g, _ = eng.lag_moran(gs, std.Z, g)
         if rows:
-            for q in (16, 32):  # wider column blocks per group (SC_LAG_GROUP_Q)
-                os.environ["SC_LAG_GROUP_Q"] = str(q)
-                res[f"group{rows}_q{q}_lag_ms"] = round(timed(lambda: eng.lag_moran(gs, std.Z, g)), 3)
-            del os.environ["SC_LAG_GROUP_Q"]
-        if rows:
-            num_g, _, _, _ = eng.lag_moran(gs, std.Z, g, want_lag=False)
-            res[f"group{rows}_num_rel_diff_vs_default"] = float(((num_g - num_ref).abs() / num_ref.abs().clamp_min(1e-30)).max())
-            res[f"group{rows}_values_null_ms_per_perm"] = round(timed(lambda: eng.perm_null_values(gs, std.Z, g, 2, seed=1), reps=2) / 2, 3)
-        else:
-            num_ref, _, _, _ = eng.lag_moran(gs, std.Z, g, want_lag=False)
-    gs.groups = None
-    out["lag_row_groups"] = res
+            res[f"rows{rows}_lag_bitwise_equal_to_gather_kernel"] = bool(torch.equal(lag_g, lag_ref))
+            res[f"rows{rows}_num_rel_diff"] = float(((num_g - num_ref).abs() / num_ref.abs().clamp_min(1e-30)).max())
+            ms = timed(lambda: eng.perm_null_values(gs, std.Z, g, 2, seed=1), reps=2) / 2
+            res[f"rows{rows}_values_null"] = dict(ms_per_perm=round(ms, 3), gene_perms_per_s=round(g / (ms / 1e3), 1))
+        del lag_g
+    gs.tiles = None
+    eng.tile_graph(gs)
+    del lag_ref
+    out["lag_tiles"] = res
 
 if want("values"):
     k1 = nnz / n + 1.0

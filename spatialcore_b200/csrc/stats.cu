@@ -339,17 +339,15 @@ __device__ __forceinline__ void fma4(float4& a, float w, const float4& v) {
   a.x += w * v.x; a.y += w * v.y; a.z += w * v.z; a.w += w * v.w;
 }
 
-// UNR = neighbour rows fetched per inner iteration (loads in flight per thread).  The kernel is bound by
-// exposed L1-miss latency (ncu: long-scoreboard stalls, time inversely proportional to resident warps),
-// and the register file caps warps x loads-in-flight, so fewer warps with deeper unrolling carry more
-// bytes in flight: UNR = 4 -> 56 registers, 32 warps/SM; 8 -> 24 warps; 16 -> 16 warps.  Measured on
-// B200 (C4 / C2, ms): UNR 4: 32.8 / 1.44, 8: 45 / 1.57, 16: 45-55 / 2.2-2.6 -- occupancy wins, so 4 is
-// the default.  (One 16-byte load for four column indices was also tried: 38 / 1.72, slower.)
-// Q = lanes (column quads) per row: a warp-wide load touches 32/Q different rows, and it completes only
-// when the slowest of them has arrived (P(all hit L1) = hit^(32/Q)); wider Q means fewer rows per load
-// but a larger per-row footprint in L1.
+// Fallback lag kernel: one (row, float4 lane) per thread, neighbour rows gathered through L1.  It serves
+// explicitly weighted graphs, graphs without the tile form and matrices narrower than 32 columns; the
+// shared-memory tile kernel (lag_tile.cu) is the fast path.  Measured on B200 (C4: 33 ms, C2: 1.45 ms):
+// bound by the L1 load path (~46 B/clk/SM for 128-byte row pieces), insensitive to row alignment, lanes per
+// row (8/16/32), chunk size and unroll depth (profiles/r02_lag_experiments.json).
+// A row's neighbours are added one by one in ascending column order (the order of lag_tile.cu, so the two
+// kernels agree bit for bit); four gathers are in flight per thread.
 template <bool HAS_W, int UNR, int Q>
-__global__ void __launch_bounds__(kStatThreads, UNR >= 16 ? 2 : (UNR >= 8 ? 3 : 4))
+__global__ void __launch_bounds__(kStatThreads, 4)
 lag_stat_kernel(const int32_t* __restrict__ indptr, const int32_t* __restrict__ indices,
                 const float* __restrict__ weights, int64_t n, int k_fixed,
                 const float* __restrict__ Zself, const float* __restrict__ Zlag, int64_t ldz,
@@ -391,29 +389,17 @@ lag_stat_kernel(const int32_t* __restrict__ indptr, const int32_t* __restrict__ 
 #pragma unroll
         for (int u = 0; u < UNR; ++u) v[u] = ldg4_row(zbase, j[u], ldzb);
 #pragma unroll
-        for (int u = 0; u < UNR; u += 4) {  // groups of four, summed in the same order for every UNR
-          acc.x += w[u] * v[u].x + w[u + 1] * v[u + 1].x + w[u + 2] * v[u + 2].x + w[u + 3] * v[u + 3].x;
-          acc.y += w[u] * v[u].y + w[u + 1] * v[u + 1].y + w[u + 2] * v[u + 2].y + w[u + 3] * v[u + 3].y;
-          acc.z += w[u] * v[u].z + w[u + 1] * v[u + 1].z + w[u + 2] * v[u + 2].z + w[u + 3] * v[u + 3].z;
-          acc.w += w[u] * v[u].w + w[u + 1] * v[u + 1].w + w[u + 2] * v[u + 2].w + w[u + 3] * v[u + 3].w;
-        }
-      }
-      if (UNR > 4) {
-#pragma unroll 1
-        for (; t + 4 <= deg; t += 4) {
-          const int j0 = ip[t], j1 = ip[t + 1], j2 = ip[t + 2], j3 = ip[t + 3];
-          float w0 = 1.f, w1 = 1.f, w2 = 1.f, w3 = 1.f;
-          if (HAS_W) { w0 = wp[t]; w1 = wp[t + 1]; w2 = wp[t + 2]; w3 = wp[t + 3]; }
-          const float4 v0 = ldg4_row(zbase, j0, ldzb), v1 = ldg4_row(zbase, j1, ldzb);
-          const float4 v2 = ldg4_row(zbase, j2, ldzb), v3 = ldg4_row(zbase, j3, ldzb);
-          acc.x += w0 * v0.x + w1 * v1.x + w2 * v2.x + w3 * v3.x;
-          acc.y += w0 * v0.y + w1 * v1.y + w2 * v2.y + w3 * v3.y;
-          acc.z += w0 * v0.z + w1 * v1.z + w2 * v2.z + w3 * v3.z;
-          acc.w += w0 * v0.w + w1 * v1.w + w2 * v2.w + w3 * v3.w;
+        for (int u = 0; u < UNR; ++u) {
+          if (HAS_W) fma4(acc, w[u], v[u]);
+          else { acc.x += v[u].x; acc.y += v[u].y; acc.z += v[u].z; acc.w += v[u].w; }
         }
       }
 #pragma unroll 1
-      for (; t < deg; ++t) fma4(acc, HAS_W ? wp[t] : 1.f, ldg4_row(zbase, ip[t], ldzb));
+      for (; t < deg; ++t) {
+        const float4 v = ldg4_row(zbase, ip[t], ldzb);
+        if (HAS_W) fma4(acc, wp[t], v);
+        else { acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w; }
+      }
       if (!HAS_W) {
         const float inv = (deg > 0) ? 1.f / (float)deg : 0.f;
         acc.x *= inv; acc.y *= inv; acc.z *= inv; acc.w *= inv;
@@ -447,115 +433,6 @@ lag_stat_kernel(const int32_t* __restrict__ indptr, const int32_t* __restrict__ 
       double a = 0, d = 0;
 #pragma unroll 4
       for (int r = 0; r < kRows; ++r) { a += sh[0][r][q][c]; d += sh[1][r][q][c]; }
-      p[c] = a; p[ldz + c] = d;
-    }
-  }
-}
-
-// ---- lag through shared memory ---------------------------------------------------------------------
-// In spatial order ~87 % of a row's neighbours lie inside its own 512-row chunk (measured on uniform
-// 2-D points at degree 20).  The chunk's own rows are contiguous, so the CTA stages them once
-// (cp.async, 128 B per row) and serves in-chunk neighbours from shared memory (LDS: 128 B/clk/SM)
-// while only the halo goes through L1 (LDG: ~70 B/clk/SM, 2 cycles per extra line).  Same arithmetic,
-// same summation order as lag_stat_kernel.
-__device__ __forceinline__ void cp_async16(void* smem, const void* gmem) {
-  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(smem)), "l"(gmem) : "memory");
-}
-__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
-
-template <bool HAS_W>
-__global__ void __launch_bounds__(kStatThreads, 3)
-lag_stat_tile_kernel(const int32_t* __restrict__ indptr, const int32_t* __restrict__ indices,
-                     const float* __restrict__ weights, int64_t n, int k_fixed,
-                     const float* __restrict__ Zself, const float* __restrict__ Zlag, int64_t ldz,
-                     float* __restrict__ lag, float* __restrict__ local, int64_t ldl,
-                     double* __restrict__ partial, const float* __restrict__ cell_obs,
-                     int32_t* __restrict__ cell_cnt, int64_t ldc, int64_t n_chunks, int chunk_rows) {
-  extern __shared__ __align__(128) unsigned char lag_smem[];
-  float4* tile = reinterpret_cast<float4*>(lag_smem);  // [chunk_rows][8] float4
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int q = lane & (kLagColQuads - 1);
-  const int rslot = warp * (32 / kLagColQuads) + (lane >> 3);
-  const int64_t col = ((int64_t)blockIdx.x * kLagColQuads + q) * 4;
-  const bool active = col < ldz;
-  const char* zbase = reinterpret_cast<const char*>(Zlag + col);
-  const uint32_t ldzb = (uint32_t)ldz * 4u;
-  double num[4] = {0, 0, 0, 0}, den[4] = {0, 0, 0, 0};
-
-  for (int64_t chunk = blockIdx.y; chunk < n_chunks; chunk += gridDim.y) {
-    const int r0 = (int)(chunk * chunk_rows);
-    const int rows_here = (int)min((int64_t)chunk_rows, n - r0);
-    __syncthreads();  // previous chunk's readers are done with the tile
-    if (active)
-      for (int r = rslot; r < rows_here; r += kLagRowsPerPass)
-        cp_async16(&tile[r * kLagColQuads + q], zbase + (uint64_t)(uint32_t)(r0 + r) * ldzb);
-    cp_async_wait_all();
-    __syncthreads();
-#pragma unroll 1
-    for (int pass = 0; pass < rows_here; pass += kLagRowsPerPass) {
-      const int lrow = pass + rslot;
-      if (lrow >= rows_here || !active) continue;
-      const int64_t row = (int64_t)r0 + lrow;
-      int64_t b;
-      int deg;
-      if (indptr) { b = indptr[row]; deg = indptr[row + 1] - (int)b; } else { b = row * k_fixed; deg = k_fixed; }
-      const int32_t* __restrict__ ip = indices + b;
-      const float* __restrict__ wp = HAS_W ? weights + b : nullptr;
-      float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-      auto fetch = [&](int j) -> float4 {
-        const uint32_t off = (uint32_t)(j - r0);
-        if (off < (uint32_t)rows_here) return tile[off * kLagColQuads + q];
-        return ldg4_row(zbase, j, ldzb);
-      };
-      int t = 0;
-#pragma unroll 1
-      for (; t + 4 <= deg; t += 4) {
-        const int j0 = ip[t], j1 = ip[t + 1], j2 = ip[t + 2], j3 = ip[t + 3];
-        float w0 = 1.f, w1 = 1.f, w2 = 1.f, w3 = 1.f;
-        if (HAS_W) { w0 = wp[t]; w1 = wp[t + 1]; w2 = wp[t + 2]; w3 = wp[t + 3]; }
-        const float4 v0 = fetch(j0), v1 = fetch(j1), v2 = fetch(j2), v3 = fetch(j3);
-        acc.x += w0 * v0.x + w1 * v1.x + w2 * v2.x + w3 * v3.x;
-        acc.y += w0 * v0.y + w1 * v1.y + w2 * v2.y + w3 * v3.y;
-        acc.z += w0 * v0.z + w1 * v1.z + w2 * v2.z + w3 * v3.z;
-        acc.w += w0 * v0.w + w1 * v1.w + w2 * v2.w + w3 * v3.w;
-      }
-#pragma unroll 1
-      for (; t < deg; ++t) fma4(acc, HAS_W ? wp[t] : 1.f, fetch(ip[t]));
-      if (!HAS_W) {
-        const float inv = (deg > 0) ? 1.f / (float)deg : 0.f;
-        acc.x *= inv; acc.y *= inv; acc.z *= inv; acc.w *= inv;
-      }
-      const float4 z = Zself ? ldg4(Zself + row * ldz + col) : tile[lrow * kLagColQuads + q];
-      const float4 loc = make_float4(z.x * acc.x, z.y * acc.y, z.z * acc.z, z.w * acc.w);
-      if (lag) *reinterpret_cast<float4*>(lag + row * ldl + col) = acc;
-      if (local) *reinterpret_cast<float4*>(local + row * ldl + col) = loc;
-      if (cell_cnt) {
-        const float4 o = ldg4(cell_obs + row * ldc + col);
-        int4* cp = reinterpret_cast<int4*>(cell_cnt + row * ldc + col);
-        int4 cc = *cp;
-        cc.x += fabsf(loc.x) >= fabsf(o.x); cc.y += fabsf(loc.y) >= fabsf(o.y);
-        cc.z += fabsf(loc.z) >= fabsf(o.z); cc.w += fabsf(loc.w) >= fabsf(o.w);
-        *cp = cc;
-      }
-      const double zx = z.x, zy = z.y, zz = z.z, zw = z.w;
-      num[0] = fma(zx, (double)acc.x, num[0]); den[0] = fma(zx, zx, den[0]);
-      num[1] = fma(zy, (double)acc.y, num[1]); den[1] = fma(zy, zy, den[1]);
-      num[2] = fma(zz, (double)acc.z, num[2]); den[2] = fma(zz, zz, den[2]);
-      num[3] = fma(zw, (double)acc.w, num[3]); den[3] = fma(zw, zw, den[3]);
-    }
-  }
-  __syncthreads();
-  double (*sh)[kLagRowsPerPass][kLagColQuads][4] = reinterpret_cast<double (*)[kLagRowsPerPass][kLagColQuads][4]>(lag_smem);
-#pragma unroll
-  for (int c = 0; c < 4; ++c) { sh[0][rslot][q][c] = num[c]; sh[1][rslot][q][c] = den[c]; }
-  __syncthreads();
-  if (rslot == 0 && active) {
-    double* p = partial + ((int64_t)blockIdx.y * 2) * ldz + col;
-#pragma unroll
-    for (int c = 0; c < 4; ++c) {
-      double a = 0, d = 0;
-#pragma unroll 4
-      for (int r = 0; r < kLagRowsPerPass; ++r) { a += sh[0][r][q][c]; d += sh[1][r][q][c]; }
       p[c] = a; p[ldz + c] = d;
     }
   }
@@ -654,32 +531,6 @@ perm_rows_kernel(const float* __restrict__ A, int64_t lda, const float* __restri
 // per SM = (stages-1) x rows-per-stage x (PB+1) x ld x 4, i.e. 100-200 KB.
 // ------------------------------------------------------------------------------------------------
 
-__device__ __forceinline__ uint32_t smem_u32(const void* p) {
-  return (uint32_t)__cvta_generic_to_shared(p);
-}
-__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
-}
-__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes)
-               : "memory");
-}
-__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
-  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
-  asm volatile(
-      "{\n"
-      ".reg .pred p;\n"
-      "WAIT_%=:\n"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
-      "@p bra DONE_%=;\n"
-      "bra WAIT_%=;\n"
-      "DONE_%=:\n"
-      "}\n" ::"r"(smem_u32(bar)),
-      "r"(parity)
-      : "memory");
-}
 // global -> shared bulk copy (bytes % 16 == 0, both addresses 16-byte aligned), completes on `bar`
 __device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src_gmem, uint32_t bytes,
                                          uint64_t* bar, uint64_t policy) {
@@ -1143,72 +994,24 @@ static void fill_batch(PermBatch* pb, int source, const int32_t* perm_idx, uint6
 constexpr int kMaxStatBlocks = 148 * 8;
 
 // Launch lag_stat_kernel; *by_out = number of partial rows written ([by][2][ldz] doubles).
-// SC_LAG_UNR (4|8|16), SC_LAG_Q (8|16|32), SC_LAG_CHUNK (multiple of 32) and SC_LAG_VARIANT=tile override
-// the geometry for experiments.
-template <bool HAS_W, int UNR, int Q>
-static void launch_lag_stat_t(dim3 grid, cudaStream_t st, const int32_t* indptr, const int32_t* indices,
-                              const float* weights, int64_t n, int k_fixed, const float* Zself,
-                              const float* Zlag, int64_t ldz, float* lag, float* local, int64_t ldl,
-                              double* partial, const float* cell_obs, int32_t* cell_cnt, int64_t ldc,
-                              int64_t n_chunks, int chunk_rows) {
-  lag_stat_kernel<HAS_W, UNR, Q><<<grid, kStatThreads, 0, st>>>(indptr, indices, weights, n, k_fixed, Zself, Zlag, ldz, lag,
-                                                             local, ldl, partial, cell_obs, cell_cnt, ldc, n_chunks,
-                                                             chunk_rows);
-}
-
 static int launch_lag_stat(const int32_t* indptr, const int32_t* indices, const float* weights,
                            int64_t n, int k_fixed, const float* Zself, const float* Zlag, int64_t ldz,
                            float* lag, float* local, int64_t ldl, double* partial,
                            const float* cell_obs, int32_t* cell_cnt, int64_t ldc, int* by_out,
                            cudaStream_t st) {
-  int unr = kLagDefaultUnr;
   int chunk_rows = 512;
   while (chunk_rows > 64 && ((n + chunk_rows - 1) / chunk_rows) * ((ldz + 31) / 32) < 4 * (int64_t)sm_count()) chunk_rows /= 2;
-  if (const char* e = getenv("SC_LAG_UNR")) { int v = atoi(e); if (v == 4 || v == 8 || v == 16) unr = v; }
-  int quads = kLagColQuads;
-  if (const char* e = getenv("SC_LAG_Q")) { int v = atoi(e); if (v == 8 || v == 16 || v == 32) quads = v; }
-  if (ldz < 4 * quads) quads = kLagColQuads;
-  if (const char* e = getenv("SC_LAG_CHUNK")) { int v = atoi(e); if (v >= 32 && v % 32 == 0 && v <= 4096) chunk_rows = v; }
-  // SC_LAG_VARIANT=tile selects the shared-memory variant.  Measured on B200: it wins on C2 (kNN k=15,
-  // 500 k x 400: 1.22 vs 1.44 ms) and loses on C4 (radius, 5 M x 1000: 42 vs 33 ms) -- the tile's 64 KB
-  // per CTA costs resident warps, and this kernel's time is inversely proportional to them.
-  const char* variant = getenv("SC_LAG_VARIANT");
-  const bool tile = ldz >= 32 && variant && !strcmp(variant, "tile");
-  const int bx = tile ? (int)((ldz + 31) / 32) : (int)((ldz + 4 * quads - 1) / (4 * quads));
+  const int bx = (int)((ldz + 4 * kLagColQuads - 1) / (4 * kLagColQuads));
   const int64_t n_chunks = (n + chunk_rows - 1) / chunk_rows;
   int64_t by = ((int64_t)sm_count() * 8 + bx - 1) / bx;
   if (by > n_chunks) by = n_chunks;
   if (by > kMaxStatBlocks) by = kMaxStatBlocks;
   if (by < 1) by = 1;
   dim3 grid(bx, (unsigned)by);
-  if (tile) {
-    size_t dyn = (size_t)chunk_rows * kLagColQuads * sizeof(float4);
-    if (dyn < sizeof(double) * 2 * kLagRowsPerPass * kLagColQuads * 4) dyn = sizeof(double) * 2 * kLagRowsPerPass * kLagColQuads * 4;
-    if (weights) {
-      SC_CUDA_OK(cudaFuncSetAttribute(lag_stat_tile_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn));
-      lag_stat_tile_kernel<true><<<grid, kStatThreads, dyn, st>>>(indptr, indices, weights, n, k_fixed, Zself, Zlag, ldz, lag, local, ldl, partial, cell_obs, cell_cnt, ldc, n_chunks, chunk_rows);
-    } else {
-      SC_CUDA_OK(cudaFuncSetAttribute(lag_stat_tile_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn));
-      lag_stat_tile_kernel<false><<<grid, kStatThreads, dyn, st>>>(indptr, indices, weights, n, k_fixed, Zself, Zlag, ldz, lag, local, ldl, partial, cell_obs, cell_cnt, ldc, n_chunks, chunk_rows);
-    }
-    SC_LAUNCH_OK();
-    *by_out = (int)by;
-    return SC_OK;
-  }
-#define SC_LAG_ARGS grid, st, indptr, indices, weights, n, k_fixed, Zself, Zlag, ldz, lag, local, ldl, partial, cell_obs, cell_cnt, ldc, n_chunks, chunk_rows
-#define SC_LAG_Q(W, U)                                                                      \
-  do {                                                                                      \
-    if (quads == 32) launch_lag_stat_t<W, U, 32>(SC_LAG_ARGS);                              \
-    else if (quads == 16) launch_lag_stat_t<W, U, 16>(SC_LAG_ARGS);                         \
-    else launch_lag_stat_t<W, U, 8>(SC_LAG_ARGS);                                           \
-  } while (0)
-  if (weights) {
-    if (unr == 16) SC_LAG_Q(true, 16); else if (unr == 8) SC_LAG_Q(true, 8); else SC_LAG_Q(true, 4);
-  } else {
-    if (unr == 16) SC_LAG_Q(false, 16); else if (unr == 8) SC_LAG_Q(false, 8); else SC_LAG_Q(false, 4);
-  }
-#undef SC_LAG_Q
-#undef SC_LAG_ARGS
+  if (weights)
+    lag_stat_kernel<true, kLagDefaultUnr, kLagColQuads><<<grid, kStatThreads, 0, st>>>(indptr, indices, weights, n, k_fixed, Zself, Zlag, ldz, lag, local, ldl, partial, cell_obs, cell_cnt, ldc, n_chunks, chunk_rows);
+  else
+    lag_stat_kernel<false, kLagDefaultUnr, kLagColQuads><<<grid, kStatThreads, 0, st>>>(indptr, indices, weights, n, k_fixed, Zself, Zlag, ldz, lag, local, ldl, partial, cell_obs, cell_cnt, ldc, n_chunks, chunk_rows);
   SC_LAUNCH_OK();
   *by_out = (int)by;
   return SC_OK;

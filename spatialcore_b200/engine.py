@@ -79,21 +79,9 @@ def _workspace(nbytes: int, device) -> torch.Tensor:
     return torch.empty(max(int(nbytes), 256), dtype=torch.uint8, device=device)
 
 
-def _row_align() -> int:
-    """Row alignment of the N x G matrices in floats.  8 (32-byte sectors) is the measured default;
-    ``SC_ROW_ALIGN=16|32`` is an experiment switch: 32 makes every row start on a 128-byte line, which
-    halves the lines a 128-byte gather of the lag kernel touches at the price of up to 2.4 % more bytes
-    for the streaming kernels.  The kernels accept any ld in [g, round_up(g, 32)]."""
-    a = int(os.environ.get("SC_ROW_ALIGN", "8"))
-    if a not in (8, 16, 32):
-        raise ValueError(f"SC_ROW_ALIGN must be 8, 16 or 32, got {a}")
-    return a
-
-
 def padded_ld(g: int) -> int:
     """Leading dimension used for every N x G matrix: multiple of 8 floats (32-byte sectors)."""
-    a = _row_align()
-    return (g + a - 1) // a * a
+    return (g + 7) // 8 * 8
 
 
 @dataclass
@@ -107,9 +95,8 @@ class DeviceGraph:
     k_fixed: int = 0
     weights: Optional[torch.Tensor] = None
     dist: Optional[torch.Tensor] = None
-    # experimental row-group form for the lag kernel: (group_rows, union words int32[nnz + 8 * n_groups + 8],
-    # union length per group int32[n_groups]), n_groups = ceil(n / group_rows); see group_graph()
-    groups: Optional[Tuple[int, torch.Tensor, torch.Tensor]] = None
+    # shared-memory tile form for the lag kernel: (group_rows, opaque device buffer); see tile_graph()
+    tiles: Optional[Tuple[int, torch.Tensor]] = None
 
     @property
     def nnz(self) -> int:
@@ -301,41 +288,47 @@ def relabel_graph(graph: DeviceGraph, co: CellOrder) -> DeviceGraph:
         "sc_graph_relabel",
     )
     out = DeviceGraph(n=graph.n, indices=out_idx, indptr=out_ptr, k_fixed=graph.k_fixed, weights=out_w)
-    rows = _lag_group_rows()
-    if rows and out_w is None and graph.n <= 2 ** (32 - rows):
-        group_graph(out, rows)
+    if out_w is None and tile_rows() > 0:
+        tile_graph(out)
     return out
 
 
-def _lag_group_rows() -> int:
-    """``SC_LAG_GROUP=2|4|8`` (experiment switch, default off): graphs put into spatial order also get the
-    row-group form, and ``lag_moran`` then runs ``sc_csr_lag_moran_grouped`` on them."""
-    v = os.environ.get("SC_LAG_GROUP", "")
-    if v in ("", "0"):
-        return 0
-    if v not in ("2", "4", "8"):
-        raise ValueError(f"SC_LAG_GROUP must be 2, 4 or 8, got '{v}'")
+def tile_rows() -> int:
+    """Rows per group of the shared-memory lag tiles (``SC_LAG_TILE_ROWS``: 1, 2 or 4; 0 disables the tile
+    form and leaves every lag to the L1-gather kernel)."""
+    v = os.environ.get("SC_LAG_TILE_ROWS", "")
+    if v == "":
+        return _DEFAULT_TILE_ROWS
+    if v not in ("0", "1", "2", "4"):
+        raise ValueError(f"SC_LAG_TILE_ROWS must be 0, 1, 2 or 4, got '{v}'")
     return int(v)
 
 
+_DEFAULT_TILE_ROWS = 1
+
+
 @_on_device
-def group_graph(graph: DeviceGraph, group_rows: int) -> DeviceGraph:
-    """``sc_graph_group_build``: merge the neighbour lists of every ``group_rows`` consecutive rows into one
-    union list with membership masks (rows must be column-sorted; binary graphs only).  Pays off when
-    consecutive rows are spatial neighbours, i.e. after ``relabel_graph``."""
+def tile_graph(graph: DeviceGraph, group_rows: Optional[int] = None) -> DeviceGraph:
+    """``sc_graph_tile_build``: the shared-memory tile form of a row-standardised binary graph in spatial
+    order (per chunk of 256 rows the union of neighbour rows, per group of rows the merged neighbour list
+    as 16-bit words).  ``lag_moran`` and ``perm_null_values`` use it when present."""
     if graph.weights is not None:
-        raise ValueError("group_graph: explicitly weighted graphs are not supported")
+        raise ValueError("tile_graph: explicitly weighted graphs are not supported")
+    rows = tile_rows() if group_rows is None else int(group_rows)
+    if rows not in (1, 2, 4):
+        raise ValueError(f"group_rows must be 1, 2 or 4, got {rows}")
     L = _lib.lib()
-    dev = graph.indices.device
-    n_groups = (graph.n + group_rows - 1) // group_rows
-    uwords = torch.empty(graph.nnz + 8 * n_groups + 8, dtype=torch.int32, device=dev)  # 16-byte aligned, padded lists
-    ucnt = torch.empty(n_groups, dtype=torch.int32, device=dev)
+    nbytes = int(L.sc_graph_tile_bytes(graph.n, graph.nnz, rows))
+    if nbytes == 0 or graph.nnz == 0:
+        graph.tiles = None
+        return graph
+    buf = torch.empty(nbytes, dtype=torch.uint8, device=graph.indices.device)
     check(
-        L.sc_graph_group_build(_ptr(graph.indptr), _ptr(graph.indices), graph.n, int(graph.k_fixed), int(group_rows),
-                               _ptr(uwords), _ptr(ucnt), _stream()),
-        "sc_graph_group_build",
+        L.sc_graph_tile_build(_ptr(graph.indptr), _ptr(graph.indices), graph.n, int(graph.k_fixed), graph.nnz, rows,
+                              _ptr(buf), nbytes, _stream()),
+        "sc_graph_tile_build",
     )
-    graph.groups = (int(group_rows), uwords, ucnt)
+    graph.tiles = (rows, buf)
     return graph
 
 
@@ -572,6 +565,27 @@ def expression_to_device(X, gene_idx: Optional[np.ndarray], device="cuda") -> Tu
 # --------------------------------------------------------------------------------------------------
 
 
+def _use_tiles(graph: DeviceGraph, ld: int) -> bool:
+    return graph.tiles is not None and graph.weights is None and ld >= 32
+
+
+def _lag_tiled(graph: DeviceGraph, Z: torch.Tensor, Zself: Optional[torch.Tensor], perm: Optional[torch.Tensor], g: int,
+               lag: Optional[torch.Tensor], local: Optional[torch.Tensor], num: torch.Tensor, den: torch.Tensor,
+               cell_obs: Optional[torch.Tensor], cell_cnt: Optional[torch.Tensor], ws: torch.Tensor) -> None:
+    """``sc_csr_lag_moran_tiled`` on the graph's tile form."""
+    L = _lib.lib()
+    n, ld = Z.shape
+    rows, buf = graph.tiles
+    ldl = lag.shape[1] if lag is not None else (local.shape[1] if local is not None else ld)
+    check(
+        L.sc_csr_lag_moran_tiled(_ptr(graph.indptr), _ptr(graph.indices), n, int(graph.k_fixed), graph.nnz, rows, _ptr(buf),
+                                 buf.numel(), _ptr(Zself), _ptr(Z), _ptr(perm), ld, g, _ptr(lag), _ptr(local), ldl, _ptr(num),
+                                 _ptr(den), _ptr(cell_obs), _ptr(cell_cnt), cell_cnt.shape[1] if cell_cnt is not None else 0,
+                                 _ptr(ws), ws.numel(), _stream()),
+        "sc_csr_lag_moran_tiled",
+    )
+
+
 @_on_device
 def lag_moran(graph: DeviceGraph, Z: torch.Tensor, g: int, want_lag: bool = True, want_local: bool = False):
     """``sc_csr_lag_moran``: returns ``(num[g], den[g], lag|None, local|None)``."""
@@ -584,14 +598,8 @@ def lag_moran(graph: DeviceGraph, Z: torch.Tensor, g: int, want_lag: bool = True
     num = torch.empty(g, dtype=torch.float64, device=dev)
     den = torch.empty(g, dtype=torch.float64, device=dev)
     ws = _workspace(L.sc_csr_lag_moran_workspace_bytes(n, g), dev)
-    if graph.groups is not None and graph.weights is None:
-        rows, uwords, ucnt = graph.groups
-        check(
-            L.sc_csr_lag_moran_grouped(_ptr(graph.indptr), n, int(graph.k_fixed), rows, _ptr(uwords), _ptr(ucnt), _ptr(Z), ld, g,
-                                       _ptr(lag), _ptr(local), ld, _ptr(num), _ptr(den), None, None, 0, _ptr(ws), ws.numel(),
-                                       _stream()),
-            "sc_csr_lag_moran_grouped",
-        )
+    if _use_tiles(graph, ld):
+        _lag_tiled(graph, Z, None, None, g, lag, local, num, den, None, None, ws)
         return num, den, lag, local
     check(
         L.sc_csr_lag_moran(_ptr(graph.indptr), _ptr(graph.indices), _ptr(graph.weights), n, int(graph.k_fixed), _ptr(Z),
@@ -638,22 +646,14 @@ def perm_null_values(graph: DeviceGraph, Zy: torch.Tensor, g: int, n_perms: int,
     n, ld = Zy.shape
     source, pidx = _perm_source(perm_idx, n, n_perms)
     sims = torch.empty((n_perms, g), dtype=torch.float64, device=Zy.device)
-    if graph.groups is not None and graph.weights is None and Zx is None and ld >= 32:
-        # experimental (SC_LAG_GROUP): the same materialised scheme -- permuted copy of Z, then lag and
-        # local statistic of the copy -- composed from sc_gather_rows and the row-group lag kernel
-        rows, uwords, ucnt = graph.groups
+    if _use_tiles(graph, ld):
+        # the tile kernel applies the permutation while staging (operand row j = Zy[perm[j]]): no permuted copy
+        # of Z is materialised; the statistic of permutation p is the Moran numerator of that pass
         ws = _workspace(L.sc_csr_lag_moran_workspace_bytes(n, g), Zy.device)
         den = torch.empty(g, dtype=torch.float64, device=Zy.device)
-        ldc = cell_cnt.shape[1] if cell_cnt is not None else 0
         for p in range(n_perms):
             perm = pidx[p] if pidx is not None else philox_permutation(seed, perm_offset + p, n, device=Zy.device)
-            Zp = gather_rows(Zy, perm)
-            check(
-                L.sc_csr_lag_moran_grouped(_ptr(graph.indptr), n, int(graph.k_fixed), rows, _ptr(uwords), _ptr(ucnt), _ptr(Zp), ld,
-                                           g, None, None, ld, _ptr(sims[p]), _ptr(den), _ptr(cell_obs), _ptr(cell_cnt), ldc,
-                                           _ptr(ws), ws.numel(), _stream()),
-                "sc_csr_lag_moran_grouped",
-            )
+            _lag_tiled(graph, Zy, Zx, perm, g, None, None, sims[p], den, cell_obs, cell_cnt, ws)
         return sims
     ws = _workspace(L.sc_perm_null_values_workspace_bytes(n, g), Zy.device)
     ldc = cell_cnt.shape[1] if cell_cnt is not None else 0

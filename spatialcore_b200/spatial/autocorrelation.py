@@ -281,10 +281,13 @@ def spatial_neighbors(adata, n_neighs: int = 6, radius: Optional[float] = None, 
     return graph
 
 
-def _existing_graph(adata, device) -> engine.DeviceGraph:
+def _existing_graph(adata, device, normalize: bool = True) -> engine.DeviceGraph:
     """``use_existing_graph=True``: squidpy L1-row-normalises whatever is stored
-    (``transformation=True``), so binary graphs map to implicit 1/deg weights."""
+    (``transformation=True``), so binary graphs map to implicit 1/deg weights; ``normalize=False``
+    (``transformation=False``) keeps the stored weights."""
     adj = sparse.csr_matrix(adata.obsp["spatial_connectivities"])
+    if not normalize:
+        return engine.graph_from_scipy(adj.astype(np.float64), device, use_weights=True)
     if adj.nnz and np.all(adj.data == 1):
         return engine.graph_from_scipy(adj, device, use_weights=False)
     adj = adj.astype(np.float64)
@@ -354,6 +357,33 @@ def moran_graph_rows_null(Z: torch.Tensor, lag: torch.Tensor, g: int, scale: tor
     return sims_all
 
 
+def moran_values_null(graph: engine.DeviceGraph, Z: torch.Tensor, g: int, scale: torch.Tensor, obs: torch.Tensor,
+                      seed: int, source: str, null: MoranNull, perm_range: Tuple[int, int],
+                      cell_order: Optional[engine.CellOrder] = None) -> None:
+    """Permutations ``perm_range`` of the VALUE-permuting null -- ``Zs = Z[perm]; sim = Σ_i Zs_i (W Zs)_i``, the
+    scheme of the reference's own ``local_morans_i`` / Lee's L [R autocorrelation.py:877-884] applied to the
+    global statistic -- folded into ``null``.  Same addressing of permutations as the graph-row null."""
+    n = Z.shape[0]
+    first, last = perm_range
+    if last <= first:
+        return
+    if source == "philox":
+        step = 64
+        for p0 in range(first, last, step):
+            cnt = min(step, last - p0)
+            sims = engine.perm_null_values(graph, Z, g, cnt, seed=seed, perm_offset=p0)
+            engine.null_accumulate(sims, scale, obs, null.cnt_ge, null.cnt_abs_ge, null.sum, null.sumsq)
+    else:
+        rng = np.random.default_rng(seed)
+        for _ in range(first):
+            rng.permutation(n)
+        for _, idx in _replay_chunks(rng, n, last - first, Z.device):
+            if cell_order is not None:
+                idx = engine.conjugate_perms(idx, cell_order)
+            sims = engine.perm_null_values(graph, Z, g, idx.shape[0], perm_idx=idx)
+            engine.null_accumulate(sims, scale, obs, null.cnt_ge, null.cnt_abs_ge, null.sum, null.sumsq)
+
+
 def morans_i(
     adata,
     genes: Optional[Union[str, List[str]]] = None,
@@ -369,6 +399,9 @@ def morans_i(
     perm_source: str = "auto",
     radius: Optional[float] = None,
     write_graph: bool = True,
+    null_mode: str = "graph_rows",
+    two_tailed: bool = False,
+    transformation: bool = True,
     shard: str = "auto",
     ingest: str = "replicated",
     group=None,
@@ -385,10 +418,27 @@ def morans_i(
     all-reduced), ``"none"`` (ranks work independently), ``"auto"`` = genes when there are at least
     500 genes per rank, else perms.  ``ingest="sharded"`` (with ``shard="perms"``): each rank uploads
     and standardises N/W cells and the blocks are all-gathered over NVLink (results agree with
-    ``"replicated"`` to the FP32 rounding of Z: pooled moments differ in the last FP64 bit)."""
+    ``"replicated"`` to the FP32 rounding of Z: pooled moments differ in the last FP64 bit).
+
+    Semantic switches.  The statistic, null and p-value conventions of the reference live in squidpy / scanpy
+    [R autocorrelation.py:565-583], which cannot be pinned offline; every recalled convention is
+    therefore a named keyword, defaulting to the recalled squidpy behaviour, so a check against real squidpy can
+    flip it without touching a kernel:
+
+    ``null_mode``       ``"graph_rows"`` (default): squidpy's ``morans_i(g[idx, :], vals)`` -- rows of the graph are
+                        permuted; ``"values"``: expression values are permuted and W re-applied, the scheme of the
+                        reference's own ``local_morans_i`` / Lee's L [R :877-884] (a true permutation test).
+    ``two_tailed``      ``False`` (default): folded one-sided permutation p ``(min(c, P-c)+1)/(P+1)`` with
+                        ``c = #{sims >= I}`` and one-sided normal p; ``True``: ``(#{|sims| >= |I|}+1)/(P+1)`` (the
+                        reference's own two-tailed count [R :330, :888-896]) and the normal p doubled (squidpy's
+                        ``two_tailed=True``).
+    ``transformation``  ``True`` (default): the graph is L1-row-normalised (squidpy's default); ``False``: binary /
+                        stored weights as they are (identical for kNN graphs, different for radius graphs)."""
     t0 = time.time()
     _check_spatial(adata, spatial_key)
     _check_counts(n_neighbors, n_permutations)
+    if null_mode not in ("graph_rows", "values"):
+        raise ValueError(f"null_mode must be 'graph_rows' or 'values', got '{null_mode}'")
     if shard not in ("auto", "genes", "perms", "none"):
         raise ValueError(f"shard must be 'auto', 'genes', 'perms' or 'none', got '{shard}'")
     if ingest not in ("replicated", "sharded"):
@@ -413,9 +463,12 @@ def morans_i(
 
     if use_existing_graph and "spatial_connectivities" in adata.obsp:
         logger.info("Using existing spatial connectivity graph (use_existing_graph=True)")
-        graph = _existing_graph(adata, device)
+        graph = _existing_graph(adata, device, normalize=transformation)
     else:
         graph = spatial_neighbors(adata, n_neighbors, radius, spatial_key, device=device, write=write_graph)
+        if not transformation:  # binary weights as stored by squidpy (transformation=False): explicit ones
+            graph = engine.DeviceGraph(n=graph.n, indices=graph.indices, indptr=graph.indptr, k_fixed=graph.k_fixed,
+                                       weights=torch.ones(graph.nnz, dtype=torch.float32, device=graph.indices.device))
 
     # cells are held in spatial (Z-curve) order on the device: every quantity below is a sum over cells
     co = engine.spatial_order(adata.obsm[spatial_key], device=device)
@@ -424,7 +477,7 @@ def morans_i(
         std = _standardize_row_sharded(adata, layer, names, device, co, group)
     else:
         std = _standardize(adata, layer, names, device, rows=co.order)
-    num, den, lag, _ = engine.lag_moran(graph_s, std.Z, g, want_lag=n_permutations > 0)
+    num, den, lag, _ = engine.lag_moran(graph_s, std.Z, g, want_lag=n_permutations > 0 and null_mode == "graph_rows")
     s0, s1, s2 = engine.graph_moments(graph_s)  # s0, s1, s2 do not depend on the labelling of the cells
     scale = (float(n) / s0) / den  # I = scale * Σ z·lag ; NaN for zero-variance genes, as 0/0 upstream
     I_dev = num * scale
@@ -433,24 +486,28 @@ def morans_i(
     var_norm = (n * n * s1 - n * s2 + 3.0 * s0 * s0) / ((n - 1.0) * (n + 1.0) * s0 * s0) - 1.0 / (n - 1.0) ** 2
     I = I_dev.cpu().numpy()
 
-    extra = {}
     if n_permutations > 0:
         source = _pick_perm_source(perm_source, n, n_permutations)
         null = MoranNull(g, std.Z.device)
         lo, hi = dist_util.my_slice(n_permutations, group) if mode == "perms" else (0, n_permutations)
-        moran_graph_rows_null(std.Z, lag, g, scale, I_dev, n_permutations, seed, source, null, (lo, hi), cell_order=co)
+        if null_mode == "graph_rows":
+            moran_graph_rows_null(std.Z, lag, g, scale, I_dev, n_permutations, seed, source, null, (lo, hi), cell_order=co)
+        else:
+            moran_values_null(graph_s, std.Z, g, scale, I_dev, seed, source, null, (lo, hi), cell_order=co)
         if mode == "perms":
             dist_util.all_reduce_null(null, group)
-        c = null.cnt_ge.cpu().numpy()
-        c = np.where(n_permutations - c < c, n_permutations - c, c)
+        if two_tailed:
+            c = null.cnt_abs_ge.cpu().numpy()
+        else:
+            c = null.cnt_ge.cpu().numpy()
+            c = np.where(n_permutations - c < c, n_permutations - c, c)
         p_value = (c + 1) / (n_permutations + 1)
-        mean_sim = (null.sum / n_permutations).cpu().numpy()
-        extra["var_sim"] = (null.sumsq / n_permutations).cpu().numpy() - mean_sim**2
-        extra["perm_source"] = source
     else:
         with np.errstate(invalid="ignore"):
             zn = (I - expected_I) / np.sqrt(var_norm)
         p_value = np.where(zn > 0, 1.0 - ndtr(zn), ndtr(zn))
+        if two_tailed:
+            p_value = p_value * 2.0
 
     if var_norm > 0:
         z_score = (I - expected_I) / np.sqrt(var_norm)
@@ -483,6 +540,9 @@ def morans_i(
             "use_existing_graph": use_existing_graph,
             "seed": seed,
             "backend": "b200",
+            "null_mode": null_mode,
+            "two_tailed": two_tailed,
+            "transformation": transformation,
         },
         outputs={"uns": key_added},
     )

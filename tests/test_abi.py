@@ -158,23 +158,25 @@ def test_argument_validation_of_the_wider_abi_without_gpu():
     assert L.sc_launch_count() >= 0
 
 
-def test_row_group_lag_core_on_the_host(tmp_path):
-    """The __host__ __device__ core of the experimental row-group lag kernel (``csrc/lag_group_core.cuh``)
-    compiled for the CPU: the union build with membership masks, and the whole per-thread body of the kernel
-    run over an emulated launch grid (lag, local statistic, per-cell counters bit-identical to plain per-row
-    sums, Moran sums to 1e-9) -- everything of that kernel except the shared-memory reduction and the launch
-    itself is verified without a GPU."""
-    import shutil
-    import subprocess
+def test_tile_exports_validate_without_a_gpu():
+    """sc_graph_tile_bytes / _build / sc_csr_lag_moran_tiled reject bad arguments before any launch."""
+    from spatialcore_b200 import _lib
 
-    nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
-    if not os.path.exists(nvcc):
-        pytest.skip("nvcc not available")
-    exe = str(tmp_path / "lag_group_host_test")
-    src = os.path.join(ROOT, "tests", "native", "lag_group_host_test.cu")
-    subprocess.run([nvcc, "-O2", "-std=c++17", "-Wno-deprecated-gpu-targets", "-o", exe, src], check=True, capture_output=True)
-    out = subprocess.run([exe], check=True, capture_output=True, text=True).stdout
-    assert out.count("union/nnz") == 21 and out.count("kernel body ok") == 7 and out.count(" ok") == 28
+    L = _lib.lib()
+    assert L.sc_graph_tile_bytes(0, 10, 1) == 0 and L.sc_graph_tile_bytes(100, 600, 3) == 0
+    small, big = L.sc_graph_tile_bytes(5_000_000, 100_000_000, 1), L.sc_graph_tile_bytes(5_000_000, 100_000_000, 4)
+    # 4 bytes per edge for the word lists (tile byte offsets) + the per-chunk union rows: about the size of the CSR itself
+    assert 400_000_000 < small < 700_000_000 and 400_000_000 < big < 700_000_000
+    assert L.sc_graph_tile_build(None, None, 100, 6, 600, 1, None, 0, None) == -1
+    assert "null argument" in L.sc_last_error().decode()
+    assert L.sc_graph_tile_build(None, 1, 100, 6, 600, 3, 1, 1 << 20, None) == -1  # group_rows
+    assert L.sc_graph_tile_build(None, 1, 100, 6, 601, 1, 1, 1 << 20, None) == -1  # nnz != n * k_fixed
+    assert L.sc_graph_tile_build(None, 1, 100, 6, 600, 1, 1, 16, None) == -2  # tile buffer too small
+    assert "too small" in L.sc_last_error().decode()
+    assert L.sc_csr_lag_moran_tiled(None, 1, 100, 6, 600, 1, 1, 1 << 20, None, 1, None, 30, 32, None, None, 0, 1, 1, None, None, 0,
+                                    1, 1 << 20, None) == -1  # ldz < g
+    assert L.sc_csr_lag_moran_tiled(None, 1, 100, 6, 600, 1, 1, 1 << 20, None, 1, None, 32, 32, None, None, 0, 1, 1, 1, None, 0,
+                                    1, 1 << 20, None) == -1  # cell_obs without cell_cnt
 
 
 def test_header_is_plain_c_and_links_from_c(tmp_path):

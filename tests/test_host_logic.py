@@ -392,6 +392,61 @@ def test_morans_i_host_logic_on_cpu_stand_in(monkeypatch):
         ac.morans_i(a, genes=sel, perm_source="sobol", device="cpu")
 
 
+def test_morans_i_semantic_switches_on_cpu_stand_in(monkeypatch):
+    """``null_mode`` / ``two_tailed`` / ``transformation`` of ``morans_i`` (the named switches for every recalled
+    squidpy convention) against the oracle's restatement of each alternative, replayed permutations,
+    on a radius graph (where row-normalised and binary weights differ) and a kNN graph (where they do not)."""
+    from oracle import restate as R
+    from spatialcore_b200 import AnnDataLite
+    from spatialcore_b200.spatial import autocorrelation as ac
+    from tests import cpu_engine
+
+    monkeypatch.setattr(ac, "engine", cpu_engine)
+    rng = np.random.default_rng(21)
+    n, g, P = 1800, 6, 39
+    coords = rng.uniform(0, 300, (n, 2))
+    X = rng.normal(size=(n, g)).astype(np.float32)  # continuous data: no lattice ties
+    X[:, 0] += np.sin(coords[:, 0] / 25.0).astype(np.float32)
+    names = [f"g{i}" for i in range(g)]
+    adj_r, _ = R.spatial_neighbors(coords, radius=14.0)
+
+    def run(**kw):
+        a = AnnDataLite(X, obsm={"spatial": coords}, var_names=names)
+        ac.morans_i(a, n_permutations=kw.pop("P", P), seed=4, perm_source="replay", device="cpu", **kw)
+        return a.uns["morans_i"], a
+
+    for null_mode in ("graph_rows", "values"):
+        for two_tailed in (False, True):
+            for transformation in (True, False):
+                df, a = run(radius=14.0, null_mode=null_mode, two_tailed=two_tailed, transformation=transformation)
+                t = R.morans_i_table(coords, X, n_perms=P, seed=4, adj=adj_r, null_mode=null_mode, two_tailed=two_tailed,
+                                     transformation=transformation)
+                np.testing.assert_allclose(df["I"].to_numpy(), t["I"], rtol=1e-5, atol=1e-7)
+                np.testing.assert_allclose(df["z_score"].to_numpy(), t["z_score"], rtol=1e-6)
+                assert np.array_equal(df["p_value"].to_numpy(), t["p_value"]), (null_mode, two_tailed, transformation)
+                par = a.uns["spatialcore_metadata"]["operations"][-1]["parameters"]
+                assert (par["null_mode"], par["two_tailed"], par["transformation"]) == (null_mode, two_tailed, transformation)
+    # the two weightings differ on a radius graph and coincide on a kNN graph
+    i_norm, i_bin = run(radius=14.0)[0]["I"].to_numpy(), run(radius=14.0, transformation=False)[0]["I"].to_numpy()
+    assert np.abs(i_norm - i_bin).max() > 1e-4
+    k_norm, k_bin = run(n_neighbors=6)[0]["I"].to_numpy(), run(n_neighbors=6, transformation=False)[0]["I"].to_numpy()
+    np.testing.assert_allclose(k_norm, k_bin, rtol=1e-5, atol=1e-7)
+    # analytic p-value: doubled by two_tailed
+    p1, p2 = run(P=0, radius=14.0)[0]["p_value"].to_numpy(), run(P=0, radius=14.0, two_tailed=True)[0]["p_value"].to_numpy()
+    np.testing.assert_allclose(p2, 2.0 * p1, rtol=1e-12)
+    # existing weighted graph, stored weights kept
+    d = AnnDataLite(X, obsm={"spatial": coords}, var_names=names)
+    w = adj_r.copy().astype(np.float64)
+    w.data = rng.uniform(0.5, 2.0, w.nnz)
+    d.obsp["spatial_connectivities"] = w
+    ac.morans_i(d, n_permutations=0, use_existing_graph=True, transformation=False, device="cpu")
+    tw = R.morans_i_table(coords, X, n_perms=0, adj=w, transformation=False)
+    np.testing.assert_allclose(d.uns["morans_i"]["I"].to_numpy(), tw["I"], rtol=1e-5, atol=1e-7)
+    import pytest as _pytest
+    with _pytest.raises(ValueError, match="null_mode"):
+        ac.morans_i(AnnDataLite(X, obsm={"spatial": coords}, var_names=names), null_mode="rows", device="cpu")
+
+
 def test_local_morans_i_host_logic_on_cpu_stand_in(monkeypatch):
     """``local_morans_i`` end to end on the numpy stand-in engine against the frozen output of the
     unmodified reference: batching over one shared permutation stream, spatial re-ordering and un-sorting,
