@@ -187,29 +187,28 @@ SC_API int sc_csr_lag_moran(const int32_t* indptr, const int32_t* indices, const
 
 /* The fast path of the same step for row-standardised binary graphs held in spatial order
  * (sc_spatial_order + sc_graph_relabel): the lag through SHARED-MEMORY TILES.  The L1 load path delivers
- * ~46 B/clk/SM for 128-byte row pieces (measured), the shared-memory crossbar 128 B/clk/SM, so:
+ * ~46 B/clk/SM for 128-byte row pieces (measured), the shared-memory crossbar 126 B/clk/SM, so:
  * sc_graph_tile_build (once per graph) finds, for every chunk of 256 consecutive rows, the sorted union of
- * its neighbour columns and own rows (`urows`, at most `cap` = 576 / 864 / 1728 rows, chosen from the mean
- * degree) and, for every group of `group_rows` (1, 2 or 4) consecutive rows, the merged neighbour list as
- * 16-bit words (membership mask << (16 - group_rows)) | index into urows, padded to a multiple of four;
- * sc_csr_lag_moran_tiled stages the urows' 128-byte pieces per column block with cp.async and walks the
- * word lists out of shared memory.  Chunks whose union exceeds `cap` are computed by direct gathers.
+ * its neighbour columns and own rows (`urows`: at most 576 rows for mean degrees up to 22, else 1280) and
+ * turns every CSR entry into a 32-bit word, the byte offset of that row inside the tile (lists padded to a
+ * multiple of four); sc_csr_lag_moran_tiled stages the urows' 128-byte pieces and the chunk's word lists
+ * per column block with cp.async and walks the lists out of shared memory (FADD2 accumulation).  Chunks
+ * whose union or word count exceeds the tile are computed by direct gathers inside the same call.
  * A row's neighbours are added in ascending column order, as in sc_csr_lag_moran: the two agree bit for bit.
  *
- * `tiles` is one caller-owned device buffer of sc_graph_tile_bytes(n, nnz, group_rows) bytes (0 = invalid
- * arguments); pass the same n / nnz / group_rows to all three calls.  nnz = n * k_fixed when indptr is NULL.
+ * `tiles` is one caller-owned device buffer of sc_graph_tile_bytes(n, nnz) bytes (0 = invalid arguments);
+ * pass the same n / nnz to all three calls.  nnz = n * k_fixed when indptr is NULL.
  * Zself f32[n, ldz] or NULL (NULL: the row's own value is the operand's); perm i32[n] or NULL: the operand
  * is Z[perm[j]] for row j -- the value-permuting null (autocorrelation.py:877-884) without materialising
  * the permuted matrix.  cell_obs / cell_cnt as in sc_perm_null_values (or NULL).
  * Workspace: sc_csr_lag_moran_workspace_bytes. */
-SC_API size_t sc_graph_tile_bytes(int64_t n, int64_t nnz, int group_rows);
+SC_API size_t sc_graph_tile_bytes(int64_t n, int64_t nnz);
 SC_API int sc_graph_tile_build(const int32_t* indptr, const int32_t* indices, int64_t n, int k_fixed,
-                               int64_t nnz, int group_rows, void* tiles, size_t tile_bytes,
-                               sc_stream_t stream);
+                               int64_t nnz, void* tiles, size_t tile_bytes, sc_stream_t stream);
 SC_API int sc_csr_lag_moran_tiled(const int32_t* indptr, const int32_t* indices, int64_t n, int k_fixed,
-                                  int64_t nnz, int group_rows, const void* tiles, size_t tile_bytes,
-                                  const float* Zself, const float* Z, const int32_t* perm, int64_t ldz,
-                                  int g, float* lag, float* local, int64_t ldl, double* num, double* den,
+                                  int64_t nnz, const void* tiles, size_t tile_bytes, const float* Zself,
+                                  const float* Z, const int32_t* perm, int64_t ldz, int g, float* lag,
+                                  float* local, int64_t ldl, double* num, double* den,
                                   const float* cell_obs, int32_t* cell_cnt, int64_t ldc, void* ws,
                                   size_t ws_bytes, sc_stream_t stream);
 

@@ -92,29 +92,22 @@ if want("lagsweep"):
     out["lag_sweep_ms_[with_lag,stat_only]"] = sweep
 
 if want("lagtile"):
-    # shared-memory tile lag (csrc/lag_tile.cu) per group size; rows = 0 is the L1-gather kernel
+    # shared-memory tile lag (csrc/lag_tile.cu) against the L1-gather kernel
     res = {}
     gs.tiles = None
     num_ref, _, lag_ref, _ = eng.lag_moran(gs, std.Z, g)
     lag_bytes = 8.0 * n * g + 4.0 * nnz + 4.0 * n
-    for rows in [int(x) for x in os.environ.get("SC_BENCH_TILE_ROWS", "0,1,2,4").split(",")]:
-        gs.tiles = None
-        if rows:
-            res[f"rows{rows}_build_ms"] = round(timed(lambda: eng.tile_graph(gs, rows)), 3)
-        t_lag = timed(lambda: eng.lag_moran(gs, std.Z, g))
-        t_stat = timed(lambda: eng.lag_moran(gs, std.Z, g, want_lag=False))
-        res[f"rows{rows}_lag"] = roof(lag_bytes, t_lag)
-        res[f"rows{rows}_stat_only_ms"] = round(t_stat, 3)
-        num_g, _, lag_g, _ = eng.lag_moran(gs, std.Z, g)
-        if rows:
-            res[f"rows{rows}_lag_bitwise_equal_to_gather_kernel"] = bool(torch.equal(lag_g, lag_ref))
-            res[f"rows{rows}_num_rel_diff"] = float(((num_g - num_ref).abs() / num_ref.abs().clamp_min(1e-30)).max())
-            ms = timed(lambda: eng.perm_null_values(gs, std.Z, g, 2, seed=1), reps=2) / 2
-            res[f"rows{rows}_values_null"] = dict(ms_per_perm=round(ms, 3), gene_perms_per_s=round(g / (ms / 1e3), 1))
-        del lag_g
-    gs.tiles = None
-    eng.tile_graph(gs)
-    del lag_ref
+    res["gather_lag"] = roof(lag_bytes, timed(lambda: eng.lag_moran(gs, std.Z, g)))
+    res["gather_stat_only_ms"] = round(timed(lambda: eng.lag_moran(gs, std.Z, g, want_lag=False)), 3)
+    res["tile_build_ms"] = round(timed(lambda: eng.tile_graph(gs)), 3)
+    res["tile_lag"] = roof(lag_bytes, timed(lambda: eng.lag_moran(gs, std.Z, g)))
+    res["tile_stat_only_ms"] = round(timed(lambda: eng.lag_moran(gs, std.Z, g, want_lag=False)), 3)
+    num_g, _, lag_g, _ = eng.lag_moran(gs, std.Z, g)
+    res["tile_lag_bitwise_equal_to_gather_kernel"] = bool(torch.equal(lag_g, lag_ref))
+    res["tile_num_rel_diff"] = float(((num_g - num_ref).abs() / num_ref.abs().clamp_min(1e-30)).max())
+    del lag_g, lag_ref
+    ms = timed(lambda: eng.perm_null_values(gs, std.Z, g, 2, seed=1), reps=2) / 2
+    res["tile_values_null"] = dict(ms_per_perm=round(ms, 3), gene_perms_per_s=round(g / (ms / 1e3), 1))
     out["lag_tiles"] = res
 
 if want("values"):

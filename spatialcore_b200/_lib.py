@@ -45,9 +45,9 @@ SIGNATURES = {
     "sc_csr_densify": (_i32, [_vp, _vp, _vp, _i32, _i64, _vp, _i32, _vp, _i64, _vp]),
     "sc_csr_lag_moran_workspace_bytes": (_sz, [_i64, _i32]),
     "sc_csr_lag_moran": (_i32, [_vp, _vp, _vp, _i64, _i32, _vp, _i64, _i32, _vp, _vp, _i64, _vp, _vp, _vp, _sz, _vp]),
-    "sc_graph_tile_bytes": (_sz, [_i64, _i64, _i32]),
-    "sc_graph_tile_build": (_i32, [_vp, _vp, _i64, _i32, _i64, _i32, _vp, _sz, _vp]),
-    "sc_csr_lag_moran_tiled": (_i32, [_vp, _vp, _i64, _i32, _i64, _i32, _vp, _sz, _vp, _vp, _vp, _i64, _i32, _vp, _vp, _i64,
+    "sc_graph_tile_bytes": (_sz, [_i64, _i64]),
+    "sc_graph_tile_build": (_i32, [_vp, _vp, _i64, _i32, _i64, _vp, _sz, _vp]),
+    "sc_csr_lag_moran_tiled": (_i32, [_vp, _vp, _i64, _i32, _i64, _vp, _sz, _vp, _vp, _vp, _i64, _i32, _vp, _vp, _i64,
                                       _vp, _vp, _vp, _vp, _i64, _vp, _sz, _vp]),
     "sc_perm_null_workspace_bytes": (_sz, [_i64, _i32]),
     "sc_perm_null_graph_rows": (_i32, [_vp, _i64, _vp, _i64, _i64, _i32, _i32, _vp, _u64, _i64, _i32, _vp, _vp, _sz, _vp]),

@@ -20,9 +20,12 @@
 //                            (group, float4 lane) walks its word list out of shared memory: all loads of the
 //                            inner loop are LDS, nothing in it waits for L2.
 //
-// With R > 1 a staged value is read from shared memory once for all rows of the group that share the
-// neighbour (consecutive rows in spatial order share most: the union of 4 lists holds 0.49 of their summed
-// lengths), which cuts crossbar traffic; the adds stay one per edge and gene.
+// The kernels are written for groups of R consecutive rows sharing one merged word list (a staged value
+// is then read once for all rows of the group that own the neighbour: the union of 4 lists holds 0.49 of their
+// summed lengths), but only R = 1 is instantiated: with R = 2 / 4 the predicated adds cost more issue slots
+// than the saved LDS wavefronts return (measured 29 / 32 ms against 24.7 ms at C4,
+// profiles/r02_lag_tile_variants.json).  The kernel is bound by the LSU data pipe (shared-memory wavefronts of
+// the gathers plus the cp.async writes: ~80 % of peak in ncu), not by HBM.
 //
 // Arithmetic: every row's neighbours are added in ascending column order in FP32, then scaled by 1/deg —
 // exactly the order of lag_stat_kernel, so the two kernels agree bit for bit.
@@ -51,8 +54,7 @@ struct TileTier { int chunk, cap, wcap; };
 TileTier tile_tier(int64_t n, int64_t nnz) {
   const double deg = n > 0 ? (double)nnz / (double)n : 0.0;
   int tier = deg <= 22.0 ? 0 : 1;
-  if (const char* e = getenv("SC_LAG_TILE_TIER")) { int v = atoi(e); if (v >= 0 && v <= 2) tier = v; }
-  if (tier == 2) return TileTier{128, 320, 2816};  // experiment: half chunks, four CTAs of 256 threads per SM
+  if (const char* e = getenv("SC_LAG_TILE_TIER")) { int v = atoi(e); if (v == 0 || v == 1) tier = v; }
   return tier == 0 ? TileTier{256, 576, 6144} : TileTier{256, 1280, 12288};
 }
 
@@ -469,234 +471,6 @@ lag_tile_kernel(const __grid_constant__ LagTileArgs A, double* __restrict__ part
   reduce_cta<kSlots>(num, den, reinterpret_cast<double*>(tile_smem), slot, q, col, active, A.ldz, partial, blockIdx.y);
 }
 
-// ------------------------------------------------------------------------------------------------
-// Pipelined variant (tier 0): ONE persistent CTA per SM, a dedicated producer warp and two tile buffers.
-//
-// The single-buffer kernel above spends ~38 % of its issue samples in staging (the CTA waits for its own
-// cp.async data and for the row-index loads in front of them; ncu, C4).  Here warp 16 does nothing but
-// staging -- it runs a full tile ahead of the 16 consumer warps, so every latency of the staging path
-// (union row indices, the permutation lookup of the value-permuting null, DRAM) is off the consumers'
-// critical path -- and the consumers only ever touch shared memory.  Buffers are handed over with
-// mbarriers: `full[s]` counts the producer lanes' cp.async completions (cp.async.mbarrier.arrive.noinc),
-// `empty[s]` one arrival per consumer warp.
-//
-// Work is the list of (column block, chunk) tiles in column-block-major order, cut into gridDim.x equal
-// contiguous ranges, so all SMs are busy whatever the number of column blocks (32 column blocks do not
-// divide 148 SMs); a range touches at most a few column blocks, and the per-thread Moran sums are flushed
-// (fixed-order reduction, no atomics) whenever the column block changes.  Consecutive tiles of a CTA are
-// consecutive chunks of one column block: the halo rows of a chunk were staged one tile earlier by the same
-// SM and are L2 hits.
-// ------------------------------------------------------------------------------------------------
-
-constexpr int kPipeConsumerWarps = 16;
-constexpr int kPipeThreads = (kPipeConsumerWarps + 1) * 32;
-
-__device__ __forceinline__ void cp_async_mbar_arrive_noinc(uint64_t* bar) {
-  asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
-
-// First CTA whose tile range [T*i/nc, T*(i+1)/nc) contains tile t.
-__host__ __device__ __forceinline__ int64_t pipe_owner(int64_t t, int64_t T, int64_t nc) {
-  int64_t i = (t * nc) / T;
-  while (i + 1 < nc && (T * (i + 1)) / nc <= t) ++i;
-  while (i > 0 && (T * i) / nc > t) --i;
-  return i;
-}
-
-template <int R, int FLAGS, int kChunk>
-__global__ void __launch_bounds__(kPipeThreads, 1)
-lag_tile_pipe_kernel(const __grid_constant__ LagTileArgs A, double* __restrict__ partial, int64_t tiles_total) {
-  extern __shared__ __align__(128) unsigned char tile_smem[];
-  constexpr int G = kChunk / R;
-  constexpr int kSlots = kPipeConsumerWarps * 32 / kQuads;  // 64 groups in flight
-  __shared__ uint64_t full_bar[2], empty_bar[2];
-  __shared__ double red[kPipeConsumerWarps][kQuads][8];
-  const size_t tile_b = (size_t)(A.cap + 1) * (kQuads * 16);
-  const size_t words_b = ((size_t)A.wcap + 4) * 4;
-  const size_t stage_b = tile_b + words_b + (size_t)G * 4 + (size_t)kChunk * 8 + (size_t)A.cap * 4;
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int64_t t0 = (tiles_total * blockIdx.x) / gridDim.x, t1 = (tiles_total * (blockIdx.x + 1)) / gridDim.x;
-
-  if (threadIdx.x == 0) {
-    for (int s = 0; s < 2; ++s) { mbar_init(&full_bar[s], 32); mbar_init(&empty_bar[s], kPipeConsumerWarps); }
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-  }
-  if (threadIdx.x < 2 * kQuads)  // the zero row of both buffers (target of pad words)
-    reinterpret_cast<float4*>(tile_smem + (threadIdx.x / kQuads) * stage_b)[A.cap * kQuads + (threadIdx.x % kQuads)] = make_float4(0.f, 0.f, 0.f, 0.f);
-  __syncthreads();
-
-  int64_t cb = t0 / A.n_chunks, chunk = t0 % A.n_chunks;
-  if (warp == kPipeConsumerWarps) {
-    // ===== producer warp ==========================================================================
-    const int q = lane & (kQuads - 1), sub = lane >> 3;
-    int it = 0;
-    for (int64_t t = t0; t < t1; ++t, ++it) {
-      const int s = it & 1;
-      const uint32_t ph = (uint32_t)(it >> 1) & 1u;
-      const int U = A.ucount[chunk];
-      mbar_wait(&empty_bar[s], ph ^ 1u);
-      if (U < 0) {
-        mbar_arrive(&full_bar[s]);  // nothing staged for an overflow chunk; the consumers skip it as well
-      } else {
-        unsigned char* stage = tile_smem + (size_t)s * stage_b;
-        uint32_t* swords = reinterpret_cast<uint32_t*>(stage + tile_b);
-        uint32_t* sginfo = reinterpret_cast<uint32_t*>(stage + tile_b + words_b);
-        uint32_t* sself = sginfo + G;
-        float* sinv = reinterpret_cast<float*>(sself + kChunk);
-        int32_t* s_ur = reinterpret_cast<int32_t*>(sinv + kChunk);
-        const int nW = A.wtotal[chunk];
-        const int64_t r0 = chunk * kChunk;
-        // 1. the chunk's union row indices (the only data the producer itself waits for)
-        const int32_t* __restrict__ ur = A.urows + chunk * A.cap;
-        for (int p = lane; p * 4 < U; p += 32) cp_async16(s_ur + p * 4, ur + p * 4);
-        cp_async_wait_all();
-        __syncwarp();
-        if (A.perm) {  // value-permuting null: operand row j is Z[perm[j]]
-          for (int p0 = lane; p0 < U; p0 += 32 * 8) {
-            int32_t v[8];
-#pragma unroll
-            for (int b = 0; b < 8; ++b) { const int p = p0 + b * 32; v[b] = p < U ? s_ur[p] : 0; }
-#pragma unroll
-            for (int b = 0; b < 8; ++b) v[b] = A.perm[v[b]];
-#pragma unroll
-            for (int b = 0; b < 8; ++b) { const int p = p0 + b * 32; if (p < U) s_ur[p] = v[b]; }
-          }
-          __syncwarp();
-        }
-        // 2. word lists and per-row / per-group tables
-        int64_t e0;
-        int d_unused;
-        row_span(A.indptr, A.k_fixed, r0, &e0, &d_unused);
-        const uint32_t* wsrc = A.words + chunk_words_base(e0, chunk * G);
-        for (int i = lane; i * 4 < nW; i += 32) cp_async16(swords + i * 4, wsrc + i * 4);
-        for (int i = lane; i < G / 4; i += 32) cp_async16(sginfo + i * 4, A.ginfo + chunk * G + i * 4);
-        for (int i = lane; i < kChunk / 4; i += 32) {
-          cp_async16(sself + i * 4, A.selfoff + r0 + i * 4);
-          cp_async16(sinv + i * 4, A.rinv + r0 + i * 4);
-        }
-        // 3. the 128-byte row pieces of this column block
-        const int64_t col = (cb * kQuads + q) * 4;
-        if (col < A.ldz) {
-          const float* zcol = A.Z + col;
-          unsigned char* dst = stage + q * 16;
-#pragma unroll 4
-          for (int u = sub; u < U; u += 4) cp_async16(dst + (size_t)u * (kQuads * 16), zcol + (int64_t)s_ur[u] * A.ldz);
-        }
-        cp_async_mbar_arrive_noinc(&full_bar[s]);
-      }
-      if (++chunk == A.n_chunks) { chunk = 0; ++cb; }
-    }
-    return;
-  }
-
-  // ===== consumer warps ============================================================================
-  const int tid = threadIdx.x;
-  const int q = tid & (kQuads - 1);
-  const int slot = tid >> 3;
-  double num[4] = {0, 0, 0, 0}, den[4] = {0, 0, 0, 0};
-  int64_t cur_cb = -1, col = 0;
-  bool active = false;
-
-  auto flush = [&]() {
-    // fixed-order reduction: the four group slots of a warp by shuffles, the 16 warps through shared memory
-#pragma unroll
-    for (int c = 0; c < 4; ++c) {
-      num[c] += shfl_xor_f64(num[c], 8);  num[c] += shfl_xor_f64(num[c], 16);
-      den[c] += shfl_xor_f64(den[c], 8);  den[c] += shfl_xor_f64(den[c], 16);
-    }
-    if (lane < kQuads) {
-#pragma unroll
-      for (int c = 0; c < 4; ++c) { red[warp][lane][c] = num[c]; red[warp][lane][4 + c] = den[c]; }
-    }
-    asm volatile("bar.sync 1, %0;" ::"n"(kPipeConsumerWarps * 32) : "memory");
-    if (warp == 0 && lane < kQuads && active) {
-      const int64_t k = (int64_t)blockIdx.x - pipe_owner(cur_cb * A.n_chunks, tiles_total, gridDim.x);
-      double* p = partial + (k * 2) * A.ldz + col;
-#pragma unroll
-      for (int c = 0; c < 4; ++c) {
-        double a = 0, d = 0;
-#pragma unroll 4
-        for (int w = 0; w < kPipeConsumerWarps; ++w) { a += red[w][lane][c]; d += red[w][lane][4 + c]; }
-        p[c] = a; p[A.ldz + c] = d;
-      }
-    }
-    asm volatile("bar.sync 1, %0;" ::"n"(kPipeConsumerWarps * 32) : "memory");
-#pragma unroll
-    for (int c = 0; c < 4; ++c) { num[c] = 0; den[c] = 0; }
-  };
-
-  int U_next = t0 < t1 ? A.ucount[chunk] : -1;
-  int it = 0;
-  for (int64_t t = t0; t < t1; ++t, ++it) {
-    const int s = it & 1;
-    const uint32_t ph = (uint32_t)(it >> 1) & 1u;
-    if (cb != cur_cb) {
-      if (cur_cb >= 0) flush();
-      cur_cb = cb;
-      col = (cb * kQuads + q) * 4;
-      active = col < A.ldz;
-    }
-    const int U = U_next;
-    const int64_t r0 = chunk * kChunk;
-    {  // the next tile's overflow flag is fetched a tile ahead
-      int64_t nchunk = chunk + 1;
-      if (nchunk == A.n_chunks) nchunk = 0;
-      if (t + 1 < t1) U_next = A.ucount[nchunk];
-    }
-    mbar_wait(&full_bar[s], ph);
-    if (U >= 0 && active) {
-      const unsigned char* stage = tile_smem + (size_t)s * stage_b;
-      const uint32_t* swords = reinterpret_cast<const uint32_t*>(stage + tile_b);
-      const uint32_t* sginfo = reinterpret_cast<const uint32_t*>(stage + tile_b + words_b);
-      const uint32_t* sself = sginfo + G;
-      const float* sinv = reinterpret_cast<const float*>(sself + kChunk);
-      const unsigned char* tq = stage + q * 16;
-      const int64_t out0 = r0 * A.ldl + col;
-      const int64_t cnt0 = r0 * A.ldc + col;
-#pragma unroll 1
-      for (int gl = slot; gl < G; gl += kSlots) {
-        if (r0 + (int64_t)gl * R >= A.n) break;
-        const uint32_t gi = sginfo[gl];
-        const uint4* __restrict__ wp = reinterpret_cast<const uint4*>(swords + (gi >> 8));
-        const int nq = (int)(gi & 255u);
-        F4 acc[R];
-#pragma unroll
-        for (int r = 0; r < R; ++r) acc[r] = f4_zero();
-        uint4 w4 = wp[0];
-#pragma unroll 1
-        for (int i = 0; i < nq; ++i) {
-          const uint32_t w[4] = {w4.x, w4.y, w4.z, w4.w};
-          w4 = wp[i + 1];
-          F4 v[4];
-#pragma unroll
-          for (int u = 0; u < 4; ++u) v[u] = f4_load(tq + (R == 1 ? w[u] : (w[u] & kOffMask)));
-#pragma unroll
-          for (int u = 0; u < 4; ++u) {
-            if (R == 1) {
-              f4_add(acc[0], v[u]);
-            } else {
-#pragma unroll
-              for (int r = 0; r < R; ++r) f4_add_if(acc[r], v[u], w[u] & (1u << (28 + r)));
-            }
-          }
-        }
-#pragma unroll
-        for (int r = 0; r < R; ++r) {
-          const int lrow = gl * R + r;
-          if (r0 + lrow >= A.n) break;
-          const float4 z = A.Zself ? ldg4(A.Zself + (r0 + lrow) * A.ldz + col)
-                                   : *reinterpret_cast<const float4*>(tq + sself[lrow]);
-          finish_row<FLAGS>(A, out0 + (int64_t)lrow * A.ldl, cnt0 + (int64_t)lrow * A.ldc, sinv[lrow], f4_unpack(acc[r]), z, num, den);
-        }
-      }
-    }
-    __syncwarp();
-    if (lane == 0) mbar_arrive(&empty_bar[s]);
-    if (++chunk == A.n_chunks) { chunk = 0; ++cb; }
-  }
-  if (cur_cb >= 0) flush();
-}
-
 // Chunks whose union did not fit the tile (ucount < 0): direct gathers through L1, same arithmetic.
 // One row per (slot, lane) as in lag_stat_kernel; normally there is nothing to do and the kernel only
 // reads ucount.
@@ -782,50 +556,6 @@ int launch_tile(const LagTileArgs& A, int g, double* num, double* den, double* p
   return SC_OK;
 }
 
-size_t pipe_smem_bytes(const LagTileArgs& A, int R) {
-  const int G = A.chunk / R;
-  const size_t stage = (size_t)(A.cap + 1) * kQuads * 16 + ((size_t)A.wcap + 4) * 4 + (size_t)G * 4 + (size_t)A.chunk * 8 + (size_t)A.cap * 4;
-  return 2 * stage;
-}
-
-template <int R, int FLAGS>
-int launch_pipe(const LagTileArgs& A, int g, double* num, double* den, double* partial, cudaStream_t st) {
-  const size_t smem = pipe_smem_bytes(A, R);
-  static thread_local size_t configured = 0;
-  if (configured < smem) {
-    SC_CUDA_OK(cudaFuncSetAttribute(lag_tile_pipe_kernel<R, FLAGS, 256>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    configured = smem;
-  }
-  const int64_t bx = (A.ldz + 4 * kQuads - 1) / (4 * kQuads);
-  const int64_t T = bx * A.n_chunks;
-  int64_t nc = sm_count();
-  if (nc > T) nc = T;
-  // partial rows: the k-th CTA touching a column block writes row k of that block's columns; rows nobody writes stay zero
-  int64_t kmax = 1;
-  for (int64_t cb = 0; cb < bx; ++cb) {
-    const int64_t k = pipe_owner((cb + 1) * A.n_chunks - 1, T, nc) - pipe_owner(cb * A.n_chunks, T, nc) + 1;
-    if (k > kmax) kmax = k;
-  }
-  if (kmax > kMaxBlocksY - 16) { set_error("sc_csr_lag_moran_tiled: too many partial rows"); return SC_ERR_UNSUPPORTED; }
-  SC_CUDA_OK(cudaMemsetAsync(partial, 0, sizeof(double) * 2 * (size_t)kmax * (size_t)A.ldz, st));
-  lag_tile_pipe_kernel<R, FLAGS, 256><<<(unsigned)nc, kPipeThreads, smem, st>>>(A, partial, T);
-  SC_LAUNCH_OK();
-  int64_t by2 = A.n_chunks < 16 ? A.n_chunks : 16;
-  lag_overflow_kernel<<<dim3((unsigned)bx, (unsigned)by2), 256, 0, st>>>(A, partial, (int)kmax);
-  SC_LAUNCH_OK();
-  tile_reduce_kernel<<<(g + 127) / 128, 128, 0, st>>>(partial, (int)(kmax + by2), A.ldz, g, num, den);
-  SC_LAUNCH_OK();
-  return SC_OK;
-}
-
-template <int R>
-int launch_pipe_flags(const LagTileArgs& A, int g, double* num, double* den, double* partial, cudaStream_t st) {
-  const int flags = (A.lag ? 1 : 0) | (A.local ? 2 : 0) | (A.cell_cnt ? 4 : 0);
-  if (flags == 0) return launch_pipe<R, 0>(A, g, num, den, partial, st);
-  if (flags == 1) return launch_pipe<R, 1>(A, g, num, den, partial, st);
-  return launch_pipe<R, 8>(A, g, num, den, partial, st);
-}
-
 template <int R, int kChunk, int kTileThreads>
 int launch_tile_flags(const LagTileArgs& A, int g, double* num, double* den, double* partial, cudaStream_t st) {
   const int flags = (A.lag ? 1 : 0) | (A.local ? 2 : 0) | (A.cell_cnt ? 4 : 0);
@@ -834,35 +564,24 @@ int launch_tile_flags(const LagTileArgs& A, int g, double* num, double* den, dou
   return launch_tile<R, 8, kChunk, kTileThreads>(A, g, num, den, partial, st);
 }
 
-template <int R>
-int launch_tile_geometry(const LagTileArgs& A, int g, double* num, double* den, double* partial, cudaStream_t st) {
-  const char* e = getenv("SC_LAG_TILE_PIPE");  // "1" selects the producer/consumer variant (experiment; measured slower)
-  const bool pipe = A.chunk == 256 && A.cap == 576 && e && e[0] == '1';
-  if (pipe) return launch_pipe_flags<R>(A, g, num, den, partial, st);
-  if (A.chunk == 128) return launch_tile_flags<R, 128, 256>(A, g, num, den, partial, st);
-  return launch_tile_flags<R, 256, 512>(A, g, num, den, partial, st);
-}
-
 }  // namespace
 }  // namespace sc
 
 using namespace sc;
 
-extern "C" size_t sc_graph_tile_bytes(int64_t n, int64_t nnz, int group_rows) {
-  if (n < 1 || nnz < 0 || (group_rows != 1 && group_rows != 2 && group_rows != 4)) return 0;
-  return tile_layout(n, nnz, group_rows).bytes;
+extern "C" size_t sc_graph_tile_bytes(int64_t n, int64_t nnz) {
+  if (n < 1 || nnz < 0) return 0;
+  return tile_layout(n, nnz, 1).bytes;
 }
 
 extern "C" int sc_graph_tile_build(const int32_t* indptr, const int32_t* indices, int64_t n, int k_fixed,
-                                   int64_t nnz, int group_rows, void* tiles, size_t tile_bytes,
-                                   sc_stream_t stream) {
+                                   int64_t nnz, void* tiles, size_t tile_bytes, sc_stream_t stream) {
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   SC_CHECK_ARG(indices && tiles, "sc_graph_tile_build: null argument");
   SC_CHECK_ARG(indptr || k_fixed > 0, "sc_graph_tile_build: need indptr or k_fixed");
-  SC_CHECK_ARG(group_rows == 1 || group_rows == 2 || group_rows == 4, "sc_graph_tile_build: group_rows must be 1, 2 or 4");
   SC_CHECK_ARG(n >= 1 && n < (1ll << 31) && nnz >= 0 && nnz < (1ll << 31), "sc_graph_tile_build: n and nnz must be below 2^31");
   SC_CHECK_ARG(indptr || nnz == n * (int64_t)k_fixed, "sc_graph_tile_build: nnz must equal n * k_fixed");
-  const TileLayout L = tile_layout(n, nnz, group_rows);
+  const TileLayout L = tile_layout(n, nnz, 1);
   if (tile_bytes < L.bytes) { set_error("sc_graph_tile_build: tile buffer too small (%zu < %zu)", tile_bytes, L.bytes); return SC_ERR_WORKSPACE; }
   char* base = static_cast<char*>(tiles);
   int32_t* ucount = reinterpret_cast<int32_t*>(base + L.off_ucount);
@@ -873,21 +592,13 @@ extern "C" int sc_graph_tile_build(const int32_t* indptr, const int32_t* indices
   uint32_t* ginfo = reinterpret_cast<uint32_t*>(base + L.off_ginfo);
   uint32_t* words = reinterpret_cast<uint32_t*>(base + L.off_words);
   const int blocks = (int)(L.n_chunks > 148 * 16 ? 148 * 16 : L.n_chunks);
-#define SC_TILE_BUILD(RR)                                                                                               \
-  do {                                                                                                                  \
-    if (L.chunk == 128) tile_build_kernel<RR, 128><<<blocks, kBuildThreads, 0, st>>>(indptr, indices, n, k_fixed, L.cap, L.wcap, L.n_chunks, ucount, wtotal, urows, selfoff, rinv, ginfo, words); \
-    else tile_build_kernel<RR, 256><<<blocks, kBuildThreads, 0, st>>>(indptr, indices, n, k_fixed, L.cap, L.wcap, L.n_chunks, ucount, wtotal, urows, selfoff, rinv, ginfo, words); \
-  } while (0)
-  if (group_rows == 1) SC_TILE_BUILD(1);
-  else if (group_rows == 2) SC_TILE_BUILD(2);
-  else SC_TILE_BUILD(4);
-#undef SC_TILE_BUILD
+tile_build_kernel<1, 256><<<blocks, kBuildThreads, 0, st>>>(indptr, indices, n, k_fixed, L.cap, L.wcap, L.n_chunks, ucount, wtotal, urows, selfoff, rinv, ginfo, words);
   SC_LAUNCH_OK();
   return SC_OK;
 }
 
 extern "C" int sc_csr_lag_moran_tiled(const int32_t* indptr, const int32_t* indices, int64_t n, int k_fixed,
-                                      int64_t nnz, int group_rows, const void* tiles, size_t tile_bytes,
+                                      int64_t nnz, const void* tiles, size_t tile_bytes,
                                       const float* Zself, const float* Z, const int32_t* perm, int64_t ldz,
                                       int g, float* lag, float* local, int64_t ldl, double* num, double* den,
                                       const float* cell_obs, int32_t* cell_cnt, int64_t ldc, void* ws,
@@ -895,14 +606,13 @@ extern "C" int sc_csr_lag_moran_tiled(const int32_t* indptr, const int32_t* indi
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   SC_CHECK_ARG(indices && tiles && Z && num && den && ws, "sc_csr_lag_moran_tiled: null argument");
   SC_CHECK_ARG(indptr || k_fixed > 0, "sc_csr_lag_moran_tiled: need indptr or k_fixed");
-  SC_CHECK_ARG(group_rows == 1 || group_rows == 2 || group_rows == 4, "sc_csr_lag_moran_tiled: group_rows must be 1, 2 or 4");
   SC_CHECK_ARG(n >= 1 && n < (1ll << 31) && nnz >= 0 && nnz < (1ll << 31), "sc_csr_lag_moran_tiled: n and nnz must be below 2^31");
   SC_CHECK_ARG(ldz % 4 == 0 && ldz >= g && g >= 1 && (size_t)ldz <= align_up((size_t)g, 32),
                "sc_csr_lag_moran_tiled: ldz must be a multiple of 4 in [g, round_up(g,32)]");
   SC_CHECK_ARG((!lag && !local) || (ldl % 4 == 0 && ldl >= ldz), "sc_csr_lag_moran_tiled: ldl must be a multiple of 4 and >= ldz");
   SC_CHECK_ARG((cell_cnt == nullptr) == (cell_obs == nullptr) && (!cell_cnt || (ldc % 4 == 0 && ldc >= ldz)),
                "sc_csr_lag_moran_tiled: cell_obs and cell_cnt go together, ldc a multiple of 4 and >= ldz");
-  const TileLayout L = tile_layout(n, nnz, group_rows);
+  const TileLayout L = tile_layout(n, nnz, 1);
   if (tile_bytes < L.bytes) { set_error("sc_csr_lag_moran_tiled: tile buffer too small (%zu < %zu)", tile_bytes, L.bytes); return SC_ERR_WORKSPACE; }
   if (ws_bytes < sc_csr_lag_moran_workspace_bytes(n, g)) { set_error("sc_csr_lag_moran_tiled: workspace too small"); return SC_ERR_WORKSPACE; }
   const char* base = static_cast<const char*>(tiles);
@@ -918,7 +628,5 @@ extern "C" int sc_csr_lag_moran_tiled(const int32_t* indptr, const int32_t* indi
   A.Zself = Zself; A.Z = Z; A.perm = perm; A.ldz = ldz; A.lag = lag; A.local = local; A.ldl = ldl;
   A.cell_obs = cell_obs; A.cell_cnt = cell_cnt; A.ldc = ldc;
   double* partial = static_cast<double*>(ws);
-  if (group_rows == 1) return launch_tile_geometry<1>(A, g, num, den, partial, st);
-  if (group_rows == 2) return launch_tile_geometry<2>(A, g, num, den, partial, st);
-  return launch_tile_geometry<4>(A, g, num, den, partial, st);
+  return launch_tile_flags<1, 256, 512>(A, g, num, den, partial, st);
 }

@@ -95,8 +95,8 @@ class DeviceGraph:
     k_fixed: int = 0
     weights: Optional[torch.Tensor] = None
     dist: Optional[torch.Tensor] = None
-    # shared-memory tile form for the lag kernel: (group_rows, opaque device buffer); see tile_graph()
-    tiles: Optional[Tuple[int, torch.Tensor]] = None
+    # shared-memory tile form for the lag kernel (opaque device buffer); see tile_graph()
+    tiles: Optional[torch.Tensor] = None
 
     @property
     def nnz(self) -> int:
@@ -272,9 +272,10 @@ def spatial_order(coords, device="cuda") -> CellOrder:
 
 
 @_on_device
-def relabel_graph(graph: DeviceGraph, co: CellOrder) -> DeviceGraph:
+def relabel_graph(graph: DeviceGraph, co: CellOrder, tiles: bool = True) -> DeviceGraph:
     """``sc_graph_relabel``: the same graph on sorted positions (rows permuted, columns mapped and
-    re-sorted; weights follow their edges)."""
+    re-sorted; weights follow their edges).  ``tiles``: also build the shared-memory tile form of the lag
+    kernel (``tile_graph``; row-standardised binary graphs only)."""
     L = _lib.lib()
     dev = graph.indices.device
     out_idx = torch.empty_like(graph.indices)
@@ -288,47 +289,39 @@ def relabel_graph(graph: DeviceGraph, co: CellOrder) -> DeviceGraph:
         "sc_graph_relabel",
     )
     out = DeviceGraph(n=graph.n, indices=out_idx, indptr=out_ptr, k_fixed=graph.k_fixed, weights=out_w)
-    if out_w is None and tile_rows() > 0:
+    if tiles and out_w is None and tile_rows() > 0:
         tile_graph(out)
     return out
 
 
 def tile_rows() -> int:
-    """Rows per group of the shared-memory lag tiles (``SC_LAG_TILE_ROWS``: 1, 2 or 4; 0 disables the tile
-    form and leaves every lag to the L1-gather kernel)."""
-    v = os.environ.get("SC_LAG_TILE_ROWS", "")
-    if v == "":
-        return _DEFAULT_TILE_ROWS
-    if v not in ("0", "1", "2", "4"):
-        raise ValueError(f"SC_LAG_TILE_ROWS must be 0, 1, 2 or 4, got '{v}'")
+    """1 when graphs put into spatial order also get the shared-memory tile form of the lag kernel (the
+    default); ``SC_LAG_TILE_ROWS=0`` leaves every lag to the L1-gather kernel (cross-check / comparison)."""
+    v = os.environ.get("SC_LAG_TILE_ROWS", "1")
+    if v not in ("0", "1"):
+        raise ValueError(f"SC_LAG_TILE_ROWS must be 0 or 1, got '{v}'")
     return int(v)
 
 
-_DEFAULT_TILE_ROWS = 1
-
-
 @_on_device
-def tile_graph(graph: DeviceGraph, group_rows: Optional[int] = None) -> DeviceGraph:
+def tile_graph(graph: DeviceGraph) -> DeviceGraph:
     """``sc_graph_tile_build``: the shared-memory tile form of a row-standardised binary graph in spatial
-    order (per chunk of 256 rows the union of neighbour rows, per group of rows the merged neighbour list
-    as 16-bit words).  ``lag_moran`` and ``perm_null_values`` use it when present."""
+    order (per chunk of 256 rows the union of neighbour rows, per CSR entry the byte offset of its row inside
+    the tile).  ``lag_moran`` and ``perm_null_values`` use it when present."""
     if graph.weights is not None:
         raise ValueError("tile_graph: explicitly weighted graphs are not supported")
-    rows = tile_rows() if group_rows is None else int(group_rows)
-    if rows not in (1, 2, 4):
-        raise ValueError(f"group_rows must be 1, 2 or 4, got {rows}")
     L = _lib.lib()
-    nbytes = int(L.sc_graph_tile_bytes(graph.n, graph.nnz, rows))
+    nbytes = int(L.sc_graph_tile_bytes(graph.n, graph.nnz))
     if nbytes == 0 or graph.nnz == 0:
         graph.tiles = None
         return graph
     buf = torch.empty(nbytes, dtype=torch.uint8, device=graph.indices.device)
     check(
-        L.sc_graph_tile_build(_ptr(graph.indptr), _ptr(graph.indices), graph.n, int(graph.k_fixed), graph.nnz, rows,
+        L.sc_graph_tile_build(_ptr(graph.indptr), _ptr(graph.indices), graph.n, int(graph.k_fixed), graph.nnz,
                               _ptr(buf), nbytes, _stream()),
         "sc_graph_tile_build",
     )
-    graph.tiles = (rows, buf)
+    graph.tiles = buf
     return graph
 
 
@@ -575,10 +568,10 @@ def _lag_tiled(graph: DeviceGraph, Z: torch.Tensor, Zself: Optional[torch.Tensor
     """``sc_csr_lag_moran_tiled`` on the graph's tile form."""
     L = _lib.lib()
     n, ld = Z.shape
-    rows, buf = graph.tiles
+    buf = graph.tiles
     ldl = lag.shape[1] if lag is not None else (local.shape[1] if local is not None else ld)
     check(
-        L.sc_csr_lag_moran_tiled(_ptr(graph.indptr), _ptr(graph.indices), n, int(graph.k_fixed), graph.nnz, rows, _ptr(buf),
+        L.sc_csr_lag_moran_tiled(_ptr(graph.indptr), _ptr(graph.indices), n, int(graph.k_fixed), graph.nnz, _ptr(buf),
                                  buf.numel(), _ptr(Zself), _ptr(Z), _ptr(perm), ld, g, _ptr(lag), _ptr(local), ldl, _ptr(num),
                                  _ptr(den), _ptr(cell_obs), _ptr(cell_cnt), cell_cnt.shape[1] if cell_cnt is not None else 0,
                                  _ptr(ws), ws.numel(), _stream()),

@@ -260,24 +260,75 @@ def build_spatial_weights(
     return graph.to_scipy("weights", np.float32)
 
 
+class GraphSlots:
+    """squidpy's ``spatial_neighbors`` side effects [R autocorrelation.py:565-570] -- FP64 binary
+    ``obsp['spatial_connectivities']``, FP64 ``obsp['spatial_distances']``, ``uns['spatial_neighbors']`` --
+    materialised from the device graph.  On a CUDA device the index / distance arrays start their way to
+    pinned host memory on a side stream as soon as the graph exists, and :meth:`finish` assembles the scipy
+    matrices on the host; ``morans_i`` calls it after the permutation kernels are enqueued, so the ~10^8-edge
+    host assembly of a CosMx-scale graph overlaps the device work instead of preceding it."""
+
+    def __init__(self, adata, graph: engine.DeviceGraph, n_neighs: int, radius: Optional[float]) -> None:
+        self.adata, self.graph, self.n_neighs, self.radius = adata, graph, n_neighs, radius
+        self.event = None
+        self.host = None
+        idx = graph.indices
+        if isinstance(idx, torch.Tensor) and idx.is_cuda:
+            stream = torch.cuda.Stream(device=idx.device)
+            stream.wait_stream(torch.cuda.current_stream(idx.device))
+            with torch.cuda.stream(stream):
+                parts = [idx.reshape(-1), graph.dist.reshape(-1)] + ([graph.indptr] if graph.indptr is not None else [])
+                self.host = []
+                for t in parts:
+                    h = torch.empty(t.shape, dtype=t.dtype, pin_memory=True)
+                    h.copy_(t, non_blocking=True)
+                    t.record_stream(stream)
+                    self.host.append(h)
+                self.event = torch.cuda.Event()
+                self.event.record(stream)
+
+    def finish(self) -> None:
+        if self.adata is None:
+            return
+        g = self.graph
+        n = g.n
+        if self.host is not None:
+            self.event.synchronize()
+            indices = self.host[0].numpy().copy()  # out of the pinned staging buffers (returned to torch's host cache)
+            dist = self.host[1].numpy().copy()
+            indptr = self.host[2].numpy().copy() if g.indptr is not None else np.arange(0, (n + 1) * g.k_fixed, g.k_fixed, dtype=np.int32)
+            self.host = None
+            conn = sparse.csr_matrix((np.ones(indices.size, dtype=np.float64), indices, indptr), shape=(n, n))
+            dst = sparse.csr_matrix((dist, indices.copy(), indptr.copy()), shape=(n, n))
+        else:
+            conn = g.to_scipy("ones", np.float64)
+            dst = g.to_scipy("dist", np.float64)
+        self.adata.obsp["spatial_connectivities"] = conn
+        self.adata.obsp["spatial_distances"] = dst
+        self.adata.uns["spatial_neighbors"] = {
+            "connectivities_key": "spatial_connectivities",
+            "distances_key": "spatial_distances",
+            "params": {"n_neighbors": self.n_neighs, "coord_type": "generic", "radius": self.radius, "transform": None},
+        }
+        self.adata = None
+
+
 def spatial_neighbors(adata, n_neighs: int = 6, radius: Optional[float] = None, spatial_key: str = "spatial",
-                      *, device="cuda", write: bool = True) -> engine.DeviceGraph:
+                      *, device="cuda", write: bool = True, defer: bool = False):
     """squidpy-style ``spatial_neighbors(coord_type='generic')`` side effects, as triggered by
     ``morans_i`` [R autocorrelation.py:565-570]: binary FP64 ``obsp['spatial_connectivities']``,
-    FP64 ``obsp['spatial_distances']`` and ``uns['spatial_neighbors']``."""
+    FP64 ``obsp['spatial_distances']`` and ``uns['spatial_neighbors']``.  Returns the device graph; with
+    ``defer=True`` returns ``(graph, GraphSlots | None)`` and the caller finishes the slots."""
     _check_spatial(adata, spatial_key)
     if radius is None:
         graph, _, _ = engine.knn_graph(adata.obsm[spatial_key], n_neighs, want_dist=write, device=device)
     else:
         graph, _ = engine.radius_graph(adata.obsm[spatial_key], radius, want_dist=write, device=device)
-    if write:
-        adata.obsp["spatial_connectivities"] = graph.to_scipy("ones", np.float64)
-        adata.obsp["spatial_distances"] = graph.to_scipy("dist", np.float64)
-        adata.uns["spatial_neighbors"] = {
-            "connectivities_key": "spatial_connectivities",
-            "distances_key": "spatial_distances",
-            "params": {"n_neighbors": n_neighs, "coord_type": "generic", "radius": radius, "transform": None},
-        }
+    slots = GraphSlots(adata, graph, n_neighs, radius) if write else None
+    if defer:
+        return graph, slots
+    if slots is not None:
+        slots.finish()
     return graph
 
 
@@ -461,11 +512,12 @@ def morans_i(
         names = all_names
     g = len(names)
 
+    slots = None
     if use_existing_graph and "spatial_connectivities" in adata.obsp:
         logger.info("Using existing spatial connectivity graph (use_existing_graph=True)")
         graph = _existing_graph(adata, device, normalize=transformation)
     else:
-        graph = spatial_neighbors(adata, n_neighbors, radius, spatial_key, device=device, write=write_graph)
+        graph, slots = spatial_neighbors(adata, n_neighbors, radius, spatial_key, device=device, write=write_graph, defer=True)
         if not transformation:  # binary weights as stored by squidpy (transformation=False): explicit ones
             graph = engine.DeviceGraph(n=graph.n, indices=graph.indices, indptr=graph.indptr, k_fixed=graph.k_fixed,
                                        weights=torch.ones(graph.nnz, dtype=torch.float32, device=graph.indices.device))
@@ -494,6 +546,8 @@ def morans_i(
             moran_graph_rows_null(std.Z, lag, g, scale, I_dev, n_permutations, seed, source, null, (lo, hi), cell_order=co)
         else:
             moran_values_null(graph_s, std.Z, g, scale, I_dev, seed, source, null, (lo, hi), cell_order=co)
+        if slots is not None:
+            slots.finish()  # host assembly of the obsp slots while the permutation kernels run
         if mode == "perms":
             dist_util.all_reduce_null(null, group)
         if two_tailed:
@@ -509,6 +563,8 @@ def morans_i(
         if two_tailed:
             p_value = p_value * 2.0
 
+    if slots is not None:
+        slots.finish()
     if var_norm > 0:
         z_score = (I - expected_I) / np.sqrt(var_norm)
     else:

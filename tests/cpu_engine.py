@@ -109,7 +109,7 @@ def _to_scipy(graph):
     return sparse.csr_matrix((vals, idx, indptr), shape=(graph.n, graph.n))
 
 
-def relabel_graph(graph, co):
+def relabel_graph(graph, co, tiles=True):
     o = co.order.numpy()
     A = _to_scipy(graph)[o][:, o].tocsr()
     A.sort_indices()

@@ -163,19 +163,18 @@ def test_tile_exports_validate_without_a_gpu():
     from spatialcore_b200 import _lib
 
     L = _lib.lib()
-    assert L.sc_graph_tile_bytes(0, 10, 1) == 0 and L.sc_graph_tile_bytes(100, 600, 3) == 0
-    small, big = L.sc_graph_tile_bytes(5_000_000, 100_000_000, 1), L.sc_graph_tile_bytes(5_000_000, 100_000_000, 4)
+    assert L.sc_graph_tile_bytes(0, 10) == 0 and L.sc_graph_tile_bytes(100, -1) == 0
+    big = L.sc_graph_tile_bytes(5_000_000, 100_000_000)
     # 4 bytes per edge for the word lists (tile byte offsets) + the per-chunk union rows: about the size of the CSR itself
-    assert 400_000_000 < small < 700_000_000 and 400_000_000 < big < 700_000_000
-    assert L.sc_graph_tile_build(None, None, 100, 6, 600, 1, None, 0, None) == -1
+    assert 400_000_000 < big < 700_000_000
+    assert L.sc_graph_tile_build(None, None, 100, 6, 600, None, 0, None) == -1
     assert "null argument" in L.sc_last_error().decode()
-    assert L.sc_graph_tile_build(None, 1, 100, 6, 600, 3, 1, 1 << 20, None) == -1  # group_rows
-    assert L.sc_graph_tile_build(None, 1, 100, 6, 601, 1, 1, 1 << 20, None) == -1  # nnz != n * k_fixed
-    assert L.sc_graph_tile_build(None, 1, 100, 6, 600, 1, 1, 16, None) == -2  # tile buffer too small
+    assert L.sc_graph_tile_build(None, 1, 100, 6, 601, 1, 1 << 20, None) == -1  # nnz != n * k_fixed
+    assert L.sc_graph_tile_build(None, 1, 100, 6, 600, 1, 16, None) == -2  # tile buffer too small
     assert "too small" in L.sc_last_error().decode()
-    assert L.sc_csr_lag_moran_tiled(None, 1, 100, 6, 600, 1, 1, 1 << 20, None, 1, None, 30, 32, None, None, 0, 1, 1, None, None, 0,
+    assert L.sc_csr_lag_moran_tiled(None, 1, 100, 6, 600, 1, 1 << 20, None, 1, None, 30, 32, None, None, 0, 1, 1, None, None, 0,
                                     1, 1 << 20, None) == -1  # ldz < g
-    assert L.sc_csr_lag_moran_tiled(None, 1, 100, 6, 600, 1, 1, 1 << 20, None, 1, None, 32, 32, None, None, 0, 1, 1, 1, None, 0,
+    assert L.sc_csr_lag_moran_tiled(None, 1, 100, 6, 600, 1, 1 << 20, None, 1, None, 32, 32, None, None, 0, 1, 1, 1, None, 0,
                                     1, 1 << 20, None) == -1  # cell_obs without cell_cnt
 
 

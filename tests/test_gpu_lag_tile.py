@@ -1,7 +1,7 @@
 """GPU tests of the shared-memory tile lag (``csrc/lag_tile.cu``): it must reproduce the L1-gather kernel
 (``lag_stat_kernel``) BIT FOR BIT -- both add a row's neighbours in ascending column order -- on kNN and
 radius graphs (empty rows, ragged tails), on graphs whose chunk unions overflow the tile (random graphs:
-the direct-gather fallback inside the same call), for every group size, and with the permutation applied
+the direct-gather fallback inside the same call), and with the permutation applied
 while staging (value-permuting null) against an explicitly permuted copy."""
 
 import numpy as np
@@ -43,19 +43,18 @@ def _graphs(eng, n, seed):
     return out
 
 
-@pytest.mark.parametrize("rows", [1, 2, 4])
-@pytest.mark.parametrize("n,g", [(3001, 40), (5120, 130), (777, 32)])
-def test_tiled_lag_bit_identical_to_gather_kernel(eng, rows, n, g):
-    graphs = _graphs(eng, n, seed=n + rows)
+@pytest.mark.parametrize("n,g", [(3001, 40), (5120, 130), (777, 32), (20011, 1000)])
+def test_tiled_lag_bit_identical_to_gather_kernel(eng, n, g):
+    graphs = _graphs(eng, n, seed=n)
     Z = eng.zscore_dense(torch.from_numpy(np.random.default_rng(g).normal(size=(n, g)).astype(np.float32)).cuda()).Z
     for kind, gr in graphs.items():
         gr.tiles = None
         num0, den0, lag0, loc0 = eng.lag_moran(gr, Z, g, want_lag=True, want_local=True)
-        eng.tile_graph(gr, rows)
-        assert gr.tiles is not None and gr.tiles[0] == rows
+        eng.tile_graph(gr)
+        assert gr.tiles is not None
         num1, den1, lag1, loc1 = eng.lag_moran(gr, Z, g, want_lag=True, want_local=True)
-        assert torch.equal(lag0[:, :g], lag1[:, :g]), (kind, rows, (lag0 - lag1).abs().max().item())
-        assert torch.equal(loc0[:, :g], loc1[:, :g]), (kind, rows)
+        assert torch.equal(lag0[:, :g], lag1[:, :g]), (kind, (lag0 - lag1).abs().max().item())
+        assert torch.equal(loc0[:, :g], loc1[:, :g]), kind
         np.testing.assert_allclose(num1.cpu().numpy(), num0.cpu().numpy(), rtol=1e-11, atol=1e-9)
         np.testing.assert_allclose(den1.cpu().numpy(), den0.cpu().numpy(), rtol=1e-12)
         # statistic only (no lag written)
@@ -64,8 +63,7 @@ def test_tiled_lag_bit_identical_to_gather_kernel(eng, rows, n, g):
         gr.tiles = None
 
 
-@pytest.mark.parametrize("rows", [1, 4])
-def test_tiled_values_null_matches_permuted_copy(eng, rows):
+def test_tiled_values_null_matches_permuted_copy(eng):
     """perm applied while staging == lag of an explicitly permuted copy (bitwise per cell), Moran and Lee form,
     per-cell exceedance counters included; replayed and Philox permutations."""
     n, g, P = 4099, 70, 4
@@ -86,7 +84,7 @@ def test_tiled_values_null_matches_permuted_copy(eng, rows):
             want_cnt += (locp.abs() >= loc.abs()).int()
             _, _, lagp, _ = eng.lag_moran(gr, Zp, g, want_lag=True)
             want_lee.append((Z.double() * lagp.double()).sum(0)[:g])
-        eng.tile_graph(gr, rows)
+        eng.tile_graph(gr)
         cnt = torch.zeros(Z.shape, dtype=torch.int32, device="cuda")
         sims = eng.perm_null_values(gr, Z, g, P, perm_idx=pidx, cell_obs=loc, cell_cnt=cnt)
         np.testing.assert_allclose(sims.cpu().numpy(), torch.stack(want_sims).cpu().numpy(), rtol=1e-11, atol=1e-9)
