@@ -109,73 +109,168 @@ def _symmetric_z(n: int, ld: int, dev: torch.device, group):
     return _symm_cache[key]
 
 
-def _standardize_row_sharded(adata, layer, names: List[str], device, co: engine.CellOrder, group) -> engine.Standardized:
-    """Row-sharded ingest (multi-GPU, ``shard="perms"``): every rank uploads and standardises only
-    its block of N/W cells, the per-gene moments are pooled over the ranks (one all-gather of
-    [3, G] FP64), and every rank ends up with all of Z in spatial order.
+last_ingest_ms = {}  # breakdown of the most recent row-sharded ingest when SC_INGEST_PROFILE=1 (bench.py reports it)
 
-    Fused path (dense FP32 ``X``, all columns): ONE kernel standardises the block and stores each row
-    straight into the Z buffer of every GPU at its spatial position, through NVLink peer mappings
-    (``sc_zscore_scatter``) -- no staging copy, no NCCL collective on the data path, no re-order pass.
-    Otherwise (sparse input, gene subsets, ``SC_INGEST_NCCL=1``): ``sc_zscore_apply`` on the block, one
-    ``all_gather_into_tensor`` and a row gather into spatial order."""
-    import os
 
-    import torch.distributed as dist
+class ShardedIngest:
+    """Row-sharded ingest (multi-GPU, ``shard="perms"``): every rank uploads only its block of N/W cells, the
+    per-gene moments are pooled over ranks (one all-gather of [S, 3, G] FP64 per rank), and every rank ends up
+    with all of Z in spatial order.
 
-    rank, world = dist_util.world(group)
-    X = _expression(adata, layer)
-    n = adata.n_obs
-    per, lo, hi = dist_util.row_block(n, rank, world)
-    pos = _gene_positions(adata, names)
-    g = len(names)
-    ld = engine.padded_ld(g)
-    dev = torch.device(device) if not isinstance(device, torch.device) else device
-    if dev.type == "cuda" and dev.index is None:
-        dev = torch.device("cuda", torch.cuda.current_device())
-    have = hi - lo
-    stats = torch.zeros((3, g), dtype=torch.float64, device=dev)  # rows: count, mean, std of this block
-    Xd = cols = None
-    if have > 0:
-        Xd, cols = engine.expression_to_device(X[lo:hi], pos, dev)
-        part = engine.zscore_dense(Xd, cols=cols, want_z=False)
-        stats[0].fill_(float(have)); stats[1].copy_(part.mean); stats[2].copy_(part.std)
-    allst = torch.empty((world * 3, g), dtype=torch.float64, device=dev)  # concatenation form (gloo and NCCL)
-    dist.all_gather_into_tensor(allst, stats, group=group)
-    h = allst.view(world, 3, g).cpu().numpy()
-    live = h[:, 0, 0] > 0
-    mean, std, zero = dist_util.combine_moments(h[live, 0, 0], h[live, 1], h[live, 2])
-    mean_d = torch.from_numpy(mean).to(dev)
-    std_d = torch.from_numpy(std).to(dev)
-    zero_d = torch.from_numpy(zero.astype(np.uint8)).to(dev)
+    Fused path (dense FP32 ``X``, all columns), pipelined so that PCIe, NVLink and the graph build overlap:
 
-    fused = (cols is None and (Xd is None or (Xd.dtype == torch.float32 and Xd.stride(1) == 1 and Xd.stride(0) % 4 == 0
-                                               and Xd.stride(0) >= (g + 3) // 4 * 4 and Xd.data_ptr() % 16 == 0))
-             and world <= 16 and not os.environ.get("SC_INGEST_NCCL"))
-    flag = torch.tensor([1 if fused else 0], dtype=torch.int32, device=dev)
-    dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=group)  # every rank must take the same path
-    if int(flag.item()) == 1:
-        try:
-            Z, hdl = _symmetric_z(n, ld, dev, group)
-        except Exception as exc:  # no peer access / symmetric memory on this system: every rank falls back
-            logger.warning(f"symmetric memory unavailable ({exc}); using the NCCL all-gather ingest")
-            Z = hdl = None
-        flag.fill_(0 if hdl is None else 1)
-        dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=group)
-    if int(flag.item()) == 1:
-        hdl.barrier()  # peers are done reading the previous contents of the cached buffer
-        if have > 0:
-            engine.zscore_scatter(Xd, mean_d, std_d, zero_d, co.rank[lo:hi], hdl.buffer_ptrs, ld)
-        hdl.barrier()  # every peer's rows have landed
+    * ``__init__`` enqueues the block's host->device copy in ``slabs`` row slabs on a copy stream; as each slab
+      lands, a second stream computes its column moments and stores its RAW rows straight into the symmetric Z
+      buffer of every GPU at their spatial positions (``sc_zscore_scatter`` with identity moments: one kernel =
+      all-gather + re-order over NVLink peer memory, no staging copy, no NCCL collective on the data path).
+      The caller builds the neighbour graph meanwhile.
+    * ``finish`` pools the moments (Chan's update over ranks x slabs), waits for every peer's rows
+      (signal-pad barrier) and standardises the local copy in place (``sc_zscore_apply``: one pass at HBM speed).
+
+    Otherwise (sparse input, gene subsets, ``SC_INGEST_NCCL=1``, no symmetric memory): ``sc_zscore_apply`` on the
+    block, one ``all_gather_into_tensor`` and a row gather into spatial order.  All variants produce bit-identical
+    Z; it differs from the replicated ingest only through the pooled moments (last FP64 bit)."""
+
+    def __init__(self, adata, layer, names: List[str], device, co: engine.CellOrder, group, slabs: int = 4) -> None:
+        import os
+
+        import torch.distributed as dist
+
+        self.group, self.co = group, co
+        rank, world = dist_util.world(group)
+        self.rank, self.world = rank, world
+        X = _expression(adata, layer)
+        n = adata.n_obs
+        self.n = n
+        self.per, self.lo, self.hi = dist_util.row_block(n, rank, world)
+        pos = _gene_positions(adata, names)
+        g = len(names)
+        self.g, self.ld = g, engine.padded_ld(g)
+        dev = torch.device(device) if not isinstance(device, torch.device) else device
+        if dev.type == "cuda" and dev.index is None:
+            dev = torch.device("cuda", torch.cuda.current_device())
+        self.dev = dev
+        have = self.hi - self.lo
+        self.have = have
+        self.profile = bool(os.environ.get("SC_INGEST_PROFILE")) and dev.type == "cuda"
+        self.events = {}
+        dense = isinstance(X, np.ndarray) and X.dtype == np.float32 and X.ndim == 2 and (X.strides[1] == 4 or X.shape[1] == 1)
+        fused = (dense and pos is None and dev.type == "cuda" and X.strides[0] % 16 == 0 and X.ctypes.data % 16 == 0
+                 and world <= 16 and not os.environ.get("SC_INGEST_NCCL"))
+        flag = torch.tensor([1 if fused else 0], dtype=torch.int32, device=dev)
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=group)  # every rank must take the same path
+        self.hdl = self.Z = None
+        if int(flag.item()) == 1:
+            try:
+                self.Z, self.hdl = _symmetric_z(n, self.ld, dev, group)
+            except Exception as exc:  # no peer access / symmetric memory on this system: every rank falls back
+                logger.warning(f"symmetric memory unavailable ({exc}); using the NCCL all-gather ingest")
+            flag.fill_(0 if self.hdl is None else 1)
+            dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=group)
+        self.fused = int(flag.item()) == 1
+        self.X, self.pos = X, pos
+        if not self.fused:
+            self.hdl = self.Z = None
+            return
+        self._mark("start")
+        self.hdl.barrier()  # peers are done reading the previous contents of the cached buffer
+        cur = torch.cuda.current_stream(dev)
+        self.copy_stream, self.work_stream = torch.cuda.Stream(device=dev), torch.cuda.Stream(device=dev)
+        self.copy_stream.wait_stream(cur)
+        self.work_stream.wait_stream(cur)
+        n_slabs = max(1, min(slabs, have)) if have > 0 else 0
+        self.stats = torch.zeros((max(slabs, 1), 3, g), dtype=torch.float64, device=dev)  # rows: count, mean, std per slab
+        self.Xd = torch.empty((max(have, 1), g), dtype=torch.float32, device=dev)
+        ident_mean = torch.zeros(g, dtype=torch.float64, device=dev)
+        ident_std = torch.ones(g, dtype=torch.float64, device=dev)
+        ident_zero = torch.zeros(g, dtype=torch.uint8, device=dev)
+        self._keep = (ident_mean, ident_std, ident_zero)
+        for s_i in range(n_slabs):
+            a, b2 = dist_util.block_slice(have, s_i, n_slabs)
+            src = torch.from_numpy(X[self.lo + a:self.lo + b2])
+            with torch.cuda.stream(self.copy_stream):
+                self.Xd[a:b2].copy_(src, non_blocking=True)
+                landed = torch.cuda.Event()
+                landed.record(self.copy_stream)
+            with torch.cuda.stream(self.work_stream):
+                self.work_stream.wait_event(landed)
+                part = engine.zscore_dense(self.Xd[a:b2], want_z=False)
+                self.stats[s_i, 0].fill_(float(b2 - a))
+                self.stats[s_i, 1].copy_(part.mean)
+                self.stats[s_i, 2].copy_(part.std)
+                engine.zscore_scatter(self.Xd[a:b2], ident_mean, ident_std, ident_zero, co.rank[self.lo + a:self.lo + b2],
+                                      self.hdl.buffer_ptrs, self.ld)
+        with torch.cuda.stream(self.copy_stream):
+            self._mark("h2d_done", self.copy_stream)
+        with torch.cuda.stream(self.work_stream):
+            self._mark("scatter_done", self.work_stream)
+        self.done = torch.cuda.Event()
+        self.done.record(self.work_stream)
+        self.Xd.record_stream(self.work_stream)
+
+    def _mark(self, name: str, stream=None) -> None:
+        if self.profile:
+            ev = torch.cuda.Event(enable_timing=True)
+            ev.record(stream if stream is not None else torch.cuda.current_stream(self.dev))
+            self.events[name] = ev
+
+    def _pooled(self, stats: torch.Tensor):
+        import torch.distributed as dist
+
+        rows = stats.shape[0]
+        allst = torch.empty((self.world * rows * 3, self.g), dtype=torch.float64, device=self.dev)  # concatenation form (gloo and NCCL)
+        dist.all_gather_into_tensor(allst, stats.reshape(rows * 3, self.g).contiguous(), group=self.group)
+        h = allst.view(self.world * rows, 3, self.g).cpu().numpy()
+        live = h[:, 0, 0] > 0
+        mean, std, zero = dist_util.combine_moments(h[live, 0, 0], h[live, 1], h[live, 2])
+        return (torch.from_numpy(mean).to(self.dev), torch.from_numpy(std).to(self.dev),
+                torch.from_numpy(zero.astype(np.uint8)).to(self.dev))
+
+    def finish(self) -> engine.Standardized:
+        import torch.distributed as dist
+
+        dev, g, ld, n = self.dev, self.g, self.ld, self.n
+        if self.fused:
+            torch.cuda.current_stream(dev).wait_event(self.done)
+            self._mark("wait_done")
+            mean_d, std_d, zero_d = self._pooled(self.stats)
+            self._mark("stats_pooled")
+            self.hdl.barrier()  # every peer's rows have landed
+            self._mark("peers_landed")
+            engine.zscore_apply(self.Z[:, :g], mean_d, std_d, zero_d, out=self.Z)  # in place, one pass at HBM speed
+            self._mark("zscored")
+            if self.profile:
+                torch.cuda.synchronize(dev)
+                ev = self.events
+                last_ingest_ms.clear()
+                last_ingest_ms.update({
+                    "h2d": ev["start"].elapsed_time(ev["h2d_done"]), "scatter_done": ev["start"].elapsed_time(ev["scatter_done"]),
+                    "resumed": ev["start"].elapsed_time(ev["wait_done"]), "stats_pooled": ev["start"].elapsed_time(ev["stats_pooled"]),
+                    "peers_landed": ev["start"].elapsed_time(ev["peers_landed"]), "zscored": ev["start"].elapsed_time(ev["zscored"]),
+                    "note": "ms since the ingest started (entry barrier included); h2d = last slab on the device, scatter_done = "
+                            "last slab stored to all peers, resumed = main stream past the graph build and the ingest"})
+            self.Xd = None
+            return engine.Standardized(Z=self.Z, g=g, mean=mean_d, std=std_d, zero_var=zero_d)
+
+        # NCCL path: moments of the block, pooled; z-score the block; all-gather; re-order
+        stats = torch.zeros((1, 3, g), dtype=torch.float64, device=dev)
+        Xd = cols = None
+        if self.have > 0:
+            Xd, cols = engine.expression_to_device(self.X[self.lo:self.hi], self.pos, dev)
+            part = engine.zscore_dense(Xd, cols=cols, want_z=False)
+            stats[0, 0].fill_(float(self.have)); stats[0, 1].copy_(part.mean); stats[0, 2].copy_(part.std)
+        mean_d, std_d, zero_d = self._pooled(stats)
+        Zu = torch.empty((self.world * self.per, ld), dtype=torch.float32, device=dev)  # user order, padded to W equal blocks
+        if self.have > 0:
+            engine.zscore_apply(Xd, mean_d, std_d, zero_d, cols=cols, out=Zu[self.lo:self.hi])
+        del Xd
+        dist.all_gather_into_tensor(Zu, Zu[self.rank * self.per:(self.rank + 1) * self.per], group=self.group)
+        Z = engine.gather_rows(Zu[:n], self.co.order)
         return engine.Standardized(Z=Z, g=g, mean=mean_d, std=std_d, zero_var=zero_d)
 
-    Zu = torch.empty((world * per, ld), dtype=torch.float32, device=dev)  # user order, padded to W equal blocks
-    if have > 0:
-        engine.zscore_apply(Xd, mean_d, std_d, zero_d, cols=cols, out=Zu[lo:hi])
-    del Xd
-    dist.all_gather_into_tensor(Zu, Zu[rank * per:(rank + 1) * per], group=group)
-    Z = engine.gather_rows(Zu[:n], co.order)
-    return engine.Standardized(Z=Z, g=g, mean=mean_d, std=std_d, zero_var=zero_d)
+
+def _standardize_row_sharded(adata, layer, names: List[str], device, co: engine.CellOrder, group) -> engine.Standardized:
+    return ShardedIngest(adata, layer, names, device, co, group).finish()
 
 
 def _pick_perm_source(perm_source: str, n: int, n_perms: int) -> str:
@@ -512,6 +607,13 @@ def morans_i(
         names = all_names
     g = len(names)
 
+    # cells are held in spatial (Z-curve) order on the device: every quantity below is a sum over cells
+    co = engine.spatial_order(adata.obsm[spatial_key], device=device)
+    ingest_job = None
+    if mode == "perms" and ingest == "sharded":
+        # host->device copy, column moments and the NVLink all-gather of this rank's cell block start now and
+        # overlap the graph build below
+        ingest_job = ShardedIngest(adata, layer, names, device, co, group)
     slots = None
     if use_existing_graph and "spatial_connectivities" in adata.obsp:
         logger.info("Using existing spatial connectivity graph (use_existing_graph=True)")
@@ -522,11 +624,9 @@ def morans_i(
             graph = engine.DeviceGraph(n=graph.n, indices=graph.indices, indptr=graph.indptr, k_fixed=graph.k_fixed,
                                        weights=torch.ones(graph.nnz, dtype=torch.float32, device=graph.indices.device))
 
-    # cells are held in spatial (Z-curve) order on the device: every quantity below is a sum over cells
-    co = engine.spatial_order(adata.obsm[spatial_key], device=device)
     graph_s = engine.relabel_graph(graph, co)
-    if mode == "perms" and ingest == "sharded":
-        std = _standardize_row_sharded(adata, layer, names, device, co, group)
+    if ingest_job is not None:
+        std = ingest_job.finish()
     else:
         std = _standardize(adata, layer, names, device, rows=co.order)
     num, den, lag, _ = engine.lag_moran(graph_s, std.Z, g, want_lag=n_permutations > 0 and null_mode == "graph_rows")

@@ -27,7 +27,7 @@ def _graphs(eng, n, seed):
     cd = torch.from_numpy(coords).cuda()
     co = eng.spatial_order(cd)
     knn, _, _ = eng.knn_graph(cd, 7)
-    rad, _ = eng.radius_graph(cd, 9.0)
+    rad, _ = eng.radius_graph(cd, float(np.sqrt(6.0 * 160000.0 / (np.pi * n))))  # mean degree ~6 on the uniform part: some empty rows
     assert (np.diff(rad.indptr.cpu().numpy()) == 0).any()  # empty rows
     # a graph with no spatial structure: every chunk's union overflows the tile -> direct-gather fallback
     cols = np.sort(rng.integers(0, n, (n, 6)), axis=1)
