@@ -565,10 +565,13 @@ perm_rows_bulk_kernel(const float* __restrict__ A, int64_t lda, const float* __r
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int rpp = kBulkConsumerWarps / wpr;
   const int count = pb.count;
+  const int64_t col0 = (int64_t)blockIdx.y * 1024;  // first column of this CTA's column block
+  // the last column block of a matrix whose width is not a multiple of 1024 is narrower: it stages (and
+  // expects) fewer bytes per row; the stage layout is per CTA, so nothing else changes
+  if (lda - col0 < cols) cols = (int)(lda - col0);
   const uint32_t row_bytes = (uint32_t)cols * 4u;
   const uint32_t unit_bytes = (uint32_t)(PB + 1) * row_bytes;
   const uint32_t stage_bytes = (uint32_t)rpp * unit_bytes;
-  const int64_t col0 = (int64_t)blockIdx.y * 1024;  // first column of this CTA's column block
   const int64_t n_groups = (n + rpp - 1) / rpp;
 
   for (int t = threadIdx.x; t < kMaxPermBatch * kFeistelRounds; t += blockDim.x)
@@ -1268,9 +1271,7 @@ static int launch_perm_rows_bulk(const float* A, int64_t lda, const float* B, in
                                  double* partial, cudaStream_t st) {
   RowGeom rg = row_geom(lda);
   const int by = (int)((lda + 1023) / 1024);
-  // every column block stages the same number of floats per row (the last block may be narrower:
-  // it is handled as a separate launch geometry only when lda is not a multiple of 1024 and by > 1)
-  if (by > 1 && lda % 1024 != 0) return SC_ERR_UNSUPPORTED;
+  // column blocks of 1024 floats; the last one may be narrower (the kernel trims its row segment)
   const int cols = (int)(by > 1 ? 1024 : lda);
   const size_t stage_bytes = (size_t)rg.rpp * (PB + 1) * cols * 4;
   int max_smem = 0, dev = 0;

@@ -40,7 +40,7 @@ def _target_device(args, kwargs) -> Optional[torch.device]:
             t = a.indices if isinstance(a, DeviceGraph) else (a.order if isinstance(a, CellOrder) else a.Z)
             if t is not None and t.is_cuda:
                 return t.device
-        elif isinstance(a, KMeansDevice):
+        elif isinstance(a, KMeansDevice) and getattr(a, "X", None) is not None:
             return a.X.device
     dev = kwargs.get("device")
     if dev is not None:

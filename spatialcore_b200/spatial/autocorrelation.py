@@ -776,10 +776,21 @@ def local_morans_i(
     if source == "replay":
         for _ in range(b_lo * n_permutations):  # the draws of the batches other ranks own
             rng.permutation(n)
+    # the expression matrix goes to the device once; a batch is a column selector (dense) or a host-side column
+    # slice (sparse: only the batch's columns are densified on the device)
+    X_is_sparse = sparse.issparse(X)
+    Xd_all = None
+    if X_is_sparse:
+        X_csc = X.tocsc()  # the reference converts to CSC up front as well [R autocorrelation.py:813-816]
+    elif b_hi > b_lo:
+        Xd_all, _ = engine.expression_to_device(X, None, device)
     for b in range(b_lo, b_hi):
         s, e = b * batch_size, min((b + 1) * batch_size, g)
         gb = e - s
-        Xd, cols = engine.expression_to_device(X, pos_all[s:e], device)
+        if X_is_sparse:
+            Xd, cols = engine.expression_to_device(X_csc[:, pos_all[s:e]], None, device)
+        else:
+            Xd, cols = Xd_all, torch.from_numpy(np.asarray(pos_all[s:e], dtype=np.int32)).to(Xd_all.device)
         std = engine.zscore_dense(Xd, cols=cols, rows=co.order)
         _, _, lag, loc = engine.lag_moran(graph, std.Z, gb, want_lag=True, want_local=True)
         zero_mask[s:e] = std.zero_var.cpu().numpy().astype(bool)

@@ -393,6 +393,22 @@ def test_lees_l_zero_variance_and_continuous(api, golden_dir):
     assert r[0] == {"gene_x": "g2", "gene_y": "g1", "L": 0.0, "p_value": 1.0}
 
 
+def _local_flip_margins(coords, X, k, perms, mism):
+    """FP64 oracle margins at the (cell, gene) entries where a per-cell permutation p-value differs: the smallest
+    relative distance between |I_perm| and |I_obs| over the permutations (a flip is legitimate only at a near tie)."""
+    cells, genes = np.nonzero(mism)
+    if cells.size == 0:
+        return np.zeros(0)
+    Z = R.zscore(X.astype(np.float64))[0]
+    W = R.build_spatial_weights(coords, k).astype(np.float64)
+    obs = np.abs(Z * (W @ Z))[cells, genes]
+    best = np.full(cells.size, np.inf)
+    for pm in perms:
+        Zs = Z[pm]
+        best = np.minimum(best, np.abs(np.abs(Zs * (W @ Zs))[cells, genes] - obs))
+    return best / np.maximum(obs, 1e-300)
+
+
 def test_local_morans_i_matches_reference(api, golden_dir):
     ref = np.load(os.path.join(golden_dir, "ref_g0.npz"))
     coords, X = inputs.g0_continuous()
@@ -405,6 +421,12 @@ def test_local_morans_i_matches_reference(api, golden_dir):
     np.testing.assert_allclose(lag, ref["lmc_lag"], rtol=5e-5, atol=2e-6)
     mism = p != ref["lmc_p"]
     assert mism.mean() < 2e-4, f"per-cell p-value flips: {mism.sum()} of {mism.size}"
+    # every flip must be a near tie: in an FP64 evaluation of the same permutations some |I_perm| lies within FP32
+    # rounding of |I_obs| for that (cell, gene) -- the margins are printed
+    margins = _local_flip_margins(coords, X[:, :3], 6, R.squidpy_perm_indices(len(coords), 99, 0), mism)
+    print(f"local Moran: {int(mism.sum())} p-value flips of {mism.size}; oracle margins min|abs(I_p)-abs(I)|/abs(I) at the flips: "
+          f"{np.sort(margins)[-5:] if margins.size else margins}")
+    assert margins.size == 0 or margins.max() < 2e-5
     q = a.obsm["local_morans_quadrant"]
     assert (q != ref["lmc_quadrant"]).mean() < 2e-4
     prm = a.uns["local_morans_params"]
@@ -949,3 +971,24 @@ def test_moran_known_answers_on_a_torus(api):
     api.morans_i(a, n_permutations=99, use_existing_graph=True, perm_source="philox", key_added="perm")
     p = a.uns["perm"]["p_value"].to_numpy()
     assert p[0] == 0.01 and p[1] == 0.01
+
+
+def test_calls_run_on_the_device_of_their_operands(api, g0):
+    """``device='cuda:1'`` while ``cuda:0`` is current: every library call must switch to the device of its operands
+    (the library launches on the CURRENT device and takes the current stream)."""
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two CUDA devices")
+    coords, X, _ = g0
+    torch.cuda.set_device(0)
+    a0 = _adata(X[:, :8], coords)
+    api.morans_i(a0, n_neighbors=6, n_permutations=19, seed=0, perm_source="replay", device="cuda:0")
+    a1 = _adata(X[:, :8], coords)
+    api.morans_i(a1, n_neighbors=6, n_permutations=19, seed=0, perm_source="replay", device="cuda:1")
+    assert torch.cuda.current_device() == 0
+    pd.testing.assert_frame_equal(a0.uns["morans_i"], a1.uns["morans_i"])
+    assert (a0.obsp["spatial_connectivities"] != a1.obsp["spatial_connectivities"]).nnz == 0
+    b1 = _adata(X[:, :3], coords)
+    api.local_morans_i(b1, n_permutations=9, perm_source="philox", device="cuda:1")
+    b0 = _adata(X[:, :3], coords)
+    api.local_morans_i(b0, n_permutations=9, perm_source="philox", device="cuda:0")
+    assert np.array_equal(b0.obsm["local_morans_p"], b1.obsm["local_morans_p"])

@@ -867,3 +867,26 @@ def test_host_building_blocks_properties():
     block_slices_tile_the_range()
     pooled_moments_equal_global_moments()
     bh_matches_the_oracle_and_is_monotone()
+
+
+def test_three_dimensional_coordinates_are_refused_not_truncated():
+    """The kernels are 2-D; the reference hands every column of ``obsm['spatial']`` to its tree libraries, so a
+    varying third coordinate must raise instead of being dropped silently; constant extra columns are harmless."""
+    import pytest as _pytest
+    import torch
+
+    from spatialcore_b200 import engine
+
+    rng = np.random.default_rng(0)
+    xy = rng.uniform(0, 10, (50, 2))
+    flat = np.concatenate([xy, np.zeros((50, 1))], axis=1)
+    out = engine._coords_tensor(flat, "cpu")
+    assert out.shape == (50, 2) and np.array_equal(out.numpy(), xy)
+    assert engine._coords_tensor(torch.from_numpy(flat), "cpu").shape == (50, 2)
+    xyz = np.concatenate([xy, rng.uniform(0, 1, (50, 1))], axis=1)
+    with _pytest.raises(ValueError, match="only 2-D coordinates are supported"):
+        engine._coords_tensor(xyz, "cpu")
+    with _pytest.raises(ValueError, match="only 2-D coordinates are supported"):
+        engine._coords_tensor(torch.from_numpy(xyz), "cpu")
+    with _pytest.raises(ValueError, match="shape"):
+        engine._coords_tensor(xy[:, :1], "cpu")
