@@ -18,8 +18,8 @@
 // release the stage to the MMA warp.  No split copies of the operands exist in HBM.
 //
 // Work decomposition: CTA = one 128 x 256 output tile x a span of consecutive `chunk`-cell chunks.
-// The tensor core truncates when it adds into its FP32 accumulator, so a chunk is kept short (256
-// cells = 96 accumulate steps); chunks alternate between two 256-column TMEM accumulators, and while
+// The tensor core truncates when it adds into its FP32 accumulator, so a chunk is kept short (64
+// cells = 24 accumulate steps); chunks alternate between two 256-column TMEM accumulators, and while
 // the MMA warp fills one the eight epilogue warps drain the other into FP32 REGISTER accumulators
 // (round-to-nearest adds).  One FP32 tile per CTA goes to a small partial buffer ([splits] tiles,
 // ~40 MB instead of one tile per chunk = 3.3 GB at C3) and the splits are summed in FP64.
@@ -308,9 +308,12 @@ static TcPlan tc_plan(int64_t n, int g) {
   TcPlan p;
   p.ldt = (int64_t)align_up((size_t)g, kTcN);
   // The tensor core truncates (RZ) when it adds into the FP32 accumulator: a chunk of c cells makes
-  // 3c/8 accumulate steps and leaves a relative bias of ~(3c/16)*2^-24.  Shorter chunks are more
-  // accurate but write more partial tiles.  SC_LEE_TC_CHUNK overrides (multiple of 8).
-  int64_t chunk = 256;
+  // 3c/8 accumulate steps and leaves a relative bias of ~(3c/16)*2^-24 of the accumulator.  Shorter chunks
+  // are more accurate and cost more drains.  Measured at C3 size on uncorrelated data (B200,
+  // scripts/lee_tc_chunk.py; error in units of 2^-24 * sum|terms|, median / p99): 512 cells 0.158 / 0.61 at
+  // 2.31 ms, 256: 0.086 / 0.33 at 2.30 ms, 128: 0.050 / 0.20 at 2.33 ms, 64: 0.033 / 0.13 at 2.38 ms, 32: 0.028 /
+  // 0.12 at 2.47 ms -- 64 buys 2.6x the accuracy of 256 for 3.5 % of the time.  SC_LEE_TC_CHUNK overrides.
+  int64_t chunk = 64;
   if (const char* e = getenv("SC_LEE_TC_CHUNK")) { long v = atol(e); if (v >= 8) chunk = (v + 7) / 8 * 8; }
   p.chunk = chunk;
   p.chunks = (int)((n + chunk - 1) / chunk);

@@ -544,7 +544,7 @@ def morans_i(
     *,
     perm_source: str = "auto",
     radius: Optional[float] = None,
-    write_graph: bool = True,
+    write_graph: Union[bool, str] = True,
     null_mode: str = "graph_rows",
     two_tailed: bool = False,
     transformation: bool = True,
@@ -565,6 +565,12 @@ def morans_i(
     500 genes per rank, else perms.  ``ingest="sharded"`` (with ``shard="perms"``): each rank uploads
     and standardises N/W cells and the blocks are all-gathered over NVLink (results agree with
     ``"replicated"`` to the FP32 rounding of Z: pooled moments differ in the last FP64 bit).
+
+    ``write_graph``: ``True`` (default, the reference's behaviour) materialises squidpy's graph slots
+    (``obsp['spatial_connectivities']``, ``obsp['spatial_distances']``, ``uns['spatial_neighbors']``); in a sharded
+    multi-process run the slots are written on rank 0 of ``group`` only -- the other ranks hold worker replicas of
+    the AnnData, and assembling a 10^8-edge FP64 scipy graph eight times over would cost more host time than the
+    whole 8-GPU job -- unless ``write_graph="all"``; ``False`` skips them.
 
     Semantic switches.  The statistic, null and p-value conventions of the reference live in squidpy / scanpy
     [R autocorrelation.py:565-583], which cannot be pinned offline; every recalled convention is
@@ -600,6 +606,12 @@ def morans_i(
         mode = "genes" if len(all_names) >= 500 * world else "perms"
     else:
         mode = shard
+    if write_graph not in (True, False, "all"):
+        raise ValueError(f"write_graph must be True, False or 'all', got {write_graph!r}")
+    if mode == "none" or write_graph == "all":
+        write_graph = bool(write_graph)
+    else:
+        write_graph = bool(write_graph) and rank == 0
     if mode == "genes":
         g_lo, g_hi = dist_util.block_slice(len(all_names), rank, world)
         names = all_names[g_lo:g_hi]

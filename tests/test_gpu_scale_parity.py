@@ -175,7 +175,7 @@ def test_c3_lee_entries_against_fp64_at_full_size(eng):
     # pairwise FP32 sum [R autocorrelation.py:307-315]) is printed beside ours for comparison
     L2 = eng.lee_gemm(std.Z, lag, g, impl=2).cpu().numpy().astype(np.float64)[ii, jj]
     big = np.abs(ref) >= 0.05 * mag
-    assert big.sum() > 50 and np.all(np.abs(L2 - ref)[big] <= 1e-5 * np.abs(ref)[big])
+    assert big.sum() > 10 and np.all(np.abs(L2 - ref)[big] <= 1e-5 * np.abs(ref)[big])
     z32, l32 = std.Z[:, :g].cpu().numpy(), lag[:, :g].cpu().numpy()
     np32 = np.array([(z32[:, a] * l32[:, b]).sum(dtype=np.float32) for a, b in zip(ii[:500], jj[:500])], dtype=np.float64)
     rel32 = np.abs(np32 - ref[:500]) / np.maximum(np.abs(ref[:500]), 1e-300)
