@@ -130,25 +130,31 @@ def all_gather_columns(local, total_cols: int, device, group=None):
 
 
 def all_gather_column_blocks(local, sizes, device, group=None, max_rows: int = 1 << 20):
-    """Every rank contributes the columns it owns of a per-cell matrix (numpy ``[n, sizes[rank]]``, any
-    dtype); returns the full ``[n, sum(sizes)]`` matrix in rank order on every rank.  The exchange goes
+    """Every rank contributes the columns it owns of a per-cell matrix (numpy or device tensor ``[n, sizes[rank]]``,
+    any dtype); returns the full ``[n, sum(sizes)]`` matrix in rank order on every rank.  The exchange goes
     through ``device`` in row chunks (NCCL all-gather on GPUs, gloo on CPU), so the staging buffers stay
     small next to the matrices themselves.  Ranks may own zero columns."""
     import numpy as np
 
     rank, ws = world(group)
+    on_device = isinstance(local, torch.Tensor)  # columns already on `device`: no host round trip before the gather
     if ws == 1:
-        return local
+        return local.cpu().numpy() if on_device else local
     n = local.shape[0]
     pad = max(max(sizes), 1)
-    tdtype = torch.from_numpy(np.empty(0, dtype=local.dtype)).dtype
-    out = np.empty((n, int(sum(sizes))), dtype=local.dtype)
+    if on_device:
+        tdtype = local.dtype
+        np_dtype = torch.empty(0, dtype=tdtype).numpy().dtype
+    else:
+        np_dtype = local.dtype
+        tdtype = torch.from_numpy(np.empty(0, dtype=np_dtype)).dtype
+    out = np.empty((n, int(sum(sizes))), dtype=np_dtype)
     starts = np.concatenate([[0], np.cumsum(sizes)]).astype(np.int64)
     for r0 in range(0, n, max_rows):
         r1 = min(n, r0 + max_rows)
         buf = torch.zeros((r1 - r0, pad), dtype=tdtype, device=device)
         if sizes[rank] > 0:
-            buf[:, : sizes[rank]] = torch.from_numpy(np.ascontiguousarray(local[r0:r1])).to(device)
+            buf[:, : sizes[rank]] = local[r0:r1] if on_device else torch.from_numpy(np.ascontiguousarray(local[r0:r1])).to(device)
         parts = [torch.empty_like(buf) for _ in range(ws)]
         dist.all_gather(parts, buf, group=group)
         for r in range(ws):

@@ -777,14 +777,22 @@ def local_morans_i(
     # the batches are assembled in host matrices
     single = n_batches == 1 and world == 1
     zero_mask = np.zeros(g, dtype=bool)
-    if not single:
+    b_lo, b_hi = dist_util.block_slice(n_batches, rank, world)
+    c_lo, c_hi = min(b_lo * batch_size, g), min(b_hi * batch_size, g)
+    # sharded runs keep this rank's columns on the device until the all-gather (no host round trip before it)
+    dev_out = None
+    if world > 1:
+        gdev = co.order.device
+        dev_out = [torch.zeros((n, c_hi - c_lo), dtype=torch.float32, device=gdev) for _ in range(3)]
+        dev_out += [torch.ones((n, c_hi - c_lo), dtype=torch.float32, device=gdev) for _ in range(2)]
+        dev_out.append(torch.zeros((n, c_hi - c_lo), dtype=torch.int8, device=gdev))
+    elif not single:
         local_I = np.zeros((n, g), dtype=np.float32)
         z_values = np.zeros((n, g), dtype=np.float32)
         lag_values = np.zeros((n, g), dtype=np.float32)
         p_values = np.ones((n, g), dtype=np.float32)
         p_adj = np.ones((n, g), dtype=np.float32)
         quadrants = np.zeros((n, g), dtype=np.int8)
-    b_lo, b_hi = dist_util.block_slice(n_batches, rank, world)
     if source == "replay":
         for _ in range(b_lo * n_permutations):  # the draws of the batches other ranks own
             rng.permutation(n)
@@ -824,6 +832,10 @@ def local_morans_i(
             z_values, lag_values, local_I, p_values, p_adj, quadrants = (
                 np.ascontiguousarray(t.cpu().numpy()) for t in (z_d, lag_d, loc_d, p_d, pa_d, q_d))
             continue
+        if dev_out is not None:
+            for dst, t in zip(dev_out, (loc_d, z_d, lag_d, p_d, pa_d, q_d)):
+                dst[:, s - c_lo:e - c_lo] = t
+            continue
         z_values[:, s:e] = z_d.cpu().numpy()
         lag_values[:, s:e] = lag_d.cpu().numpy()
         local_I[:, s:e] = loc_d.cpu().numpy()
@@ -834,15 +846,9 @@ def local_morans_i(
     if world > 1:  # every rank ends up with every gene's columns
         spans = [dist_util.block_slice(n_batches, r, world) for r in range(world)]
         sizes = [min(hi * batch_size, g) - min(lo * batch_size, g) for lo, hi in spans]
-        c_lo, c_hi = min(b_lo * batch_size, g), min(b_hi * batch_size, g)
-        gdev = co.order.device
-
-        def gathered(a: np.ndarray) -> np.ndarray:
-            return dist_util.all_gather_column_blocks(a[:, c_lo:c_hi], sizes, gdev, group)
-
         local_I, z_values, lag_values, p_values, p_adj, quadrants = (
-            gathered(a) for a in (local_I, z_values, lag_values, p_values, p_adj, quadrants))
-        zero_mask = gathered(zero_mask.astype(np.uint8)[None, :])[0].astype(bool)
+            dist_util.all_gather_column_blocks(t, sizes, gdev, group) for t in dev_out)
+        zero_mask = dist_util.all_gather_column_blocks(zero_mask.astype(np.uint8)[None, c_lo:c_hi], sizes, gdev, group)[0].astype(bool)
 
     zero_genes = [names[i] for i in np.where(zero_mask)[0]]
     if zero_mask.any():
