@@ -484,7 +484,13 @@ lag_overflow_kernel(const __grid_constant__ LagTileArgs A, double* __restrict__ 
   const bool active = col < A.ldz;
   const float* zcol = A.Z + col;
   double num[4] = {0, 0, 0, 0}, den[4] = {0, 0, 0, 0};
-  for (int64_t chunk = blockIdx.y; chunk < A.n_chunks; chunk += gridDim.y) {
+  // Normally no chunk is flagged: the flags are scanned 256 at a time (one coalesced load per thread and a
+  // block-wide OR), so the empty case costs a few microseconds instead of one dependent L2 round trip per chunk.
+  for (int64_t base = (int64_t)blockIdx.y * 256; base < A.n_chunks; base += (int64_t)gridDim.y * 256) {
+    const int64_t mine = base + tid;
+    const int flagged = (mine < A.n_chunks && A.ucount[mine] < 0) ? 1 : 0;
+    if (!__syncthreads_or(flagged)) continue;
+  for (int64_t chunk = base; chunk < A.n_chunks && chunk < base + 256; ++chunk) {
     if (A.ucount[chunk] >= 0 || !active) continue;
     const int64_t r0 = chunk * A.chunk;
 #pragma unroll 1
@@ -507,6 +513,7 @@ lag_overflow_kernel(const __grid_constant__ LagTileArgs A, double* __restrict__ 
       const float4 z = A.Zself ? ldg4(A.Zself + row * A.ldz + col) : ldg4(zcol + self * A.ldz);
       finish_row<8>(A, row * A.ldl + col, row * A.ldc + col, deg > 0 ? 1.f / (float)deg : 0.f, acc, z, num, den);
     }
+  }
   }
   reduce_cta<32>(num, den, sh, slot, q, col, active, A.ldz, partial, partial_row0 + blockIdx.y);
 }

@@ -580,9 +580,14 @@ def _lag_tiled(graph: DeviceGraph, Z: torch.Tensor, Zself: Optional[torch.Tensor
 
 
 @_on_device
-def lag_moran(graph: DeviceGraph, Z: torch.Tensor, g: int, want_lag: bool = True, want_local: bool = False):
-    """``sc_csr_lag_moran``: returns ``(num[g], den[g], lag|None, local|None)``."""
+def lag_moran(graph: DeviceGraph, Z: torch.Tensor, g: int, want_lag: bool = True, want_local: bool = False,
+              perm: Optional[torch.Tensor] = None):
+    """``sc_csr_lag_moran`` / ``sc_csr_lag_moran_tiled``: returns ``(num[g], den[g], lag|None, local|None)``.
+    ``perm`` (int32 [n]): the operand is ``Z[perm]`` -- applied while staging on the tile path, through a permuted
+    copy otherwise."""
     _require_cuda(Z, "Z")
+    if perm is not None and not _use_tiles(graph, Z.shape[1]):
+        Z, perm = gather_rows(Z, perm), None
     L = _lib.lib()
     n, ld = Z.shape
     dev = Z.device
@@ -592,7 +597,7 @@ def lag_moran(graph: DeviceGraph, Z: torch.Tensor, g: int, want_lag: bool = True
     den = torch.empty(g, dtype=torch.float64, device=dev)
     ws = _workspace(L.sc_csr_lag_moran_workspace_bytes(n, g), dev)
     if _use_tiles(graph, ld):
-        _lag_tiled(graph, Z, None, None, g, lag, local, num, den, None, None, ws)
+        _lag_tiled(graph, Z, None, perm, g, lag, local, num, den, None, None, ws)
         return num, den, lag, local
     check(
         L.sc_csr_lag_moran(_ptr(graph.indptr), _ptr(graph.indices), _ptr(graph.weights), n, int(graph.k_fixed), _ptr(Z),

@@ -1063,8 +1063,7 @@ def lees_l_matrix(
     cnt = torch.zeros((g, g), dtype=torch.int32, device=Lm.device)
 
     def one(idx_sorted: torch.Tensor) -> None:
-        Zp = engine.gather_rows(std.Z, idx_sorted)
-        _, _, lag_p, _ = engine.lag_moran(graph, Zp, g, want_lag=True)
+        _, _, lag_p, _ = engine.lag_moran(graph, std.Z, g, want_lag=True, perm=idx_sorted)  # W @ Z[perm], no permuted copy
         engine.lee_abs_ge_accumulate(engine.lee_gemm(std.Z, lag_p, g, impl=impl), Lm, cnt)
 
     _, world = dist_util.world(group) if shard != "none" else (0, 1)

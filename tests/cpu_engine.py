@@ -226,9 +226,9 @@ def perm_null_values(graph, Zy, g, n_perms, Zx=None, perm_idx=None, seed=0, perm
     return torch.from_numpy(sims)
 
 
-def lag_moran(graph, Z, g, want_lag=True, want_local=False):  # noqa: F811  (adds the local statistic)
+def lag_moran(graph, Z, g, want_lag=True, want_local=False, perm=None):  # noqa: F811  (adds the local statistic)
     W = _to_scipy(graph).astype(np.float32)
-    z32 = Z.numpy()
+    z32 = Z.numpy() if perm is None else Z.numpy()[perm.numpy()]
     lag = (W @ z32).astype(np.float32)
     z = z32.astype(np.float64)
     num = (z[:, :g] * lag[:, :g].astype(np.float64)).sum(0)
