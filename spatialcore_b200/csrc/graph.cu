@@ -685,8 +685,10 @@ knn_tile_kernel(const GridParams* __restrict__ gp, const int32_t* __restrict__ c
 // radius graph: count pass, scan, fill pass with in-row rank sort
 // ------------------------------------------------------------------------------------------------
 
+constexpr int kFillCap = 64;
+
 template <bool FILL>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 5)
 radius_query_kernel(const GridParams* __restrict__ gp, const int32_t* __restrict__ cell_start,
                     const double* __restrict__ xs, const double* __restrict__ ys,
                     const int32_t* __restrict__ order, int64_t n, double r2,
@@ -697,11 +699,17 @@ radius_query_kernel(const GridParams* __restrict__ gp, const int32_t* __restrict
                     const int32_t* __restrict__ labels, int n_types, float* __restrict__ profile,
                     const int32_t* __restrict__ todo, const int* __restrict__ todo_count) {
   extern __shared__ int s_hist[];
+  // FILL: a row's hits wait for their rank in shared memory (rows of up to kFillCap neighbours; longer rows go
+  // through the global scratch).  Reading them back from the scratch costs an L2 round trip per row.
+  __shared__ int s_fill_idx[FILL ? 8 * kFillCap : 1];
+  __shared__ double s_fill_dist[FILL ? 8 * kFillCap : 1];
   const GridParams g = *gp;
   const int lane = threadIdx.x & 31;
   const int warp_in_block = threadIdx.x >> 5;
   const int warps_per_block = blockDim.x >> 5;
   int* hist = s_hist + warp_in_block * n_types;
+  int* fill_idx = s_fill_idx + (FILL ? warp_in_block * kFillCap : 0);
+  double* fill_dist = s_fill_dist + (FILL ? warp_in_block * kFillCap : 0);
   if (!FILL && profile)
     for (int t = lane; t < n_types; t += 32) hist[t] = 0;
 
@@ -724,14 +732,22 @@ radius_query_kernel(const GridParams* __restrict__ gp, const int32_t* __restrict
     const int xlo = max(cx - 1, 0), xhi = min(cx + 1, g.nx - 1);
     int count = 0;
     const int64_t start = FILL ? (int64_t)indptr[self_id] : 0;
-    for (int yy = max(cy - 1, 0); yy <= min(cy + 1, g.ny - 1); ++yy) {
-      const int b = cell_start[yy * g.nx + xlo], e = cell_start[yy * g.nx + xhi + 1];
-      for (int base = b; base < e; base += 32) {
-        int t = base + lane;
+    const bool in_smem = FILL && indptr[FILL ? self_id + 1 : 0] - (int)start <= kFillCap;
+    // the three cell rows of the 3x3 block as one flattened candidate list: their six range lookups are issued
+    // together (one exposed latency instead of three) and the 32-wide batches are fuller
+    int rb0 = 0, rb1 = 0, rb2 = 0, rn0 = 0, rn1 = 0, rn2 = 0;
+    if (cy > 0) { rb0 = cell_start[(cy - 1) * g.nx + xlo]; rn0 = cell_start[(cy - 1) * g.nx + xhi + 1] - rb0; }
+    { rb1 = cell_start[cy * g.nx + xlo]; rn1 = cell_start[cy * g.nx + xhi + 1] - rb1; }
+    if (cy + 1 < g.ny) { rb2 = cell_start[(cy + 1) * g.nx + xlo]; rn2 = cell_start[(cy + 1) * g.nx + xhi + 1] - rb2; }
+    const int n01 = rn0 + rn1, n_cand = n01 + rn2;
+    {
+      for (int base = 0; base < n_cand; base += 32) {
+        const int u = base + lane;
         bool hit = false;
         int cid = 0;
         double d2 = 0;
-        if (t < e) {
+        if (u < n_cand) {
+          const int t = u < rn0 ? rb0 + u : (u < n01 ? rb1 + (u - rn0) : rb2 + (u - n01));
           cid = order[t];
           d2 = sq_dist(qx, qy, xs[t], ys[t]);
           hit = (cid != self_id) && (d2 <= r2);
@@ -740,8 +756,13 @@ radius_query_kernel(const GridParams* __restrict__ gp, const int32_t* __restrict
         if (FILL) {
           if (hit) {
             int off = count + __popc(m & ((1u << lane) - 1u));
-            tmp_idx[start + off] = cid;
-            if (tmp_dist) tmp_dist[start + off] = sqrt(d2);
+            if (in_smem) {
+              fill_idx[off] = cid;
+              if (dist) fill_dist[off] = sqrt(d2);
+            } else {
+              tmp_idx[start + off] = cid;
+              if (tmp_dist) tmp_dist[start + off] = sqrt(d2);
+            }
           }
         } else if (profile && hit) {
           atomicAdd(&hist[labels[cid]], 1);
@@ -758,13 +779,24 @@ radius_query_kernel(const GridParams* __restrict__ gp, const int32_t* __restrict
         __syncwarp();
       }
     } else {
-      __syncwarp();  // orders the warp's tmp writes before the reads below
-      for (int e = lane; e < count; e += 32) {
-        int my = tmp_idx[start + e];
-        int rk = 0;
-        for (int j = 0; j < count; ++j) rk += tmp_idx[start + j] < my;
-        indices[start + rk] = my;
-        if (dist) dist[start + rk] = tmp_dist[start + e];
+      __syncwarp();  // orders the warp's writes before the reads below
+      if (in_smem) {
+        for (int e = lane; e < count; e += 32) {
+          const int my = fill_idx[e];
+          int rk = 0;
+          for (int j = 0; j < count; ++j) rk += fill_idx[j] < my;
+          indices[start + rk] = my;
+          if (dist) dist[start + rk] = fill_dist[e];
+        }
+        __syncwarp();  // the next row overwrites the buffer
+      } else {
+        for (int e = lane; e < count; e += 32) {
+          int my = tmp_idx[start + e];
+          int rk = 0;
+          for (int j = 0; j < count; ++j) rk += tmp_idx[start + j] < my;
+          indices[start + rk] = my;
+          if (dist) dist[start + rk] = tmp_dist[start + e];
+        }
       }
     }
   }
@@ -772,8 +804,9 @@ radius_query_kernel(const GridParams* __restrict__ gp, const int32_t* __restrict
 
 // Thread-per-query degree count of the radius graph over a shared-memory staged tile (same tiling as
 // knn_tile_kernel): 0.64 ms at 5 M cells / 10^8 edges against 1.39 ms for the warp-per-query count.
-// (The fill pass stays warp-per-query: collecting, ranking and writing a row is warp-cooperative work
-// and a thread-per-query variant measured the same 2.4-2.5 ms.)
+// (The fill pass stays warp-per-query: collecting, ranking and writing a row is warp-cooperative work.
+// Thread-per-query fills over the same tiles were measured twice -- round 1: the same 2.4-2.5 ms; round 2,
+// private shared-memory lists + insertion sort + per-thread row writes: 2.8 ms against 2.1 ms.)
 __global__ void __launch_bounds__(kTileThreads)
 radius_count_tile_kernel(const GridParams* __restrict__ gp, const int32_t* __restrict__ cell_start,
                    const double* __restrict__ xs, const double* __restrict__ ys,
