@@ -36,12 +36,12 @@ namespace sc {
 constexpr int kTcM = 128;      // UMMA M (genes x)
 constexpr int kTcN = 256;      // UMMA N (genes y)
 constexpr int kTcK = 8;        // cells per stage = one tf32 UMMA K step
-constexpr int kTcStages = 8;
+constexpr int kTcMaxStages = 16;
 constexpr int kTcThreads = 320;
 constexpr int kTcEpiWarps = 8;
-constexpr uint32_t kTcABytes = kTcM * kTcK * 4;  // 4 KB per hi / lo
-constexpr uint32_t kTcBBytes = kTcN * kTcK * 4;  // 8 KB per hi / lo
-constexpr uint32_t kTcStageBytes = 2 * kTcABytes + 2 * kTcBBytes;  // 24 KB
+constexpr uint32_t kTcABytes = kTcM * kTcK * 4;  // 4 KB
+constexpr uint32_t kTcBBytes = kTcN * kTcK * 4;  // 8 KB
+constexpr uint32_t kTcStageBytes = kTcABytes + kTcBBytes;  // 12 KB: a raw stage [A | B] or a lo stage [A_lo | B_lo]
 constexpr int kLeeTcMaxChunks = 1024;
 
 __device__ __forceinline__ uint32_t tc_smem_u32(const void* p) {
@@ -113,11 +113,19 @@ __device__ __forceinline__ void tc_mbar_arrive(uint64_t* bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(tc_smem_u32(bar)) : "memory");
 }
 
+// R raw stages (TMA destinations, read by the tensor core as the hi parts) and LR lo stages.  The raw ring is
+// what hides the TMA latency -- the kernel is bound by bytes in flight per SM, not by the tensor pipe or the
+// split (profiles/r02_lee_tc_sensitivity.txt) -- and a lo stage only lives from the split to the retirement of
+// the three MMAs that read it, so few of them are needed: 12 + 4 stages in the 192 KB the old 8 x (raw + lo)
+// ring took.  Stage `it` uses raw slot it % R and lo slot it % LR; both are released by the commit of its MMAs
+// (empty_bar[it % R]), which the split warps consult for iteration it - LR before they overwrite the lo slot.
+template <bool RAW_HI, int R, int LR, int SG>
 __global__ void __launch_bounds__(kTcThreads, 1)
 lee_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
               int64_t n, int64_t chunk, int chunks_per_cta, float* __restrict__ partial, int64_t ldt) {
   extern __shared__ __align__(1024) unsigned char tc_smem[];
-  __shared__ uint64_t full_bar[kTcStages], split_bar[kTcStages], empty_bar[kTcStages];
+  static_assert(LR >= 2 && LR <= R && R <= kTcMaxStages, "ring sizes");
+  __shared__ uint64_t full_bar[R], split_bar[R], empty_bar[R];
   __shared__ uint64_t tmem_full_bar[2], tmem_empty_bar[2];
   __shared__ uint32_t tmem_base_slot;
 
@@ -131,11 +139,13 @@ lee_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__
   const uint32_t raw = tc_smem_u32(tc_smem);
   const uint32_t ring = (raw + 1023u) & ~1023u;
   unsigned char* ring_ptr = tc_smem + (ring - raw);
+  unsigned char* lo_ptr = ring_ptr + (size_t)R * kTcStageBytes;
+  const uint32_t lo_ring = ring + (uint32_t)R * kTcStageBytes;
 
   if (threadIdx.x == 0) {
-    for (int s = 0; s < kTcStages; ++s) {
+    for (int s = 0; s < R; ++s) {
       tc_mbar_init(&full_bar[s], 1);
-      tc_mbar_init(&split_bar[s], kTcEpiWarps / 2);
+      tc_mbar_init(&split_bar[s], kTcEpiWarps / SG);
       tc_mbar_init(&empty_bar[s], 1);
     }
     for (int b = 0; b < 2; ++b) { tc_mbar_init(&tmem_full_bar[b], 1); tc_mbar_init(&tmem_empty_bar[b], kTcEpiWarps); }
@@ -158,8 +168,8 @@ lee_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__
     if (lane == 0) {
       const int total_steps = (int)((cta_end - cta_begin + kTcK - 1) / kTcK);
       for (int it = 0; it < total_steps; ++it) {
-        const int s = it % kTcStages;
-        const uint32_t ph = (uint32_t)(it / kTcStages) & 1u;
+        const int s = it % R;
+        const uint32_t ph = (uint32_t)(it / R) & 1u;
         tc_mbar_wait(&empty_bar[s], ph ^ 1u);
         tc_mbar_expect_tx(&full_bar[s], kTcABytes + kTcBBytes);
         unsigned char* st = ring_ptr + (size_t)s * kTcStageBytes;
@@ -168,7 +178,7 @@ lee_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__
         for (int a = 0; a < kTcM / 32; ++a) tma_load_2d(st + a * 1024, &map_a, m0 + 32 * a, cell, &full_bar[s]);
 #pragma unroll
         for (int a = 0; a < kTcN / 32; ++a)
-          tma_load_2d(st + 2 * kTcABytes + a * 1024, &map_b, n0 + 32 * a, cell, &full_bar[s]);
+          tma_load_2d(st + kTcABytes + a * 1024, &map_b, n0 + 32 * a, cell, &full_bar[s]);
       }
     }
   } else if (warp == 1) {
@@ -183,15 +193,16 @@ lee_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__
         const int steps = (int)((min(cta_end, kb + chunk) - kb + kTcK - 1) / kTcK);
         const uint32_t acc = tmem_d + (uint32_t)(buf * kTcN);
         for (int ks = 0; ks < steps; ++ks, ++it) {
-          const int s = it % kTcStages;
-          const uint32_t ph = (uint32_t)(it / kTcStages) & 1u;
+          const int s = it % R;
+          const uint32_t ph = (uint32_t)(it / R) & 1u;
           tc_mbar_wait(&split_bar[s], ph);
           asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
           const uint32_t base = ring + (uint32_t)s * kTcStageBytes;
+          const uint32_t lbase = lo_ring + (uint32_t)(it % LR) * kTcStageBytes;
           const uint64_t ahi = umma_desc_mn_sw128(base, 1024, 512);
-          const uint64_t alo = umma_desc_mn_sw128(base + kTcABytes, 1024, 512);
-          const uint64_t bhi = umma_desc_mn_sw128(base + 2 * kTcABytes, 1024, 512);
-          const uint64_t blo = umma_desc_mn_sw128(base + 2 * kTcABytes + kTcBBytes, 1024, 512);
+          const uint64_t alo = umma_desc_mn_sw128(lbase, 1024, 512);
+          const uint64_t bhi = umma_desc_mn_sw128(base + kTcABytes, 1024, 512);
+          const uint64_t blo = umma_desc_mn_sw128(lbase + kTcABytes, 1024, 512);
           umma_tf32(acc, alo, bhi, ks > 0 ? 1u : 0u);  // small terms first
           umma_tf32(acc, ahi, blo, 1u);
           umma_tf32(acc, ahi, bhi, 1u);
@@ -244,22 +255,28 @@ lee_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__
       for (int ks = 0; ks < steps; ++ks, ++it) {
         // split stage `it`: 768 float4 (A 256, B 512), in place hi + separate lo.  The two column
         // halves of the epilogue (4 warps each) take alternate stages, so two stages are in flight.
-        if (((it ^ half) & 1) == 0) {
-        const int s = it % kTcStages;
-        tc_mbar_wait(&full_bar[s], (uint32_t)(it / kTcStages) & 1u);
+        if (it % SG == ew / (kTcEpiWarps / SG)) {
+        const int s = it % R;
+        tc_mbar_wait(&full_bar[s], (uint32_t)(it / R) & 1u);
+        if (it >= LR) {  // the lo slot is free once the MMAs of stage it - LR have retired
+          const int j = it - LR;
+          tc_mbar_wait(&empty_bar[j % R], (uint32_t)(j / R) & 1u);
+        }
         unsigned char* st = ring_ptr + (size_t)s * kTcStageBytes;
+        unsigned char* lst = lo_ptr + (size_t)(it % LR) * kTcStageBytes;
+        constexpr int kSplitThreads = 32 * kTcEpiWarps / SG;  // threads sharing one stage
 #pragma unroll
-        for (int u = 0; u < 6; ++u) {
-          const int idx = (et & 127) + u * 128;
-          unsigned char* hp = idx < 256 ? st + idx * 16 : st + 2 * kTcABytes + (idx - 256) * 16;
-          unsigned char* lp = hp + (idx < 256 ? kTcABytes : kTcBBytes);
+        for (int u = 0; u < 768 / kSplitThreads; ++u) {
+          const int idx = (et % kSplitThreads) + u * kSplitThreads;  // float4 index in the 12 KB stage ([A | B] in both rings)
+          unsigned char* hp = st + idx * 16;
+          unsigned char* lp = lst + idx * 16;
           const float4 x = *reinterpret_cast<const float4*>(hp);
           float4 h, l;
           h.x = __uint_as_float(__float_as_uint(x.x) & 0xFFFFE000u); l.x = x.x - h.x;
           h.y = __uint_as_float(__float_as_uint(x.y) & 0xFFFFE000u); l.y = x.y - h.y;
           h.z = __uint_as_float(__float_as_uint(x.z) & 0xFFFFE000u); l.z = x.z - h.z;
           h.w = __uint_as_float(__float_as_uint(x.w) & 0xFFFFE000u); l.w = x.w - h.w;
-          *reinterpret_cast<float4*>(hp) = h;
+          if (!RAW_HI) *reinterpret_cast<float4*>(hp) = h;
           *reinterpret_cast<float4*>(lp) = l;
         }
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic writes -> visible to UMMA / TMA
@@ -283,6 +300,239 @@ lee_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__
   if (warp == 1) {
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_d), "n"(2 * kTcN) : "memory");
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// CTA-pair variant (cta_group::2): two CTAs of one TPC compute a 256 x 256 output tile, each holding its own 128
+// rows of A and HALF of the B tile (128 genes).  Per SM and K step the shared memory then carries 8 KB of TMA
+// writes, 8 + 8 KB of split traffic and 3 x 8 KB of operand reads instead of 12 / 12 + 12 / 3 x 12 KB -- the
+// single-CTA kernel is bound by exactly that traffic and by the TMA box rate (profiles/r02_lee_tc_sensitivity.txt).
+// The leader (cluster rank 0) issues the MMAs; split warps and epilogue warps of both CTAs arrive on the
+// leader's barriers through the cluster window, and the MMA commits are multicast to both CTAs.
+// ------------------------------------------------------------------------------------------------
+constexpr int kTc2Raw = 12, kTc2Lo = 8;
+constexpr uint32_t kTc2BBytes = (kTcN / 2) * kTcK * 4;          // 4 KB: this CTA's half of the B tile
+constexpr uint32_t kTc2StageBytes = kTcABytes + kTc2BBytes;     // 8 KB
+// kind::tf32, D = F32, both MN-major, M = 256 (pair), N = 256
+constexpr uint32_t kTc2Idesc = (1u << 4) | (2u << 7) | (2u << 10) | (1u << 15) | (1u << 16) |
+                               ((uint32_t)(kTcN >> 3) << 17) | ((uint32_t)((2 * kTcM) >> 4) << 24);
+
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// address of `local` (a shared-memory object of this CTA) in CTA `rank` of the cluster
+__device__ __forceinline__ uint32_t cluster_map(const void* local, uint32_t rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(tc_smem_u32(local)), "r"(rank));
+  return r;
+}
+__device__ __forceinline__ void tc_mbar_arrive_cluster(uint32_t cluster_addr) {
+  // default (CTA-scope release) semantics: a cluster-scope release costs a full memory barrier per arrival
+  // (43 % of the stall samples when it was tried); the data handed over lives in shared memory and is made
+  // visible to the async proxy by the fence.proxy.async before the arrival
+  asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+__device__ __forceinline__ void umma2_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::2.kind::tf32 [%0], %1, %2, %3, p;\n"
+      "}\n" ::"r"(tmem_d),
+      "l"(adesc), "l"(bdesc), "r"(kTc2Idesc), "r"(accumulate)
+      : "memory");
+}
+// arrives on the barrier at this CTA-relative address in both CTAs of the pair
+__device__ __forceinline__ void umma2_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(
+                   tc_smem_u32(bar)),
+               "h"((uint16_t)3)
+               : "memory");
+}
+
+__global__ void __launch_bounds__(kTcThreads, 1)
+lee_tc2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
+               int64_t n, int64_t chunk, int chunks_per_cta, float* __restrict__ partial, int64_t ldt) {
+  constexpr int R = kTc2Raw, LR = kTc2Lo;
+  extern __shared__ __align__(1024) unsigned char tc_smem[];
+  __shared__ uint64_t full_bar[R], split_bar[R], empty_bar[R];
+  __shared__ uint64_t tmem_full_bar[2], tmem_empty_bar[2];
+  __shared__ uint32_t tmem_base_slot;
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();  // 0 = leader; the pair is (blockIdx.x even, odd): a CTA pair lies along x
+  const int n0 = blockIdx.y * kTcN, m0 = blockIdx.x * kTcM;
+  const int nb0 = n0 + (int)rank * (kTcN / 2);  // this CTA's half of the B tile
+  const int64_t cta_begin = (int64_t)blockIdx.z * chunks_per_cta * chunk;
+  const int64_t cta_end = min(n, cta_begin + (int64_t)chunks_per_cta * chunk);
+  const int n_chunks = cta_end > cta_begin ? (int)((cta_end - cta_begin + chunk - 1) / chunk) : 0;
+
+  const uint32_t raw = tc_smem_u32(tc_smem);
+  const uint32_t ring = (raw + 1023u) & ~1023u;
+  unsigned char* ring_ptr = tc_smem + (ring - raw);
+  unsigned char* lo_ptr = ring_ptr + (size_t)R * kTc2StageBytes;
+  const uint32_t lo_ring = ring + (uint32_t)R * kTc2StageBytes;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < R; ++s) {
+      tc_mbar_init(&full_bar[s], 1);
+      tc_mbar_init(&split_bar[s], 2 * (kTcEpiWarps / 2));  // the split warps of both CTAs (leader's copy is used)
+      tc_mbar_init(&empty_bar[s], 1);
+    }
+    for (int b = 0; b < 2; ++b) { tc_mbar_init(&tmem_full_bar[b], 1); tc_mbar_init(&tmem_empty_bar[b], 2 * kTcEpiWarps); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(
+                     tc_smem_u32(&tmem_base_slot)),
+                 "n"(2 * kTcN)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  cluster_sync_all();  // barriers of both CTAs initialised, TMEM allocated on both SMs
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem_d = tmem_base_slot;
+
+  if (warp == 0) {
+    // ===== TMA producer: this CTA's 128 rows of A and 128 columns of B =====
+    if (lane == 0) {
+      const int total_steps = (int)((cta_end - cta_begin + kTcK - 1) / kTcK);
+      for (int it = 0; it < total_steps; ++it) {
+        const int s = it % R;
+        const uint32_t ph = (uint32_t)(it / R) & 1u;
+        tc_mbar_wait(&empty_bar[s], ph ^ 1u);
+        tc_mbar_expect_tx(&full_bar[s], kTc2StageBytes);
+        unsigned char* st = ring_ptr + (size_t)s * kTc2StageBytes;
+        const int cell = (int)(cta_begin + (int64_t)it * kTcK);
+#pragma unroll
+        for (int a = 0; a < kTcM / 32; ++a) tma_load_2d(st + a * 1024, &map_a, m0 + 32 * a, cell, &full_bar[s]);
+#pragma unroll
+        for (int a = 0; a < kTcN / 64; ++a)
+          tma_load_2d(st + kTcABytes + a * 1024, &map_b, nb0 + 32 * a, cell, &full_bar[s]);
+      }
+    }
+  } else if (warp == 1) {
+    // ===== MMA issuer: one lane of the leader CTA =====
+    if (lane == 0 && rank == 0) {
+      int it = 0;
+      for (int c = 0; c < n_chunks; ++c) {
+        const int buf = c & 1;
+        tc_mbar_wait(&tmem_empty_bar[buf], (((uint32_t)c >> 1) & 1u) ^ 1u);  // both epilogues drained it
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const int64_t kb = cta_begin + (int64_t)c * chunk;
+        const int steps = (int)((min(cta_end, kb + chunk) - kb + kTcK - 1) / kTcK);
+        const uint32_t acc = tmem_d + (uint32_t)(buf * kTcN);
+        for (int ks = 0; ks < steps; ++ks, ++it) {
+          const int s = it % R;
+          const uint32_t ph = (uint32_t)(it / R) & 1u;
+          tc_mbar_wait(&split_bar[s], ph);  // both CTAs have staged and split this K step
+          asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+          const uint32_t base = ring + (uint32_t)s * kTc2StageBytes;
+          const uint32_t lbase = lo_ring + (uint32_t)(it % LR) * kTc2StageBytes;
+          const uint64_t ahi = umma_desc_mn_sw128(base, 1024, 512);
+          const uint64_t alo = umma_desc_mn_sw128(lbase, 1024, 512);
+          const uint64_t bhi = umma_desc_mn_sw128(base + kTcABytes, 1024, 512);
+          const uint64_t blo = umma_desc_mn_sw128(lbase + kTcABytes, 1024, 512);
+          umma2_tf32(acc, alo, bhi, ks > 0 ? 1u : 0u);  // small terms first
+          umma2_tf32(acc, ahi, blo, 1u);
+          umma2_tf32(acc, ahi, bhi, 1u);
+          umma2_commit(&empty_bar[s]);  // frees the stage in both CTAs
+        }
+        umma2_commit(&tmem_full_bar[buf]);  // this chunk's accumulators (both CTAs' halves) are complete
+      }
+    }
+  } else {
+    // ===== split + epilogue warps =====
+    const int ew = warp - 2, et = threadIdx.x - 64;   // 0..7, 0..255
+    const int lane_grp = warp & 3;               // TMEM lanes this warp may touch: 32*(warp % 4) ..
+    const int half = ew >> 2;                    // column half (128 of the 256 accumulator columns)
+    float acc[128];
+#pragma unroll
+    for (int j = 0; j < 128; ++j) acc[j] = 0.f;
+
+    auto drain = [&](int c) {
+      const int buf = c & 1;
+      tc_mbar_wait(&tmem_full_bar[buf], ((uint32_t)c >> 1) & 1u);
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        uint32_t v[32];
+        const uint32_t taddr = tmem_d + ((uint32_t)(lane_grp * 32) << 16) + (uint32_t)(buf * kTcN + half * 128 + q * 32);
+        asm volatile(
+            "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+            "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,"
+            "%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+            : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+              "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]),
+              "=r"(v[15]), "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]),
+              "=r"(v[22]), "=r"(v[23]), "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]),
+              "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+            : "r"(taddr));
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+        for (int j = 0; j < 32; ++j) acc[q * 32 + j] += __uint_as_float(v[j]);
+      }
+      asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+      __syncwarp();
+      if (lane == 0) tc_mbar_arrive_cluster(cluster_map(&tmem_empty_bar[buf], 0));
+    };
+
+    int it = 0;
+    for (int c = 0; c < n_chunks; ++c) {
+      const int64_t kb = cta_begin + (int64_t)c * chunk;
+      const int steps = (int)((min(cta_end, kb + chunk) - kb + kTcK - 1) / kTcK);
+      for (int ks = 0; ks < steps; ++ks, ++it) {
+        // split stage `it`: 512 float4 ([A | B half]); the two groups of four warps take alternate stages
+        if ((it & 1) == half) {
+          const int s = it % R;
+          tc_mbar_wait(&full_bar[s], (uint32_t)(it / R) & 1u);
+          if (it >= LR) {  // the lo slot is free once the MMAs of stage it - LR have retired
+            const int j = it - LR;
+            tc_mbar_wait(&empty_bar[j % R], (uint32_t)(j / R) & 1u);
+          }
+          const unsigned char* st = ring_ptr + (size_t)s * kTc2StageBytes;
+          unsigned char* lst = lo_ptr + (size_t)(it % LR) * kTc2StageBytes;
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            const int idx = (et & 127) + u * 128;
+            const float4 x = *reinterpret_cast<const float4*>(st + idx * 16);
+            float4 l;  // the tensor core reads the raw tile as its TF32 hi part (it ignores the low 13 bits)
+            l.x = x.x - __uint_as_float(__float_as_uint(x.x) & 0xFFFFE000u);
+            l.y = x.y - __uint_as_float(__float_as_uint(x.y) & 0xFFFFE000u);
+            l.z = x.z - __uint_as_float(__float_as_uint(x.z) & 0xFFFFE000u);
+            l.w = x.w - __uint_as_float(__float_as_uint(x.w) & 0xFFFFE000u);
+            *reinterpret_cast<float4*>(lst + idx * 16) = l;
+          }
+          asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic writes -> visible to UMMA
+          __syncwarp();
+          if (lane == 0) tc_mbar_arrive_cluster(cluster_map(&split_bar[s], 0));
+        }
+        if (c > 0 && ks == (steps > 4 ? 4 : steps - 1)) drain(c - 1);
+      }
+    }
+    if (n_chunks > 0) drain(n_chunks - 1);
+    const int row = m0 + lane_grp * 32 + lane;   // output row (gene x)
+    float* dst = partial + ((int64_t)blockIdx.z * ldt + row) * ldt + n0 + half * 128;
+#pragma unroll
+    for (int j = 0; j < 128; j += 4)
+      *reinterpret_cast<float4*>(dst + j) = make_float4(acc[j], acc[j + 1], acc[j + 2], acc[j + 3]);
+  }
+
+  // no CTA of the pair may leave (or free its TMEM) while the other can still be read or signalled
+  __syncwarp();
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  cluster_sync_all();
+  if (warp == 1) {
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_d), "n"(2 * kTcN) : "memory");
   }
 }
 
@@ -383,10 +633,49 @@ int lee_tc_launch(const float* A, int64_t lda, const float* B, int64_t ldb, int6
   if ((rc = make_map(&ma, A, n, lda))) return rc;
   if ((rc = make_map(&mb, B, n, ldb))) return rc;
 
-  const size_t dyn = (size_t)kTcStages * kTcStageBytes + 1024;
-  SC_CUDA_OK(cudaFuncSetAttribute(lee_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn));
   dim3 grid((unsigned)(p.ldt / kTcN), (unsigned)(p.ldt / kTcM), (unsigned)p.splits);
-  lee_tc_kernel<<<grid, kTcThreads, dyn, st>>>(ma, mb, n, p.chunk, p.chunks_per_cta, partial, p.ldt);
+  // SC_LEE_TC_MASK_HI=1 rewrites the raw tile as its TF32 hi part instead of letting the tensor core truncate it
+  // (bit-identical results, measured); SC_LEE_TC_CTA2=0 forces the single-CTA kernel.
+  const char* mask = getenv("SC_LEE_TC_MASK_HI");
+  const bool raw_hi = !(mask && mask[0] == '1');
+  const char* c2 = getenv("SC_LEE_TC_CTA2");
+  const bool pair = raw_hi && !(c2 && c2[0] == '0');
+#define SC_LEE_GO(RH, RR, LL, SG)                                                                               \
+  do {                                                                                                          \
+    const size_t dyn = (size_t)(RR + LL) * kTcStageBytes + 1024;                                                \
+    SC_CUDA_OK(cudaFuncSetAttribute(lee_tc_kernel<RH, RR, LL, SG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn)); \
+    lee_tc_kernel<RH, RR, LL, SG><<<grid, kTcThreads, dyn, st>>>(ma, mb, n, p.chunk, p.chunks_per_cta, partial, p.ldt); \
+  } while (0)
+  if (pair) {
+    const size_t dyn = (size_t)(kTc2Raw + kTc2Lo) * kTc2StageBytes + 1024;
+    SC_CUDA_OK(cudaFuncSetAttribute(lee_tc2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn));
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(grid.y, grid.x, grid.z);  // x = 128-row tiles (the pair), y = 256-column blocks
+    cfg.blockDim = dim3(kTcThreads);
+    cfg.dynamicSmemBytes = dyn;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;  // the pair: two consecutive 128-row tiles of one column block
+    attr[0].val.clusterDim.x = 2;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    cudaError_t le = cudaLaunchKernelEx(&cfg, lee_tc2_kernel, ma, mb, n, p.chunk, p.chunks_per_cta, partial, p.ldt);
+    if (le != cudaSuccess) {
+      int clusters = -1;
+      cudaOccupancyMaxActiveClusters(&clusters, lee_tc2_kernel, &cfg);
+      set_error("lee_tc2_kernel launch failed: %s (grid %u x %u x %u, %zu B dynamic smem, max active clusters %d)",
+                cudaGetErrorString(le), cfg.gridDim.x, cfg.gridDim.y, cfg.gridDim.z, dyn, clusters);
+      (void)cudaGetLastError();
+      return SC_ERR_CUDA;
+    }
+  } else if (raw_hi) {
+    SC_LEE_GO(true, 8, 8, 2);
+  } else {
+    SC_LEE_GO(false, 8, 8, 2);
+  }
+#undef SC_LEE_GO
   SC_LAUNCH_OK();
   dim3 blk(32, 8);
   dim3 grd((g + 31) / 32, (g + 7) / 8);
