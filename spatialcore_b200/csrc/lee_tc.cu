@@ -12,18 +12,20 @@
 // lands as one such atom: K groups (4 cells) SBO = 512 B apart, gene atoms LBO = 1024 B apart --
 // no transpose of Z or lag is ever made, and genes beyond the matrix width are zero-filled by TMA.
 //
-// The hi/lo split is fused: TMA brings the RAW FP32 tiles of Z and lag, the epilogue warps (idle
-// between accumulator drains) rewrite each staged element in place as hi and store lo next to it
-// (an element-wise map, so the swizzled layout is irrelevant), fence the generic->async proxy and
-// release the stage to the MMA warp.  No split copies of the operands exist in HBM.
+// The hi/lo split is fused: TMA brings the RAW FP32 tiles of Z and lag.  The tensor core reads a raw tile as its
+// TF32 hi part -- it ignores the low 13 mantissa bits (measured: bit-identical to rewriting the tile masked) --
+// and the epilogue warps (idle between accumulator drains) write the lo parts into a second, shorter ring,
+// fence the generic->async proxy and release the stage to the MMA lane.  No split copies exist in HBM.
 //
-// Work decomposition: CTA = one 128 x 256 output tile x a span of consecutive `chunk`-cell chunks.
-// The tensor core truncates when it adds into its FP32 accumulator, so a chunk is kept short (64
-// cells = 24 accumulate steps); chunks alternate between two 256-column TMEM accumulators, and while
-// the MMA warp fills one the eight epilogue warps drain the other into FP32 REGISTER accumulators
+// Work decomposition: a CTA PAIR (cta_group::2, lee_tc2_kernel) = one 256 x 256 output tile x a span of
+// consecutive `chunk`-cell chunks; each CTA stages its 128 rows of A and half of the B tile, 16 cells per stage.
+// (lee_tc_kernel is the single-CTA form, 128 x 256 per CTA: SC_LEE_TC_CTA2=0.)
+// The tensor core truncates when it adds into its FP32 accumulator, so a chunk is kept short (128
+// cells = 48 accumulate steps); chunks alternate between two 256-column TMEM accumulators, and while
+// the MMA lane fills one the eight epilogue warps drain the other into FP32 REGISTER accumulators
 // (round-to-nearest adds).  One FP32 tile per CTA goes to a small partial buffer ([splits] tiles,
 // ~40 MB instead of one tile per chunk = 3.3 GB at C3) and the splits are summed in FP64.
-// Warp roles: 0 = TMA producer, 1 = TMEM allocator + MMA issuer, 2..9 = epilogue.
+// Warp roles: 0 = TMA producer, 1 = TMEM allocator + MMA issuer, 2..9 = split + epilogue.
 #include <cuda.h>
 #include <cudaTypedefs.h>
 
@@ -311,9 +313,8 @@ lee_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__
 // The leader (cluster rank 0) issues the MMAs; split warps and epilogue warps of both CTAs arrive on the
 // leader's barriers through the cluster window, and the MMA commits are multicast to both CTAs.
 // ------------------------------------------------------------------------------------------------
-constexpr int kTc2Raw = 12, kTc2Lo = 8;
-constexpr uint32_t kTc2BBytes = (kTcN / 2) * kTcK * 4;          // 4 KB: this CTA's half of the B tile
-constexpr uint32_t kTc2StageBytes = kTcABytes + kTc2BBytes;     // 8 KB
+constexpr int kTc2Raw = 8, kTc2Lo = 4;  // stages of the raw / lo rings (16 KB each: 192 KB)
+constexpr int kTc2KS = 16;                                       // cells per stage
 // kind::tf32, D = F32, both MN-major, M = 256 (pair), N = 256
 constexpr uint32_t kTc2Idesc = (1u << 4) | (2u << 7) | (2u << 10) | (1u << 15) | (1u << 16) |
                                ((uint32_t)(kTcN >> 3) << 17) | ((uint32_t)((2 * kTcM) >> 4) << 24);
@@ -357,10 +358,16 @@ __device__ __forceinline__ void umma2_commit(uint64_t* bar) {
                : "memory");
 }
 
+template <int R, int LR, int KS>
 __global__ void __launch_bounds__(kTcThreads, 1)
 lee_tc2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
                int64_t n, int64_t chunk, int chunks_per_cta, float* __restrict__ partial, int64_t ldt) {
-  constexpr int R = kTc2Raw, LR = kTc2Lo;
+  // KS cells per stage (KS / 8 tf32 K steps): the per-stage costs -- three barrier hand-overs, the MMA lane's
+  // wait / descriptor / commit sequence -- are paid once per KS cells
+  static_assert(KS == 8 || KS == 16 || KS == 32, "cells per stage");
+  constexpr uint32_t kA = kTcM * KS * 4;           // this CTA's A rows
+  constexpr uint32_t kStage = kA + (kTcN / 2) * KS * 4;  // + its half of the B tile
+  constexpr uint32_t kAtom = 128 * KS;             // one 32-gene atom of a stage (TMA box of 32 genes x KS cells)
   extern __shared__ __align__(1024) unsigned char tc_smem[];
   __shared__ uint64_t full_bar[R], split_bar[R], empty_bar[R];
   __shared__ uint64_t tmem_full_bar[2], tmem_empty_bar[2];
@@ -377,8 +384,8 @@ lee_tc2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
   const uint32_t raw = tc_smem_u32(tc_smem);
   const uint32_t ring = (raw + 1023u) & ~1023u;
   unsigned char* ring_ptr = tc_smem + (ring - raw);
-  unsigned char* lo_ptr = ring_ptr + (size_t)R * kTc2StageBytes;
-  const uint32_t lo_ring = ring + (uint32_t)R * kTc2StageBytes;
+  unsigned char* lo_ptr = ring_ptr + (size_t)R * kStage;
+  const uint32_t lo_ring = ring + (uint32_t)R * kStage;
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < R; ++s) {
@@ -404,19 +411,19 @@ lee_tc2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
   if (warp == 0) {
     // ===== TMA producer: this CTA's 128 rows of A and 128 columns of B =====
     if (lane == 0) {
-      const int total_steps = (int)((cta_end - cta_begin + kTcK - 1) / kTcK);
+      const int total_steps = (int)((cta_end - cta_begin + KS - 1) / KS);
       for (int it = 0; it < total_steps; ++it) {
         const int s = it % R;
         const uint32_t ph = (uint32_t)(it / R) & 1u;
         tc_mbar_wait(&empty_bar[s], ph ^ 1u);
-        tc_mbar_expect_tx(&full_bar[s], kTc2StageBytes);
-        unsigned char* st = ring_ptr + (size_t)s * kTc2StageBytes;
-        const int cell = (int)(cta_begin + (int64_t)it * kTcK);
+        tc_mbar_expect_tx(&full_bar[s], kStage);
+        unsigned char* st = ring_ptr + (size_t)s * kStage;
+        const int cell = (int)(cta_begin + (int64_t)it * KS);
 #pragma unroll
-        for (int a = 0; a < kTcM / 32; ++a) tma_load_2d(st + a * 1024, &map_a, m0 + 32 * a, cell, &full_bar[s]);
+        for (int a = 0; a < kTcM / 32; ++a) tma_load_2d(st + a * kAtom, &map_a, m0 + 32 * a, cell, &full_bar[s]);
 #pragma unroll
         for (int a = 0; a < kTcN / 64; ++a)
-          tma_load_2d(st + kTcABytes + a * 1024, &map_b, nb0 + 32 * a, cell, &full_bar[s]);
+          tma_load_2d(st + kA + a * kAtom, &map_b, nb0 + 32 * a, cell, &full_bar[s]);
       }
     }
   } else if (warp == 1) {
@@ -428,22 +435,26 @@ lee_tc2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         tc_mbar_wait(&tmem_empty_bar[buf], (((uint32_t)c >> 1) & 1u) ^ 1u);  // both epilogues drained it
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         const int64_t kb = cta_begin + (int64_t)c * chunk;
-        const int steps = (int)((min(cta_end, kb + chunk) - kb + kTcK - 1) / kTcK);
+        const int steps = (int)((min(cta_end, kb + chunk) - kb + KS - 1) / KS);
         const uint32_t acc = tmem_d + (uint32_t)(buf * kTcN);
         for (int ks = 0; ks < steps; ++ks, ++it) {
           const int s = it % R;
           const uint32_t ph = (uint32_t)(it / R) & 1u;
           tc_mbar_wait(&split_bar[s], ph);  // both CTAs have staged and split this K step
           asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-          const uint32_t base = ring + (uint32_t)s * kTc2StageBytes;
-          const uint32_t lbase = lo_ring + (uint32_t)(it % LR) * kTc2StageBytes;
-          const uint64_t ahi = umma_desc_mn_sw128(base, 1024, 512);
-          const uint64_t alo = umma_desc_mn_sw128(lbase, 1024, 512);
-          const uint64_t bhi = umma_desc_mn_sw128(base + kTcABytes, 1024, 512);
-          const uint64_t blo = umma_desc_mn_sw128(lbase + kTcABytes, 1024, 512);
-          umma2_tf32(acc, alo, bhi, ks > 0 ? 1u : 0u);  // small terms first
-          umma2_tf32(acc, ahi, blo, 1u);
-          umma2_tf32(acc, ahi, bhi, 1u);
+          const uint32_t base = ring + (uint32_t)s * kStage;
+          const uint32_t lbase = lo_ring + (uint32_t)(it % LR) * kStage;
+          const uint64_t ahi = umma_desc_mn_sw128(base, kAtom, 512);
+          const uint64_t alo = umma_desc_mn_sw128(lbase, kAtom, 512);
+          const uint64_t bhi = umma_desc_mn_sw128(base + kA, kAtom, 512);
+          const uint64_t blo = umma_desc_mn_sw128(lbase + kA, kAtom, 512);
+#pragma unroll
+          for (int j = 0; j < KS / 8; ++j) {  // K step j: two 4-cell groups, 1024 B further into every atom
+            const uint64_t off = (uint64_t)(j * 1024 >> 4);
+            umma2_tf32(acc, alo + off, bhi + off, (ks > 0 || j > 0) ? 1u : 0u);  // small terms first
+            umma2_tf32(acc, ahi + off, blo + off, 1u);
+            umma2_tf32(acc, ahi + off, bhi + off, 1u);
+          }
           umma2_commit(&empty_bar[s]);  // frees the stage in both CTAs
         }
         umma2_commit(&tmem_full_bar[buf]);  // this chunk's accumulators (both CTAs' halves) are complete
@@ -488,9 +499,9 @@ lee_tc2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     int it = 0;
     for (int c = 0; c < n_chunks; ++c) {
       const int64_t kb = cta_begin + (int64_t)c * chunk;
-      const int steps = (int)((min(cta_end, kb + chunk) - kb + kTcK - 1) / kTcK);
+      const int steps = (int)((min(cta_end, kb + chunk) - kb + KS - 1) / KS);
       for (int ks = 0; ks < steps; ++ks, ++it) {
-        // split stage `it`: 512 float4 ([A | B half]); the two groups of four warps take alternate stages
+        // split stage `it` ([A | B half], kStage / 16 float4); the two groups of four warps take alternate stages
         if ((it & 1) == half) {
           const int s = it % R;
           tc_mbar_wait(&full_bar[s], (uint32_t)(it / R) & 1u);
@@ -498,10 +509,10 @@ lee_tc2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
             const int j = it - LR;
             tc_mbar_wait(&empty_bar[j % R], (uint32_t)(j / R) & 1u);
           }
-          const unsigned char* st = ring_ptr + (size_t)s * kTc2StageBytes;
-          unsigned char* lst = lo_ptr + (size_t)(it % LR) * kTc2StageBytes;
+          const unsigned char* st = ring_ptr + (size_t)s * kStage;
+          unsigned char* lst = lo_ptr + (size_t)(it % LR) * kStage;
 #pragma unroll
-          for (int u = 0; u < 4; ++u) {
+          for (int u = 0; u < (int)(kStage / 16 / 128); ++u) {
             const int idx = (et & 127) + u * 128;
             const float4 x = *reinterpret_cast<const float4*>(st + idx * 16);
             float4 l;  // the tensor core reads the raw tile as its TF32 hi part (it ignores the low 13 bits)
@@ -515,7 +526,7 @@ lee_tc2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
           __syncwarp();
           if (lane == 0) tc_mbar_arrive_cluster(cluster_map(&split_bar[s], 0));
         }
-        if (c > 0 && ks == (steps > 4 ? 4 : steps - 1)) drain(c - 1);
+        if (c > 0 && ks == (steps > 32 / KS ? 32 / KS : steps - 1)) drain(c - 1);  // ~32 cells into the next chunk
       }
     }
     if (n_chunks > 0) drain(n_chunks - 1);
@@ -559,12 +570,13 @@ static TcPlan tc_plan(int64_t n, int g) {
   p.ldt = (int64_t)align_up((size_t)g, kTcN);
   // The tensor core truncates (RZ) when it adds into the FP32 accumulator: a chunk of c cells makes
   // 3c/8 accumulate steps and leaves a relative bias of ~(3c/16)*2^-24 of the accumulator.  Shorter chunks
-  // are more accurate and cost more drains.  Measured at C3 size on uncorrelated data (B200,
-  // scripts/lee_tc_chunk.py; error in units of 2^-24 * sum|terms|, median / p99): 512 cells 0.158 / 0.61 at
-  // 2.31 ms, 256: 0.086 / 0.33 at 2.30 ms, 128: 0.050 / 0.20 at 2.33 ms, 64: 0.033 / 0.13 at 2.38 ms, 32: 0.028 /
-  // 0.12 at 2.47 ms -- 64 buys 2.6x the accuracy of 256 for 3.5 % of the time.  SC_LEE_TC_CHUNK overrides.
-  int64_t chunk = 64;
-  if (const char* e = getenv("SC_LEE_TC_CHUNK")) { long v = atol(e); if (v >= 8) chunk = (v + 7) / 8 * 8; }
+  // are more accurate and cost more drains.  Measured at C3 size on uncorrelated data with the CTA-pair kernel
+  // (B200, scripts/lee_tc_chunk.py; error in units of 2^-24 * sum|terms|, median / p99 / max): 512 cells
+  // 0.158 / 0.61 / 5.7 at 1.51 ms, 256: 0.086 / 0.33 / 3.1 at 1.51 ms, 128: 0.050 / 0.20 / 1.9 at 1.53 ms,
+  // 64: 0.033 / 0.13 / 1.4 at 1.64 ms, 32: 0.028 / 0.12 / 1.2 at 1.83 ms -- 128 buys 1.7x the accuracy of 256
+  // for 1 % of the time.  SC_LEE_TC_CHUNK overrides.
+  int64_t chunk = 128;
+  if (const char* e = getenv("SC_LEE_TC_CHUNK")) { long v = atol(e); if (v >= 8) chunk = (v + 31) / 32 * 32; }  // a multiple of every stage length
   p.chunk = chunk;
   p.chunks = (int)((n + chunk - 1) / chunk);
   // one CTA per SM (512 TMEM columns): ~2 waves of CTAs over the (tiles x splits) grid
@@ -593,12 +605,12 @@ static PFN_cuTensorMapEncodeTiled_v12000 get_encode() {
 // 2-D view of a cell-major [n][ld] FP32 matrix: (ld genes, n cells); a box of (32 genes, 8 cells)
 // lands as one MN-major SW128_32B atom (1024 B, two 4-cell K groups).  Genes >= ld and cells >= n are
 // out of bounds for the map and arrive as zeros.
-static int make_map(CUtensorMap* map, const float* base, int64_t n, int64_t ld) {
+static int make_map(CUtensorMap* map, const float* base, int64_t n, int64_t ld, int box_cells = kTcK) {
   PFN_cuTensorMapEncodeTiled_v12000 enc = get_encode();
   if (!enc) { set_error("cuTensorMapEncodeTiled entry point not available"); return SC_ERR_CUDA; }
   cuuint64_t dims[2] = {(cuuint64_t)ld, (cuuint64_t)n};
   cuuint64_t strides[1] = {(cuuint64_t)ld * 4};
-  cuuint32_t box[2] = {32, (cuuint32_t)kTcK};
+  cuuint32_t box[2] = {32, (cuuint32_t)box_cells};
   cuuint32_t estr[2] = {1, 1};
   CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), dims, strides, box, estr,
                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B,
@@ -647,8 +659,20 @@ int lee_tc_launch(const float* A, int64_t lda, const float* B, int64_t ldb, int6
     lee_tc_kernel<RH, RR, LL, SG><<<grid, kTcThreads, dyn, st>>>(ma, mb, n, p.chunk, p.chunks_per_cta, partial, p.ldt); \
   } while (0)
   if (pair) {
-    const size_t dyn = (size_t)(kTc2Raw + kTc2Lo) * kTc2StageBytes + 1024;
-    SC_CUDA_OK(cudaFuncSetAttribute(lee_tc2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn));
+    int cfgv = 0;  // SC_LEE_TC2_CFG = KS * 10000 + R * 100 + LR (experiments)
+    if (const char* e = getenv("SC_LEE_TC2_CFG")) cfgv = atoi(e);
+    int ks = kTc2KS, rr = kTc2Raw, ll = kTc2Lo;
+    void (*kern)(const CUtensorMap, const CUtensorMap, int64_t, int64_t, int, float*, int64_t) = lee_tc2_kernel<kTc2Raw, kTc2Lo, kTc2KS>;
+#define SC_TC2_PICK(K, RR, LL) if (cfgv == K * 10000 + RR * 100 + LL) { kern = lee_tc2_kernel<RR, LL, K>; ks = K; rr = RR; ll = LL; }
+    SC_TC2_PICK(16, 6, 4) SC_TC2_PICK(8, 12, 8) SC_TC2_PICK(32, 3, 2)
+#undef SC_TC2_PICK
+    if (p.chunk % ks != 0) { set_error("sc_lee_gemm: chunk must be a multiple of the stage length"); return SC_ERR_INVALID; }
+    if (ks != kTcK) {
+      if ((rc = make_map(&ma, A, n, lda, ks))) return rc;
+      if ((rc = make_map(&mb, B, n, ldb, ks))) return rc;
+    }
+    const size_t dyn = (size_t)(rr + ll) * (size_t)((kTcM + kTcN / 2) * ks * 4) + 1024;
+    SC_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn));
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(grid.y, grid.x, grid.z);  // x = 128-row tiles (the pair), y = 256-column blocks
     cfg.blockDim = dim3(kTcThreads);
@@ -661,10 +685,10 @@ int lee_tc_launch(const float* A, int64_t lda, const float* B, int64_t ldb, int6
     attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    cudaError_t le = cudaLaunchKernelEx(&cfg, lee_tc2_kernel, ma, mb, n, p.chunk, p.chunks_per_cta, partial, p.ldt);
+    cudaError_t le = cudaLaunchKernelEx(&cfg, kern, ma, mb, n, p.chunk, p.chunks_per_cta, partial, p.ldt);
     if (le != cudaSuccess) {
       int clusters = -1;
-      cudaOccupancyMaxActiveClusters(&clusters, lee_tc2_kernel, &cfg);
+      cudaOccupancyMaxActiveClusters(&clusters, kern, &cfg);
       set_error("lee_tc2_kernel launch failed: %s (grid %u x %u x %u, %zu B dynamic smem, max active clusters %d)",
                 cudaGetErrorString(le), cfg.gridDim.x, cfg.gridDim.y, cfg.gridDim.z, dyn, clusters);
       (void)cudaGetLastError();
