@@ -326,7 +326,7 @@ def lee_leg(spatial, AnnDataLite, engine, synthetic, dev, gpu_index):
     tf32_peak = float(peaks.get("bf16_tflops", 1630.8)) / 2.0
     useful = 2.0 * n * g * g / (ms_tc / 1e3) / 1e12
     return {"workload": "C3: Lee's L over all gene pairs, 200k cells x 1000 genes, kNN k=6", "ms": round(ms_tc, 3),
-            "useful_tflops": round(useful, 1), "issued_tf32_tflops": round(3.0 * useful, 1), "impl": "tcgen05 kind::tf32, 3xTF32 (impl=2)",
+            "useful_tflops": round(useful, 1), "issued_tf32_tflops": round(3.0 * useful, 1), "impl": "tcgen05 kind::tf32 cta_group::2 (CTA pair, 256 x 256 tile), 3xTF32 (impl=2)",
             "roofline": {"bound": "tensor", "achieved": round(3.0 * useful, 1), "peak": round(tf32_peak, 1), "unit": "TFLOP/s",
                          "frac": round(3.0 * useful / tf32_peak, 4), "peak_source": "MEASURED_PEAKS.json bf16_tflops / 2 (dense TF32, burst)"},
             "fp64_exact_ms": round(ms_f64, 3), "lag_ms": round(ms_lag, 3),
