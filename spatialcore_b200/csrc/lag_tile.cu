@@ -47,7 +47,9 @@ constexpr int kMaxBlocksY = 148 * 8;
 // Shared-memory budget per chunk: `cap` staged rows of 128 bytes and `wcap` 32-bit words.
 // Expected union of a square patch of kChunk cells whose neighbourhoods reach rho = sqrt(deg / pi) cell
 // spacings: (sqrt(kChunk) + 2 rho)^2 (443 at degree 20; measured mean 450, max 546 on uniform points).
-// Tier 0 (mean degree <= 22): 576 rows + 6 144 words = 99 KB, two CTAs of 512 threads per SM.
+// Tier 0 (mean degree <= 22): 576 rows + 7 168 words = 103 KB, two CTAs of 512 threads per SM.  (With 6 144 words
+// 1.9 % of the C4 chunks -- degree-20 radius graph, lists padded to multiples of four: up to 6 692 words -- fell
+// to the fallback and cost 1.5 ms of a 25 ms pass; the unions themselves stay below 561 rows: scripts/tile_stats.py.)
 // Tier 1: 1 280 rows + 12 288 words = 213 KB, one CTA per SM (unions up to degree ~120, words to degree ~44
 // at one row per group).  Chunks that exceed the budget are computed by direct gathers (lag_overflow_kernel).
 struct TileTier { int chunk, cap, wcap; };
@@ -55,7 +57,7 @@ TileTier tile_tier(int64_t n, int64_t nnz) {
   const double deg = n > 0 ? (double)nnz / (double)n : 0.0;
   int tier = deg <= 22.0 ? 0 : 1;
   if (const char* e = getenv("SC_LAG_TILE_TIER")) { int v = atoi(e); if (v == 0 || v == 1) tier = v; }
-  return tier == 0 ? TileTier{256, 576, 6144} : TileTier{256, 1280, 12288};
+  return tier == 0 ? TileTier{256, 576, 7168} : TileTier{256, 1280, 12288};
 }
 
 struct TileLayout {
