@@ -652,6 +652,7 @@ int lee_tc_launch(const float* A, int64_t lda, const float* B, int64_t ldb, int6
   const bool raw_hi = !(mask && mask[0] == '1');
   const char* c2 = getenv("SC_LEE_TC_CTA2");
   const bool pair = raw_hi && !(c2 && c2[0] == '0');
+  bool pair_failed = false;
 #define SC_LEE_GO(RH, RR, LL, SG)                                                                               \
   do {                                                                                                          \
     const size_t dyn = (size_t)(RR + LL) * kTcStageBytes + 1024;                                                \
@@ -686,7 +687,15 @@ int lee_tc_launch(const float* A, int64_t lda, const float* B, int64_t ldb, int6
     cfg.attrs = attr;
     cfg.numAttrs = 1;
     cudaError_t le = cudaLaunchKernelEx(&cfg, kern, ma, mb, n, p.chunk, p.chunks_per_cta, partial, p.ldt);
-    if (le != cudaSuccess) {
+    if (le == cudaErrorInvalidClusterSize || le == cudaErrorLaunchOutOfResources) {
+      // a device (partition) on which the pair cannot be co-scheduled: the single-CTA kernel computes the same bits
+      (void)cudaGetLastError();
+      pair_failed = true;
+      if (ks != kTcK) {
+        if ((rc = make_map(&ma, A, n, lda))) return rc;
+        if ((rc = make_map(&mb, B, n, ldb))) return rc;
+      }
+    } else if (le != cudaSuccess) {
       int clusters = -1;
       cudaOccupancyMaxActiveClusters(&clusters, kern, &cfg);
       set_error("lee_tc2_kernel launch failed: %s (grid %u x %u x %u, %zu B dynamic smem, max active clusters %d)",
@@ -694,10 +703,10 @@ int lee_tc_launch(const float* A, int64_t lda, const float* B, int64_t ldb, int6
       (void)cudaGetLastError();
       return SC_ERR_CUDA;
     }
-  } else if (raw_hi) {
-    SC_LEE_GO(true, 8, 8, 2);
-  } else {
-    SC_LEE_GO(false, 8, 8, 2);
+  }
+  if (!pair || pair_failed) {
+    if (raw_hi) SC_LEE_GO(true, 8, 8, 2);
+    else SC_LEE_GO(false, 8, 8, 2);
   }
 #undef SC_LEE_GO
   SC_LAUNCH_OK();
