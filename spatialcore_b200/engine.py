@@ -9,6 +9,7 @@ from __future__ import annotations
 
 import functools
 import os
+import warnings
 from dataclasses import dataclass
 from typing import Optional, Tuple
 
@@ -544,10 +545,12 @@ def expression_to_device(X, gene_idx: Optional[np.ndarray], device="cuda") -> Tu
     if isinstance(X, torch.Tensor):
         Xd = X.to(device, non_blocking=True)
     else:
-        a = np.asarray(X)
+        a = np.asarray(X)  # a read-only numpy.memmap (on-disk X) stays a mapping: the upload pages it in
         if a.dtype not in (np.float32, np.float64):
             a = a.astype(np.float32)
-        Xd = torch.from_numpy(a).to(device, non_blocking=True)
+        with warnings.catch_warnings():
+            warnings.filterwarnings("ignore", message="The given NumPy array is not writable")  # it is only read
+            Xd = torch.from_numpy(a).to(device, non_blocking=True)
     if gene_idx is not None:
         cols = torch.from_numpy(np.asarray(gene_idx, dtype=np.int32)).to(device)
     return Xd, cols
