@@ -201,7 +201,7 @@ SC_API int sc_csr_lag_moran(const int32_t* indptr, const int32_t* indices, const
  * Zself f32[n, ldz] or NULL (NULL: the row's own value is the operand's); perm i32[n] or NULL: the operand
  * is Z[perm[j]] for row j -- the value-permuting null (autocorrelation.py:877-884) without materialising
  * the permuted matrix.  cell_obs / cell_cnt as in sc_perm_null_values (or NULL).
- * Workspace: sc_csr_lag_moran_workspace_bytes. */
+ * Workspace: sc_csr_lag_moran_workspace_bytes (partial sums + room for the chunk unions composed with `perm`). */
 SC_API size_t sc_graph_tile_bytes(int64_t n, int64_t nnz);
 SC_API int sc_graph_tile_build(const int32_t* indptr, const int32_t* indices, int64_t n, int k_fixed,
                                int64_t nnz, void* tiles, size_t tile_bytes, sc_stream_t stream);

@@ -288,6 +288,7 @@ struct LagTileArgs {
   const float* Zself;   // or NULL: the row's own value comes from the staged tile
   const float* Z;       // operand of the lag
   const int32_t* perm;  // or NULL; row j of the operand is Z[perm[j]] (value-permuting null, never materialised)
+  const int32_t* purows;  // or NULL: urows already composed with perm (perm[urows[.]]), same layout
   int64_t ldz;
   float* lag;    // or NULL
   float* local;  // or NULL
@@ -414,7 +415,7 @@ lag_tile_kernel(const __grid_constant__ LagTileArgs A, double* __restrict__ part
     if (U < 0) continue;  // left to lag_overflow_kernel (uniform over the CTA)
     const int nW = A.wtotal[chunk];
     const int64_t r0 = chunk * kChunk;
-    const int32_t* __restrict__ ur = A.urows + chunk * A.cap;
+    const int32_t* __restrict__ ur = (A.purows ? A.purows : A.urows) + chunk * A.cap;
     __syncthreads();  // the previous chunk's readers are done with the tile
     {  // ---- stage: row pieces, word lists, group info, self offsets, inverse degrees ----------------------
       int64_t e0;
@@ -432,7 +433,7 @@ lag_tile_kernel(const __grid_constant__ LagTileArgs A, double* __restrict__ part
           int32_t src[kStageBatch];
 #pragma unroll
           for (int b = 0; b < kStageBatch; ++b) { const int u = u0 + b * kSlots; src[b] = u < U ? ur[u] : -1; }
-          if (A.perm) {
+          if (A.perm && !A.purows) {
 #pragma unroll
             for (int b = 0; b < kStageBatch; ++b) if (src[b] >= 0) src[b] = A.perm[src[b]];
           }
@@ -541,6 +542,17 @@ lag_overflow_kernel(const __grid_constant__ LagTileArgs A, double* __restrict__ 
   }
   }
   reduce_cta<32>(num, den, sh, slot, q, col, active, A.ldz, partial, partial_row0 + blockIdx.y);
+}
+
+// purows[chunk][u] = perm[urows[chunk][u]]: done once per permutation instead of once per (chunk, column block)
+// inside the staging loop, where it is a dependent load in front of every row piece.
+__global__ void compose_urows_kernel(const int32_t* __restrict__ urows, const int32_t* __restrict__ ucount,
+                                     const int32_t* __restrict__ perm, int64_t n_chunks, int cap,
+                                     int32_t* __restrict__ out) {
+  for (int64_t chunk = blockIdx.x; chunk < n_chunks; chunk += gridDim.x) {
+    const int U = ucount[chunk];
+    for (int u = threadIdx.x; u < U; u += blockDim.x) out[chunk * cap + u] = perm[urows[chunk * cap + u]];
+  }
 }
 
 // out[col] = sum over partial rows, fixed order (bitwise reproducible).
@@ -657,8 +669,15 @@ extern "C" int sc_csr_lag_moran_tiled(const int32_t* indptr, const int32_t* indi
   A.rinv = reinterpret_cast<const float*>(base + L.off_inv);
   A.ginfo = reinterpret_cast<const uint32_t*>(base + L.off_ginfo);
   A.words = reinterpret_cast<const uint32_t*>(base + L.off_words);
-  A.Zself = Zself; A.Z = Z; A.perm = perm; A.ldz = ldz; A.lag = lag; A.local = local; A.ldl = ldl;
+  A.Zself = Zself; A.Z = Z; A.perm = perm; A.purows = nullptr; A.ldz = ldz; A.lag = lag; A.local = local; A.ldl = ldl;
   A.cell_obs = cell_obs; A.cell_cnt = cell_cnt; A.ldc = ldc;
   double* partial = static_cast<double*>(ws);
+  if (perm) {
+    int32_t* purows = reinterpret_cast<int32_t*>(static_cast<char*>(ws) + sc_csr_lag_moran_workspace_bytes(0, g));
+    const int blocks = (int)(L.n_chunks > 148 * 8 ? 148 * 8 : L.n_chunks);
+    compose_urows_kernel<<<blocks, 256, 0, st>>>(A.urows, A.ucount, perm, L.n_chunks, L.cap, purows);
+    SC_LAUNCH_OK();
+    A.purows = purows;
+  }
   return launch_tile_flags<1, 256, 512>(A, g, num, den, partial, st);
 }

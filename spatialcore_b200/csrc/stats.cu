@@ -1193,10 +1193,13 @@ extern "C" int sc_csr_densify(const int64_t* indptr, const int32_t* indices, con
 // Largest leading dimension the partial buffers are sized for.
 static size_t max_ld(int g) { return align_up((size_t)(g > 0 ? g : 1), 32); }
 
+// [partial sums][512 B slack][sc_csr_lag_moran_tiled with a permutation: the chunk unions composed with it,
+// at most 1 280 rows per 256-row chunk]
 extern "C" size_t sc_csr_lag_moran_workspace_bytes(int64_t n, int g) {
-  (void)n;
   size_t ld = max_ld(g);
-  return align_up(sizeof(double) * 2 * (size_t)kMaxStatBlocks * ld, 256) + 512;
+  size_t bytes = align_up(sizeof(double) * 2 * (size_t)kMaxStatBlocks * ld, 256) + 512;
+  if (n > 0) bytes += align_up(sizeof(int32_t) * (size_t)((n + 255) / 256) * 1280, 256);
+  return bytes;
 }
 
 extern "C" int sc_csr_lag_moran(const int32_t* indptr, const int32_t* indices,
