@@ -190,7 +190,7 @@ SC_API int sc_csr_lag_moran(const int32_t* indptr, const int32_t* indices, const
  * ~46 B/clk/SM for 128-byte row pieces (measured), the shared-memory crossbar 126 B/clk/SM, so:
  * sc_graph_tile_build (once per graph) finds, for every chunk of 256 consecutive rows, the sorted union of
  * its neighbour columns and own rows (`urows`: at most 576 rows for mean degrees up to 22, else 1280) and
- * turns every CSR entry into a 32-bit word, the byte offset of that row inside the tile (lists padded to a
+ * turns every CSR entry into a 16-bit word, the index of that row inside the tile (lists padded to a
  * multiple of four); sc_csr_lag_moran_tiled stages the urows' 128-byte pieces and the chunk's word lists
  * per column block with cp.async and walks the lists out of shared memory (FADD2 accumulation).  Chunks
  * whose union or word count exceeds the tile are computed by direct gathers inside the same call.

@@ -44,13 +44,13 @@ constexpr int kHash = 4096;     // open-addressing slots of the build kernel (> 
 constexpr int kSortMax = 2048;  // power of two >= largest cap
 constexpr int kMaxBlocksY = 148 * 8;
 
-// Shared-memory budget per chunk: `cap` staged rows of 128 bytes and `wcap` 32-bit words.
+// Shared-memory budget per chunk: `cap` staged rows of 128 bytes and `wcap` 16-bit words.
 // Expected union of a square patch of kChunk cells whose neighbourhoods reach rho = sqrt(deg / pi) cell
 // spacings: (sqrt(kChunk) + 2 rho)^2 (443 at degree 20; measured mean 450, max 546 on uniform points).
-// Tier 0 (mean degree <= 22): 576 rows + 7 168 words = 103 KB, two CTAs of 512 threads per SM.  (With 6 144 words
+// Tier 0 (mean degree <= 22): 576 rows + 7 168 words = 94 KB, two CTAs of 512 threads per SM.  (With 6 144 words
 // 1.9 % of the C4 chunks -- degree-20 radius graph, lists padded to multiples of four: up to 6 692 words -- fell
 // to the fallback and cost 1.5 ms of a 25 ms pass; the unions themselves stay below 561 rows: scripts/tile_stats.py.)
-// Tier 1: 1 280 rows + 12 288 words = 213 KB, one CTA per SM (unions up to degree ~120, words to degree ~44
+// Tier 1: 1 280 rows + 12 288 words = 202 KB, one CTA per SM (unions up to degree ~120, words to degree ~44
 // at one row per group).  Chunks that exceed the budget are computed by direct gathers (lag_overflow_kernel).
 struct TileTier { int chunk, cap, wcap; };
 TileTier tile_tier(int64_t n, int64_t nnz) {
@@ -82,7 +82,7 @@ TileLayout tile_layout(int64_t n, int64_t nnz, int rows) {
   L.off_self = off;   off += align_up(sizeof(uint32_t) * (size_t)L.n_chunks * (size_t)L.chunk, 256);
   L.off_inv = off;    off += align_up(sizeof(float) * (size_t)L.n_chunks * (size_t)L.chunk, 256);
   L.off_ginfo = off;  off += align_up(sizeof(uint32_t) * (size_t)L.n_chunks * (size_t)L.groups_per_chunk, 256);
-  L.off_words = off;  off += align_up(sizeof(uint32_t) * ((size_t)nnz + 4 * (size_t)L.n_chunks * (size_t)L.groups_per_chunk + 64), 256);
+  L.off_words = off;  off += align_up(sizeof(uint16_t) * ((size_t)nnz + 4 * (size_t)L.n_chunks * (size_t)L.groups_per_chunk + 64), 256);
   L.bytes = off;
   return L;
 }
@@ -102,12 +102,12 @@ __host__ __device__ __forceinline__ void row_span(const int32_t* __restrict__ in
 // First word of a chunk's packed word block: 16-byte aligned.  Group lists are padded to a multiple of four
 // words, so a chunk with G groups and E edges needs at most E + 3 G words, and round_up(e0, 4) + 4 * (groups
 // before it) leaves room for that without a scan over chunks (e0 = CSR offset of the chunk's first row).
+// (Words are 16 bits -- the index of the row in the chunk's union -- so the base is kept a multiple of 8.)
 __host__ __device__ __forceinline__ int64_t chunk_words_base(int64_t e0, int64_t groups_before) {
-  return ((e0 + 3) & ~(int64_t)3) + 4 * groups_before;
+  return ((e0 + 7) & ~(int64_t)7) + 4 * groups_before;
 }
 
-// A word: byte offset of the staged row piece inside the tile (index * 128) | membership mask << 28.
-constexpr uint32_t kOffMask = 0x0fffffffu;
+// A word: the index of the staged row piece inside the tile (16 bits; the piece lives at index * 128 bytes).
 
 __device__ __forceinline__ uint32_t hash_slot(int32_t c) { return mix32((uint32_t)c) & (kHash - 1); }
 
@@ -124,7 +124,8 @@ tile_build_kernel(const int32_t* __restrict__ indptr, const int32_t* __restrict_
                   int k_fixed, int cap, int wcap, int64_t n_chunks, int32_t* __restrict__ ucount,
                   int32_t* __restrict__ wtotal, int32_t* __restrict__ urows,
                   uint32_t* __restrict__ selfoff, float* __restrict__ rinv,
-                  uint32_t* __restrict__ ginfo, uint32_t* __restrict__ words) {
+                  uint32_t* __restrict__ ginfo, uint16_t* __restrict__ words) {
+  static_assert(R == 1, "16-bit words carry no membership mask: one row per group");
   constexpr int G = kChunk / R;
   __shared__ int32_t hkeys[kHash];
   __shared__ uint16_t hrank[kHash];
@@ -201,7 +202,7 @@ tile_build_kernel(const int32_t* __restrict__ indptr, const int32_t* __restrict_
       return hrank[h];
     };
     // merge of group gl's rows; `out` == nullptr only counts (and records the rows' inverse degrees)
-    auto merge = [&](int gl, uint32_t* out) -> int {
+    auto merge = [&](int gl, uint16_t* out) -> int {
       int64_t beg[R];
       int len[R], pos[R];
 #pragma unroll
@@ -224,12 +225,13 @@ tile_build_kernel(const int32_t* __restrict__ indptr, const int32_t* __restrict_
 #pragma unroll
         for (int r = 0; r < R; ++r)
           if (pos[r] < len[r] && indices[beg[r] + pos[r]] == best) { mask |= 1u << r; ++pos[r]; }
-        if (out) out[t] = (R == 1 ? 0u : (mask << 28)) | (rank_of(best) * (kQuads * 16u));
+        (void)mask;
+        if (out) out[t] = (uint16_t)rank_of(best);
         ++t;
       }
       if (!out) gtail[gl] = (unsigned char)(t & 3);
-      if (out)  // pad to a multiple of four: R = 1 points at the tile's zero row, R > 1 uses owner-less words
-        for (; t & 3; ++t) out[t] = (R == 1) ? (uint32_t)cap * (kQuads * 16u) : 0u;
+      if (out)  // pad to a multiple of four with the tile's zero row (never gathered: the run kernel knows the tail)
+        for (; t & 3; ++t) out[t] = (uint16_t)cap;
       return (t + 3) & ~3;
     };
     const int groups_here = (int)((r1 - r0 + R - 1) / R);
@@ -263,7 +265,7 @@ tile_build_kernel(const int32_t* __restrict__ indptr, const int32_t* __restrict_
     // ginfo: first word of the list << 8 | quads << 2 | entries of the last quad that are real (0 = all four)
     for (int gl = tid; gl < G; gl += kBuildThreads)
       gi[gl] = ((uint32_t)glen[gl] << 8) | ((uint32_t)((glen[gl + 1] - glen[gl]) >> 2) << 2) | (uint32_t)gtail[gl];
-    uint32_t* wb = words + chunk_words_base(e0, chunk * G);
+    uint16_t* wb = words + chunk_words_base(e0, chunk * G);
     for (int gl = tid; gl < groups_here; gl += kBuildThreads) merge(gl, wb + glen[gl]);
   }
 }
@@ -284,7 +286,7 @@ struct LagTileArgs {
   const uint32_t* selfoff;
   const float* rinv;
   const uint32_t* ginfo;
-  const uint32_t* words;
+  const uint16_t* words;
   const float* Zself;   // or NULL: the row's own value comes from the staged tile
   const float* Z;       // operand of the lag
   const int32_t* perm;  // or NULL; row j of the operand is Z[perm[j]] (value-permuting null, never materialised)
@@ -393,13 +395,14 @@ __device__ __forceinline__ void reduce_cta(double (&num)[4], double (&den)[4], d
 template <int R, int FLAGS, int kChunk, int kTileThreads>
 __global__ void __launch_bounds__(kTileThreads, kTileThreads == 512 ? 2 : 4)
 lag_tile_kernel(const __grid_constant__ LagTileArgs A, double* __restrict__ partial) {
+  static_assert(R == 1, "one row per group");
   extern __shared__ __align__(128) unsigned char tile_smem[];
   constexpr int kSlots = kTileThreads / kQuads;  // groups in flight per CTA
   constexpr int G = kChunk / R;                  // groups per chunk
   constexpr int kStageBatch = 5;
   unsigned char* tile = tile_smem;  // [cap + 1][128 bytes]; row cap is the zero row
-  uint32_t* swords = reinterpret_cast<uint32_t*>(tile_smem + (size_t)(A.cap + 1) * kQuads * 16);  // [wcap]
-  uint32_t* sginfo = swords + A.wcap + 4;                                                           // [G]
+  uint16_t* swords = reinterpret_cast<uint16_t*>(tile_smem + (size_t)(A.cap + 1) * kQuads * 16);  // [wcap + 8]
+  uint32_t* sginfo = reinterpret_cast<uint32_t*>(swords + A.wcap + 8);                              // [G]
   uint32_t* sself = sginfo + G;                                                                    // [kChunk]
   float* sinv = reinterpret_cast<float*>(sself + kChunk);                                          // [kChunk]
   const int tid = threadIdx.x;
@@ -445,8 +448,8 @@ lag_tile_kernel(const __grid_constant__ LagTileArgs A, double* __restrict__ part
     __syncthreads();  // the previous chunk's readers are done with the tile and with the other header buffer
     if (chunk + gridDim.y < A.n_chunks) prefetch(chunk + gridDim.y, buf ^ 1);
     if (U >= 0) {  // ---- stage: row pieces, word lists, group info, self offsets, inverse degrees -----------
-      const uint32_t* wsrc = A.words + chunk_words_base(e0, chunk * G);
-      for (int i = tid; i * 4 < nW; i += kTileThreads) cp_async16(swords + i * 4, wsrc + i * 4);
+      const uint16_t* wsrc = A.words + chunk_words_base(e0, chunk * G);
+      for (int i = tid; i * 8 < nW; i += kTileThreads) cp_async16(swords + i * 8, wsrc + i * 8);
       if (tid < G / 4) cp_async16(sginfo + tid * 4, A.ginfo + chunk * G + tid * 4);
       else if (tid >= 64 && tid < 64 + kChunk / 4) cp_async16(sself + (tid - 64) * 4, A.selfoff + r0 + (tid - 64) * 4);
       else if (tid >= 128 && tid < 128 + kChunk / 4) cp_async16(sinv + (tid - 128) * 4, A.rinv + r0 + (tid - 128) * 4);
@@ -476,37 +479,29 @@ lag_tile_kernel(const __grid_constant__ LagTileArgs A, double* __restrict__ part
     for (int gl = slot; gl < G; gl += kSlots) {
       if (r0 + (int64_t)gl * R >= A.n) break;
       const uint32_t gi = sginfo[gl];
-      const uint4* __restrict__ wp = reinterpret_cast<const uint4*>(swords + (gi >> 8));
-      // lists are padded to a multiple of four words; for R = 1 the pads of the last quad are not even loaded
-      // (7 % of the gathers at degree 20): `tail` of its entries are real and are added under a predicate
-      const int tail = R == 1 ? (int)(gi & 3u) : 0;
+      const uint2* __restrict__ wp = reinterpret_cast<const uint2*>(swords + (gi >> 8));
+      // lists are padded to a multiple of four words (one LDS.64 = four neighbours); the pads of the last quad
+      // are not even loaded (7 % of the gathers at degree 20): `tail` of its entries are real and are added
+      // under a predicate
+      const int tail = (int)(gi & 3u);
       const int nq = (int)((gi >> 2) & 63u) - (tail != 0 ? 1 : 0);
       F4 acc[R];
-#pragma unroll
-      for (int r = 0; r < R; ++r) acc[r] = f4_zero();
-      uint4 w4 = wp[0];  // (an empty list reads the next group's first quad or the slack behind the block: unused)
+      acc[0] = f4_zero();
+      uint2 w2 = wp[0];  // (an empty list reads the next group's first quad or the slack behind the block: unused)
 #pragma unroll 1
       for (int i = 0; i < nq; ++i) {
-        const uint32_t w[4] = {w4.x, w4.y, w4.z, w4.w};
-        w4 = wp[i + 1];  // next quad while this one is consumed (one quad of slack behind every block)
+        const uint32_t w[4] = {(w2.x & 0xffffu) << 7, (w2.x >> 16) << 7, (w2.y & 0xffffu) << 7, (w2.y >> 16) << 7};
+        w2 = wp[i + 1];  // next quad while this one is consumed (one quad of slack behind every block)
         F4 v[4];
 #pragma unroll
-        for (int u = 0; u < 4; ++u) v[u] = f4_load(tq + (R == 1 ? w[u] : (w[u] & kOffMask)));
+        for (int u = 0; u < 4; ++u) v[u] = f4_load(tq + w[u]);
 #pragma unroll
-        for (int u = 0; u < 4; ++u) {
-          if (R == 1) {
-            f4_add(acc[0], v[u]);  // pad words add the zero row
-          } else {
-#pragma unroll
-            for (int r = 0; r < R; ++r) f4_add_if(acc[r], v[u], w[u] & (1u << (28 + r)));
-          }
-        }
+        for (int u = 0; u < 4; ++u) f4_add(acc[0], v[u]);
       }
-      if (R == 1) {  // w4 holds the partial quad (or the slack behind a full list: all three predicates off)
-        f4_load_add_if(acc[0], tq_s + w4.x, tail > 0);
-        f4_load_add_if(acc[0], tq_s + w4.y, tail > 1);
-        f4_load_add_if(acc[0], tq_s + w4.z, tail > 2);
-      }
+      // w2 holds the partial quad (or the slack behind a full list: all three predicates off)
+      f4_load_add_if(acc[0], tq_s + ((w2.x & 0xffffu) << 7), tail > 0);
+      f4_load_add_if(acc[0], tq_s + ((w2.x >> 16) << 7), tail > 1);
+      f4_load_add_if(acc[0], tq_s + ((w2.y & 0xffffu) << 7), tail > 2);
 #pragma unroll
       for (int r = 0; r < R; ++r) {
         const int lrow = gl * R + r;
@@ -595,7 +590,8 @@ __global__ void tile_reduce_kernel(const double* __restrict__ partial, int nrows
 
 size_t tile_smem_bytes(const LagTileArgs& A, int R) {
   const int G = A.chunk / R;
-  return (size_t)(A.cap + 1) * kQuads * 16 + sizeof(uint32_t) * ((size_t)A.wcap + 4 + G + 2 * A.chunk + 2 * ((size_t)A.cap + 4));
+  return (size_t)(A.cap + 1) * kQuads * 16 + sizeof(uint16_t) * ((size_t)A.wcap + 8) +
+         sizeof(uint32_t) * ((size_t)G + 2 * A.chunk + 2 * ((size_t)A.cap + 4));
 }
 
 template <int R, int FLAGS, int kChunk, int kTileThreads>
@@ -658,7 +654,7 @@ extern "C" int sc_graph_tile_build(const int32_t* indptr, const int32_t* indices
   uint32_t* selfoff = reinterpret_cast<uint32_t*>(base + L.off_self);
   float* rinv = reinterpret_cast<float*>(base + L.off_inv);
   uint32_t* ginfo = reinterpret_cast<uint32_t*>(base + L.off_ginfo);
-  uint32_t* words = reinterpret_cast<uint32_t*>(base + L.off_words);
+  uint16_t* words = reinterpret_cast<uint16_t*>(base + L.off_words);
   const int blocks = (int)(L.n_chunks > 148 * 16 ? 148 * 16 : L.n_chunks);
 tile_build_kernel<1, 256><<<blocks, kBuildThreads, 0, st>>>(indptr, indices, n, k_fixed, L.cap, L.wcap, L.n_chunks, ucount, wtotal, urows, selfoff, rinv, ginfo, words);
   SC_LAUNCH_OK();
@@ -692,7 +688,7 @@ extern "C" int sc_csr_lag_moran_tiled(const int32_t* indptr, const int32_t* indi
   A.selfoff = reinterpret_cast<const uint32_t*>(base + L.off_self);
   A.rinv = reinterpret_cast<const float*>(base + L.off_inv);
   A.ginfo = reinterpret_cast<const uint32_t*>(base + L.off_ginfo);
-  A.words = reinterpret_cast<const uint32_t*>(base + L.off_words);
+  A.words = reinterpret_cast<const uint16_t*>(base + L.off_words);
   A.Zself = Zself; A.Z = Z; A.perm = perm; A.purows = nullptr; A.ldz = ldz; A.lag = lag; A.local = local; A.ldl = ldl;
   A.cell_obs = cell_obs; A.cell_cnt = cell_cnt; A.ldc = ldc;
   double* partial = static_cast<double*>(ws);

@@ -165,8 +165,8 @@ def test_tile_exports_validate_without_a_gpu():
     L = _lib.lib()
     assert L.sc_graph_tile_bytes(0, 10) == 0 and L.sc_graph_tile_bytes(100, -1) == 0
     big = L.sc_graph_tile_bytes(5_000_000, 100_000_000)
-    # 4 bytes per edge for the word lists (tile byte offsets) + the per-chunk union rows: about the size of the CSR itself
-    assert 400_000_000 < big < 700_000_000
+    # 2 bytes per edge for the word lists (16-bit union indices) + the per-chunk union rows: less than the CSR itself
+    assert 250_000_000 < big < 450_000_000
     assert L.sc_graph_tile_build(None, None, 100, 6, 600, None, 0, None) == -1
     assert "null argument" in L.sc_last_error().decode()
     assert L.sc_graph_tile_build(None, 1, 100, 6, 601, 1, 1 << 20, None) == -1  # nnz != n * k_fixed
