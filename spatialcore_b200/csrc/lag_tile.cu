@@ -13,19 +13,19 @@
 // chunk of 256 consecutive cells needs (its own rows plus a halo) number ~1.76 x 256, so:
 //
 //   build (once per graph):  per chunk, the sorted union `urows` of all neighbour columns (+ own rows) and,
-//                            per group of R consecutive rows, the merged neighbour list as 16-bit words
-//                            (R-bit membership mask | local index into urows), packed per chunk;
+//                            per row, its neighbour list as 16-bit words (index into urows), packed per
+//                            chunk, padded to quads, with the count of real entries in the last quad;
 //   run (per column block):  stage the urows' 128-byte pieces AND the chunk's word lists, offsets, degrees
-//                            with cp.async (L1 bypass, every byte read once per chunk), then every
-//                            (group, float4 lane) walks its word list out of shared memory: all loads of the
-//                            inner loop are LDS, nothing in it waits for L2.
+//                            with cp.async (L1 bypass, every byte read once per chunk; the chunk header and
+//                            the union list themselves arrive one chunk ahead), then every (row, float4
+//                            lane) walks its word list out of shared memory: all loads of the inner loop
+//                            are LDS, nothing in it waits for L2.
 //
-// The kernels are written for groups of R consecutive rows sharing one merged word list (a staged value
-// is then read once for all rows of the group that own the neighbour: the union of 4 lists holds 0.49 of their
-// summed lengths), but only R = 1 is instantiated: with R = 2 / 4 the predicated adds cost more issue slots
-// than the saved LDS wavefronts return (measured 29 / 32 ms against 24.7 ms at C4,
-// profiles/r02_lag_tile_variants.json).  The kernel is bound by the LSU data pipe (shared-memory wavefronts of
-// the gathers plus the cp.async writes: ~80 % of peak in ncu), not by HBM.
+// One row per list: sharing a merged list between 2 / 4 consecutive rows (the union of 4 lists holds 0.49 of
+// their summed lengths) was measured and lost -- the predicated adds cost more issue slots than the saved LDS
+// wavefronts return (29 / 32 ms against 24.7 ms at C4, profiles/r02_lag_tile_variants.json).  The kernel is
+// bound by the LSU data pipe (shared-memory wavefronts of the gathers, the word loads and the cp.async
+// writes: 75 % of peak in ncu at 20.2 ms), not by HBM.
 //
 // Arithmetic: every row's neighbours are added in ascending column order in FP32, then scaled by 1/deg —
 // exactly the order of lag_stat_kernel, so the two kernels agree bit for bit.
@@ -319,10 +319,6 @@ __device__ __forceinline__ F4 f4_load(const void* smem_ptr) {
 __device__ __forceinline__ void f4_add(F4& a, const F4& v) {
   asm("add.rn.f32x2 %0, %0, %1;" : "+l"(a.lo) : "l"(v.lo));
   asm("add.rn.f32x2 %0, %0, %1;" : "+l"(a.hi) : "l"(v.hi));
-}
-__device__ __forceinline__ void f4_add_if(F4& a, const F4& v, uint32_t bit) {
-  asm("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t@p add.rn.f32x2 %0, %0, %2;\n\t@p add.rn.f32x2 %1, %1, %3;\n\t}"
-      : "+l"(a.lo), "+l"(a.hi) : "l"(v.lo), "l"(v.hi), "r"(bit));
 }
 // acc += the row piece at shared address `saddr` if `cond` (predicated load and adds: no wavefront when off)
 __device__ __forceinline__ void f4_load_add_if(F4& a, uint32_t saddr, int cond) {
