@@ -27,6 +27,7 @@ def _graphs(eng, n, seed):
     cd = torch.from_numpy(coords).cuda()
     co = eng.spatial_order(cd)
     knn, _, _ = eng.knn_graph(cd, 7)
+    knn30, _, _ = eng.knn_graph(cd, 30)  # mean degree above 22: the 1 280-row / one-CTA-per-SM tile budget
     rad, _ = eng.radius_graph(cd, float(np.sqrt(6.0 * 160000.0 / (np.pi * n))))  # mean degree ~6 on the uniform part: some empty rows
     assert (np.diff(rad.indptr.cpu().numpy()) == 0).any()  # empty rows
     # a graph with no spatial structure: every chunk's union overflows the tile -> direct-gather fallback
@@ -36,7 +37,7 @@ def _graphs(eng, n, seed):
     A.data[:] = 1.0
     rnd = eng.graph_from_scipy(A)
     out = {}
-    for name, g in (("knn", knn), ("radius", rad)):
+    for name, g in (("knn", knn), ("radius", rad), ("knn30", knn30)):
         out[name] = eng.relabel_graph(g, co)
         out[name].tiles = None
     out["random"] = rnd
